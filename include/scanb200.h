@@ -1,0 +1,218 @@
+/*
+ * scanb200.h -- C ABI of the B200-native normalize -> PCA path of scan-rs.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, opaque handles,
+ * int status codes, no C++/torch types.  A Rust crate binds exactly these symbols from
+ * its build.rs (INTEGRATION.md shows the `extern "C"` block and the safe wrappers that
+ * keep the reference's entry points: `AdaptiveMat` -> upload, `normalize(..)`,
+ * `Pca::run_pca_cancellable`).  Each entry point cites the reference interface it
+ * replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - Matrix orientation is the reference's: features/genes are ROWS, barcodes/cells are
+ *     COLUMNS (scan-rs/src/mtx.rs:10-51).  m = genes, n = cells.
+ *   - All dense blocks are row-major ("standard layout" of ndarray), f64.
+ *   - Host buffers are caller-allocated and caller-owned; the library never keeps a host
+ *     pointer after the call returns.  Handles own device memory.
+ *   - One sb_ctx drives one GPU from one host thread.  For cell-sharded multi-GPU runs
+ *     every rank (one process per GPU) creates its own context, joins a communicator
+ *     with sb_comm_init and then makes the SAME sequence of calls on its own cell shard;
+ *     gene-sized results (totals, U, sigma) come back replicated, cell-sized results
+ *     (cell totals, V) come back for the local shard only.
+ *   - Every function returns SB_OK (0) or an error code; sb_last_error() returns the
+ *     thread-local message.  Nothing panics or aborts across the ABI.
+ *   - There is NO CPU fallback: without a CUDA device sb_init fails with SB_ERR_CUDA.
+ */
+#ifndef SCANB200_H
+#define SCANB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_VERSION 100
+
+#if defined(__GNUC__)
+#define SB_API __attribute__((visibility("default")))
+#else
+#define SB_API
+#endif
+
+/* status codes */
+enum {
+    SB_OK = 0,
+    SB_ERR_INVALID_SHAPE = 1, /* "The input matrix must be at least 2x2."  bk_svd.rs:73-75 */
+    SB_ERR_INVALID_K = 2,     /* "invalid k"                                 bk_svd.rs:77-79 */
+    SB_ERR_CANCELLED = 3,     /* snoop::CancellationError                    snoop/src/lib.rs:5-18 */
+    SB_ERR_CUDA = 4,
+    SB_ERR_NCCL = 5,
+    SB_ERR_OOM = 6,
+    SB_ERR_INVALID_ARG = 7,   /* the reference's assert!/panic! programmer errors */
+    SB_ERR_UNSUPPORTED = 8,
+    SB_ERR_LINALG = 9         /* cuSOLVER failure (the reference's LAPACK `?` errors) */
+};
+
+/* storage order of host CSR/CSC arrays handed to sb_upload (sprs::CSR / sprs::CSC of a
+ * genes x cells matrix, sqz/src/mat.rs:45-65) */
+enum { SB_GENE_MAJOR = 0, SB_CELL_MAJOR = 1 };
+
+/* scan_rs::normalization::Normalization (scan-rs/src/normalization.rs:11-28) */
+enum {
+    SB_NORM_CELLRANGER = 0,
+    SB_NORM_CELLRANGER8 = 1,
+    SB_NORM_SEURATLOG = 2,
+    SB_NORM_BINOMIAL_DEVIANCE = 3,
+    SB_NORM_BINOMIAL_PEARSON = 4,
+    SB_NORM_WITH_SIZE_FACTORS = 5,
+    SB_NORM_LOG_TRANSFORM = 6
+};
+
+/* scan_rs::normalization::LogBase (normalization.rs:105-112) */
+enum { SB_LOG_E = 1, SB_LOG_TWO = 2, SB_LOG_TEN = 10 };
+
+typedef struct sb_ctx sb_ctx;   /* device context (+ optional NCCL communicator) */
+typedef struct sb_mat sb_mat;   /* device-resident u32 count matrix: AdaptiveMat<u32> (sqz/src/mat.rs:34-42) */
+typedef struct sb_nmat sb_nmat; /* normalized matrix: LowRankOffset<D, impl MatrixMap<u32,f64>> (sqz/src/low_rank_offset.rs:12-16) */
+
+/* progress / cancel token: CancelProgress::set_progress_check (snoop/src/lib.rs:45-57).
+ * Called on the calling thread with the reference's milestones (0.8*i/n_iter, 0.82, 0.93,
+ * 1.0; bk_svd.rs:96-114).  A non-zero return cancels: the call stops at that milestone and
+ * returns SB_ERR_CANCELLED. */
+typedef int (*sb_progress_cb)(double fraction, void *user);
+
+/* ---------------------------------------------------------------- context */
+SB_API int sb_version(void);
+SB_API const char *sb_last_error(void);
+SB_API int sb_init(int device, sb_ctx **out);
+SB_API void sb_shutdown(sb_ctx *ctx);
+/* Multi-GPU: rank 0 calls sb_comm_unique_id, ships the 128 bytes to the other ranks by any
+ * means (torch.distributed, MPI, a file), then every rank calls sb_comm_init. */
+SB_API int sb_comm_unique_id(char id[128]);
+SB_API int sb_comm_init(sb_ctx *ctx, int nranks, int rank, const char id[128]);
+SB_API int sb_sync(sb_ctx *ctx);
+
+/* ---------------------------------------------------------------- count matrix
+ * sb_upload replaces AdaptiveMat::from_csmat / new (sqz/src/mat.rs:81-124): the Rust side
+ * decodes each AdaptiveVec once (vec.rs `foreach` :1230-1273) into these arrays.  `major`
+ * says whether indptr runs over genes (idx = cell) or over cells (idx = gene).  n_local is
+ * this rank's number of cells.  Indices must be strictly ascending inside each vector and
+ * counts non-zero (what AdaptiveVec guarantees); zeros are dropped. */
+SB_API int sb_upload(sb_ctx *ctx, int major, uint32_t m, uint64_t n_local, const uint64_t *indptr,
+              const uint32_t *idx, const uint32_t *cnt, sb_mat **out);
+/* rows(), cols(), shape() (mat.rs:160-176) + nnz() (:155-157); n_global == n_local without a communicator */
+SB_API int sb_mat_shape(const sb_mat *mat, uint32_t *m, uint64_t *n_local, uint64_t *n_global, uint64_t *nnz_local);
+/* to_csmat (mat.rs:207-239): sizes from sb_mat_shape; indptr has m+1 or n_local+1 entries */
+SB_API int sb_download(const sb_mat *mat, int major, uint64_t *indptr, uint32_t *idx, uint32_t *cnt);
+SB_API void sb_free_mat(sb_mat *mat);
+
+/* sum_axis::<u32>(Axis(0)) (mat.rs:377-406; normalization.rs:159,161): per-cell UMI totals, wrapping u32 */
+SB_API int sb_cell_totals(sb_mat *mat, uint32_t *out_n_local);
+/* per-gene totals as u64 (hdf5-io/src/matrix.rs:106-114; sum_axis(Axis(1))); all-reduced over ranks.
+ * square != 0 gives sum of v*v (HVG moments, builder-defined) */
+SB_API int sb_gene_totals(sb_mat *mat, int square, uint64_t *out_m);
+/* number of stored non-zeros per gene, all-reduced */
+SB_API int sb_gene_nnz(sb_mat *mat, uint64_t *out_m);
+/* median_mut over the cell totals of ALL ranks (scan-rs/src/stats.rs:13-38): u32 midpoint.
+ * *nonempty = 0 when there are no cells (the caller then uses 1.0, normalization.rs:166) */
+SB_API int sb_median_cell_total(sb_mat *mat, uint32_t *median, int *nonempty);
+
+/* partition_on_thresholds (mat.rs:772-889).  Single-rank only.  `rows_out`/`cols_out` need room
+ * for m / n_local entries and receive the selected indices; kept/residual may be NULL. */
+SB_API int sb_partition(sb_mat *mat, int has_row_thr, double row_thr, int has_col_thr, double col_thr,
+                 sb_mat **kept, sb_mat **residual, uint64_t *rows_out, uint64_t *n_rows_out,
+                 uint64_t *cols_out, uint64_t *n_cols_out);
+/* select_rows / select_cols (mat.rs:1004-1071): new matrix with the given rows/cols in the given order */
+SB_API int sb_select_rows(sb_mat *mat, const uint32_t *rows, uint32_t count, sb_mat **out);
+SB_API int sb_select_cols(sb_mat *mat, const uint64_t *cols, uint64_t count, sb_mat **out);
+/* Highly-variable-gene selection (NOT in the reference; builder-defined): exact u64
+ * sums -> dispersion var/mean in f64 -> top n_top, ties to the lower index; out sorted ascending. */
+SB_API int sb_hvg_select(sb_mat *mat, uint32_t n_top, uint32_t *out_idx, uint32_t *out_count);
+
+/* ---------------------------------------------------------------- normalization
+ * normalize / normalize_with_size_factor (normalization.rs:46-102) plus the two binomial
+ * residual constructors the CLI dispatches to (normalization.rs:233-260, 307-323;
+ * tools/src/bin/cmd.rs:67-81).  size_factors (u32[n_local]) only for SB_NORM_WITH_SIZE_FACTORS.
+ * The result borrows `mat`: free it before the matrix. */
+SB_API int sb_normalize(sb_mat *mat, int norm, const uint32_t *size_factors, sb_nmat **out);
+/* log_normalize_with_size_factor (+ optional scale_and_center) with every knob exposed
+ * (normalization.rs:138-178; mat.rs:986-1001): has_target=0 -> median of cell totals;
+ * center_scale: 0 = sparse log-normalized matrix only, 1 = scale_and_center(Axis(1), None),
+ * 2 = scale_and_center(Axis(1), Some(sd_override[m])). */
+SB_API int sb_log_normalize(sb_mat *mat, int has_target, double target, int log_base, const uint32_t *size_factors,
+                     int center_scale, const double *sd_override, sb_nmat **out);
+/* log1p_normalize_fixed_point (normalization.rs:191-213) */
+SB_API int sb_normalize_fixed_point(sb_mat *mat, int log_base, uint32_t base, uint32_t exponent, sb_nmat **out);
+/* The derived tables: col_scale[n_local], row_scale[m] (1/sd), u[m], v[n_local]; any pointer may be NULL */
+SB_API int sb_nmat_params(const sb_nmat *a, double *col_scale, double *row_scale, double *u, double *v);
+/* LowRankOffset::to_dense (low_rank_offset.rs:55-57): m x n_local row-major; test/debug sizes only */
+SB_API int sb_nmat_to_dense(sb_nmat *a, double *out);
+/* LowRankOffset . Array2 (low_rank_offset.rs:68-81): out[m x w] = A . x[n_local x w], all-reduced over ranks */
+SB_API int sb_nmat_dot(sb_nmat *a, const double *x, uint32_t w, double *out);
+/* Array2 . LowRankOffset (low_rank_offset.rs:83-96): out[w x n_local] = b[w x m] . A */
+SB_API int sb_nmat_rdot(sb_nmat *a, const double *b, uint32_t w, double *out);
+SB_API void sb_free_nmat(sb_nmat *a);
+
+/* ---------------------------------------------------------------- PCA
+ * The start block: SmallRng::seed_from_u64(seed) + Uniform::new(-1.0, 1.0), row-major fill
+ * (bk_svd.rs:83-84, :90, :118).  Host-side, deterministic. */
+SB_API int sb_omega(uint64_t seed, uint64_t rows, uint64_t cols, double *out);
+
+/* svd_bk (scan-rs/src/dim_red/bk_svd.rs:57-146).  b is clamped to min(m, n, b) (:81).  `omega`
+ * may be NULL (generated from `seed` as above) or the caller's start block, row-major:
+ * (b x m) when n > m, (n_local x b) when m >= n.  Outputs: U[m x k], S[k], V[n_local x k]
+ * row-major -- V is already `vt.reversed_axes()` as run_pca returns it (bk_svd.rs:51). */
+SB_API int sb_bksvd(sb_nmat *a, uint32_t k, uint32_t b, uint32_t n_iter, uint64_t seed, const double *omega,
+             sb_progress_cb cb, void *user, double *U, double *S, double *V);
+/* BkSvd::run_pca_cancellable (bk_svd.rs:48-52): b = ceil(k * k_multiplier), seed 0 */
+SB_API int sb_bksvd_run_pca(sb_nmat *a, uint32_t k, double k_multiplier, uint32_t n_iter, sb_progress_cb cb,
+                     void *user, double *U, double *S, double *V);
+/* svd_rand (scan-rs/src/dim_red/rand_svd.rs:54-129); omega: (l x m) when n > m, (n_local x l) when m >= n */
+SB_API int sb_randsvd(sb_nmat *a, uint32_t k, uint32_t l, uint32_t n_iter, uint64_t seed, const double *omega,
+               double *U, double *S, double *V);
+/* RandSvd::run_pca_cancellable (rand_svd.rs:44-49): l = max(k + 4, floor(k * l_multiplier)), seed 0 */
+SB_API int sb_randsvd_run_pca(sb_nmat *a, uint32_t k, double l_multiplier, uint32_t n_iter, double *U, double *S,
+                       double *V);
+
+/* ---------------------------------------------------------------- measurement
+ * Device-side timing on the context's own stream (CUDA events) and per-kernel accounting;
+ * bench.py builds its roofline object from these.  Not part of the reference interface. */
+typedef struct {
+    double spmm_t_ms;     /* K7: out[cells x w]  = A^T . Y  (cell-major gather) */
+    double spmm_n_ms;     /* K8: out[genes x w]  = A . X    (gene-major panel gather) */
+    double moments_ms;    /* K5 */
+    double reduce_ms;     /* integer reductions K1/K2 */
+    double dense_ms;      /* QR / Gram / eigh / small GEMMs */
+    double comm_ms;       /* NCCL collectives */
+    double spmm_t_bytes;  /* algorithmic bytes summed over launches (SURVEY 8d formula) */
+    double spmm_n_bytes;
+    double spmm_t_flops;
+    double spmm_n_flops;
+    uint64_t spmm_t_launches;
+    uint64_t spmm_n_launches;
+    uint64_t kernel_launches; /* every kernel this library launched (own + library calls) */
+    uint64_t own_kernel_launches;
+} sb_profile;
+SB_API int sb_profile_enable(sb_ctx *ctx, int on); /* on: record a CUDA-event pair around every phase */
+SB_API int sb_profile_reset(sb_ctx *ctx);
+SB_API int sb_profile_get(sb_ctx *ctx, sb_profile *out);
+SB_API int sb_timer_begin(sb_ctx *ctx);            /* records an event on the context stream */
+SB_API int sb_timer_end(sb_ctx *ctx, float *ms);   /* records, synchronises, returns elapsed ms */
+/* write >= 2x L2 worth of bytes so the next timed step starts cold */
+SB_API int sb_flush_l2(sb_ctx *ctx);
+
+/* ---------------------------------------------------------------- synthetic workload
+ * Test/bench utility, not part of the reference interface: negative-binomial count matrix
+ * from a counter-based hash keyed by (seed, gene, global cell), identical bit for bit to
+ * the CPU generator in synth/ (see synth_nb.h).  pf[n_clusters x m] are per-cluster gene
+ * abundances, depth[n_local] per-cell depths, cluster[n_local] cluster ids. */
+SB_API int sb_synth_generate(sb_ctx *ctx, uint32_t m, uint64_t n_local, uint64_t cell_offset, uint64_t seed,
+                      uint32_t n_clusters, const double *pf, const double *depth, const uint8_t *cluster,
+                      uint32_t r_dispersion, sb_mat **out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCANB200_H */

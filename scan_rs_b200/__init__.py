@@ -1,0 +1,17 @@
+"""scan_rs_b200 -- B200-native normalize -> PCA hot path of scan-rs behind a C ABI.
+
+The package mirrors the reference's module layout for this path only:
+  sqz            AdaptiveMat (device-resident counts), LowRankOffset (normalized matrix)
+  normalization  Normalization, normalize, normalize_with_size_factor, ...
+  dim_red        BkSvd, RandSvd, svd_bk, svd_rand
+  snoop          NoOpSnoop, AtomicSnoop
+  synth          synthetic workloads (test / bench utility)
+All compute runs in scan_rs_b200/libscanb200.so (hand-written sm_100a CUDA + cuSOLVER/cuBLAS for the
+small dense steps); there is no CPU fallback."""
+from ._lib import CancellationError, ScanB200Error, LIB_PATH  # noqa: F401
+from .sqz import AdaptiveMat, Context, LowRankOffset  # noqa: F401
+from .normalization import (LogBase, Normalization, binom_deviance_resid, binom_pearson_resid,  # noqa: F401
+                            log1p_normalize_fixed_point, log_normalize, log_normalize_with_size_factor,
+                            normalize, normalize_with_size_factor)
+from .dim_red import BkSvd, RandSvd, omega, svd_bk, svd_rand  # noqa: F401
+from .snoop import AtomicSnoop, NoOpSnoop  # noqa: F401

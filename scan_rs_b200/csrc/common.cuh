@@ -1,0 +1,179 @@
+// common.cuh -- internal structures of libscanb200 (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cublas_v2.h>
+#include <cusolverDn.h>
+#include <nccl.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/scanb200.h"
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+// ---------------------------------------------------------------- errors
+void sb_set_error(const char *fmt, ...);
+int sb_fail(int code, const char *fmt, ...);
+
+#define SB_CUDA(expr)                                                                         \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return sb_fail(_e == cudaErrorMemoryAllocation ? SB_ERR_OOM : SB_ERR_CUDA,        \
+                           "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__,      \
+                           __LINE__, cudaGetErrorString(_e));                                 \
+    } while (0)
+#define SB_CUBLAS(expr)                                                                       \
+    do {                                                                                      \
+        cublasStatus_t _s = (expr);                                                           \
+        if (_s != CUBLAS_STATUS_SUCCESS)                                                      \
+            return sb_fail(SB_ERR_LINALG, "cuBLAS error %d at %s:%d", (int)_s, __FILE__, __LINE__); \
+    } while (0)
+#define SB_CUSOLVER(expr)                                                                     \
+    do {                                                                                      \
+        cusolverStatus_t _s = (expr);                                                         \
+        if (_s != CUSOLVER_STATUS_SUCCESS)                                                    \
+            return sb_fail(SB_ERR_LINALG, "cuSOLVER error %d at %s:%d", (int)_s, __FILE__, __LINE__); \
+    } while (0)
+#define SB_NCCL(expr)                                                                         \
+    do {                                                                                      \
+        ncclResult_t _r = (expr);                                                             \
+        if (_r != ncclSuccess)                                                                \
+            return sb_fail(SB_ERR_NCCL, "NCCL error %s at %s:%d", ncclGetErrorString(_r),     \
+                           __FILE__, __LINE__);                                               \
+    } while (0)
+#define SB_TRY(expr)                 \
+    do {                             \
+        int _rc = (expr);            \
+        if (_rc != SB_OK) return _rc; \
+    } while (0)
+
+// ---------------------------------------------------------------- device buffer (RAII)
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    int alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+        if (e != cudaSuccess) {
+            p = nullptr;
+            n = 0;
+            return sb_fail(e == cudaErrorMemoryAllocation ? SB_ERR_OOM : SB_ERR_CUDA,
+                           "cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+        }
+        return SB_OK;
+    }
+    int ensure(size_t count) { return count <= n && p ? SB_OK : alloc(count); }
+    void swap(DevBuf &o) {
+        T *tp = p; p = o.p; o.p = tp;
+        size_t tn = n; n = o.n; o.n = tn;
+    }
+};
+
+// ---------------------------------------------------------------- profile phases
+enum Phase { PH_SPMM_T = 0, PH_SPMM_N, PH_MOMENTS, PH_REDUCE, PH_DENSE, PH_COMM, PH_COUNT };
+
+struct sb_ctx {
+    int device = 0;
+    int sm_count = 148;
+    size_t l2_bytes = 0;
+    cudaStream_t stream = nullptr;
+    cublasHandle_t cublas = nullptr;
+    cusolverDnHandle_t cusolver = nullptr;
+    ncclComm_t comm = nullptr;
+    int nranks = 1, rank = 0;
+    // profiling
+    bool profile_on = false;
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending;  // phase, (start, stop)
+    std::vector<cudaEvent_t> event_pool;
+    sb_profile prof;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    DevBuf<char> flush_buf;
+    // scratch reused by reductions / collectives
+    DevBuf<char> scratch;
+    void *pinned = nullptr;  // small pinned staging (4 KB)
+};
+
+// The packed gene-major entry: x = gene | (cell_local << SB_GENE_BITS), y = count.
+#define SB_GENE_BITS 22
+#define SB_GENE_MASK 0x3FFFFFu
+#define SB_MAX_PANEL_CELLS 1024
+
+struct sb_mat {
+    sb_ctx *ctx = nullptr;
+    u32 m = 0;            // genes
+    u64 n = 0;            // local cells
+    u64 n_global = 0;     // cells over all ranks
+    u64 cell_offset = 0;  // global index of local cell 0
+    u64 nnz = 0;          // local non-zeros
+    // cell-major copy: cm_ptr[n+1], cm[nnz] = {gene, count}, genes ascending inside a cell
+    DevBuf<u64> cm_ptr;
+    DevBuf<uint2> cm;
+    // gene-major panelled copy: cells are cut into panels of `pc` cells; inside a panel entries are
+    // sorted by (gene, cell): gm[k] = {gene | cell_local << 22, count}.  gm_base[np+1] are panel
+    // starts.  unit_ptr[np*ur+1] cuts every panel into `ur` gene ranges of similar nnz (work units).
+    u32 pc = 0, np = 0, ur = 1;
+    DevBuf<uint2> gm;
+    DevBuf<u64> gm_base;
+    DevBuf<u64> unit_ptr;
+    // cached integer reductions
+    DevBuf<u32> cell_tot;
+    bool have_cell_tot = false;
+};
+
+// device view of the per-nonzero map (sqz/src/matrix_map.rs): see MapDev in map.cuh
+struct sb_nmat {
+    sb_mat *mat = nullptr;
+    int kind = 1;      // 1 log chain, 2 binomial deviance, 3 binomial Pearson
+    int log_base = 0;  // 0 none, 1 ln, 2 log2, 10 log10
+    DevBuf<double> col_scale;  // [n] (kind 1) or binomial n[c]
+    DevBuf<double> row_scale;  // [m] 1/sd (kind 1; may be empty) or binomial pi[r]
+    bool has_row_scale = false;
+    bool has_offset = false;
+    bool v_ones = true;
+    DevBuf<double> u;  // [m]
+    DevBuf<double> v;  // [n] (only when !v_ones)
+};
+
+// ---------------------------------------------------------------- profiling helpers (ctx.cu)
+void prof_begin(sb_ctx *ctx, int phase);
+void prof_end(sb_ctx *ctx, int phase);
+void prof_collect(sb_ctx *ctx);
+static inline void count_launch(sb_ctx *ctx, bool own = true) {
+    ctx->prof.kernel_launches++;
+    if (own) ctx->prof.own_kernel_launches++;
+}
+struct ProfScope {
+    sb_ctx *c;
+    int ph;
+    ProfScope(sb_ctx *ctx, int phase) : c(ctx), ph(phase) { prof_begin(c, ph); }
+    ~ProfScope() { prof_end(c, ph); }
+};
+
+int ctx_scratch(sb_ctx *ctx, size_t bytes, void **out);
+int comm_allreduce_f64(sb_ctx *ctx, double *buf, size_t count);
+int comm_allreduce_u64(sb_ctx *ctx, u64 *buf, size_t count);
+int comm_allreduce_max_i32(sb_ctx *ctx, int *host_val);
+int comm_allgather_u64_host(sb_ctx *ctx, u64 mine, std::vector<u64> &all);
+
+static inline unsigned cdiv(u64 a, u64 b) { return (unsigned)((a + b - 1) / b); }

@@ -1,0 +1,243 @@
+// ctx.cu -- context, errors, communicator, timers and per-phase accounting.
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void sb_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int sb_fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+extern "C" const char *sb_last_error(void) { return g_err; }
+extern "C" int sb_version(void) { return SB_VERSION; }
+
+extern "C" int sb_init(int device, sb_ctx **out) {
+    if (!out) return sb_fail(SB_ERR_INVALID_ARG, "sb_init: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return sb_fail(SB_ERR_CUDA, "sb_init: no CUDA device (%s); this library has no CPU fallback",
+                       e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= ndev) return sb_fail(SB_ERR_INVALID_ARG, "sb_init: device %d of %d", device, ndev);
+    SB_CUDA(cudaSetDevice(device));
+    sb_ctx *ctx = new sb_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    SB_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->l2_bytes = (size_t)prop.l2CacheSize;
+    SB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    SB_CUBLAS(cublasCreate(&ctx->cublas));
+    SB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
+    SB_CUSOLVER(cusolverDnCreate(&ctx->cusolver));
+    SB_CUSOLVER(cusolverDnSetStream(ctx->cusolver, ctx->stream));
+    SB_CUDA(cudaEventCreate(&ctx->t0));
+    SB_CUDA(cudaEventCreate(&ctx->t1));
+    SB_CUDA(cudaMallocHost(&ctx->pinned, 4096));
+    memset(&ctx->prof, 0, sizeof(ctx->prof));
+    *out = ctx;
+    return SB_OK;
+}
+
+extern "C" void sb_shutdown(sb_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    prof_collect(ctx);
+    for (auto ev : ctx->event_pool) cudaEventDestroy(ev);
+    if (ctx->comm) ncclCommDestroy(ctx->comm);
+    if (ctx->cusolver) cusolverDnDestroy(ctx->cusolver);
+    if (ctx->cublas) cublasDestroy(ctx->cublas);
+    if (ctx->t0) cudaEventDestroy(ctx->t0);
+    if (ctx->t1) cudaEventDestroy(ctx->t1);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    ctx->flush_buf.release();
+    ctx->scratch.release();
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int sb_sync(sb_ctx *ctx) {
+    if (!ctx) return sb_fail(SB_ERR_INVALID_ARG, "sb_sync: ctx is NULL");
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+
+// ---------------------------------------------------------------- communicator
+extern "C" int sb_comm_unique_id(char id[128]) {
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    ncclUniqueId uid;
+    SB_NCCL(ncclGetUniqueId(&uid));
+    memcpy(id, &uid, 128);
+    return SB_OK;
+}
+
+extern "C" int sb_comm_init(sb_ctx *ctx, int nranks, int rank, const char id[128]) {
+    if (!ctx || nranks < 1 || rank < 0 || rank >= nranks) return sb_fail(SB_ERR_INVALID_ARG, "sb_comm_init: bad arguments");
+    if (ctx->comm) return sb_fail(SB_ERR_INVALID_ARG, "sb_comm_init: communicator already initialised");
+    SB_CUDA(cudaSetDevice(ctx->device));
+    if (nranks == 1) return SB_OK;
+    ncclUniqueId uid;
+    memcpy(&uid, id, 128);
+    SB_NCCL(ncclCommInitRank(&ctx->comm, nranks, uid, rank));
+    ctx->nranks = nranks;
+    ctx->rank = rank;
+    return SB_OK;
+}
+
+int ctx_scratch(sb_ctx *ctx, size_t bytes, void **out) {
+    SB_TRY(ctx->scratch.ensure(bytes));
+    *out = ctx->scratch.p;
+    return SB_OK;
+}
+
+int comm_allreduce_f64(sb_ctx *ctx, double *buf, size_t count) {
+    if (ctx->nranks == 1 || count == 0) return SB_OK;
+    ProfScope ps(ctx, PH_COMM);
+    SB_NCCL(ncclAllReduce(buf, buf, count, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+    count_launch(ctx, false);
+    return SB_OK;
+}
+
+int comm_allreduce_u64(sb_ctx *ctx, u64 *buf, size_t count) {
+    if (ctx->nranks == 1 || count == 0) return SB_OK;
+    ProfScope ps(ctx, PH_COMM);
+    SB_NCCL(ncclAllReduce(buf, buf, count, ncclUint64, ncclSum, ctx->comm, ctx->stream));
+    count_launch(ctx, false);
+    return SB_OK;
+}
+
+int comm_allreduce_max_i32(sb_ctx *ctx, int *host_val) {
+    if (ctx->nranks == 1) return SB_OK;
+    void *d;
+    SB_TRY(ctx_scratch(ctx, 256, &d));
+    SB_CUDA(cudaMemcpyAsync(d, host_val, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    SB_NCCL(ncclAllReduce(d, d, 1, ncclInt32, ncclMax, ctx->comm, ctx->stream));
+    SB_CUDA(cudaMemcpyAsync(host_val, d, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+
+int comm_allgather_u64_host(sb_ctx *ctx, u64 mine, std::vector<u64> &all) {
+    all.assign(ctx->nranks, 0);
+    if (ctx->nranks == 1) {
+        all[0] = mine;
+        return SB_OK;
+    }
+    void *d;
+    SB_TRY(ctx_scratch(ctx, sizeof(u64) * (ctx->nranks + 1), &d));
+    u64 *dv = (u64 *)d;
+    SB_CUDA(cudaMemcpyAsync(dv + ctx->nranks, &mine, sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    SB_NCCL(ncclAllGather(dv + ctx->nranks, dv, 1, ncclUint64, ctx->comm, ctx->stream));
+    SB_CUDA(cudaMemcpyAsync(all.data(), dv, sizeof(u64) * ctx->nranks, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+
+// ---------------------------------------------------------------- profiling
+static cudaEvent_t get_event(sb_ctx *ctx) {
+    if (!ctx->event_pool.empty()) {
+        cudaEvent_t e = ctx->event_pool.back();
+        ctx->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+void prof_begin(sb_ctx *ctx, int phase) {
+    if (!ctx->profile_on) return;
+    cudaEvent_t a = get_event(ctx), b = get_event(ctx);
+    cudaEventRecord(a, ctx->stream);
+    ctx->pending.push_back({phase, {a, b}});
+}
+
+void prof_end(sb_ctx *ctx, int phase) {
+    if (!ctx->profile_on) return;
+    for (int i = (int)ctx->pending.size() - 1; i >= 0; i--)
+        if (ctx->pending[i].first == phase) {
+            cudaEventRecord(ctx->pending[i].second.second, ctx->stream);
+            ctx->pending[i].first = phase + 100;  // closed
+            return;
+        }
+}
+
+void prof_collect(sb_ctx *ctx) {
+    if (ctx->pending.empty()) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &p : ctx->pending) {
+        float ms = 0.f;
+        if (p.first >= 100) {
+            cudaEventElapsedTime(&ms, p.second.first, p.second.second);
+            switch (p.first - 100) {
+            case PH_SPMM_T: ctx->prof.spmm_t_ms += ms; break;
+            case PH_SPMM_N: ctx->prof.spmm_n_ms += ms; break;
+            case PH_MOMENTS: ctx->prof.moments_ms += ms; break;
+            case PH_REDUCE: ctx->prof.reduce_ms += ms; break;
+            case PH_DENSE: ctx->prof.dense_ms += ms; break;
+            case PH_COMM: ctx->prof.comm_ms += ms; break;
+            }
+        }
+        ctx->event_pool.push_back(p.second.first);
+        ctx->event_pool.push_back(p.second.second);
+    }
+    ctx->pending.clear();
+}
+
+extern "C" int sb_profile_enable(sb_ctx *ctx, int on) {
+    if (!ctx) return sb_fail(SB_ERR_INVALID_ARG, "ctx is NULL");
+    prof_collect(ctx);
+    ctx->profile_on = on != 0;
+    return SB_OK;
+}
+
+extern "C" int sb_profile_reset(sb_ctx *ctx) {
+    if (!ctx) return sb_fail(SB_ERR_INVALID_ARG, "ctx is NULL");
+    prof_collect(ctx);
+    memset(&ctx->prof, 0, sizeof(ctx->prof));
+    return SB_OK;
+}
+
+extern "C" int sb_profile_get(sb_ctx *ctx, sb_profile *out) {
+    if (!ctx || !out) return sb_fail(SB_ERR_INVALID_ARG, "NULL argument");
+    prof_collect(ctx);
+    *out = ctx->prof;
+    return SB_OK;
+}
+
+extern "C" int sb_timer_begin(sb_ctx *ctx) {
+    if (!ctx) return sb_fail(SB_ERR_INVALID_ARG, "ctx is NULL");
+    SB_CUDA(cudaSetDevice(ctx->device));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    SB_CUDA(cudaEventRecord(ctx->t0, ctx->stream));
+    return SB_OK;
+}
+
+extern "C" int sb_timer_end(sb_ctx *ctx, float *ms) {
+    if (!ctx || !ms) return sb_fail(SB_ERR_INVALID_ARG, "NULL argument");
+    SB_CUDA(cudaEventRecord(ctx->t1, ctx->stream));
+    SB_CUDA(cudaEventSynchronize(ctx->t1));
+    SB_CUDA(cudaEventElapsedTime(ms, ctx->t0, ctx->t1));
+    return SB_OK;
+}
+
+extern "C" int sb_flush_l2(sb_ctx *ctx) {
+    if (!ctx) return sb_fail(SB_ERR_INVALID_ARG, "ctx is NULL");
+    size_t bytes = ctx->l2_bytes ? ctx->l2_bytes * 2 : ((size_t)256 << 20);
+    SB_TRY(ctx->flush_buf.ensure(bytes));
+    SB_CUDA(cudaMemsetAsync(ctx->flush_buf.p, 1, bytes, ctx->stream));
+    count_launch(ctx, false);
+    return SB_OK;
+}

@@ -1,0 +1,121 @@
+// dense.cu -- the small dense steps around the sparse products: thin QR of tall blocks
+// (bk_svd.rs:94,98,123,127 -> LAPACK dgeqrf/dorgqr in the reference), the Gram matrix of the
+// projected block, its symmetric eigendecomposition (standing in for dgesdd on the wide
+// matrix, bk_svd.rs:105,134) and tall x small products.  All tall blocks are row-major
+// [rows x w] with an even leading dimension; cuSOLVER/cuBLAS see them as column-major
+// [w x rows].
+#include "common.cuh"
+
+// out (col-major rows x w, ld = rows)  <-  in (row-major rows x w, ld = ldi)
+__global__ void k_rm_to_cm(const double *__restrict__ in, u64 rows, u32 w, u32 ldi, double *__restrict__ out) {
+    __shared__ double tile[32][33];
+    u64 r0 = (u64)blockIdx.x * 32;
+    u32 c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        u64 r = r0 + i;
+        u32 c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (r < rows && c < w) ? in[r * ldi + c] : 0.0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        u32 c = c0 + i;
+        u64 r = r0 + threadIdx.x;
+        if (r < rows && c < w) out[(u64)c * rows + r] = tile[threadIdx.x][i];
+    }
+}
+
+// out (row-major rows x w, ld = ldo)  <-  in (col-major rows x w, ld = rows); pad columns zeroed
+__global__ void k_cm_to_rm(const double *__restrict__ in, u64 rows, u32 w, double *__restrict__ out, u32 ldo) {
+    __shared__ double tile[32][33];
+    u64 r0 = (u64)blockIdx.x * 32;
+    u32 c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        u32 c = c0 + i;
+        u64 r = r0 + threadIdx.x;
+        tile[i][threadIdx.x] = (r < rows && c < w) ? in[(u64)c * rows + r] : 0.0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        u64 r = r0 + i;
+        u32 c = c0 + threadIdx.x;
+        if (r < rows && c < ldo) out[r * ldo + c] = c < w ? tile[threadIdx.x][i] : 0.0;
+    }
+}
+
+// thin QR: A (row-major rows x w, ld) is replaced by Q (rows x min(rows, w)); returns the new width
+int qr_tall(sb_ctx *ctx, double *A, u64 rows, u32 w, u32 ld, u32 *w_out) {
+    ProfScope ps(ctx, PH_DENSE);
+    u32 kq = (u32)std::min<u64>(rows, w);
+    *w_out = kq;
+    if (rows == 0 || w == 0) return SB_OK;
+    if (rows > 0x7FFFFFFFull) return sb_fail(SB_ERR_UNSUPPORTED, "qr_tall: more than 2^31 rows");
+    DevBuf<double> cm, tau, work;
+    DevBuf<int> info;
+    SB_TRY(cm.alloc(rows * (size_t)w));
+    SB_TRY(tau.alloc(kq));
+    SB_TRY(info.alloc(1));
+    dim3 blk(32, 8), grd(cdiv(rows, 32), cdiv(w, 32));
+    k_rm_to_cm<<<grd, blk, 0, ctx->stream>>>(A, rows, w, ld, cm.p);
+    count_launch(ctx);
+    int lwork1 = 0, lwork2 = 0;
+    SB_CUSOLVER(cusolverDnDgeqrf_bufferSize(ctx->cusolver, (int)rows, (int)w, cm.p, (int)rows, &lwork1));
+    SB_CUSOLVER(cusolverDnDorgqr_bufferSize(ctx->cusolver, (int)rows, (int)kq, (int)kq, cm.p, (int)rows, tau.p, &lwork2));
+    int lwork = std::max(lwork1, lwork2);
+    SB_TRY(work.alloc(lwork));
+    SB_CUSOLVER(cusolverDnDgeqrf(ctx->cusolver, (int)rows, (int)w, cm.p, (int)rows, tau.p, work.p, lwork, info.p));
+    SB_CUSOLVER(cusolverDnDorgqr(ctx->cusolver, (int)rows, (int)kq, (int)kq, cm.p, (int)rows, tau.p, work.p, lwork, info.p));
+    count_launch(ctx, false); count_launch(ctx, false);
+    int h_info = 0;
+    SB_CUDA(cudaMemcpyAsync(&h_info, info.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    dim3 grd2(cdiv(rows, 32), cdiv(std::max(ld, w), 32));
+    k_cm_to_rm<<<grd2, blk, 0, ctx->stream>>>(cm.p, rows, kq, A, ld);
+    count_launch(ctx);
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (h_info != 0) return sb_fail(SB_ERR_LINALG, "QR failed: info = %d", h_info);
+    return SB_OK;
+}
+
+// G (col-major w x w) = A^T A for A row-major rows x w (ld); all-reduced over ranks when `reduce`
+int gram(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 ld, double *G, bool reduce) {
+    ProfScope ps(ctx, PH_DENSE);
+    if (rows > 0x7FFFFFFFull) return sb_fail(SB_ERR_UNSUPPORTED, "gram: more than 2^31 rows");
+    const double one = 1.0, zero = 0.0;
+    if (rows == 0) {
+        SB_CUDA(cudaMemsetAsync(G, 0, (size_t)w * w * sizeof(double), ctx->stream));
+    } else {
+        // A_c = A^T is (w x rows) column-major with ld; G = A_c . A_c^T
+        SB_CUBLAS(cublasDgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_T, (int)w, (int)w, (int)rows, &one, A, (int)ld, A, (int)ld, &zero, G, (int)w));
+        count_launch(ctx, false);
+    }
+    if (reduce) SB_TRY(comm_allreduce_f64(ctx, G, (size_t)w * w));
+    return SB_OK;
+}
+
+// symmetric eigendecomposition of G (col-major w x w, overwritten by eigenvectors); evals ascending
+int eigh(sb_ctx *ctx, double *G, u32 w, double *evals_dev) {
+    ProfScope ps(ctx, PH_DENSE);
+    int lwork = 0;
+    SB_CUSOLVER(cusolverDnDsyevd_bufferSize(ctx->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)w, G, (int)w, evals_dev, &lwork));
+    DevBuf<double> work;
+    DevBuf<int> info;
+    SB_TRY(work.alloc(lwork));
+    SB_TRY(info.alloc(1));
+    SB_CUSOLVER(cusolverDnDsyevd(ctx->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)w, G, (int)w, evals_dev, work.p, lwork, info.p));
+    count_launch(ctx, false);
+    int h_info = 0;
+    SB_CUDA(cudaMemcpyAsync(&h_info, info.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (h_info != 0) return sb_fail(SB_ERR_LINALG, "eigendecomposition failed: info = %d", h_info);
+    return SB_OK;
+}
+
+// Out (row-major rows x k, ldo) = A (row-major rows x w, lda) . S (col-major w x k, lds)
+int gemm_tall_small(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 lda, const double *S, u32 k, u32 lds, double *Out, u32 ldo) {
+    ProfScope ps(ctx, PH_DENSE);
+    if (rows == 0 || k == 0) return SB_OK;
+    if (rows > 0x7FFFFFFFull) return sb_fail(SB_ERR_UNSUPPORTED, "gemm: more than 2^31 rows");
+    const double one = 1.0, zero = 0.0;
+    SB_CUBLAS(cublasDgemm(ctx->cublas, CUBLAS_OP_T, CUBLAS_OP_N, (int)k, (int)rows, (int)w, &one, S, (int)lds, A, (int)lda, &zero, Out, (int)ldo));
+    count_launch(ctx, false);
+    return SB_OK;
+}

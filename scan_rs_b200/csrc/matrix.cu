@@ -1,0 +1,740 @@
+// matrix.cu -- device-resident count matrix: upload, the two device layouts, integer
+// reductions (K1-K4, K6 of SURVEY.md 2.1), selection and download.
+//
+// Layouts (DESIGN.md "Data layout in HBM"):
+//   cell-major  cm_ptr[n+1] (u64), cm[nnz] = {gene, count}                      8 B / nnz
+//   gene-major, cell-panelled: panels of `pc` cells; inside a panel entries sorted by
+//   (gene, cell); gm[k] = {gene | cell_local << 22, count}                      8 B / nnz
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <memory>
+#include <numeric>
+
+#include "common.cuh"
+
+// ---------------------------------------------------------------- small kernels
+__global__ void k_interleave(const u32 *__restrict__ idx, const u32 *__restrict__ cnt, uint2 *__restrict__ out, u64 nnz) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; i < nnz; i += stride) out[i] = make_uint2(idx[i], cnt[i]);
+}
+
+__global__ void k_max_u32(const u32 *__restrict__ v, u64 n, u32 *out) {
+    u32 mx = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) mx = max(mx, v[i]);
+    for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, mx);
+}
+
+// ptr must be non-decreasing with ptr[0] == 0; flags violations
+__global__ void k_check_ptr(const u64 *__restrict__ ptr, u64 len, int *bad) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < len && ptr[i] > ptr[i + 1]) *bad = 1;
+    if (i == 0 && ptr[0] != 0) *bad = 1;
+}
+
+// one warp per major vector: expands the vector id of every entry and emits (key, payload)
+//   mode 0: input cell-major (vec = cell): key = (cell / pc) * m + gene, payload = packed gene-major entry
+//   mode 1: input gene-major (vec = gene): key = cell,                  payload = {gene, count}
+__global__ void k_make_keys(const u64 *__restrict__ ptr, const uint2 *__restrict__ ent, u64 nvec, int mode, u32 m,
+                            u32 pc, u32 *__restrict__ keys, u64 *__restrict__ payload) {
+    u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    int lane = threadIdx.x & 31;
+    for (u64 v = warp; v < nvec; v += nwarps) {
+        u64 s = ptr[v], e = ptr[v + 1];
+        for (u64 k = s + lane; k < e; k += 32) {
+            uint2 z = ent[k];
+            if (mode == 0) {
+                u32 panel = (u32)(v / pc), cl = (u32)(v % pc);
+                keys[k] = panel * m + z.x;
+                payload[k] = ((u64)z.y << 32) | (u64)(z.x | (cl << SB_GENE_BITS));
+            } else {
+                keys[k] = z.x;  // cell
+                payload[k] = ((u64)z.y << 32) | (u64)(u32)v;
+            }
+        }
+    }
+}
+
+__global__ void k_unpack_payload(const u64 *__restrict__ payload, uint2 *__restrict__ out, u64 nnz) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (u64)gridDim.x * blockDim.x) {
+        u64 p = payload[i];
+        out[i] = make_uint2((u32)p, (u32)(p >> 32));
+    }
+}
+
+__global__ void k_hist_u32(const u32 *__restrict__ keys, u64 nnz, u32 *__restrict__ hist) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (u64)gridDim.x * blockDim.x)
+        atomicAdd(&hist[keys[i]], 1u);
+}
+
+__global__ void k_u32_to_u64(const u32 *__restrict__ in, u64 *__restrict__ out, u64 n) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) out[i] = in[i];
+}
+
+__global__ void k_panel_base(const u64 *__restrict__ cm_ptr, u64 n, u32 pc, u32 np, u64 *__restrict__ base) {
+    u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p <= np) {
+        u64 c = (u64)p * pc;
+        base[p] = cm_ptr[c < n ? c : n];
+    }
+}
+
+// K1: per-cell totals, wrapping u32 (sqz/src/mat.rs:377-406 via normalization.rs:159,161)
+__global__ void k_cell_totals(const u64 *__restrict__ ptr, const uint2 *__restrict__ cm, u64 n, u32 *__restrict__ out) {
+    u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    int lane = threadIdx.x & 31;
+    for (u64 c = warp; c < n; c += nwarps) {
+        u64 s = ptr[c], e = ptr[c + 1];
+        u32 acc = 0;
+        for (u64 k = s + lane; k < e; k += 32) acc += cm[k].y;
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) out[c] = acc;
+    }
+}
+
+// K2 / K6: per-gene u64 sums (mode 0: v, 1: v*v, 2: 1) with optional cell / gene masks (K4 sweeps).
+// Integer adds commute, so the atomics are bit-exact.  Warp-level pre-aggregation is not
+// needed for correctness; contention on the hottest genes is absorbed by the L2 atomic units.
+__global__ void k_gene_sums(const u64 *__restrict__ ptr, const uint2 *__restrict__ cm, u64 n, int mode,
+                            const unsigned char *__restrict__ excl_cells, const unsigned char *__restrict__ excl_genes,
+                            unsigned long long *__restrict__ out) {
+    u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    int lane = threadIdx.x & 31;
+    for (u64 c = warp; c < n; c += nwarps) {
+        if (excl_cells && excl_cells[c]) continue;
+        u64 s = ptr[c], e = ptr[c + 1];
+        for (u64 k = s + lane; k < e; k += 32) {
+            uint2 z = cm[k];
+            if (excl_genes && excl_genes[z.x]) continue;
+            unsigned long long v = mode == 0 ? (unsigned long long)z.y : mode == 1 ? (unsigned long long)z.y * z.y : (z.y ? 1ull : 0ull);
+            if (v) atomicAdd(&out[z.x], v);
+        }
+    }
+}
+
+// per-cell u64 sums over non-excluded genes (K4 column sweep)
+__global__ void k_cell_sums_masked(const u64 *__restrict__ ptr, const uint2 *__restrict__ cm, u64 n,
+                                   const unsigned char *__restrict__ excl_cells, const unsigned char *__restrict__ excl_genes,
+                                   unsigned long long *__restrict__ out) {
+    u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    int lane = threadIdx.x & 31;
+    for (u64 c = warp; c < n; c += nwarps) {
+        unsigned long long acc = 0;
+        if (!(excl_cells && excl_cells[c])) {
+            u64 s = ptr[c], e = ptr[c + 1];
+            for (u64 k = s + lane; k < e; k += 32) {
+                uint2 z = cm[k];
+                if (!(excl_genes && excl_genes[z.x])) acc += z.y;
+            }
+            for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        }
+        if (lane == 0) out[c] = acc;
+    }
+}
+
+// `s < threshold` on exact integer sums (sqz/src/mat.rs:784-799); sets *updated when a mask bit flips
+__global__ void k_apply_threshold(const unsigned long long *__restrict__ sums, u64 n, double thr, unsigned char *__restrict__ excl,
+                                  int *updated) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && !excl[i] && (double)sums[i] < thr) {
+        excl[i] = 1;
+        *updated = 1;
+    }
+}
+
+// select_rows pass: count / write entries whose gene survives the old->new map
+__global__ void k_select_rows(const u64 *__restrict__ ptr, const uint2 *__restrict__ cm, u64 n, const u32 *__restrict__ gene_map,
+                              const u64 *__restrict__ new_ptr, u32 *__restrict__ counts, uint2 *__restrict__ out) {
+    u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    int lane = threadIdx.x & 31;
+    for (u64 c = warp; c < n; c += nwarps) {
+        u64 s = ptr[c], e = ptr[c + 1];
+        u64 wpos = new_ptr ? new_ptr[c] : 0;
+        u32 total = 0;
+        for (u64 k0 = s; k0 < e; k0 += 32) {
+            u64 k = k0 + lane;
+            uint2 z = k < e ? cm[k] : make_uint2(0, 0);
+            u32 ng = k < e ? gene_map[z.x] : 0xFFFFFFFFu;
+            bool keep = ng != 0xFFFFFFFFu;
+            unsigned mask = __ballot_sync(0xffffffffu, keep);
+            if (out && keep) out[wpos + total + __popc(mask & ((1u << lane) - 1u))] = make_uint2(ng, z.y);
+            total += __popc(mask);
+        }
+        if (counts && lane == 0) counts[c] = total;
+    }
+}
+
+__global__ void k_gather_len(const u64 *__restrict__ ptr, const u64 *__restrict__ cols, u64 count, u32 *__restrict__ len) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) len[i] = (u32)(ptr[cols[i] + 1] - ptr[cols[i]]);
+}
+
+__global__ void k_select_cols(const u64 *__restrict__ ptr, const uint2 *__restrict__ cm, const u64 *__restrict__ cols, u64 count,
+                              const u64 *__restrict__ new_ptr, uint2 *__restrict__ out) {
+    u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    int lane = threadIdx.x & 31;
+    for (u64 j = warp; j < count; j += nwarps) {
+        u64 s = ptr[cols[j]], e = ptr[cols[j] + 1], d = new_ptr[j];
+        for (u64 k = s + lane; k < e; k += 32) out[d + (k - s)] = cm[k];
+    }
+}
+
+__global__ void k_split_entries(const uint2 *__restrict__ ent, u64 nnz, u32 *__restrict__ idx, u32 *__restrict__ cnt) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (u64)gridDim.x * blockDim.x) {
+        uint2 z = ent[i];
+        idx[i] = z.x;
+        cnt[i] = z.y;
+    }
+}
+
+static inline int grid_for(u64 work_items, int threads, sb_ctx *ctx, int per_sm = 8) {
+    u64 blocks = (work_items + threads - 1) / threads;
+    u64 cap = (u64)ctx->sm_count * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+static inline int bits_for(u64 max_value) {
+    int b = 1;
+    while (b < 64 && (max_value >> b)) b++;
+    return b;
+}
+
+// stable radix sort of (u32 key, u64 payload); result in keys / payload (buffers may be swapped)
+static int sort_pairs(sb_ctx *ctx, DevBuf<u32> &keys, DevBuf<u64> &payload, u64 count, int end_bit) {
+    if (count == 0) return SB_OK;
+    DevBuf<u32> keys2;
+    DevBuf<u64> payload2;
+    SB_TRY(keys2.alloc(count));
+    SB_TRY(payload2.alloc(count));
+    cub::DoubleBuffer<u32> dk(keys.p, keys2.p);
+    cub::DoubleBuffer<u64> dv(payload.p, payload2.p);
+    size_t tmp_bytes = 0;
+    SB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (unsigned long long)count, 0, end_bit, ctx->stream));
+    DevBuf<char> tmp;
+    SB_TRY(tmp.alloc(tmp_bytes));
+    SB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, dk, dv, (unsigned long long)count, 0, end_bit, ctx->stream));
+    count_launch(ctx, false);
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (dk.Current() != keys.p) keys.swap(keys2);
+    if (dv.Current() != payload.p) payload.swap(payload2);
+    return SB_OK;
+}
+
+static int exclusive_scan_u32_to_u64(sb_ctx *ctx, const u32 *counts, u64 n, u64 *out_ptr /* n+1 */) {
+    // out_ptr[0..n] = exclusive prefix sums, out_ptr[n] = total
+    DevBuf<u64> wide;
+    SB_TRY(wide.alloc(n + 1));
+    SB_CUDA(cudaMemsetAsync(wide.p, 0, (n + 1) * sizeof(u64), ctx->stream));
+    if (n) {
+        k_u32_to_u64<<<grid_for(n, 256, ctx), 256, 0, ctx->stream>>>(counts, wide.p, n);
+        count_launch(ctx);
+    }
+    size_t tmp_bytes = 0;
+    SB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, wide.p, out_ptr, (unsigned long long)(n + 1), ctx->stream));
+    DevBuf<char> tmp;
+    SB_TRY(tmp.alloc(tmp_bytes));
+    SB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, wide.p, out_ptr, (unsigned long long)(n + 1), ctx->stream));
+    count_launch(ctx, false);
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+
+// choose the panel geometry: panels of pc cells (power of two <= 1024) such that there are enough
+// panels to spread over the SMs, and `ur` nnz-balanced work units per panel
+static void choose_panels(sb_mat *mt) {
+    sb_ctx *ctx = mt->ctx;
+    u32 pc = SB_MAX_PANEL_CELLS;
+    while (pc > 128 && (mt->n + pc - 1) / pc < (u64)ctx->sm_count) pc >>= 1;
+    mt->pc = pc;
+    mt->np = (u32)((mt->n + pc - 1) / pc);
+    u64 target_units = (u64)ctx->sm_count * 8;
+    u32 ur = mt->np ? (u32)((target_units + mt->np - 1) / mt->np) : 1;
+    if (ur < 1) ur = 1;
+    if (ur > 64) ur = 64;
+    mt->ur = ur;
+}
+
+// builds the gene-major panelled copy from the (complete) cell-major copy
+static int build_gene_major(sb_mat *mt) {
+    sb_ctx *ctx = mt->ctx;
+    choose_panels(mt);
+    SB_TRY(mt->gm_base.alloc((size_t)mt->np + 1));
+    k_panel_base<<<cdiv(mt->np + 1, 256), 256, 0, ctx->stream>>>(mt->cm_ptr.p, mt->n, mt->pc, mt->np, mt->gm_base.p);
+    count_launch(ctx);
+    SB_TRY(mt->gm.alloc(mt->nnz));
+    if (mt->nnz == 0) return SB_OK;
+    if ((u64)mt->np * mt->m > 0xFFFFFFFFull) return sb_fail(SB_ERR_UNSUPPORTED, "panel x gene key exceeds 32 bits");
+    DevBuf<u32> keys;
+    DevBuf<u64> payload;
+    SB_TRY(keys.alloc(mt->nnz));
+    SB_TRY(payload.alloc(mt->nnz));
+    k_make_keys<<<grid_for(mt->n * 32, 256, ctx, 16), 256, 0, ctx->stream>>>(mt->cm_ptr.p, mt->cm.p, mt->n, 0, mt->m, mt->pc, keys.p, payload.p);
+    count_launch(ctx);
+    SB_TRY(sort_pairs(ctx, keys, payload, mt->nnz, bits_for((u64)mt->np * mt->m - 1)));
+    k_unpack_payload<<<grid_for(mt->nnz, 256, ctx, 16), 256, 0, ctx->stream>>>(payload.p, mt->gm.p, mt->nnz);
+    count_launch(ctx);
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+
+static int finish_matrix(sb_mat *mt) {
+    sb_ctx *ctx = mt->ctx;
+    std::vector<u64> all;
+    SB_TRY(comm_allgather_u64_host(ctx, mt->n, all));
+    mt->n_global = 0;
+    mt->cell_offset = 0;
+    for (int r = 0; r < ctx->nranks; r++) {
+        if (r < ctx->rank) mt->cell_offset += all[r];
+        mt->n_global += all[r];
+    }
+    return build_gene_major(mt);
+}
+
+extern "C" int sb_upload(sb_ctx *ctx, int major, uint32_t m, uint64_t n_local, const uint64_t *indptr, const uint32_t *idx,
+                         const uint32_t *cnt, sb_mat **out) {
+    if (!ctx || !out || !indptr) return sb_fail(SB_ERR_INVALID_ARG, "sb_upload: NULL argument");
+    if (major != SB_GENE_MAJOR && major != SB_CELL_MAJOR) return sb_fail(SB_ERR_INVALID_ARG, "sb_upload: bad major %d", major);
+    if (m > SB_GENE_MASK) return sb_fail(SB_ERR_UNSUPPORTED, "sb_upload: more than %u genes", SB_GENE_MASK);
+    if (n_local > 0xFFFFFFFFull) return sb_fail(SB_ERR_UNSUPPORTED, "sb_upload: more than 2^32 cells per rank");
+    *out = nullptr;
+    SB_CUDA(cudaSetDevice(ctx->device));
+    u64 nvec = major == SB_GENE_MAJOR ? m : n_local;
+    u64 nnz = indptr[nvec];
+    if (nnz && (!idx || !cnt)) return sb_fail(SB_ERR_INVALID_ARG, "sb_upload: NULL idx/cnt");
+    std::unique_ptr<sb_mat> mt(new sb_mat());
+    mt->ctx = ctx;
+    mt->m = m;
+    mt->n = n_local;
+    mt->nnz = nnz;
+
+    DevBuf<u64> d_ptr;
+    DevBuf<u32> d_idx, d_cnt;
+    SB_TRY(d_ptr.alloc(nvec + 1));
+    SB_TRY(d_idx.alloc(nnz));
+    SB_TRY(d_cnt.alloc(nnz));
+    SB_CUDA(cudaMemcpyAsync(d_ptr.p, indptr, (nvec + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    if (nnz) {
+        SB_CUDA(cudaMemcpyAsync(d_idx.p, idx, nnz * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+        SB_CUDA(cudaMemcpyAsync(d_cnt.p, cnt, nnz * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    // validation: pointers monotone, indices in range
+    void *scr;
+    SB_TRY(ctx_scratch(ctx, 256, &scr));
+    SB_CUDA(cudaMemsetAsync(scr, 0, 256, ctx->stream));
+    int *d_bad = (int *)scr;
+    u32 *d_max = (u32 *)scr + 1;
+    if (nvec) {
+        k_check_ptr<<<cdiv(nvec, 256), 256, 0, ctx->stream>>>(d_ptr.p, nvec, d_bad);
+        count_launch(ctx);
+    }
+    if (nnz) {
+        k_max_u32<<<grid_for(nnz, 256, ctx), 256, 0, ctx->stream>>>(d_idx.p, nnz, d_max);
+        count_launch(ctx);
+    }
+    int h[2] = {0, 0};
+    SB_CUDA(cudaMemcpyAsync(h, scr, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (h[0]) return sb_fail(SB_ERR_INVALID_ARG, "sb_upload: indptr is not monotone from 0");
+    u64 bound = major == SB_GENE_MAJOR ? n_local : (u64)m;
+    if (nnz && (u64)(u32)h[1] >= bound) return sb_fail(SB_ERR_INVALID_ARG, "sb_upload: index %u out of range %llu", (u32)h[1], (unsigned long long)bound);
+
+    if (major == SB_CELL_MAJOR) {
+        mt->cm_ptr.swap(d_ptr);
+        SB_TRY(mt->cm.alloc(nnz));
+        if (nnz) {
+            k_interleave<<<grid_for(nnz, 256, ctx, 16), 256, 0, ctx->stream>>>(d_idx.p, d_cnt.p, mt->cm.p, nnz);
+            count_launch(ctx);
+        }
+    } else {
+        // gene-major input: stable sort by cell gives the cell-major copy with ascending genes
+        DevBuf<uint2> ent;
+        SB_TRY(ent.alloc(nnz));
+        DevBuf<u32> keys;
+        DevBuf<u64> payload;
+        SB_TRY(keys.alloc(nnz));
+        SB_TRY(payload.alloc(nnz));
+        DevBuf<u32> hist;
+        SB_TRY(hist.alloc(n_local + 1));
+        SB_CUDA(cudaMemsetAsync(hist.p, 0, (n_local + 1) * sizeof(u32), ctx->stream));
+        if (nnz) {
+            k_interleave<<<grid_for(nnz, 256, ctx, 16), 256, 0, ctx->stream>>>(d_idx.p, d_cnt.p, ent.p, nnz);
+            k_make_keys<<<grid_for((u64)m * 32, 256, ctx, 16), 256, 0, ctx->stream>>>(d_ptr.p, ent.p, m, 1, m, 1, keys.p, payload.p);
+            k_hist_u32<<<grid_for(nnz, 256, ctx, 16), 256, 0, ctx->stream>>>(keys.p, nnz, hist.p);
+            count_launch(ctx); count_launch(ctx); count_launch(ctx);
+            SB_TRY(sort_pairs(ctx, keys, payload, nnz, bits_for(n_local ? n_local - 1 : 0)));
+        }
+        SB_TRY(mt->cm_ptr.alloc(n_local + 1));
+        SB_TRY(exclusive_scan_u32_to_u64(ctx, hist.p, n_local, mt->cm_ptr.p));
+        SB_TRY(mt->cm.alloc(nnz));
+        if (nnz) {
+            k_unpack_payload<<<grid_for(nnz, 256, ctx, 16), 256, 0, ctx->stream>>>(payload.p, mt->cm.p, nnz);
+            count_launch(ctx);
+        }
+    }
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    d_idx.release();
+    d_cnt.release();
+    SB_TRY(finish_matrix(mt.get()));
+    *out = mt.release();
+    return SB_OK;
+}
+
+// adopt device cell-major arrays (used by the synthetic generator and the selection routines)
+int mat_from_device_cm(sb_ctx *ctx, u32 m, u64 n, DevBuf<u64> &cm_ptr, DevBuf<uint2> &cm, u64 nnz, sb_mat **out) {
+    std::unique_ptr<sb_mat> mt(new sb_mat());
+    mt->ctx = ctx;
+    mt->m = m;
+    mt->n = n;
+    mt->nnz = nnz;
+    mt->cm_ptr.swap(cm_ptr);
+    mt->cm.swap(cm);
+    SB_TRY(finish_matrix(mt.get()));
+    *out = mt.release();
+    return SB_OK;
+}
+
+extern "C" int sb_mat_shape(const sb_mat *mat, uint32_t *m, uint64_t *n_local, uint64_t *n_global, uint64_t *nnz_local) {
+    if (!mat) return sb_fail(SB_ERR_INVALID_ARG, "sb_mat_shape: mat is NULL");
+    if (m) *m = mat->m;
+    if (n_local) *n_local = mat->n;
+    if (n_global) *n_global = mat->n_global;
+    if (nnz_local) *nnz_local = mat->nnz;
+    return SB_OK;
+}
+
+extern "C" void sb_free_mat(sb_mat *mat) {
+    if (!mat) return;
+    cudaSetDevice(mat->ctx->device);
+    cudaStreamSynchronize(mat->ctx->stream);
+    delete mat;
+}
+
+extern "C" int sb_download(const sb_mat *mat, int major, uint64_t *indptr, uint32_t *idx, uint32_t *cnt) {
+    if (!mat || !indptr) return sb_fail(SB_ERR_INVALID_ARG, "sb_download: NULL argument");
+    sb_ctx *ctx = mat->ctx;
+    SB_CUDA(cudaSetDevice(ctx->device));
+    u64 nnz = mat->nnz;
+    DevBuf<u32> d_idx, d_cnt;
+    SB_TRY(d_idx.alloc(nnz));
+    SB_TRY(d_cnt.alloc(nnz));
+    if (major == SB_CELL_MAJOR) {
+        if (nnz) {
+            k_split_entries<<<grid_for(nnz, 256, ctx, 16), 256, 0, ctx->stream>>>(mat->cm.p, nnz, d_idx.p, d_cnt.p);
+            count_launch(ctx);
+        }
+        SB_CUDA(cudaMemcpyAsync(indptr, mat->cm_ptr.p, (mat->n + 1) * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    } else if (major == SB_GENE_MAJOR) {
+        // stable sort of the cell-major stream by gene: cells ascending inside each gene
+        DevBuf<u32> keys;
+        DevBuf<u64> payload;
+        DevBuf<u32> hist;
+        DevBuf<u64> gptr;
+        DevBuf<uint2> ent;
+        SB_TRY(keys.alloc(nnz));
+        SB_TRY(payload.alloc(nnz));
+        SB_TRY(hist.alloc((size_t)mat->m + 1));
+        SB_TRY(gptr.alloc((size_t)mat->m + 1));
+        SB_TRY(ent.alloc(nnz));
+        SB_CUDA(cudaMemsetAsync(hist.p, 0, ((size_t)mat->m + 1) * sizeof(u32), ctx->stream));
+        if (nnz) {
+            // mode 1 with vec = cell: key = ent.x (gene), payload = {cell, count}
+            k_make_keys<<<grid_for(mat->n * 32, 256, ctx, 16), 256, 0, ctx->stream>>>(mat->cm_ptr.p, mat->cm.p, mat->n, 1, mat->m, 1, keys.p, payload.p);
+            k_hist_u32<<<grid_for(nnz, 256, ctx, 16), 256, 0, ctx->stream>>>(keys.p, nnz, hist.p);
+            count_launch(ctx); count_launch(ctx);
+            SB_TRY(sort_pairs(ctx, keys, payload, nnz, bits_for(mat->m ? mat->m - 1 : 0)));
+            k_unpack_payload<<<grid_for(nnz, 256, ctx, 16), 256, 0, ctx->stream>>>(payload.p, ent.p, nnz);
+            k_split_entries<<<grid_for(nnz, 256, ctx, 16), 256, 0, ctx->stream>>>(ent.p, nnz, d_idx.p, d_cnt.p);
+            count_launch(ctx); count_launch(ctx);
+        }
+        SB_TRY(exclusive_scan_u32_to_u64(ctx, hist.p, mat->m, gptr.p));
+        SB_CUDA(cudaMemcpyAsync(indptr, gptr.p, ((size_t)mat->m + 1) * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+        SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    } else {
+        return sb_fail(SB_ERR_INVALID_ARG, "sb_download: bad major %d", major);
+    }
+    if (nnz && idx) SB_CUDA(cudaMemcpyAsync(idx, d_idx.p, nnz * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    if (nnz && cnt) SB_CUDA(cudaMemcpyAsync(cnt, d_cnt.p, nnz * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+
+// ---------------------------------------------------------------- integer reductions
+int mat_cell_totals_dev(sb_mat *mat) {
+    if (mat->have_cell_tot) return SB_OK;
+    sb_ctx *ctx = mat->ctx;
+    SB_TRY(mat->cell_tot.alloc(mat->n));
+    if (mat->n) {
+        ProfScope ps(ctx, PH_REDUCE);
+        k_cell_totals<<<grid_for(mat->n * 32, 256, ctx, 16), 256, 0, ctx->stream>>>(mat->cm_ptr.p, mat->cm.p, mat->n, mat->cell_tot.p);
+        count_launch(ctx);
+    }
+    mat->have_cell_tot = true;
+    return SB_OK;
+}
+
+extern "C" int sb_cell_totals(sb_mat *mat, uint32_t *out_n_local) {
+    if (!mat || !out_n_local) return sb_fail(SB_ERR_INVALID_ARG, "sb_cell_totals: NULL argument");
+    sb_ctx *ctx = mat->ctx;
+    SB_CUDA(cudaSetDevice(ctx->device));
+    SB_TRY(mat_cell_totals_dev(mat));
+    if (mat->n) SB_CUDA(cudaMemcpyAsync(out_n_local, mat->cell_tot.p, mat->n * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+
+int mat_gene_sums_dev(sb_mat *mat, int mode, const unsigned char *excl_cells, const unsigned char *excl_genes, u64 *d_out, bool allreduce) {
+    sb_ctx *ctx = mat->ctx;
+    SB_CUDA(cudaMemsetAsync(d_out, 0, (size_t)mat->m * sizeof(u64), ctx->stream));
+    if (mat->n && mat->nnz) {
+        ProfScope ps(ctx, PH_REDUCE);
+        k_gene_sums<<<grid_for(mat->n * 32, 256, ctx, 16), 256, 0, ctx->stream>>>(mat->cm_ptr.p, mat->cm.p, mat->n, mode, excl_cells, excl_genes,
+                                                                                  (unsigned long long *)d_out);
+        count_launch(ctx);
+    }
+    if (allreduce) SB_TRY(comm_allreduce_u64(ctx, d_out, mat->m));
+    return SB_OK;
+}
+
+static int gene_sums_host(sb_mat *mat, int mode, uint64_t *out_m) {
+    if (!mat || !out_m) return sb_fail(SB_ERR_INVALID_ARG, "gene sums: NULL argument");
+    sb_ctx *ctx = mat->ctx;
+    SB_CUDA(cudaSetDevice(ctx->device));
+    DevBuf<u64> d;
+    SB_TRY(d.alloc(mat->m));
+    SB_TRY(mat_gene_sums_dev(mat, mode, nullptr, nullptr, d.p, true));
+    if (mat->m) SB_CUDA(cudaMemcpyAsync(out_m, d.p, (size_t)mat->m * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+
+extern "C" int sb_gene_totals(sb_mat *mat, int square, uint64_t *out_m) { return gene_sums_host(mat, square ? 1 : 0, out_m); }
+extern "C" int sb_gene_nnz(sb_mat *mat, uint64_t *out_m) { return gene_sums_host(mat, 2, out_m); }
+
+// K3: median of the cell totals over all ranks (scan-rs/src/stats.rs:13-38)
+int mat_median_total(sb_mat *mat, u32 *median, int *nonempty) {
+    sb_ctx *ctx = mat->ctx;
+    SB_TRY(mat_cell_totals_dev(mat));
+    u64 ng = mat->n_global;
+    *nonempty = ng > 0;
+    *median = 0;
+    if (ng == 0) return SB_OK;
+    ProfScope ps(ctx, PH_REDUCE);
+    DevBuf<u32> all, sorted;
+    SB_TRY(all.alloc(ng));
+    SB_TRY(sorted.alloc(ng));
+    if (ctx->nranks == 1) {
+        SB_CUDA(cudaMemcpyAsync(all.p, mat->cell_tot.p, ng * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        std::vector<u64> counts;
+        SB_TRY(comm_allgather_u64_host(ctx, mat->n, counts));
+        SB_NCCL(ncclGroupStart());
+        u64 off = 0;
+        for (int r = 0; r < ctx->nranks; r++) {
+            if (counts[r]) SB_NCCL(ncclBroadcast(mat->cell_tot.p, all.p + off, counts[r], ncclUint32, r, ctx->comm, ctx->stream));
+            off += counts[r];
+        }
+        SB_NCCL(ncclGroupEnd());
+        count_launch(ctx, false);
+    }
+    size_t tmp_bytes = 0;
+    SB_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, all.p, sorted.p, (unsigned long long)ng, 0, 32, ctx->stream));
+    DevBuf<char> tmp;
+    SB_TRY(tmp.alloc(tmp_bytes));
+    SB_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tmp_bytes, all.p, sorted.p, (unsigned long long)ng, 0, 32, ctx->stream));
+    count_launch(ctx, false);
+    u32 h[2] = {0, 0};
+    if (ng % 2 == 0) {
+        SB_CUDA(cudaMemcpyAsync(h, sorted.p + (ng / 2 - 1), 2 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+        SB_CUDA(cudaStreamSynchronize(ctx->stream));
+        *median = (u32)(h[0] + h[1]) / 2u;  // u32 wrapping add, integer divide (stats.rs:32)
+    } else {
+        SB_CUDA(cudaMemcpyAsync(h, sorted.p + ng / 2, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+        SB_CUDA(cudaStreamSynchronize(ctx->stream));
+        *median = h[0];
+    }
+    return SB_OK;
+}
+
+extern "C" int sb_median_cell_total(sb_mat *mat, uint32_t *median, int *nonempty) {
+    if (!mat || !median || !nonempty) return sb_fail(SB_ERR_INVALID_ARG, "sb_median_cell_total: NULL argument");
+    SB_CUDA(cudaSetDevice(mat->ctx->device));
+    return mat_median_total(mat, median, nonempty);
+}
+
+// ---------------------------------------------------------------- selection
+static int select_rows_dev(sb_mat *mat, const u32 *h_rows, u32 count, sb_mat **out) {
+    sb_ctx *ctx = mat->ctx;
+    std::vector<u32> map(mat->m, 0xFFFFFFFFu);
+    for (u32 j = 0; j < count; j++) {
+        if (h_rows[j] >= mat->m) return sb_fail(SB_ERR_INVALID_ARG, "select_rows: row %u out of range", h_rows[j]);
+        if (map[h_rows[j]] != 0xFFFFFFFFu) return sb_fail(SB_ERR_UNSUPPORTED, "select_rows: duplicate row %u", h_rows[j]);
+        map[h_rows[j]] = j;
+    }
+    DevBuf<u32> d_map, d_counts;
+    SB_TRY(d_map.alloc(mat->m));
+    SB_TRY(d_counts.alloc(mat->n));
+    if (mat->m) SB_CUDA(cudaMemcpyAsync(d_map.p, map.data(), (size_t)mat->m * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+    DevBuf<u64> new_ptr;
+    SB_TRY(new_ptr.alloc(mat->n + 1));
+    int grid = grid_for(mat->n * 32, 256, ctx, 16);
+    if (mat->n) {
+        k_select_rows<<<grid, 256, 0, ctx->stream>>>(mat->cm_ptr.p, mat->cm.p, mat->n, d_map.p, nullptr, d_counts.p, nullptr);
+        count_launch(ctx);
+    }
+    SB_TRY(exclusive_scan_u32_to_u64(ctx, d_counts.p, mat->n, new_ptr.p));
+    u64 new_nnz = 0;
+    SB_CUDA(cudaMemcpyAsync(&new_nnz, new_ptr.p + mat->n, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    DevBuf<uint2> new_cm;
+    SB_TRY(new_cm.alloc(new_nnz));
+    if (mat->n) {
+        k_select_rows<<<grid, 256, 0, ctx->stream>>>(mat->cm_ptr.p, mat->cm.p, mat->n, d_map.p, new_ptr.p, nullptr, new_cm.p);
+        count_launch(ctx);
+    }
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return mat_from_device_cm(ctx, count, mat->n, new_ptr, new_cm, new_nnz, out);
+}
+
+static int select_cols_dev(sb_mat *mat, const u64 *h_cols, u64 count, sb_mat **out) {
+    sb_ctx *ctx = mat->ctx;
+    for (u64 j = 0; j < count; j++)
+        if (h_cols[j] >= mat->n) return sb_fail(SB_ERR_INVALID_ARG, "select_cols: column %llu out of range", (unsigned long long)h_cols[j]);
+    DevBuf<u64> d_cols, new_ptr;
+    DevBuf<u32> d_len;
+    SB_TRY(d_cols.alloc(count));
+    SB_TRY(d_len.alloc(count));
+    SB_TRY(new_ptr.alloc(count + 1));
+    if (count) {
+        SB_CUDA(cudaMemcpyAsync(d_cols.p, h_cols, count * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+        k_gather_len<<<cdiv(count, 256), 256, 0, ctx->stream>>>(mat->cm_ptr.p, d_cols.p, count, d_len.p);
+        count_launch(ctx);
+    }
+    SB_TRY(exclusive_scan_u32_to_u64(ctx, d_len.p, count, new_ptr.p));
+    u64 new_nnz = 0;
+    SB_CUDA(cudaMemcpyAsync(&new_nnz, new_ptr.p + count, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    DevBuf<uint2> new_cm;
+    SB_TRY(new_cm.alloc(new_nnz));
+    if (count) {
+        k_select_cols<<<grid_for(count * 32, 256, ctx, 16), 256, 0, ctx->stream>>>(mat->cm_ptr.p, mat->cm.p, d_cols.p, count, new_ptr.p, new_cm.p);
+        count_launch(ctx);
+    }
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return mat_from_device_cm(ctx, mat->m, count, new_ptr, new_cm, new_nnz, out);
+}
+
+extern "C" int sb_select_rows(sb_mat *mat, const uint32_t *rows, uint32_t count, sb_mat **out) {
+    if (!mat || !out || (count && !rows)) return sb_fail(SB_ERR_INVALID_ARG, "sb_select_rows: NULL argument");
+    SB_CUDA(cudaSetDevice(mat->ctx->device));
+    *out = nullptr;
+    return select_rows_dev(mat, rows, count, out);
+}
+
+extern "C" int sb_select_cols(sb_mat *mat, const uint64_t *cols, uint64_t count, sb_mat **out) {
+    if (!mat || !out || (count && !cols)) return sb_fail(SB_ERR_INVALID_ARG, "sb_select_cols: NULL argument");
+    if (mat->ctx->nranks > 1) return sb_fail(SB_ERR_UNSUPPORTED, "sb_select_cols: single-rank only");
+    SB_CUDA(cudaSetDevice(mat->ctx->device));
+    *out = nullptr;
+    return select_cols_dev(mat, cols, count, out);
+}
+
+// K4: partition_on_thresholds (sqz/src/mat.rs:772-889)
+extern "C" int sb_partition(sb_mat *mat, int has_row_thr, double row_thr, int has_col_thr, double col_thr, sb_mat **kept,
+                            sb_mat **residual, uint64_t *rows_out, uint64_t *n_rows_out, uint64_t *cols_out, uint64_t *n_cols_out) {
+    if (!mat) return sb_fail(SB_ERR_INVALID_ARG, "sb_partition: mat is NULL");
+    sb_ctx *ctx = mat->ctx;
+    if (ctx->nranks > 1) return sb_fail(SB_ERR_UNSUPPORTED, "sb_partition: single-rank only");
+    SB_CUDA(cudaSetDevice(ctx->device));
+    if (kept) *kept = nullptr;
+    if (residual) *residual = nullptr;
+    DevBuf<unsigned char> ex_rows, ex_cols;
+    DevBuf<u64> sums;
+    SB_TRY(ex_rows.alloc(mat->m));
+    SB_TRY(ex_cols.alloc(mat->n));
+    SB_TRY(sums.alloc(std::max<u64>(mat->m, mat->n)));
+    SB_CUDA(cudaMemsetAsync(ex_rows.p, 0, mat->m ? mat->m : 1, ctx->stream));
+    SB_CUDA(cudaMemsetAsync(ex_cols.p, 0, mat->n ? mat->n : 1, ctx->stream));
+    void *scr;
+    SB_TRY(ctx_scratch(ctx, 256, &scr));
+    int *d_upd = (int *)scr;
+    for (;;) {
+        SB_CUDA(cudaMemsetAsync(d_upd, 0, sizeof(int), ctx->stream));
+        if (has_col_thr && mat->n) {  // mat.rs:783-790
+            k_cell_sums_masked<<<grid_for(mat->n * 32, 256, ctx, 16), 256, 0, ctx->stream>>>(mat->cm_ptr.p, mat->cm.p, mat->n, ex_cols.p, ex_rows.p,
+                                                                                            (unsigned long long *)sums.p);
+            k_apply_threshold<<<cdiv(mat->n, 256), 256, 0, ctx->stream>>>((unsigned long long *)sums.p, mat->n, col_thr, ex_cols.p, d_upd);
+            count_launch(ctx); count_launch(ctx);
+        }
+        if (has_row_thr && mat->m) {  // mat.rs:791-798
+            SB_TRY(mat_gene_sums_dev(mat, 0, ex_cols.p, ex_rows.p, sums.p, false));
+            k_apply_threshold<<<cdiv(mat->m, 256), 256, 0, ctx->stream>>>((unsigned long long *)sums.p, mat->m, row_thr, ex_rows.p, d_upd);
+            count_launch(ctx);
+        }
+        int upd = 0;
+        SB_CUDA(cudaMemcpyAsync(&upd, d_upd, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        SB_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (!upd) break;
+    }
+    std::vector<unsigned char> hr(mat->m), hc(mat->n);
+    if (mat->m) SB_CUDA(cudaMemcpy(hr.data(), ex_rows.p, mat->m, cudaMemcpyDeviceToHost));
+    if (mat->n) SB_CUDA(cudaMemcpy(hc.data(), ex_cols.p, mat->n, cudaMemcpyDeviceToHost));
+    std::vector<u32> sel_rows;
+    std::vector<u64> sel_cols, exc_cols;
+    for (u32 r = 0; r < mat->m; r++)
+        if (!hr[r]) sel_rows.push_back(r);
+    for (u64 c = 0; c < mat->n; c++) (hc[c] ? exc_cols : sel_cols).push_back(c);
+    if (rows_out)
+        for (size_t i = 0; i < sel_rows.size(); i++) rows_out[i] = sel_rows[i];
+    if (n_rows_out) *n_rows_out = sel_rows.size();
+    if (cols_out)
+        for (size_t i = 0; i < sel_cols.size(); i++) cols_out[i] = sel_cols[i];
+    if (n_cols_out) *n_cols_out = sel_cols.size();
+    if (kept || residual) {
+        sb_mat *rows_kept = nullptr;
+        SB_TRY(select_rows_dev(mat, sel_rows.data(), (u32)sel_rows.size(), &rows_kept));
+        int rc = SB_OK;
+        if (kept) rc = select_cols_dev(rows_kept, sel_cols.data(), sel_cols.size(), kept);
+        if (rc == SB_OK && residual) rc = select_cols_dev(rows_kept, exc_cols.data(), exc_cols.size(), residual);
+        sb_free_mat(rows_kept);
+        if (rc != SB_OK) {
+            if (kept && *kept) { sb_free_mat(*kept); *kept = nullptr; }
+            return rc;
+        }
+    }
+    return SB_OK;
+}
+
+// K6 + host top-N (builder-defined): exact u64 sums -> f64 dispersion -> stable top-N
+extern "C" int sb_hvg_select(sb_mat *mat, uint32_t n_top, uint32_t *out_idx, uint32_t *out_count) {
+    if (!mat || !out_idx || !out_count) return sb_fail(SB_ERR_INVALID_ARG, "sb_hvg_select: NULL argument");
+    std::vector<u64> s1(mat->m), s2(mat->m);
+    SB_TRY(sb_gene_totals(mat, 0, s1.data()));
+    SB_TRY(sb_gene_totals(mat, 1, s2.data()));
+    double n = (double)mat->n_global;
+    std::vector<double> disp(mat->m);
+    for (u32 g = 0; g < mat->m; g++) {
+        double mean = (double)s1[g] / n;
+        double var = (double)s2[g] / n - mean * mean;
+        disp[g] = mean > 0.0 ? var / mean : 0.0;
+    }
+    std::vector<u32> order(mat->m);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 b) { return disp[a] > disp[b]; });
+    u32 cnt = std::min<u32>(n_top, mat->m);
+    std::vector<u32> top(order.begin(), order.begin() + cnt);
+    std::sort(top.begin(), top.end());
+    for (u32 i = 0; i < cnt; i++) out_idx[i] = top[i];
+    *out_count = cnt;
+    return SB_OK;
+}

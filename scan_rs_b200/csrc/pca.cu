@@ -1,0 +1,330 @@
+// pca.cu -- drivers of the truncated SVD: block Krylov (scan-rs/src/dim_red/bk_svd.rs:57-146)
+// and randomized (scan-rs/src/dim_red/rand_svd.rs:54-129), both branches (m >= n and n > m),
+// on the device-resident normalized matrix.  The sparse products run in spmm.cu; QR / Gram /
+// eigh in dense.cu.  With a communicator the cells are sharded over ranks: A^T.Y stays
+// shard-local, A.X and the Gram matrix are all-reduced, the gene-side QR is replicated.
+#include <cmath>
+
+#include "common.cuh"
+
+int spmm_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo, double *uy_scratch);
+int spmm_n(sb_nmat *a, const double *X, u32 ldx, u32 w, double *P, u32 ldp);
+int qr_tall(sb_ctx *ctx, double *A, u64 rows, u32 w, u32 ld, u32 *w_out);
+int gram(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 ld, double *G, bool reduce);
+int eigh(sb_ctx *ctx, double *G, u32 w, double *evals_dev);
+int gemm_tall_small(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 lda, const double *S, u32 k, u32 lds, double *Out, u32 ldo);
+
+// ---------------------------------------------------------------- start block
+// rand 0.10.1 SmallRng on 64-bit targets = Xoshiro256++, seeded from a u64 through SplitMix64;
+// Uniform::<f64>::new(-1.0, 1.0): value1_2 = f64::from_bits((u64 >> 12) | 0x3FF0..), then
+// (value1_2 - 1.0) * 2.0 + (-1.0).  Known answers are in tests/test_host_abi.py.  (The crate
+// sources are not available offline, so bit-equality with a Rust build is unpinned)
+struct Xoshiro256pp {
+    u64 s[4];
+    explicit Xoshiro256pp(u64 seed) {
+        u64 z = seed;
+        for (int i = 0; i < 4; i++) {
+            z += 0x9E3779B97F4A7C15ULL;
+            u64 x = z;
+            x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+            x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+            s[i] = x ^ (x >> 31);
+        }
+    }
+    static inline u64 rotl(u64 x, int k) { return (x << k) | (x >> (64 - k)); }
+    u64 next() {
+        u64 r = rotl(s[0] + s[3], 23) + s[0];
+        u64 t = s[1] << 17;
+        s[2] ^= s[0];
+        s[3] ^= s[1];
+        s[1] ^= s[2];
+        s[0] ^= s[3];
+        s[2] ^= t;
+        s[3] = rotl(s[3], 45);
+        return r;
+    }
+};
+
+extern "C" int sb_omega(uint64_t seed, uint64_t rows, uint64_t cols, double *out) {
+    if (!out && rows * cols) return sb_fail(SB_ERR_INVALID_ARG, "sb_omega: out is NULL");
+    Xoshiro256pp rng(seed);
+    for (u64 i = 0; i < rows * cols; i++) {
+        u64 bits = (rng.next() >> 12) | 0x3FF0000000000000ULL;
+        double v12;
+        memcpy(&v12, &bits, 8);
+        out[i] = (v12 - 1.0) * 2.0 + (-1.0);
+    }
+    return SB_OK;
+}
+
+// ---------------------------------------------------------------- helpers
+static inline u32 even_up(u32 w) { return (w + 1) & ~1u; }
+
+struct Tall {  // row-major rows x w block, even ld, zero padded
+    DevBuf<double> buf;
+    u64 rows = 0;
+    u32 w = 0, ld = 0;
+    int init(sb_ctx *ctx, u64 r, u32 width, u64 extra_rows = 0) {
+        rows = r;
+        w = width;
+        ld = even_up(width);
+        SB_TRY(buf.alloc((rows + extra_rows) * (size_t)ld));
+        SB_CUDA(cudaMemsetAsync(buf.p, 0, std::max<size_t>(1, (rows + extra_rows) * (size_t)ld) * sizeof(double), ctx->stream));
+        return SB_OK;
+    }
+};
+
+// copies src (rows x w, ld lds) into columns [c0, c0+w) of dst (ld ldd)
+static int copy_block(sb_ctx *ctx, double *dst, u32 ldd, u32 c0, const double *src, u32 lds, u64 rows, u32 w) {
+    if (rows == 0 || w == 0) return SB_OK;
+    SB_CUDA(cudaMemcpy2DAsync(dst + c0, ldd * sizeof(double), src, lds * sizeof(double), w * sizeof(double), rows, cudaMemcpyDeviceToDevice,
+                              ctx->stream));
+    return SB_OK;
+}
+
+static int progress(sb_ctx *ctx, sb_progress_cb cb, void *user, double frac) {
+    int cancel = 0;
+    if (cb) cancel = cb(frac, user) != 0;
+    if (ctx->nranks > 1) SB_TRY(comm_allreduce_max_i32(ctx, &cancel));
+    if (cancel) return sb_fail(SB_ERR_CANCELLED, "cancelled at progress %.3f", frac);
+    return SB_OK;
+}
+
+// From the projected tall block Tt (rows_t x wq, the cell side when n > m, the gene side when
+// m >= n) and the orthonormal basis Q (rows_q x wq): Gram -> eigh -> top-k triplets.
+//   left  (rows_t x k) = Tt . W_k . diag(1/sigma)      right (rows_q x k) = Q . W_k
+// `reduce_gram` all-reduces the Gram matrix (cell-sharded Tt).
+static int finish_svd(sb_ctx *ctx, const Tall &Tt, const Tall &Q, u32 wq, u32 k, bool reduce_gram, double *S_host, Tall &from_t, Tall &from_q) {
+    DevBuf<double> G, ev, Wk;
+    SB_TRY(G.alloc((size_t)wq * wq));
+    SB_TRY(ev.alloc(wq));
+    SB_TRY(Wk.alloc((size_t)wq * k * 2));
+    SB_TRY(gram(ctx, Tt.buf.p, Tt.rows, wq, Tt.ld, G.p, reduce_gram));
+    SB_TRY(eigh(ctx, G.p, wq, ev.p));
+    std::vector<double> h_ev(wq), h_W((size_t)wq * wq);
+    SB_CUDA(cudaMemcpyAsync(h_ev.data(), ev.p, wq * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(cudaMemcpyAsync(h_W.data(), G.p, (size_t)wq * wq * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    // eigenvalues ascending -> take the k largest, descending
+    std::vector<double> Wsel((size_t)wq * k), Wscaled((size_t)wq * k);
+    for (u32 i = 0; i < k; i++) {
+        u32 src = wq - 1 - i;
+        double lam = h_ev[src];
+        double sig = lam > 0.0 ? std::sqrt(lam) : 0.0;
+        S_host[i] = sig;
+        double inv = sig > 0.0 ? 1.0 / sig : 0.0;
+        for (u32 r = 0; r < wq; r++) {
+            double x = h_W[(size_t)src * wq + r];
+            Wsel[(size_t)i * wq + r] = x;
+            Wscaled[(size_t)i * wq + r] = x * inv;
+        }
+    }
+    double *dWsel = Wk.p, *dWsc = Wk.p + (size_t)wq * k;
+    SB_CUDA(cudaMemcpyAsync(dWsel, Wsel.data(), Wsel.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    SB_CUDA(cudaMemcpyAsync(dWsc, Wscaled.data(), Wscaled.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    SB_TRY(from_t.init(ctx, Tt.rows, k));
+    SB_TRY(from_q.init(ctx, Q.rows, k));
+    SB_TRY(gemm_tall_small(ctx, Tt.buf.p, Tt.rows, wq, Tt.ld, dWsc, k, wq, from_t.buf.p, from_t.ld));
+    SB_TRY(gemm_tall_small(ctx, Q.buf.p, Q.rows, wq, Q.ld, dWsel, k, wq, from_q.buf.p, from_q.ld));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+
+static int download_tall(sb_ctx *ctx, const Tall &t, double *host) {
+    if (t.rows == 0 || t.w == 0) return SB_OK;
+    SB_CUDA(cudaMemcpy2DAsync(host, t.w * sizeof(double), t.buf.p, t.ld * sizeof(double), t.w * sizeof(double), t.rows, cudaMemcpyDeviceToHost,
+                              ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+
+// uploads a row-major host block (rows x w) into a Tall; `transpose_in`: host is (w x rows)
+static int upload_tall(sb_ctx *ctx, Tall &t, const double *host, bool transpose_in) {
+    if (t.rows == 0 || t.w == 0) return SB_OK;
+    if (!transpose_in) {
+        SB_CUDA(cudaMemcpy2DAsync(t.buf.p, t.ld * sizeof(double), host, t.w * sizeof(double), t.w * sizeof(double), t.rows, cudaMemcpyHostToDevice,
+                                  ctx->stream));
+        SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    } else {
+        std::vector<double> tmp(t.rows * (size_t)t.ld, 0.0);
+        for (u32 j = 0; j < t.w; j++)
+            for (u64 r = 0; r < t.rows; r++) tmp[r * t.ld + j] = host[(size_t)j * t.rows + r];
+        SB_CUDA(cudaMemcpy(t.buf.p, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    return SB_OK;
+}
+
+static int check_shape(const sb_nmat *a, u32 k) {
+    const sb_mat *mt = a->mat;
+    if (mt->m < 2 || mt->n_global < 2) return sb_fail(SB_ERR_INVALID_SHAPE, "The input matrix must be at least 2x2.");
+    if ((u64)k > std::min<u64>(mt->m, mt->n_global)) return sb_fail(SB_ERR_INVALID_K, "invalid k");
+    if (k == 0) return sb_fail(SB_ERR_INVALID_K, "invalid k");
+    return SB_OK;
+}
+
+// ---------------------------------------------------------------- block Krylov SVD
+extern "C" int sb_bksvd(sb_nmat *a, uint32_t k, uint32_t b, uint32_t n_iter, uint64_t seed, const double *omega, sb_progress_cb cb, void *user,
+                        double *U, double *S, double *V) {
+    if (!a || !U || !S || !V) return sb_fail(SB_ERR_INVALID_ARG, "sb_bksvd: NULL argument");
+    sb_mat *mt = a->mat;
+    sb_ctx *ctx = mt->ctx;
+    SB_CUDA(cudaSetDevice(ctx->device));
+    SB_TRY(check_shape(a, k));
+    if (n_iter == 0) return sb_fail(SB_ERR_INVALID_ARG, "sb_bksvd: n_iter must be >= 1");
+    const u32 m = mt->m;
+    const u64 n = mt->n, ng = mt->n_global;
+    b = (u32)std::min<u64>(std::min<u64>(m, ng), b);  // bk_svd.rs:81
+    if (b < k) return sb_fail(SB_ERR_INVALID_K, "invalid k");
+    DevBuf<double> uy;
+    SB_TRY(uy.alloc(even_up(b * n_iter) + 2));
+    std::vector<double> h_om;
+
+    if ((u64)m >= ng) {
+        // ---- m >= n (bk_svd.rs:89-115): block on the cell side; single rank only
+        if (ctx->nranks > 1) return sb_fail(SB_ERR_UNSUPPORTED, "sb_bksvd: the m >= n branch is single-rank");
+        Tall B, Kc, W, Z;
+        SB_TRY(B.init(ctx, n, b));
+        if (!omega) {
+            h_om.resize((size_t)n * b);
+            SB_TRY(sb_omega(seed, n, b, h_om.data()));  // :90 (n x b, row-major fill)
+            omega = h_om.data();
+        }
+        SB_TRY(upload_tall(ctx, B, omega, false));
+        SB_TRY(Kc.init(ctx, n, b * n_iter));
+        SB_TRY(W.init(ctx, m, b, 1));
+        for (u32 i = 0; i < n_iter; i++) {
+            SB_TRY(spmm_n(a, B.buf.p, B.ld, b, W.buf.p, W.ld));             // A.dot(&B)
+            SB_TRY(spmm_t(a, W.buf.p, W.ld, b, B.buf.p, B.ld, uy.p));        // (.)^T.dot(A) ^T
+            u32 wq = 0;
+            SB_TRY(qr_tall(ctx, B.buf.p, n, b, B.ld, &wq));                  // .qr()?.0   :94
+            SB_TRY(copy_block(ctx, Kc.buf.p, Kc.ld, i * b, B.buf.p, B.ld, n, b));  // :95
+            SB_TRY(progress(ctx, cb, user, (double)i / (double)n_iter * 0.8));     // :96
+        }
+        u32 wq = 0;
+        SB_TRY(qr_tall(ctx, Kc.buf.p, n, b * n_iter, Kc.ld, &wq));           // :98
+        SB_TRY(progress(ctx, cb, user, 0.82));
+        Tall T;
+        SB_TRY(T.init(ctx, m, wq, 1));
+        SB_TRY(spmm_n(a, Kc.buf.p, Kc.ld, wq, T.buf.p, T.ld));               // T = A.dot(&Q)  :102
+        SB_TRY(progress(ctx, cb, user, 0.93));
+        if (k > wq) return sb_fail(SB_ERR_INVALID_K, "invalid k");
+        Tall Uo, Vo;
+        Kc.w = wq;
+        SB_TRY(finish_svd(ctx, T, Kc, wq, k, false, S, Uo, Vo));             // :105-113
+        SB_TRY(download_tall(ctx, Uo, U));
+        SB_TRY(download_tall(ctx, Vo, V));
+        SB_TRY(progress(ctx, cb, user, 1.0));
+        return SB_OK;
+    }
+
+    // ---- n > m (bk_svd.rs:116-145): block on the gene side, replicated over ranks
+    Tall Y, Kt, T, P;
+    SB_TRY(Y.init(ctx, m, b));
+    if (!omega) {
+        h_om.resize((size_t)b * m);
+        SB_TRY(sb_omega(seed, b, m, h_om.data()));  // :118 (b x m, row-major fill)
+        omega = h_om.data();
+    }
+    SB_TRY(upload_tall(ctx, Y, omega, true));  // Y[g, j] = B[j, g]
+    SB_TRY(Kt.init(ctx, m, b * n_iter));
+    SB_TRY(T.init(ctx, n, b));
+    SB_TRY(P.init(ctx, m, b, 1));
+    for (u32 i = 0; i < n_iter; i++) {
+        SB_TRY(spmm_t(a, Y.buf.p, Y.ld, b, T.buf.p, T.ld, uy.p));            // T = B.dot(A)^T        :122
+        SB_TRY(spmm_n(a, T.buf.p, T.ld, b, P.buf.p, P.ld));                  // A.dot(&T)             :123
+        u32 wq = 0;
+        SB_TRY(qr_tall(ctx, P.buf.p, m, b, P.ld, &wq));                      // .qr()?.0
+        SB_TRY(copy_block(ctx, Y.buf.p, Y.ld, 0, P.buf.p, P.ld, m, b));
+        SB_TRY(copy_block(ctx, Kt.buf.p, Kt.ld, i * b, P.buf.p, P.ld, m, b));  // K rows i*b..   :124
+        SB_TRY(progress(ctx, cb, user, (double)i / (double)n_iter * 0.8));   // :125
+    }
+    u32 wq = 0;
+    SB_TRY(qr_tall(ctx, Kt.buf.p, m, b * n_iter, Kt.ld, &wq));               // Q = K.t().qr()?.0     :127
+    SB_TRY(progress(ctx, cb, user, 0.82));
+    Tall Tt;
+    SB_TRY(Tt.init(ctx, n, wq));
+    SB_TRY(spmm_t(a, Kt.buf.p, Kt.ld, wq, Tt.buf.p, Tt.ld, uy.p));           // T = Q.t().dot(A)      :131
+    SB_TRY(progress(ctx, cb, user, 0.93));
+    if (k > wq) return sb_fail(SB_ERR_INVALID_K, "invalid k");
+    Tall Vo, Uo;
+    Kt.w = wq;
+    SB_TRY(finish_svd(ctx, Tt, Kt, wq, k, true, S, Vo, Uo));                 // :134-142
+    SB_TRY(download_tall(ctx, Uo, U));
+    SB_TRY(download_tall(ctx, Vo, V));
+    SB_TRY(progress(ctx, cb, user, 1.0));
+    return SB_OK;
+}
+
+extern "C" int sb_bksvd_run_pca(sb_nmat *a, uint32_t k, double k_multiplier, uint32_t n_iter, sb_progress_cb cb, void *user, double *U, double *S,
+                                double *V) {
+    u32 bsize = (u32)std::ceil((double)k * k_multiplier);  // bk_svd.rs:49
+    return sb_bksvd(a, k, bsize, n_iter, 0, nullptr, cb, user, U, S, V);
+}
+
+// ---------------------------------------------------------------- randomized SVD
+extern "C" int sb_randsvd(sb_nmat *a, uint32_t k, uint32_t l, uint32_t n_iter, uint64_t seed, const double *omega, double *U, double *S, double *V) {
+    if (!a || !U || !S || !V) return sb_fail(SB_ERR_INVALID_ARG, "sb_randsvd: NULL argument");
+    sb_mat *mt = a->mat;
+    sb_ctx *ctx = mt->ctx;
+    SB_CUDA(cudaSetDevice(ctx->device));
+    SB_TRY(check_shape(a, k));
+    if (ctx->nranks > 1) return sb_fail(SB_ERR_UNSUPPORTED, "sb_randsvd: single-rank only (its QR runs on the cell side)");
+    const u32 m = mt->m;
+    const u64 n = mt->n;
+    if ((u64)l > std::min<u64>(m, n)) return sb_fail(SB_ERR_UNSUPPORTED, "sb_randsvd: l = %u exceeds min(m, n)", l);
+    if (l < k) return sb_fail(SB_ERR_INVALID_K, "invalid k");
+    DevBuf<double> uy;
+    SB_TRY(uy.alloc(even_up(l) + 2));
+    std::vector<double> h_om;
+    Tall Qm, Qn;  // gene-side (m x l, +1 row for spmm_n) and cell-side (n x l) blocks
+    SB_TRY(Qm.init(ctx, m, l, 1));
+    SB_TRY(Qn.init(ctx, n, l));
+    u32 wq = 0;
+    if ((u64)m >= n) {  // rand_svd.rs:85-105
+        if (!omega) {
+            h_om.resize((size_t)n * l);
+            SB_TRY(sb_omega(seed, n, l, h_om.data()));
+            omega = h_om.data();
+        }
+        SB_TRY(upload_tall(ctx, Qn, omega, false));
+        SB_TRY(spmm_n(a, Qn.buf.p, Qn.ld, l, Qm.buf.p, Qm.ld));              // Q = A.dot(&omega).qr()  :87
+        SB_TRY(qr_tall(ctx, Qm.buf.p, m, l, Qm.ld, &wq));
+        for (u32 i = 0; i < n_iter; i++) {
+            SB_TRY(spmm_t(a, Qm.buf.p, Qm.ld, l, Qn.buf.p, Qn.ld, uy.p));     // Q.t().dot(A)^T .qr()    :90
+            SB_TRY(qr_tall(ctx, Qn.buf.p, n, l, Qn.ld, &wq));
+            SB_TRY(spmm_n(a, Qn.buf.p, Qn.ld, l, Qm.buf.p, Qm.ld));          // A.dot(&Q).qr()          :91
+            SB_TRY(qr_tall(ctx, Qm.buf.p, m, l, Qm.ld, &wq));
+        }
+        SB_TRY(spmm_t(a, Qm.buf.p, Qm.ld, l, Qn.buf.p, Qn.ld, uy.p));         // B = Q.t().dot(A)        :96  (stored as B^T)
+        Tall Vo, Uo;
+        SB_TRY(finish_svd(ctx, Qn, Qm, l, k, false, S, Vo, Uo));              // U = Q.U_B               :104
+        SB_TRY(download_tall(ctx, Uo, U));
+        SB_TRY(download_tall(ctx, Vo, V));
+    } else {  // rand_svd.rs:106-128
+        if (!omega) {
+            h_om.resize((size_t)l * m);
+            SB_TRY(sb_omega(seed, l, m, h_om.data()));
+            omega = h_om.data();
+        }
+        SB_TRY(upload_tall(ctx, Qm, omega, true));
+        SB_TRY(spmm_t(a, Qm.buf.p, Qm.ld, l, Qn.buf.p, Qn.ld, uy.p));         // omega.dot(A)^T .qr()    :109
+        SB_TRY(qr_tall(ctx, Qn.buf.p, n, l, Qn.ld, &wq));
+        for (u32 i = 0; i < n_iter; i++) {
+            SB_TRY(spmm_n(a, Qn.buf.p, Qn.ld, l, Qm.buf.p, Qm.ld));          // A.dot(&Q).qr()          :112
+            SB_TRY(qr_tall(ctx, Qm.buf.p, m, l, Qm.ld, &wq));
+            SB_TRY(spmm_t(a, Qm.buf.p, Qm.ld, l, Qn.buf.p, Qn.ld, uy.p));     // Q.t().dot(A)^T .qr()    :113
+            SB_TRY(qr_tall(ctx, Qn.buf.p, n, l, Qn.ld, &wq));
+        }
+        SB_TRY(spmm_n(a, Qn.buf.p, Qn.ld, l, Qm.buf.p, Qm.ld));              // B = A.dot(&Q)           :118
+        Tall Uo, Vo;
+        SB_TRY(finish_svd(ctx, Qm, Qn, l, k, false, S, Uo, Vo));              // Va = Vt[:k].Q^T         :126
+        SB_TRY(download_tall(ctx, Uo, U));
+        SB_TRY(download_tall(ctx, Vo, V));
+    }
+    return SB_OK;
+}
+
+extern "C" int sb_randsvd_run_pca(sb_nmat *a, uint32_t k, double l_multiplier, uint32_t n_iter, double *U, double *S, double *V) {
+    u32 l = std::max<u32>(k + 4, (u32)((double)k * l_multiplier));  // rand_svd.rs:46
+    return sb_randsvd(a, k, l, n_iter, 0, nullptr, U, S, V);
+}

@@ -1,0 +1,85 @@
+"""Mirror of scan_rs::dim_red (scan-rs/src/dim_red/{mod,bk_svd,rand_svd}.rs) on the device path."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _lib as L
+from .snoop import NoOpSnoop
+from .sqz import LowRankOffset
+
+
+def omega(seed: int, rows: int, cols: int) -> np.ndarray:
+    """The start block: SmallRng::seed_from_u64(seed) + Uniform(-1, 1), row-major (bk_svd.rs:83-84)."""
+    out = np.zeros((rows, cols))
+    L.check(L.lib().sb_omega(C.c_uint64(seed), C.c_uint64(rows), C.c_uint64(cols), L.vp(out)))
+    return out
+
+
+def _make_cb(snoop):
+    def _cb(frac, _user):
+        # set_progress_check (snoop/src/lib.rs:45-57): cancelled -> Err before the progress is stored
+        if snoop.is_cancelled():
+            return 1
+        snoop.set_progress(frac)
+        return 0
+    return L.PROGRESS_CB(_cb)
+
+
+def svd_bk(A: LowRankOffset, k: int, b: int, n_iter: int, seed: int = 0, snoop=None, omega_block: Optional[np.ndarray] = None):
+    """bk_svd.rs:57-146 -> (U m x k, sigma k, Va k x n_local)."""
+    m, n = A.shape()
+    U, S, V = np.zeros((m, k)), np.zeros(k), np.zeros((n, k))
+    cb = _make_cb(snoop or NoOpSnoop())
+    om = None if omega_block is None else np.ascontiguousarray(omega_block, dtype=np.float64)
+    L.check(L.lib().sb_bksvd(A._h, C.c_uint32(k), C.c_uint32(b), C.c_uint32(n_iter), C.c_uint64(seed), L.vp(om), cb, None,
+                             L.vp(U), L.vp(S), L.vp(V)))
+    return U, S, V.T
+
+
+def svd_rand(A: LowRankOffset, k: int, l: int, n_iter: int, seed: int = 0, omega_block: Optional[np.ndarray] = None):
+    """rand_svd.rs:54-129 -> (U, sigma, Va k x n)."""
+    m, n = A.shape()
+    U, S, V = np.zeros((m, k)), np.zeros(k), np.zeros((n, k))
+    om = None if omega_block is None else np.ascontiguousarray(omega_block, dtype=np.float64)
+    L.check(L.lib().sb_randsvd(A._h, C.c_uint32(k), C.c_uint32(l), C.c_uint32(n_iter), C.c_uint64(seed), L.vp(om),
+                               L.vp(U), L.vp(S), L.vp(V)))
+    return U, S, V.T
+
+
+class BkSvd:
+    """bk_svd.rs:16-53: defaults k_multiplier = 2.0, n_iter = 5."""
+
+    def __init__(self, k_multiplier: float = 2.0, n_iter: int = 5):
+        self.k_multiplier, self.n_iter = k_multiplier, n_iter
+
+    def run_pca_cancellable(self, array: LowRankOffset, k: int, snoop):
+        """-> (u m x k, s k, v n x k): PcaResult with `vt.reversed_axes()` (bk_svd.rs:48-52)."""
+        m, n = array.shape()
+        U, S, V = np.zeros((m, k)), np.zeros(k), np.zeros((n, k))
+        cb = _make_cb(snoop)
+        L.check(L.lib().sb_bksvd_run_pca(array._h, C.c_uint32(k), C.c_double(self.k_multiplier), C.c_uint32(self.n_iter), cb, None,
+                                         L.vp(U), L.vp(S), L.vp(V)))
+        return U, S, V
+
+    def run_pca(self, array: LowRankOffset, k: int):  # dim_red/mod.rs:108-110
+        return self.run_pca_cancellable(array, k, NoOpSnoop())
+
+
+class RandSvd:
+    """rand_svd.rs:13-50: defaults l_multiplier = 10.0, n_iter = 2 (ignores the snoop, :44-45)."""
+
+    def __init__(self, l_multiplier: float = 10.0, n_iter: int = 2):
+        self.l_multiplier, self.n_iter = l_multiplier, n_iter
+
+    def run_pca_cancellable(self, array: LowRankOffset, k: int, _snoop=None):
+        m, n = array.shape()
+        U, S, V = np.zeros((m, k)), np.zeros(k), np.zeros((n, k))
+        L.check(L.lib().sb_randsvd_run_pca(array._h, C.c_uint32(k), C.c_double(self.l_multiplier), C.c_uint32(self.n_iter),
+                                           L.vp(U), L.vp(S), L.vp(V)))
+        return U, S, V
+
+    def run_pca(self, array: LowRankOffset, k: int):
+        return self.run_pca_cancellable(array, k)

@@ -1,0 +1,310 @@
+"""Host-side mirror of the reference's `sqz` types for the device path.
+
+`AdaptiveMat`  <-> sqz::AdaptiveMat<u32> (sqz/src/mat.rs:34-42): the count matrix, uploaded once and
+                   kept device-resident (cell-major + cell-panelled gene-major u32/u32 copies).
+`LowRankOffset` <-> sqz::LowRankOffset (sqz/src/low_rank_offset.rs:12-16): the normalized matrix
+                   A = map(counts) + u.v, never materialised.
+Method names and argument meanings follow the reference; everything calls the C ABI."""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+
+
+class Context:
+    """One GPU + stream (+ optional NCCL communicator)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        L.check(L.lib().sb_init(C.c_int(device), C.byref(self._h)))
+        self.device = device
+        self.nranks, self.rank = 1, 0
+        self._mats, self._nmats = weakref.WeakSet(), weakref.WeakSet()
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        L.check(L.lib().sb_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, nranks: int, rank: int, uid: bytes) -> None:
+        L.check(L.lib().sb_comm_init(self._h, C.c_int(nranks), C.c_int(rank), C.c_char_p(uid)))
+        self.nranks, self.rank = nranks, rank
+
+    def sync(self):
+        L.check(L.lib().sb_sync(self._h))
+
+    def timer_begin(self):
+        L.check(L.lib().sb_timer_begin(self._h))
+
+    def timer_end(self) -> float:
+        ms = C.c_float(0)
+        L.check(L.lib().sb_timer_end(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def flush_l2(self):
+        L.check(L.lib().sb_flush_l2(self._h))
+
+    def profile_enable(self, on: bool = True):
+        L.check(L.lib().sb_profile_enable(self._h, C.c_int(int(on))))
+
+    def profile_reset(self):
+        L.check(L.lib().sb_profile_reset(self._h))
+
+    def profile(self) -> dict:
+        p = L.SbProfile()
+        L.check(L.lib().sb_profile_get(self._h, C.byref(p)))
+        return p.as_dict()
+
+    def close(self):
+        if self._h:
+            for a in list(self._nmats):  # handles borrow the context: free them first
+                a.free()
+            for m in list(self._mats):
+                m.free()
+            L.lib().sb_shutdown(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+class AdaptiveMat:
+    """Device-resident genes x cells u32 count matrix (sqz/src/mat.rs:34-42)."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx, self._h = ctx, handle
+        ctx._mats.add(self)
+
+    # ---- constructors
+    @classmethod
+    def from_csr(cls, ctx: Context, rows: int, cols: int, indptr, idx, val) -> "AdaptiveMat":
+        """Gene-major CSR arrays (from_csmat on a CSR sprs matrix, mat.rs:92-124)."""
+        return cls._upload(ctx, L.SB_GENE_MAJOR, rows, cols, indptr, idx, val)
+
+    @classmethod
+    def from_csc(cls, ctx: Context, rows: int, cols: int, indptr, idx, val) -> "AdaptiveMat":
+        """Cell-major (CSC of the genes x cells matrix) arrays."""
+        return cls._upload(ctx, L.SB_CELL_MAJOR, rows, cols, indptr, idx, val)
+
+    @classmethod
+    def from_dense(cls, ctx: Context, dense) -> "AdaptiveMat":  # mat.rs:586-609
+        dense = np.asarray(dense)
+        rows, cols = dense.shape
+        indptr, idx, val = [0], [], []
+        for r in range(rows):
+            nz = np.nonzero(dense[r])[0]
+            idx.extend(nz.tolist())
+            val.extend(dense[r, nz].tolist())
+            indptr.append(len(idx))
+        return cls.from_csr(ctx, rows, cols, indptr, idx, val)
+
+    @classmethod
+    def _upload(cls, ctx, major, rows, cols, indptr, idx, val):
+        indptr = np.ascontiguousarray(indptr, dtype=np.uint64)
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        val = np.ascontiguousarray(val, dtype=np.uint32)
+        nvec = rows if major == L.SB_GENE_MAJOR else cols
+        if indptr.shape != (nvec + 1,) or idx.shape != val.shape or idx.shape[0] != int(indptr[-1]):
+            raise ValueError("inconsistent CSR/CSC arrays")
+        h = C.c_void_p()
+        L.check(L.lib().sb_upload(ctx._h, C.c_int(major), C.c_uint32(rows), C.c_uint64(cols), L.vp(indptr), L.vp(idx),
+                                  L.vp(val), C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def _synth(cls, ctx, m, n_local, cell_offset, seed, pf, depth, cluster, r):
+        h = C.c_void_p()
+        L.check(L.lib().sb_synth_generate(ctx._h, C.c_uint32(m), C.c_uint64(n_local), C.c_uint64(cell_offset), C.c_uint64(seed),
+                                          C.c_uint32(pf.shape[0]), L.vp(pf), L.vp(depth), L.vp(cluster), C.c_uint32(r),
+                                          C.byref(h)))
+        return cls(ctx, h)
+
+    # ---- shape
+    def _shape4(self):
+        m, n, ng, nnz = C.c_uint32(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        L.check(L.lib().sb_mat_shape(self._h, C.byref(m), C.byref(n), C.byref(ng), C.byref(nnz)))
+        return m.value, n.value, ng.value, nnz.value
+
+    def rows(self) -> int:
+        return self._shape4()[0]
+
+    def cols(self) -> int:
+        """Local cell count (== global without a communicator)."""
+        return self._shape4()[1]
+
+    def cols_global(self) -> int:
+        return self._shape4()[2]
+
+    def shape(self):
+        s = self._shape4()
+        return [s[0], s[1]]
+
+    def nnz(self) -> int:
+        return self._shape4()[3]
+
+    # ---- reductions
+    def sum_axis_u32(self, axis: int) -> np.ndarray:
+        """sum_axis::<u32> (mat.rs:377-406): axis 0 -> per-cell totals (wrapping u32);
+        axis 1 -> per-gene totals (computed exactly in u64 on the device, truncated like u32 `+=`)."""
+        m, n, _, _ = self._shape4()
+        if axis == 0:
+            out = np.zeros(n, dtype=np.uint32)
+            L.check(L.lib().sb_cell_totals(self._h, L.vp(out)))
+            return out
+        return (self.gene_totals() & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+
+    def gene_totals(self, square: bool = False) -> np.ndarray:
+        out = np.zeros(self.rows(), dtype=np.uint64)
+        L.check(L.lib().sb_gene_totals(self._h, C.c_int(int(square)), L.vp(out)))
+        return out
+
+    def gene_nnz(self) -> np.ndarray:
+        out = np.zeros(self.rows(), dtype=np.uint64)
+        L.check(L.lib().sb_gene_nnz(self._h, L.vp(out)))
+        return out
+
+    def median_cell_total(self) -> Optional[int]:
+        med, ok = C.c_uint32(), C.c_int()
+        L.check(L.lib().sb_median_cell_total(self._h, C.byref(med), C.byref(ok)))
+        return int(med.value) if ok.value else None
+
+    # ---- filters
+    def partition_on_threshold(self, threshold: float):  # mat.rs:766-768
+        return self.partition_on_thresholds(threshold, threshold)
+
+    def partition_on_thresholds(self, row_threshold: Optional[float], col_threshold: Optional[float]):
+        """mat.rs:772-889 -> (filtered, residual, selected_rows, selected_cols)."""
+        m, n, _, _ = self._shape4()
+        rows = np.zeros(m, dtype=np.uint64)
+        cols = np.zeros(n, dtype=np.uint64)
+        nr, nc = C.c_uint64(), C.c_uint64()
+        kept, resid = C.c_void_p(), C.c_void_p()
+        L.check(L.lib().sb_partition(self._h, C.c_int(row_threshold is not None), C.c_double(row_threshold or 0.0),
+                                     C.c_int(col_threshold is not None), C.c_double(col_threshold or 0.0),
+                                     C.byref(kept), C.byref(resid), L.vp(rows), C.byref(nr), L.vp(cols), C.byref(nc)))
+        return (AdaptiveMat(self.ctx, kept), AdaptiveMat(self.ctx, resid), rows[: nr.value].astype(np.int64),
+                cols[: nc.value].astype(np.int64))
+
+    def select_rows(self, rows: Sequence[int]) -> "AdaptiveMat":  # mat.rs:1040-1071
+        r = np.ascontiguousarray(rows, dtype=np.uint32)
+        h = C.c_void_p()
+        L.check(L.lib().sb_select_rows(self._h, L.vp(r), C.c_uint32(r.shape[0]), C.byref(h)))
+        return AdaptiveMat(self.ctx, h)
+
+    def select_cols(self, cols: Sequence[int]) -> "AdaptiveMat":  # mat.rs:1004-1037
+        c = np.ascontiguousarray(cols, dtype=np.uint64)
+        h = C.c_void_p()
+        L.check(L.lib().sb_select_cols(self._h, L.vp(c), C.c_uint64(c.shape[0]), C.byref(h)))
+        return AdaptiveMat(self.ctx, h)
+
+    def hvg_select(self, n_top: int) -> np.ndarray:
+        """Builder-defined highly-variable-gene selection (not in the reference)."""
+        out = np.zeros(self.rows(), dtype=np.uint32)
+        cnt = C.c_uint32()
+        L.check(L.lib().sb_hvg_select(self._h, C.c_uint32(n_top), L.vp(out), C.byref(cnt)))
+        return out[: cnt.value].copy()
+
+    # ---- download
+    def to_csr(self):
+        """Gene-major (indptr u64, cell idx u32, count u32): to_csmat (mat.rs:207-239)."""
+        return self._download(L.SB_GENE_MAJOR)
+
+    def to_csc(self):
+        return self._download(L.SB_CELL_MAJOR)
+
+    def _download(self, major):
+        m, n, _, nnz = self._shape4()
+        nvec = m if major == L.SB_GENE_MAJOR else n
+        indptr = np.zeros(nvec + 1, dtype=np.uint64)
+        idx = np.zeros(nnz, dtype=np.uint32)
+        cnt = np.zeros(nnz, dtype=np.uint32)
+        L.check(L.lib().sb_download(self._h, C.c_int(major), L.vp(indptr), L.vp(idx), L.vp(cnt)))
+        return indptr, idx, cnt
+
+    def to_dense(self) -> np.ndarray:
+        m, n, _, _ = self._shape4()
+        indptr, idx, cnt = self.to_csr()
+        out = np.zeros((m, n), dtype=np.uint32)
+        for r in range(m):
+            s, e = int(indptr[r]), int(indptr[r + 1])
+            out[r, idx[s:e]] = cnt[s:e]
+        return out
+
+    def free(self):
+        if self._h:
+            L.lib().sb_free_mat(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class LowRankOffset:
+    """Device-resident normalized matrix A = map(counts) + u.v (sqz/src/low_rank_offset.rs:12-16)."""
+
+    def __init__(self, mat: AdaptiveMat, handle):
+        self.mat, self._h = mat, handle
+        mat.ctx._nmats.add(self)
+
+    def rows(self) -> int:
+        return self.mat.rows()
+
+    def cols(self) -> int:
+        return self.mat.cols()
+
+    def shape(self):
+        return self.mat.shape()
+
+    def params(self):
+        """(col_scale[n], row_scale[m], u[m], v[n]) as derived on the device."""
+        m, n = self.shape()
+        cs, rs, u, v = np.zeros(n), np.zeros(m), np.zeros(m), np.zeros(n)
+        L.check(L.lib().sb_nmat_params(self._h, L.vp(cs), L.vp(rs), L.vp(u), L.vp(v)))
+        return cs, rs, u, v
+
+    def to_dense(self) -> np.ndarray:  # low_rank_offset.rs:55-57
+        m, n = self.shape()
+        out = np.zeros((m, n))
+        L.check(L.lib().sb_nmat_to_dense(self._h, L.vp(out)))
+        return out
+
+    def dot(self, rhs: np.ndarray) -> np.ndarray:  # low_rank_offset.rs:68-81
+        rhs = np.ascontiguousarray(rhs, dtype=np.float64)
+        m, n = self.shape()
+        if rhs.shape[0] != n:
+            raise ValueError("Dimension mismatch")
+        out = np.zeros((m, rhs.shape[1]))
+        L.check(L.lib().sb_nmat_dot(self._h, L.vp(rhs), C.c_uint32(rhs.shape[1]), L.vp(out)))
+        return out
+
+    def rdot(self, lhs: np.ndarray) -> np.ndarray:  # low_rank_offset.rs:83-96: lhs . A
+        lhs = np.ascontiguousarray(lhs, dtype=np.float64)
+        m, n = self.shape()
+        if lhs.shape[1] != m:
+            raise ValueError("Dimension mismatch")
+        out = np.zeros((lhs.shape[0], n))
+        L.check(L.lib().sb_nmat_rdot(self._h, L.vp(lhs), C.c_uint32(lhs.shape[0]), L.vp(out)))
+        return out
+
+    def free(self):
+        if self._h:
+            L.lib().sb_free_nmat(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

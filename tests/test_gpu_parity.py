@@ -1,0 +1,336 @@
+"""GPU parity tests: the CUDA path through the C ABI against the CPU oracle on identical inputs.
+Integer stages bit-exact; f64 stages within the tolerances north_star states (sigma 1e-6 relative,
+principal angles < 1e-5) and much tighter for single products."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import scan_rs_b200 as sb
+from oracle import oracle as orc
+from scan_rs_b200 import _lib as L
+from tests.util import check_pca_parity, synth_pair
+
+pytestmark = pytest.mark.gpu
+
+DENSE_A = np.array([[136, 936, 0, 0, 264],
+                    [134, 682, 417, 8, 391],
+                    [0, 133, 780, 0, 0],
+                    [396, 76, 96, 198, 0]], dtype=np.uint32)
+NORMS = {sb.Normalization.CellRanger: orc.CELLRANGER, sb.Normalization.CellRanger8: orc.CELLRANGER8,
+         sb.Normalization.SeuratLog: orc.SEURATLOG, sb.Normalization.LogTransform: orc.LOG_TRANSFORM}
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = sb.Context(0)
+    yield c
+    c.close()
+
+
+# ------------------------------------------------------------------ golden vectors of the reference
+def test_golden_cellranger(ctx):  # normalization.rs:539-575
+    expected = np.array([[0.61392149, 0.95459951, -1.21707302, -1.21707302, 0.86562504],
+                         [-0.11878431, 0.54279925, 0.38607315, -1.85660965, 1.04652156],
+                         [-0.78758751, 0.76437149, 1.59839105, -0.78758751, -0.78758751],
+                         [0.88718256, -0.25584717, -0.01048423, 1.09574143, -1.71659259]])
+    mtx = sb.AdaptiveMat.from_dense(ctx, DENSE_A)
+    norm_mat = sb.normalize_with_size_factor(mtx, sb.Normalization.CellRanger, None)
+    assert np.abs(expected - norm_mat.to_dense()).max() < 1e-6
+    assert np.abs(expected - sb.normalize(mtx, sb.Normalization.CellRanger).to_dense()).max() < 1e-6
+
+
+def test_golden_cellranger8(ctx):  # normalization.rs:577-612
+    expected = np.array([[2.37992764, 3.70059981, -4.71810445, -4.71810445, 3.35568145],
+                         [-0.15920674, 0.72751443, 0.51745426, -2.48841594, 1.40265399],
+                         [-2.85652852, 2.77232551, 5.79726005, -2.85652852, -2.85652852],
+                         [2.94151467, -0.84827885, -0.0347612, 3.63300591, -5.69148053]])
+    mtx = sb.AdaptiveMat.from_dense(ctx, DENSE_A)
+    out = sb.normalize_with_size_factor(mtx, sb.Normalization.CellRanger8, None).to_dense()
+    assert np.abs(expected - out).max() < 1e-6
+
+
+def test_golden_size_factors(ctx):  # normalization.rs:614-650
+    expected = np.array([[9.37098961, 9.18882221, 0., 0., 9.37609671],
+                         [9.34964848, 8.73300582, 8.4781546, 12.37964912, 9.94202202],
+                         [0., 6.3885887, 9.3796973, 0., 0.],
+                         [10.91145213, 5.59409085, 6.37267837, 17.00874593, 0.]])
+    mtx = sb.AdaptiveMat.from_dense(ctx, DENSE_A)
+    size_factors = 1 + mtx.select_rows([0, 2]).sum_axis_u32(0)
+    np.testing.assert_array_equal(size_factors, 1 + DENSE_A[[0, 2]].sum(axis=0))
+    out = sb.log_normalize_with_size_factor(mtx, None, sb.LogBase.Two, size_factors).to_dense()
+    assert np.abs(expected - out).max() < 1e-6
+
+
+def test_golden_log_transform_and_fixed_point(ctx):  # normalization.rs:652-722
+    expected = np.array([[0.50075509, 1.16407001, -1.1965938, -1.1965938, 0.72836249],
+                         [-0.14245194, 0.89844192, 0.58318993, -1.88113806, 0.54195815],
+                         [-0.80111703, 0.89623633, 1.50711477, -0.80111703, -0.80111703],
+                         [0.92609909, 0.14507504, 0.25503138, 0.59722303, -1.92342854]])
+    mtx = sb.AdaptiveMat.from_dense(ctx, DENSE_A)
+    out = sb.normalize_with_size_factor(mtx, sb.Normalization.LogTransform, None).to_dense()
+    assert np.abs(expected - out).max() < 1e-6
+    mtx10 = sb.AdaptiveMat.from_dense(ctx, DENSE_A * 10)
+    out = sb.log1p_normalize_fixed_point(mtx10, sb.LogBase.Two, 10, 1).to_dense()
+    assert np.abs(expected - out).max() < 1e-6
+
+
+def test_golden_one_dim_no_nan(ctx):  # normalization.rs:477-516
+    import os
+    row = np.loadtxt(os.path.join(os.path.dirname(__file__), "golden", "one_dim_649.txt"), dtype=np.uint32).reshape(1, 649)
+    out = sb.normalize(sb.AdaptiveMat.from_dense(ctx, row), sb.Normalization.CellRanger).to_dense()
+    assert not np.isnan(out).any()
+    ref = orc.normalize(orc.CountMatrix.from_dense(row), orc.CELLRANGER).to_dense()
+    np.testing.assert_allclose(out, ref, rtol=0, atol=1e-9)
+
+
+def test_golden_sum_fns(ctx):  # sqz/src/mat.rs:1293-1325
+    input_a = DENSE_A.copy()
+    input_a[2, 3] = 885
+    m = sb.AdaptiveMat.from_dense(ctx, input_a)
+    np.testing.assert_array_equal(m.sum_axis_u32(0), [666, 1827, 1293, 1091, 655])
+    np.testing.assert_array_equal(m.sum_axis_u32(1), [1336, 1632, 1798, 766])
+    assert m.median_cell_total() == 1091
+    assert m.shape() == [4, 5] and m.nnz() == 15
+
+
+def test_median_matches_reference_cases(ctx):  # stats.rs:67-82
+    for vals, want in [([1, 10], 5), ([1, 10, 100, 1000], 55), ([3, 1, 2], 2)]:
+        m = sb.AdaptiveMat.from_dense(ctx, np.array([vals], dtype=np.uint32))
+        assert m.median_cell_total() == want
+
+
+# ------------------------------------------------------------------ integer stages, bit exact
+@pytest.mark.parametrize("n_cells,n_genes", [(1500, 3000), (4100, 900)])
+def test_integer_stages_bit_exact(ctx, n_cells, n_genes):
+    cfg, cm, dm, (ip, g, c) = synth_pair(ctx, n_cells, n_genes, seed=11)
+    assert dm.shape() == [n_genes, n_cells] and dm.nnz() == cm.nnz
+    np.testing.assert_array_equal(dm.sum_axis_u32(0), cm.sum_axis_u32(0))
+    np.testing.assert_array_equal(dm.gene_totals(), cm.sum_axis_u64(1))
+    np.testing.assert_array_equal(dm.gene_totals(square=True), cm.sum_axis_u64(1, square=True))
+    np.testing.assert_array_equal(dm.gene_nnz(), np.diff(cm.indptr.astype(np.int64)))
+    assert dm.median_cell_total() == orc.median_mut(cm.sum_axis_u32(0))
+    # both upload orders give the same matrix; downloads round-trip
+    dm2 = sb.AdaptiveMat.from_csr(ctx, n_genes, n_cells, cm.indptr, cm.idx, cm.val)
+    for a, b in zip(dm2.to_csc(), (ip, g, c)):
+        np.testing.assert_array_equal(a, b)
+    for a, b in zip(dm.to_csr(), (cm.indptr, cm.idx, cm.val)):
+        np.testing.assert_array_equal(a, b)
+    # HVG selection (builder-defined): identical index list
+    np.testing.assert_array_equal(dm.hvg_select(200), orc.hvg_select(cm.sum_axis_u64(1), cm.sum_axis_u64(1, True), n_cells, 200))
+
+
+def test_synth_gpu_equals_cpu(ctx):
+    from scan_rs_b200.synth import SynthConfig, generate_device, generate_host
+    cfg = SynthConfig(n_cells=700, n_genes=5000, seed=5, n_dense=20)
+    ip, g, c = generate_host(cfg)
+    dm = generate_device(ctx, cfg)
+    for a, b in zip(dm.to_csc(), (ip, g, c)):
+        np.testing.assert_array_equal(a, b)
+    # a shard generated on the device equals the slice
+    ds = generate_device(ctx, cfg, 128, 640)
+    s, e = int(ip[128]), int(ip[640])
+    ips, gs, cs = ds.to_csc()
+    np.testing.assert_array_equal(gs, g[s:e])
+    np.testing.assert_array_equal(cs, c[s:e])
+
+
+def test_empty_and_ragged(ctx):
+    dense = np.zeros((6, 9), dtype=np.uint32)
+    dense[1, 2] = 3
+    dense[4, 2] = 1
+    dense[4, 8] = 70000
+    m = sb.AdaptiveMat.from_dense(ctx, dense)
+    np.testing.assert_array_equal(m.sum_axis_u32(0), dense.sum(axis=0))
+    np.testing.assert_array_equal(m.to_dense(), dense)
+    ref = orc.normalize(orc.CountMatrix.from_dense(dense), orc.CELLRANGER)
+    out = sb.normalize(m, sb.Normalization.CellRanger)
+    # cells with zero total have an infinite, never used column scale (normalization.rs:169)
+    np.testing.assert_allclose(out.to_dense(), ref.to_dense(), rtol=1e-12, atol=1e-12)
+    z = sb.AdaptiveMat.from_dense(ctx, np.zeros((3, 4), dtype=np.uint32))
+    assert z.nnz() == 0 and z.median_cell_total() == 0
+    np.testing.assert_array_equal(z.sum_axis_u32(0), np.zeros(4, dtype=np.uint32))
+
+
+def test_partition_and_select(ctx):
+    cfg, cm, dm, _ = synth_pair(ctx, 600, 1500, seed=4, depth=40.0)
+    for thr in [(3.0, 3.0), (5.0, None), (None, 30.0)]:
+        f_o, r_o, rows_o, cols_o = cm.partition_on_thresholds(*thr)
+        f_g, r_g, rows_g, cols_g = dm.partition_on_thresholds(*thr)
+        np.testing.assert_array_equal(rows_g, rows_o)
+        np.testing.assert_array_equal(cols_g, cols_o)
+        assert len(rows_o) < 1500 or len(cols_o) < 600
+        for a, b in zip(f_g.to_csr(), (f_o.indptr, f_o.idx, f_o.val)):
+            np.testing.assert_array_equal(a, b)
+        for a, b in zip(r_g.to_csr(), (r_o.indptr, r_o.idx, r_o.val)):
+            np.testing.assert_array_equal(a, b)
+    rows = [7, 3, 1200, 44]
+    s_o, s_g = cm.select_rows(rows), dm.select_rows(rows)
+    for a, b in zip(s_g.to_csr(), (s_o.indptr, s_o.idx, s_o.val)):
+        np.testing.assert_array_equal(a, b)
+    cols = [5, 0, 599, 5, 17]
+    s_o, s_g = cm.select_cols(cols), dm.select_cols(cols)
+    for a, b in zip(s_g.to_csr(), (s_o.indptr, s_o.idx, s_o.val)):
+        np.testing.assert_array_equal(a, b)
+
+
+# ------------------------------------------------------------------ sparse products
+def _identity_nmat(dm):
+    """log_base 0, target 1, size factors 1: the map is v as f64 (MatrixIntoMap) -- integer data"""
+    h = C.c_void_p()
+    ones = np.ones(dm.cols(), dtype=np.uint32)
+    L.check(L.lib().sb_log_normalize(dm._h, C.c_int(1), C.c_double(1.0), C.c_int(0), L.vp(ones), C.c_int(0), None, C.byref(h)))
+    return sb.LowRankOffset(dm, h)
+
+
+@pytest.mark.parametrize("w", [1, 2, 3, 7, 16, 20, 33, 50, 100, 130])
+def test_spmm_exact_on_integer_data(ctx, w):
+    """Recipe of sqz/src/mat.rs:1406-1486: integer counts x integer dense block => exact equality."""
+    cfg, cm, dm, _ = synth_pair(ctx, 1300, 700, seed=9, depth=300.0)
+    a = _identity_nmat(dm)
+    dense = cm.to_dense().astype(np.float64)
+    rng = np.random.default_rng(w)
+    x = rng.integers(0, 100, size=(1300, w)).astype(np.float64)
+    np.testing.assert_array_equal(a.dot(x), dense.dot(x))
+    y = rng.integers(0, 100, size=(w, 700)).astype(np.float64)
+    np.testing.assert_array_equal(a.rdot(y), y.dot(dense))
+
+
+@pytest.mark.parametrize("norm", list(NORMS))
+@pytest.mark.parametrize("w", [1, 20, 45])
+def test_normalized_products_match_oracle(ctx, norm, w):
+    """LowRankOffset dot in both directions (low_rank_offset.rs:144-173 uses rtol 1e-7 / atol 1e-12;
+    here 1e-11 relative to the block norm)."""
+    cfg, cm, dm, _ = synth_pair(ctx, 2500, 1800, seed=21)
+    a_o = orc.normalize_with_size_factor(cm, NORMS[norm], None)
+    a_g = sb.normalize_with_size_factor(dm, norm, None)
+    cs, rs, u, v = a_g.params()
+    np.testing.assert_allclose(cs, a_o.mat.spec.col_scale, rtol=1e-15)
+    np.testing.assert_allclose(rs, a_o.mat.spec.row_scale, rtol=1e-11)
+    np.testing.assert_allclose(u, a_o.u.ravel(), rtol=1e-9, atol=1e-13)
+    rng = np.random.default_rng(w)
+    x = rng.standard_normal((2500, w))
+    ref = a_o.dot(x)
+    assert np.abs(a_g.dot(x) - ref).max() <= 1e-11 * np.abs(ref).max()
+    y = rng.standard_normal((w, 1800))
+    ref = a_o.rdot(y)
+    assert np.abs(a_g.rdot(y) - ref).max() <= 1e-11 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("kind", ["deviance", "pearson"])
+def test_binomial_residual_products(ctx, kind):
+    cfg, cm, dm, _ = synth_pair(ctx, 900, 1100, seed=22)
+    a_o = orc.binom_deviance_resid(cm) if kind == "deviance" else orc.binom_pearson_resid(cm)
+    a_g = sb.binom_deviance_resid(dm) if kind == "deviance" else sb.binom_pearson_resid(dm)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((900, 12))
+    ref = a_o.dot(x)
+    assert np.abs(a_g.dot(x) - ref).max() <= 1e-10 * np.abs(ref).max()
+    y = rng.standard_normal((12, 1100))
+    ref = a_o.rdot(y)
+    assert np.abs(a_g.rdot(y) - ref).max() <= 1e-10 * np.abs(ref).max()
+
+
+# ------------------------------------------------------------------ PCA parity
+@pytest.mark.parametrize("n_cells,n_genes,k", [(4000, 1500, 10), (1200, 3000, 10), (5000, 2000, 3)])
+def test_bksvd_matches_oracle(ctx, n_cells, n_genes, k):
+    """Both branches of svd_bk (n > m and m >= n) with the shared start block."""
+    cfg, cm, dm, _ = synth_pair(ctx, n_cells, n_genes, seed=31)
+    a_o = orc.normalize(cm, orc.CELLRANGER)
+    a_g = sb.normalize(dm, sb.Normalization.CellRanger)
+    res_o = orc.BkSvd().run_pca(a_o, k)
+    res_g = sb.BkSvd().run_pca(a_g, k)
+    check_pca_parity(res_g, res_o)
+    # the reference's own acceptance metric: ||A v - u s||_F / size < 1e-3 (dim_red/test.rs:69-75)
+    u, s, v = res_g
+    assert orc.frobenius(a_g.dot(v) - u * s) < 1e-3
+
+
+def test_bksvd_seurat_and_binomial(ctx):
+    cfg, cm, dm, _ = synth_pair(ctx, 3000, 1200, seed=32)
+    check_pca_parity(sb.BkSvd().run_pca(sb.normalize(dm, sb.Normalization.SeuratLog), 8),
+                     orc.BkSvd().run_pca(orc.normalize(cm, orc.SEURATLOG), 8))
+    check_pca_parity(sb.BkSvd().run_pca(sb.binom_pearson_resid(dm), 6),
+                     orc.BkSvd().run_pca(orc.binom_pearson_resid(cm), 6))
+    check_pca_parity(sb.BkSvd().run_pca(sb.binom_deviance_resid(dm), 6),
+                     orc.BkSvd().run_pca(orc.binom_deviance_resid(cm), 6))
+
+
+@pytest.mark.parametrize("n_cells,n_genes", [(3000, 1000), (900, 2500)])
+def test_randsvd_matches_oracle(ctx, n_cells, n_genes):
+    cfg, cm, dm, _ = synth_pair(ctx, n_cells, n_genes, seed=33)
+    res_o = orc.RandSvd().run_pca(orc.normalize(cm, orc.CELLRANGER), 10)
+    res_g = sb.RandSvd().run_pca(sb.normalize(dm, sb.Normalization.CellRanger), 10)
+    check_pca_parity(res_g, res_o)
+
+
+def test_svd_bk_explicit_block_and_seed(ctx):
+    cfg, cm, dm, _ = synth_pair(ctx, 2000, 800, seed=34)
+    a_o, a_g = orc.normalize(cm, orc.CELLRANGER), sb.normalize(dm, sb.Normalization.CellRanger)
+    u1, s1, vt1 = sb.svd_bk(a_g, 5, 10, 5, seed=3)
+    uo, so, vto = orc.svd_bk(a_o, 5, 10, 5, seed=3)
+    check_pca_parity((u1, s1, vt1.T), (uo, so, vto.T))
+    om = np.random.default_rng(1).uniform(-1, 1, size=(10, 800))
+    u2, s2, vt2 = sb.svd_bk(a_g, 5, 10, 5, omega_block=om)
+    uo, so, vto = orc.svd_bk(a_o, 5, 10, 5, omega_block=om)
+    check_pca_parity((u2, s2, vt2.T), (uo, so, vto.T))
+
+
+def test_errors_and_cancellation(ctx):  # bk_svd.rs:73-79, :96; snoop/src/lib.rs:45-57
+    dm = sb.AdaptiveMat.from_dense(ctx, np.array([[1, 2, 3, 4]], dtype=np.uint32))
+    with pytest.raises(sb.ScanB200Error, match="The input matrix must be at least 2x2."):
+        sb.BkSvd().run_pca(sb.normalize(dm, sb.Normalization.CellRanger), 1)
+    cfg, cm, dm, _ = synth_pair(ctx, 400, 300, seed=35)
+    a = sb.normalize(dm, sb.Normalization.CellRanger)
+    with pytest.raises(sb.ScanB200Error, match="invalid k") as ei:
+        sb.BkSvd().run_pca(a, 301)
+    assert ei.value.code == L.SB_ERR_INVALID_K
+    snoop = sb.AtomicSnoop()
+    sb.BkSvd().run_pca_cancellable(a, 4, snoop)
+    assert snoop.history == [0.0, 0.16000000000000003, 0.32000000000000006, 0.48, 0.64, 0.82, 0.93, 1.0]
+
+    class CancelAfter(sb.AtomicSnoop):
+        def set_progress(self, f):
+            super().set_progress(f)
+            if len(self.history) == 2:
+                self.cancel()
+
+    s2 = CancelAfter()
+    with pytest.raises(sb.CancellationError):
+        sb.BkSvd().run_pca_cancellable(a, 4, s2)
+    assert s2.history == [0.0, 0.16000000000000003]
+    with pytest.raises(NotImplementedError):
+        sb.normalize(dm, sb.Normalization.LogTransform)
+    with pytest.raises(AssertionError):
+        sb.normalize_with_size_factor(dm, sb.Normalization.WithSizeFactors, np.ones(3, dtype=np.uint32))
+
+
+# ------------------------------------------------------------------ BASELINE config 1 in full, then properties at scale
+def test_config1_full_parity(ctx):
+    """configs[0]: 10k cells x 33,538 genes, normalize + PCA k=10 (m >= n branch) against the oracle."""
+    cfg, cm, dm, _ = synth_pair(ctx, 10000, 33538, seed=1)
+    res_o = orc.BkSvd().run_pca(orc.normalize(cm, orc.CELLRANGER), 10)
+    res_g = sb.BkSvd().run_pca(sb.normalize(dm, sb.Normalization.CellRanger), 10)
+    check_pca_parity(res_g, res_o)
+
+
+def test_properties_at_scale(ctx):
+    """200k cells x 33,538 genes on the device generator: size-independent properties --
+    checksum of checksums of the integer stages, orthonormal factors, A v = u s, A^T u = v s."""
+    from scan_rs_b200.synth import SynthConfig, generate_device
+    cfg = SynthConfig(n_cells=200_000, n_genes=33538, seed=2)
+    dm = generate_device(ctx, cfg)
+    cell_tot = dm.sum_axis_u32(0).astype(np.uint64)
+    gene_tot = dm.gene_totals()
+    assert cell_tot.sum() == gene_tot.sum() and dm.gene_nnz().sum() == dm.nnz()
+    assert dm.median_cell_total() == int(np.sort(cell_tot)[[99_999, 100_000]].sum() // 2)
+    a = sb.normalize(dm, sb.Normalization.CellRanger)
+    u, s, v = sb.BkSvd().run_pca(a, 10)
+    assert np.all(np.diff(s) <= 0) and s[-1] > 0
+    assert np.abs(u.T.dot(u) - np.eye(10)).max() < 1e-10
+    assert np.abs(v.T.dot(v) - np.eye(10)).max() < 1e-10
+    av = a.dot(v)
+    assert np.abs(av - u * s).max() < 1e-8 * s[0]
+    atu = a.rdot(u.T).T
+    # Ritz pairs of a 5-block Krylov space: residual small relative to sigma_1 but not at rounding level
+    assert np.linalg.norm(atu - v * s) < 2e-2 * s[0]

@@ -1,0 +1,74 @@
+"""CPU-side checks of the boundary: the C-ABI library loads, exports every symbol the header
+declares, fails loudly without a GPU, and its host-side pieces (the start-block RNG, the
+Normalization parser) give the reference's known answers.  No compute calls (no GPU here)."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import scan_rs_b200 as sb
+from scan_rs_b200 import _lib as L
+from tests.conftest import HAVE_GPU
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "scanb200.h")).read()
+    declared = set(re.findall(r"SB_API\s+[\w\s\*]+?\b(sb_\w+)\s*\(", hdr))
+    assert declared == set(L.SYMBOLS), declared ^ set(L.SYMBOLS)
+    out = subprocess.run(["nm", "-D", "--defined-only", L.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r"\bT (sb_\w+)", out))
+    assert declared <= exported, declared - exported
+    lib = L.lib()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.sb_version() == 100
+
+
+def test_only_sm100a_code_is_embedded():
+    out = subprocess.run(["cuobjdump", "-lelf", L.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+@pytest.mark.skipif(HAVE_GPU, reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    with pytest.raises(sb.ScanB200Error) as ei:
+        sb.Context(0)
+    assert ei.value.code == L.SB_ERR_CUDA
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_omega_known_answers():
+    om = sb.omega(0, 2, 2).ravel()
+    np.testing.assert_array_equal(om, [-0.35084946393718663, -0.23552140697665314,
+                                       -0.2807655847052897, -0.977088982130693])
+    from oracle import oracle as orc
+    np.testing.assert_array_equal(sb.omega(7, 13, 5), orc.omega(7, (13, 5)))
+    np.testing.assert_array_equal(sb.omega(0, 20, 40), orc.omega(0, (20, 40)))
+
+
+def test_normalization_from_str():  # normalization.rs:30-43
+    assert sb.Normalization.from_str("cellranger") == sb.Normalization.CellRanger
+    assert sb.Normalization.from_str("seuratlog") == sb.Normalization.SeuratLog
+    assert sb.Normalization.from_str("binomialpearson") == sb.Normalization.BinomialPearson
+    with pytest.raises(ValueError, match="Normalization not recognized: foo"):
+        sb.Normalization.from_str("foo")
+
+
+def test_synth_cpu_is_deterministic_and_shardable():
+    from scan_rs_b200.synth import SynthConfig, generate_host
+    cfg = SynthConfig(n_cells=300, n_genes=2000, seed=3)
+    ip, g, c = generate_host(cfg)
+    ip2, g2, c2 = generate_host(cfg)
+    np.testing.assert_array_equal(g, g2)
+    np.testing.assert_array_equal(c, c2)
+    # a shard generated on its own equals the slice of the whole
+    ipa, ga, ca = generate_host(cfg, 100, 250)
+    s, e = int(ip[100]), int(ip[250])
+    np.testing.assert_array_equal(ga, g[s:e])
+    np.testing.assert_array_equal(ca, c[s:e])
+    assert (c > 0).all() and (np.diff(ip.astype(np.int64)) > 0).all()
