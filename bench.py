@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py -- normalize + PCA(k=10) throughput on the BASELINE.json workload.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--cells C]
+
+One "step" = normalize(CellRanger) + BkSvd::run_pca(k=10) over the whole synthetic
+1.3M-cell x 33,538-gene count matrix (BASELINE.json configs[2]; cells sharded over the N ranks,
+strong scaling).  `value`: counts already device-resident (both device layouts built) -> U, sigma, V
+on the host.  `e2e`: the same call sequence starting from pinned HOST CSC buffers (sb_upload's
+H2D copies and the device-side layout build are inside the timed region) -> U, sigma, V on the host.
+Timing is on the device (CUDA events on the library's stream), max over ranks.
+
+`--impl reference` times the CPU restatement of the reference (oracle/, all host threads) on a
+bounded sample of the same workload; the default run also reports a 1-thread `cpu_baseline`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_GENES = 33538
+K = 10
+METRIC = "normalize+PCA cells/s, 1.3Mx33.5k, k=10"
+CPU_SAMPLE_CELLS = 40_000  # > n_genes so the CPU sample takes the same n > m branch of svd_bk
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def pinned_u(n, dtype):
+    """Pinned host buffer as a numpy array (torch is plumbing: page-locked allocation only)."""
+    import torch
+    nbytes = int(n) * np.dtype(dtype).itemsize
+    t = torch.empty(max(nbytes, 8), dtype=torch.uint8, pin_memory=True)
+    return t.numpy()[:nbytes].view(dtype), t
+
+
+def run_reference(args):
+    """CPU arm: the oracle restatement of the reference path with all host threads, on a bounded
+    sample (CPU_SAMPLE_CELLS cells of the same generator and shape) per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    from scan_rs_b200.synth import SynthConfig, generate_host
+    orc.build()
+    n = CPU_SAMPLE_CELLS
+    cfg = SynthConfig(n_cells=n, n_genes=N_GENES, seed=3)
+    ip, g, c = generate_host(cfg)
+    cm = orc.CountMatrix.from_cell_major(N_GENES, n, ip, g, c)
+    threads = orc.lib().orc_num_threads()
+
+    def step():
+        a = orc.normalize(cm, orc.CELLRANGER)
+        return orc.BkSvd().run_pca(a, K, threads=True)
+
+    for _ in range(args.warmup_ref):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = n / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "cells/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup_ref, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"normalize(CellRanger)+BkSvd k={K}, {N_GENES} genes; CPU sample of {n} cells per step"},
+            "cpu_baseline": {"value": val, "unit": "cells/s", "cores": threads, "kind": "port",
+                             "sample": f"{n} cells x {N_GENES} genes (nnz {cm.nnz}), oracle port with OpenMP SpMM, whole normalize+PCA per step"},
+            "e2e": {"value": val, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_1thread():
+    """1-thread oracle (faithful to the single-threaded reference path) on the bounded sample."""
+    from oracle import oracle as orc
+    from scan_rs_b200.synth import SynthConfig, generate_host
+    n = CPU_SAMPLE_CELLS
+    cfg = SynthConfig(n_cells=n, n_genes=N_GENES, seed=3)
+    ip, g, c = generate_host(cfg)
+    cm = orc.CountMatrix.from_cell_major(N_GENES, n, ip, g, c)
+    t0 = time.perf_counter()
+    a = orc.normalize(cm, orc.CELLRANGER)
+    orc.BkSvd().run_pca(a, K, threads=False)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "cells/s", "cores": 1, "kind": "port",
+            "sample": f"{n} cells x {N_GENES} genes (nnz {cm.nnz}), one normalize+PCA k={K}, {dt:.1f} s; the oracle reads plain u32 CSR "
+                      "(no AdaptiveVec decode), so it is an optimistic stand-in for the reference"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--cells", type=int, default=1_300_000)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup_ref = min(args.warmup, 1)
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import scan_rs_b200 as sb
+    from scan_rs_b200.synth import SynthConfig, generate_device
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ctx = sb.Context(local_rank)
+    if world > 1:
+        obj = [sb.Context.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        ctx.comm_init(world, rank, obj[0])
+
+    n_total = args.cells
+    lo = n_total * rank // world
+    hi = n_total * (rank + 1) // world
+    cfg = SynthConfig(n_cells=n_total, n_genes=N_GENES, seed=3)
+    dm = generate_device(ctx, cfg, lo, hi)
+    nnz_local = dm.nnz()
+
+    def step(mat):
+        a = sb.normalize(mat, sb.Normalization.CellRanger)
+        res = sb.BkSvd().run_pca(a, K)
+        a.free()
+        return res
+
+    # ---------------- device-resident arm
+    for _ in range(args.warmup):
+        step(dm)
+    ctx.profile_enable(True)
+    ctx.profile_reset()
+    sampler = ClockSampler(local_rank)
+    ctx.sync()
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t_wall = time.perf_counter()
+    ctx.timer_begin()
+    for _ in range(args.steps):
+        res = step(dm)
+    ms = ctx.timer_end()
+    barrier()
+    wall = time.perf_counter() - t_wall
+    clocks = sampler.stop() if rank == 0 else None
+    prof = ctx.profile()
+    ctx.profile_enable(False)
+    ms = max_over_ranks(ms)
+    ms_per_step = ms / args.steps
+    value = n_total / (ms_per_step * 1e-3)
+
+    # ---------------- end-to-end arm: pinned host CSC buffers -> results on host
+    ip, g, c = dm.to_csc()
+    h_ip, k1 = pinned_u(len(ip), np.uint64)
+    h_g, k2 = pinned_u(len(g), np.uint32)
+    h_c, k3 = pinned_u(len(c), np.uint32)
+    h_ip[:], h_g[:], h_c[:] = ip, g, c
+    del ip, g, c
+    n_loc = hi - lo
+
+    def e2e_step():
+        m2 = sb.AdaptiveMat.from_csc(ctx, N_GENES, n_loc, h_ip, h_g, h_c)
+        r = step(m2)
+        m2.free()
+        return r
+
+    e2e_step()  # warm-up
+    ctx.sync()
+    barrier()
+    ctx.timer_begin()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    e_ms = max_over_ranks(ctx.timer_end()) / args.e2e_steps
+    barrier()
+    h2d = int(h_ip.nbytes + h_g.nbytes + h_c.nbytes)
+    d2h = int((N_GENES * K + K + n_loc * K) * 8)
+
+    if rank == 0:
+        hbm_peak, peak_src = peaks()
+        kt, kn = prof["spmm_t_ms"], prof["spmm_n_ms"]
+        dom = "spmm_t" if kt >= kn else "spmm_n"
+        d_ms, d_bytes, d_flops, d_launch = ((kt, prof["spmm_t_bytes"], prof["spmm_t_flops"], prof["spmm_t_launches"]) if dom == "spmm_t"
+                                            else (kn, prof["spmm_n_bytes"], prof["spmm_n_flops"], prof["spmm_n_launches"]))
+        achieved = d_bytes / (d_ms * 1e-3) / 1e9 if d_ms > 0 else 0.0
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(dom)
+        roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                    "launches": int(d_launch), "avg_launch_ms": d_ms / max(1, d_launch),
+                    "algorithmic_bytes_per_launch": d_bytes / max(1, d_launch),
+                    "fp64_tflops": d_flops / (d_ms * 1e-3) / 1e12 if d_ms > 0 else 0.0,
+                    "phase_ms_per_step": {k: prof[k] / args.steps for k in ("spmm_t_ms", "spmm_n_ms", "moments_ms", "reduce_ms", "dense_ms", "comm_ms")},
+                    "other": {"kernel": "k_spmm_n" if dom == "spmm_t" else "k_spmm_t",
+                              "achieved": ((prof["spmm_n_bytes"] / (kn * 1e-3) / 1e9) if dom == "spmm_t" and kn > 0 else
+                                           (prof["spmm_t_bytes"] / (kt * 1e-3) / 1e9) if kt > 0 else 0.0)}}
+        line = {"metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": f"synthetic {n_total} cells x {N_GENES} genes (NB counts, ~2k UMI/cell), normalize(CellRanger)+BkSvd k={K} "
+                                       f"(b=20, n_iter=5)", "nnz_rank0": int(nnz_local), "cell_sharding": f"{world} ranks, contiguous cell ranges",
+                           "l2": "inputs (2 x 8 B/nnz device layouts) far larger than L2; no flush needed"},
+                "e2e": {"value": n_total / (e_ms * 1e-3), "unit": "cells/s", "ms_per_step": e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "steps": args.e2e_steps},
+                "gpu_launches": int(prof["own_kernel_launches"]), "library_launches": int(prof["kernel_launches"] - prof["own_kernel_launches"]),
+                "roofline": roofline, "clocks": clocks, "wall_s_timed_region": wall}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_1thread()
+        print(json.dumps(line), flush=True)
+    barrier()
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

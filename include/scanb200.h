@@ -93,6 +93,9 @@ SB_API void sb_shutdown(sb_ctx *ctx);
 SB_API int sb_comm_unique_id(char id[128]);
 SB_API int sb_comm_init(sb_ctx *ctx, int nranks, int rank, const char id[128]);
 SB_API int sb_sync(sb_ctx *ctx);
+/* Options: "direct_projection" (0/1, default 0): 1 forces the wide projection pass T = Q^T A of
+ * bk_svd.rs:102,131 to run as a sparse product; 0 lets the library use Q^T A = R^-T (K^T A) when R is usable. */
+SB_API int sb_set_option(sb_ctx *ctx, const char *name, double value);
 
 /* ---------------------------------------------------------------- count matrix
  * sb_upload replaces AdaptiveMat::from_csmat / new (sqz/src/mat.rs:81-124): the Rust side

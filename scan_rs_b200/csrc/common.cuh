@@ -3,7 +3,7 @@
 #include <cuda_runtime.h>
 #include <cublas_v2.h>
 #include <cusolverDn.h>
-#include <nccl.h>
+#include "nccl_shim.h"
 
 #include <cstdarg>
 #include <cstdint>
@@ -57,16 +57,24 @@ int sb_fail(int code, const char *fmt, ...);
     } while (0)
 
 // ---------------------------------------------------------------- device buffer (RAII)
+// Stream-ordered allocations from the device's default memory pool (release threshold raised to
+// "never" in sb_init), so the dozens of temporaries per PCA call cost microseconds instead of a
+// cudaMalloc/cudaFree device synchronisation each.  The stream is the calling context's stream,
+// published by every API entry through sb_set_alloc_stream().
+cudaStream_t sb_alloc_stream();
+void sb_set_alloc_stream(cudaStream_t s);
+
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
+    cudaStream_t st = nullptr;
     DevBuf() {}
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, st);
         p = nullptr;
         n = 0;
     }
@@ -74,12 +82,14 @@ struct DevBuf {
         release();
         n = count;
         if (count == 0) count = 1;
-        cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+        st = sb_alloc_stream();
+        cudaError_t e = cudaMallocAsync((void **)&p, count * sizeof(T), st);
         if (e != cudaSuccess) {
             p = nullptr;
             n = 0;
+            cudaGetLastError();
             return sb_fail(e == cudaErrorMemoryAllocation ? SB_ERR_OOM : SB_ERR_CUDA,
-                           "cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+                           "cudaMallocAsync of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
         }
         return SB_OK;
     }
@@ -87,6 +97,7 @@ struct DevBuf {
     void swap(DevBuf &o) {
         T *tp = p; p = o.p; o.p = tp;
         size_t tn = n; n = o.n; o.n = tn;
+        cudaStream_t ts = st; st = o.st; o.st = ts;
     }
 };
 
@@ -102,6 +113,7 @@ struct sb_ctx {
     cusolverDnHandle_t cusolver = nullptr;
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
+    bool direct_projection = false;  // true: always run the wide Q^T A pass (bk_svd.rs:102,131) instead of the R^-T identity
     // profiling
     bool profile_on = false;
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending;  // phase, (start, stop)
@@ -175,5 +187,12 @@ int comm_allreduce_f64(sb_ctx *ctx, double *buf, size_t count);
 int comm_allreduce_u64(sb_ctx *ctx, u64 *buf, size_t count);
 int comm_allreduce_max_i32(sb_ctx *ctx, int *host_val);
 int comm_allgather_u64_host(sb_ctx *ctx, u64 mine, std::vector<u64> &all);
+
+// every API entry: select the device and publish the stream used for stream-ordered allocations
+#define SB_ENTER(ctx_ptr)                         \
+    do {                                          \
+        SB_CUDA(cudaSetDevice((ctx_ptr)->device)); \
+        sb_set_alloc_stream((ctx_ptr)->stream);    \
+    } while (0)
 
 static inline unsigned cdiv(u64 a, u64 b) { return (unsigned)((a + b - 1) / b); }

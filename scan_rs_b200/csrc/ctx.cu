@@ -1,7 +1,12 @@
 // ctx.cu -- context, errors, communicator, timers and per-phase accounting.
+#include <dlfcn.h>
+
 #include "common.cuh"
 
 static thread_local char g_err[1024] = "";
+static thread_local cudaStream_t g_alloc_stream = nullptr;
+cudaStream_t sb_alloc_stream() { return g_alloc_stream; }
+void sb_set_alloc_stream(cudaStream_t s) { g_alloc_stream = s; }
 
 void sb_set_error(const char *fmt, ...) {
     va_list ap;
@@ -38,6 +43,13 @@ extern "C" int sb_init(int device, sb_ctx **out) {
     ctx->sm_count = prop.multiProcessorCount;
     ctx->l2_bytes = (size_t)prop.l2CacheSize;
     SB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    {
+        cudaMemPool_t pool;
+        SB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t never = UINT64_MAX;
+        SB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &never));
+    }
+    sb_set_alloc_stream(ctx->stream);
     SB_CUBLAS(cublasCreate(&ctx->cublas));
     SB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
     SB_CUSOLVER(cusolverDnCreate(&ctx->cusolver));
@@ -53,6 +65,7 @@ extern "C" int sb_init(int device, sb_ctx **out) {
 extern "C" void sb_shutdown(sb_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    sb_set_alloc_stream(ctx->stream);
     cudaStreamSynchronize(ctx->stream);
     prof_collect(ctx);
     for (auto ev : ctx->event_pool) cudaEventDestroy(ev);
@@ -64,8 +77,22 @@ extern "C" void sb_shutdown(sb_ctx *ctx) {
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     ctx->flush_buf.release();
     ctx->scratch.release();
+    cudaStreamSynchronize(ctx->stream);
+    {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+extern "C" int sb_set_option(sb_ctx *ctx, const char *name, double value) {
+    if (!ctx || !name) return sb_fail(SB_ERR_INVALID_ARG, "sb_set_option: NULL argument");
+    if (!strcmp(name, "direct_projection")) {
+        ctx->direct_projection = value != 0.0;
+        return SB_OK;
+    }
+    return sb_fail(SB_ERR_INVALID_ARG, "sb_set_option: unknown option %s", name);
 }
 
 extern "C" int sb_sync(sb_ctx *ctx) {
@@ -75,9 +102,63 @@ extern "C" int sb_sync(sb_ctx *ctx) {
 }
 
 // ---------------------------------------------------------------- communicator
+#undef ncclGetUniqueId
+#undef ncclCommInitRank
+#undef ncclCommDestroy
+#undef ncclAllReduce
+#undef ncclAllGather
+#undef ncclBroadcast
+#undef ncclGroupStart
+#undef ncclGroupEnd
+#undef ncclGetErrorString
+const NcclApi *sb_nccl() {
+    static NcclApi api;
+    static int state = 0;  // 0 untried, 1 ok, -1 failed
+    if (state == 1) return &api;
+    if (state == -1) return nullptr;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+        sb_set_error("cannot load libnccl.so.2: %s", dlerror());
+        state = -1;
+        return nullptr;
+    }
+    bool ok = true;
+    auto sym = [&](const char *name) {
+        void *p = dlsym(h, name);
+        if (!p) ok = false;
+        return p;
+    };
+    api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+    api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+    api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+    api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+    api.Broadcast = (decltype(api.Broadcast))sym("ncclBroadcast");
+    api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+    api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+    api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+    if (!ok) {
+        sb_set_error("libnccl.so.2 lacks a required symbol");
+        state = -1;
+        return nullptr;
+    }
+    state = 1;
+    return &api;
+}
+#define ncclGetUniqueId sb_nccl()->GetUniqueId
+#define ncclCommInitRank sb_nccl()->CommInitRank
+#define ncclCommDestroy sb_nccl()->CommDestroy
+#define ncclAllReduce sb_nccl()->AllReduce
+#define ncclAllGather sb_nccl()->AllGather
+#define ncclBroadcast sb_nccl()->Broadcast
+#define ncclGroupStart sb_nccl()->GroupStart
+#define ncclGroupEnd sb_nccl()->GroupEnd
+#define ncclGetErrorString sb_nccl()->GetErrorString
 extern "C" int sb_comm_unique_id(char id[128]) {
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
     ncclUniqueId uid;
+    if (!sb_nccl()) return SB_ERR_NCCL;
     SB_NCCL(ncclGetUniqueId(&uid));
     memcpy(id, &uid, 128);
     return SB_OK;
@@ -89,6 +170,7 @@ extern "C" int sb_comm_init(sb_ctx *ctx, int nranks, int rank, const char id[128
     SB_CUDA(cudaSetDevice(ctx->device));
     if (nranks == 1) return SB_OK;
     ncclUniqueId uid;
+    if (!sb_nccl()) return SB_ERR_NCCL;
     memcpy(&uid, id, 128);
     SB_NCCL(ncclCommInitRank(&ctx->comm, nranks, uid, rank));
     ctx->nranks = nranks;
@@ -219,7 +301,7 @@ extern "C" int sb_profile_get(sb_ctx *ctx, sb_profile *out) {
 
 extern "C" int sb_timer_begin(sb_ctx *ctx) {
     if (!ctx) return sb_fail(SB_ERR_INVALID_ARG, "ctx is NULL");
-    SB_CUDA(cudaSetDevice(ctx->device));
+    SB_ENTER(ctx);
     SB_CUDA(cudaStreamSynchronize(ctx->stream));
     SB_CUDA(cudaEventRecord(ctx->t0, ctx->stream));
     return SB_OK;
@@ -235,6 +317,7 @@ extern "C" int sb_timer_end(sb_ctx *ctx, float *ms) {
 
 extern "C" int sb_flush_l2(sb_ctx *ctx) {
     if (!ctx) return sb_fail(SB_ERR_INVALID_ARG, "ctx is NULL");
+    SB_ENTER(ctx);
     size_t bytes = ctx->l2_bytes ? ctx->l2_bytes * 2 : ((size_t)256 << 20);
     SB_TRY(ctx->flush_buf.ensure(bytes));
     SB_CUDA(cudaMemsetAsync(ctx->flush_buf.p, 1, bytes, ctx->stream));

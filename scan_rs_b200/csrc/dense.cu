@@ -42,8 +42,18 @@ __global__ void k_cm_to_rm(const double *__restrict__ in, u64 rows, u32 w, doubl
     }
 }
 
-// thin QR: A (row-major rows x w, ld) is replaced by Q (rows x min(rows, w)); returns the new width
-int qr_tall(sb_ctx *ctx, double *A, u64 rows, u32 w, u32 ld, u32 *w_out) {
+// copies the upper triangle of the leading w x w block of a column-major (ld = rows) factor into R (col-major w x w)
+__global__ void k_extract_r(const double *__restrict__ cm, u64 rows, u32 w, double *__restrict__ R) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < w * w) {
+        u32 c = i / w, r = i % w;
+        R[i] = (r <= c && r < rows) ? cm[(u64)c * rows + r] : 0.0;
+    }
+}
+
+// thin QR: A (row-major rows x w, ld) is replaced by Q (rows x min(rows, w)); returns the new width.
+// R_out (device, col-major w x w) optionally receives the triangular factor (needs rows >= w).
+int qr_tall(sb_ctx *ctx, double *A, u64 rows, u32 w, u32 ld, u32 *w_out, double *R_out) {
     ProfScope ps(ctx, PH_DENSE);
     u32 kq = (u32)std::min<u64>(rows, w);
     *w_out = kq;
@@ -63,6 +73,10 @@ int qr_tall(sb_ctx *ctx, double *A, u64 rows, u32 w, u32 ld, u32 *w_out) {
     int lwork = std::max(lwork1, lwork2);
     SB_TRY(work.alloc(lwork));
     SB_CUSOLVER(cusolverDnDgeqrf(ctx->cusolver, (int)rows, (int)w, cm.p, (int)rows, tau.p, work.p, lwork, info.p));
+    if (R_out && rows >= w) {
+        k_extract_r<<<cdiv((u64)w * w, 256), 256, 0, ctx->stream>>>(cm.p, rows, w, R_out);
+        count_launch(ctx);
+    }
     SB_CUSOLVER(cusolverDnDorgqr(ctx->cusolver, (int)rows, (int)kq, (int)kq, cm.p, (int)rows, tau.p, work.p, lwork, info.p));
     count_launch(ctx, false); count_launch(ctx, false);
     int h_info = 0;
@@ -116,6 +130,19 @@ int gemm_tall_small(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 lda, cons
     if (rows > 0x7FFFFFFFull) return sb_fail(SB_ERR_UNSUPPORTED, "gemm: more than 2^31 rows");
     const double one = 1.0, zero = 0.0;
     SB_CUBLAS(cublasDgemm(ctx->cublas, CUBLAS_OP_T, CUBLAS_OP_N, (int)k, (int)rows, (int)w, &one, S, (int)lds, A, (int)lda, &zero, Out, (int)ldo));
+    count_launch(ctx, false);
+    return SB_OK;
+}
+
+// A (row-major rows x w, ld) <- A . R^-1 for upper-triangular R (col-major w x w): the column-major
+// view A_c = A^T (w x rows) gets R^-T applied from the left.
+int trsm_right_upper(sb_ctx *ctx, double *A, u64 rows, u32 w, u32 ld, const double *R) {
+    ProfScope ps(ctx, PH_DENSE);
+    if (rows == 0 || w == 0) return SB_OK;
+    if (rows > 0x7FFFFFFFull) return sb_fail(SB_ERR_UNSUPPORTED, "trsm: more than 2^31 rows");
+    const double one = 1.0;
+    SB_CUBLAS(cublasDtrsm(ctx->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, (int)w, (int)rows, &one, R, (int)w,
+                          A, (int)ld));
     count_launch(ctx, false);
     return SB_OK;
 }

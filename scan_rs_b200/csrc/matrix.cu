@@ -308,7 +308,7 @@ extern "C" int sb_upload(sb_ctx *ctx, int major, uint32_t m, uint64_t n_local, c
     if (m > SB_GENE_MASK) return sb_fail(SB_ERR_UNSUPPORTED, "sb_upload: more than %u genes", SB_GENE_MASK);
     if (n_local > 0xFFFFFFFFull) return sb_fail(SB_ERR_UNSUPPORTED, "sb_upload: more than 2^32 cells per rank");
     *out = nullptr;
-    SB_CUDA(cudaSetDevice(ctx->device));
+    SB_ENTER(ctx);
     u64 nvec = major == SB_GENE_MAJOR ? m : n_local;
     u64 nnz = indptr[nvec];
     if (nnz && (!idx || !cnt)) return sb_fail(SB_ERR_INVALID_ARG, "sb_upload: NULL idx/cnt");
@@ -416,6 +416,7 @@ extern "C" int sb_mat_shape(const sb_mat *mat, uint32_t *m, uint64_t *n_local, u
 extern "C" void sb_free_mat(sb_mat *mat) {
     if (!mat) return;
     cudaSetDevice(mat->ctx->device);
+    sb_set_alloc_stream(mat->ctx->stream);
     cudaStreamSynchronize(mat->ctx->stream);
     delete mat;
 }
@@ -423,7 +424,7 @@ extern "C" void sb_free_mat(sb_mat *mat) {
 extern "C" int sb_download(const sb_mat *mat, int major, uint64_t *indptr, uint32_t *idx, uint32_t *cnt) {
     if (!mat || !indptr) return sb_fail(SB_ERR_INVALID_ARG, "sb_download: NULL argument");
     sb_ctx *ctx = mat->ctx;
-    SB_CUDA(cudaSetDevice(ctx->device));
+    SB_ENTER(ctx);
     u64 nnz = mat->nnz;
     DevBuf<u32> d_idx, d_cnt;
     SB_TRY(d_idx.alloc(nnz));
@@ -486,7 +487,7 @@ int mat_cell_totals_dev(sb_mat *mat) {
 extern "C" int sb_cell_totals(sb_mat *mat, uint32_t *out_n_local) {
     if (!mat || !out_n_local) return sb_fail(SB_ERR_INVALID_ARG, "sb_cell_totals: NULL argument");
     sb_ctx *ctx = mat->ctx;
-    SB_CUDA(cudaSetDevice(ctx->device));
+    SB_ENTER(ctx);
     SB_TRY(mat_cell_totals_dev(mat));
     if (mat->n) SB_CUDA(cudaMemcpyAsync(out_n_local, mat->cell_tot.p, mat->n * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
     SB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -509,7 +510,7 @@ int mat_gene_sums_dev(sb_mat *mat, int mode, const unsigned char *excl_cells, co
 static int gene_sums_host(sb_mat *mat, int mode, uint64_t *out_m) {
     if (!mat || !out_m) return sb_fail(SB_ERR_INVALID_ARG, "gene sums: NULL argument");
     sb_ctx *ctx = mat->ctx;
-    SB_CUDA(cudaSetDevice(ctx->device));
+    SB_ENTER(ctx);
     DevBuf<u64> d;
     SB_TRY(d.alloc(mat->m));
     SB_TRY(mat_gene_sums_dev(mat, mode, nullptr, nullptr, d.p, true));
@@ -568,7 +569,7 @@ int mat_median_total(sb_mat *mat, u32 *median, int *nonempty) {
 
 extern "C" int sb_median_cell_total(sb_mat *mat, uint32_t *median, int *nonempty) {
     if (!mat || !median || !nonempty) return sb_fail(SB_ERR_INVALID_ARG, "sb_median_cell_total: NULL argument");
-    SB_CUDA(cudaSetDevice(mat->ctx->device));
+    SB_ENTER(mat->ctx);
     return mat_median_total(mat, median, nonempty);
 }
 
@@ -636,7 +637,7 @@ static int select_cols_dev(sb_mat *mat, const u64 *h_cols, u64 count, sb_mat **o
 
 extern "C" int sb_select_rows(sb_mat *mat, const uint32_t *rows, uint32_t count, sb_mat **out) {
     if (!mat || !out || (count && !rows)) return sb_fail(SB_ERR_INVALID_ARG, "sb_select_rows: NULL argument");
-    SB_CUDA(cudaSetDevice(mat->ctx->device));
+    SB_ENTER(mat->ctx);
     *out = nullptr;
     return select_rows_dev(mat, rows, count, out);
 }
@@ -644,7 +645,7 @@ extern "C" int sb_select_rows(sb_mat *mat, const uint32_t *rows, uint32_t count,
 extern "C" int sb_select_cols(sb_mat *mat, const uint64_t *cols, uint64_t count, sb_mat **out) {
     if (!mat || !out || (count && !cols)) return sb_fail(SB_ERR_INVALID_ARG, "sb_select_cols: NULL argument");
     if (mat->ctx->nranks > 1) return sb_fail(SB_ERR_UNSUPPORTED, "sb_select_cols: single-rank only");
-    SB_CUDA(cudaSetDevice(mat->ctx->device));
+    SB_ENTER(mat->ctx);
     *out = nullptr;
     return select_cols_dev(mat, cols, count, out);
 }
@@ -655,7 +656,7 @@ extern "C" int sb_partition(sb_mat *mat, int has_row_thr, double row_thr, int ha
     if (!mat) return sb_fail(SB_ERR_INVALID_ARG, "sb_partition: mat is NULL");
     sb_ctx *ctx = mat->ctx;
     if (ctx->nranks > 1) return sb_fail(SB_ERR_UNSUPPORTED, "sb_partition: single-rank only");
-    SB_CUDA(cudaSetDevice(ctx->device));
+    SB_ENTER(ctx);
     if (kept) *kept = nullptr;
     if (residual) *residual = nullptr;
     DevBuf<unsigned char> ex_rows, ex_cols;
@@ -687,8 +688,9 @@ extern "C" int sb_partition(sb_mat *mat, int has_row_thr, double row_thr, int ha
         if (!upd) break;
     }
     std::vector<unsigned char> hr(mat->m), hc(mat->n);
-    if (mat->m) SB_CUDA(cudaMemcpy(hr.data(), ex_rows.p, mat->m, cudaMemcpyDeviceToHost));
-    if (mat->n) SB_CUDA(cudaMemcpy(hc.data(), ex_cols.p, mat->n, cudaMemcpyDeviceToHost));
+    if (mat->m) SB_CUDA(cudaMemcpyAsync(hr.data(), ex_rows.p, mat->m, cudaMemcpyDeviceToHost, ctx->stream));
+    if (mat->n) SB_CUDA(cudaMemcpyAsync(hc.data(), ex_cols.p, mat->n, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
     std::vector<u32> sel_rows;
     std::vector<u64> sel_cols, exc_cols;
     for (u32 r = 0; r < mat->m; r++)

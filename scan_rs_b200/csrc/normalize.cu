@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) k_moments(const uint2 *__restrict__ gm, c
             const u32 gene = z.x & SB_GENE_MASK, cl = z.x >> SB_GENE_BITS;
             double l1 = 0.0, l2 = 0.0;
             if (valid) {
-                l1 = map_log_part(log_base, col[cell0 + cl], z.y);
+                l1 = map_log_part(log_base, col[cell0 + cl], z.y, sb_log_table);
                 l2 = l1 * l1;
             }
             const u32 key = valid ? gene : 0xFFFFFFFFu;
@@ -113,7 +113,7 @@ extern "C" int sb_log_normalize(sb_mat *mat, int has_target, double target, int 
     if (center_scale < 0 || center_scale > 2 || (center_scale == 2 && !sd_override))
         return sb_fail(SB_ERR_INVALID_ARG, "sb_log_normalize: bad center_scale");
     sb_ctx *ctx = mat->ctx;
-    SB_CUDA(cudaSetDevice(ctx->device));
+    SB_ENTER(ctx);
     *out = nullptr;
     std::unique_ptr<sb_nmat> a(new sb_nmat());
     a->mat = mat;
@@ -222,7 +222,7 @@ static int normalize_binomial(sb_mat *mat, int deviance, sb_nmat **out) {
 
 extern "C" int sb_normalize(sb_mat *mat, int norm, const uint32_t *size_factors, sb_nmat **out) {
     if (!mat || !out) return sb_fail(SB_ERR_INVALID_ARG, "sb_normalize: NULL argument");
-    SB_CUDA(cudaSetDevice(mat->ctx->device));
+    SB_ENTER(mat->ctx);
     *out = nullptr;
     switch (norm) {
     case SB_NORM_CELLRANGER:  // normalization.rs:53, :84
@@ -251,7 +251,7 @@ extern "C" int sb_normalize(sb_mat *mat, int norm, const uint32_t *size_factors,
 extern "C" int sb_normalize_fixed_point(sb_mat *mat, int log_base, uint32_t base, uint32_t exponent, sb_nmat **out) {
     if (!mat || !out) return sb_fail(SB_ERR_INVALID_ARG, "sb_normalize_fixed_point: NULL argument");
     sb_ctx *ctx = mat->ctx;
-    SB_CUDA(cudaSetDevice(ctx->device));
+    SB_ENTER(ctx);
     // ones / (base.pow(exponent) as f64)  (normalization.rs:203-206): u32 pow, wrapping like release Rust
     u32 pw = 1;
     for (u32 i = 0; i < exponent; i++) pw *= base;
@@ -264,6 +264,7 @@ extern "C" int sb_normalize_fixed_point(sb_mat *mat, int log_base, uint32_t base
 extern "C" void sb_free_nmat(sb_nmat *a) {
     if (!a) return;
     cudaSetDevice(a->mat->ctx->device);
+    sb_set_alloc_stream(a->mat->ctx->stream);
     cudaStreamSynchronize(a->mat->ctx->stream);
     delete a;
 }
@@ -272,7 +273,7 @@ extern "C" int sb_nmat_params(const sb_nmat *a, double *col_scale, double *row_s
     if (!a) return sb_fail(SB_ERR_INVALID_ARG, "sb_nmat_params: NULL argument");
     sb_mat *mt = a->mat;
     sb_ctx *ctx = mt->ctx;
-    SB_CUDA(cudaSetDevice(ctx->device));
+    SB_ENTER(ctx);
     if (col_scale && mt->n) SB_CUDA(cudaMemcpyAsync(col_scale, a->col_scale.p, mt->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (row_scale) {
         if (a->has_row_scale) {
@@ -303,7 +304,7 @@ extern "C" int sb_nmat_dot(sb_nmat *a, const double *x, uint32_t w, double *out)
     if (!a || !x || !out || w == 0) return sb_fail(SB_ERR_INVALID_ARG, "sb_nmat_dot: bad argument");
     sb_mat *mt = a->mat;
     sb_ctx *ctx = mt->ctx;
-    SB_CUDA(cudaSetDevice(ctx->device));
+    SB_ENTER(ctx);
     u32 ld = even_up(w);
     DevBuf<double> X, P;
     SB_TRY(X.alloc((size_t)mt->n * ld));
@@ -322,7 +323,7 @@ extern "C" int sb_nmat_rdot(sb_nmat *a, const double *b, uint32_t w, double *out
     if (!a || !b || !out || w == 0) return sb_fail(SB_ERR_INVALID_ARG, "sb_nmat_rdot: bad argument");
     sb_mat *mt = a->mat;
     sb_ctx *ctx = mt->ctx;
-    SB_CUDA(cudaSetDevice(ctx->device));
+    SB_ENTER(ctx);
     u32 ld = even_up(w);
     // Y[g, j] = b[j, g]
     std::vector<double> hy((size_t)mt->m * ld, 0.0);

@@ -9,7 +9,8 @@
 
 int spmm_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo, double *uy_scratch);
 int spmm_n(sb_nmat *a, const double *X, u32 ldx, u32 w, double *P, u32 ldp);
-int qr_tall(sb_ctx *ctx, double *A, u64 rows, u32 w, u32 ld, u32 *w_out);
+int qr_tall(sb_ctx *ctx, double *A, u64 rows, u32 w, u32 ld, u32 *w_out, double *R_out = nullptr);
+int trsm_right_upper(sb_ctx *ctx, double *A, u64 rows, u32 w, u32 ld, const double *R);
 int gram(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 ld, double *G, bool reduce);
 int eigh(sb_ctx *ctx, double *G, u32 w, double *evals_dev);
 int gemm_tall_small(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 lda, const double *S, u32 k, u32 lds, double *Out, u32 ldo);
@@ -149,8 +150,30 @@ static int upload_tall(sb_ctx *ctx, Tall &t, const double *host, bool transpose_
         std::vector<double> tmp(t.rows * (size_t)t.ld, 0.0);
         for (u32 j = 0; j < t.w; j++)
             for (u64 r = 0; r < t.rows; r++) tmp[r * t.ld + j] = host[(size_t)j * t.rows + r];
-        SB_CUDA(cudaMemcpy(t.buf.p, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice));
+        // same stream as the allocation and the zero-fill: a default-stream copy would race with them
+        SB_CUDA(cudaMemcpyAsync(t.buf.p, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        SB_CUDA(cudaStreamSynchronize(ctx->stream));
     }
+    return SB_OK;
+}
+
+// The projection T = Q^T A (bk_svd.rs:102,131) costs a sparse pass of width b*n_iter.  With K = Q R,
+// Q^T A = R^-T (K^T A), and the blocks of K^T A are the products the Krylov loop forms anyway (plus one
+// more width-b pass for the last block), so the wide pass becomes a triangular solve on the tall block.
+// R is ill-conditioned by construction (Krylov blocks are nearly dependent); the solve is used only when
+// min|r_ii| / max|r_ii| stays above `min_ratio`, otherwise the direct wide pass runs ("Projection").
+static int r_usable(sb_ctx *ctx, const double *R_dev, u32 w, double min_ratio, bool *ok) {
+    std::vector<double> h((size_t)w * w);
+    SB_CUDA(cudaMemcpyAsync(h.data(), R_dev, h.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    double mn = INFINITY, mx = 0.0;
+    for (u32 i = 0; i < w; i++) {
+        double d = std::fabs(h[(size_t)i * w + i]);
+        if (!(d == d)) { *ok = false; return SB_OK; }
+        mn = std::min(mn, d);
+        mx = std::max(mx, d);
+    }
+    *ok = mx > 0.0 && mn / mx >= min_ratio;
     return SB_OK;
 }
 
@@ -168,7 +191,7 @@ extern "C" int sb_bksvd(sb_nmat *a, uint32_t k, uint32_t b, uint32_t n_iter, uin
     if (!a || !U || !S || !V) return sb_fail(SB_ERR_INVALID_ARG, "sb_bksvd: NULL argument");
     sb_mat *mt = a->mat;
     sb_ctx *ctx = mt->ctx;
-    SB_CUDA(cudaSetDevice(ctx->device));
+    SB_ENTER(ctx);
     SB_TRY(check_shape(a, k));
     if (n_iter == 0) return sb_fail(SB_ERR_INVALID_ARG, "sb_bksvd: n_iter must be >= 1");
     const u32 m = mt->m;
@@ -182,7 +205,9 @@ extern "C" int sb_bksvd(sb_nmat *a, uint32_t k, uint32_t b, uint32_t n_iter, uin
     if ((u64)m >= ng) {
         // ---- m >= n (bk_svd.rs:89-115): block on the cell side; single rank only
         if (ctx->nranks > 1) return sb_fail(SB_ERR_UNSUPPORTED, "sb_bksvd: the m >= n branch is single-rank");
-        Tall B, Kc, W, Z;
+        Tall B, Kc, W, WK;
+        const u32 bq = b * n_iter;
+        const bool fast = !ctx->direct_projection && (b % 2 == 0) && (u64)bq <= n;
         SB_TRY(B.init(ctx, n, b));
         if (!omega) {
             h_om.resize((size_t)n * b);
@@ -190,22 +215,37 @@ extern "C" int sb_bksvd(sb_nmat *a, uint32_t k, uint32_t b, uint32_t n_iter, uin
             omega = h_om.data();
         }
         SB_TRY(upload_tall(ctx, B, omega, false));
-        SB_TRY(Kc.init(ctx, n, b * n_iter));
+        SB_TRY(Kc.init(ctx, n, bq));
         SB_TRY(W.init(ctx, m, b, 1));
+        if (fast) SB_TRY(WK.init(ctx, m, bq, 1));  // column block i-1 keeps A . B_i (B_i = block i of K)
         for (u32 i = 0; i < n_iter; i++) {
-            SB_TRY(spmm_n(a, B.buf.p, B.ld, b, W.buf.p, W.ld));             // A.dot(&B)
-            SB_TRY(spmm_t(a, W.buf.p, W.ld, b, B.buf.p, B.ld, uy.p));        // (.)^T.dot(A) ^T
+            double *Wp = (fast && i > 0) ? WK.buf.p + (size_t)(i - 1) * b : W.buf.p;
+            u32 Wld = (fast && i > 0) ? WK.ld : W.ld;
+            SB_TRY(spmm_n(a, B.buf.p, B.ld, b, Wp, Wld));                   // A.dot(&B)
+            SB_TRY(spmm_t(a, Wp, Wld, b, B.buf.p, B.ld, uy.p));              // (.)^T.dot(A) ^T
             u32 wq = 0;
             SB_TRY(qr_tall(ctx, B.buf.p, n, b, B.ld, &wq));                  // .qr()?.0   :94
             SB_TRY(copy_block(ctx, Kc.buf.p, Kc.ld, i * b, B.buf.p, B.ld, n, b));  // :95
             SB_TRY(progress(ctx, cb, user, (double)i / (double)n_iter * 0.8));     // :96
         }
         u32 wq = 0;
-        SB_TRY(qr_tall(ctx, Kc.buf.p, n, b * n_iter, Kc.ld, &wq));           // :98
+        DevBuf<double> R;
+        SB_TRY(R.alloc((size_t)bq * bq));
+        if (fast) SB_TRY(spmm_n(a, B.buf.p, B.ld, b, WK.buf.p + (size_t)(n_iter - 1) * b, WK.ld));  // A . B_q
+        SB_TRY(qr_tall(ctx, Kc.buf.p, n, bq, Kc.ld, &wq, R.p));              // :98
         SB_TRY(progress(ctx, cb, user, 0.82));
-        Tall T;
-        SB_TRY(T.init(ctx, m, wq, 1));
-        SB_TRY(spmm_n(a, Kc.buf.p, Kc.ld, wq, T.buf.p, T.ld));               // T = A.dot(&Q)  :102
+        bool use_r = false;
+        if (fast && wq == bq) SB_TRY(r_usable(ctx, R.p, bq, 1e-12, &use_r));
+        Tall Tdirect;
+        Tall *Tp = &WK;
+        if (use_r) {
+            SB_TRY(trsm_right_upper(ctx, WK.buf.p, m, bq, WK.ld, R.p));      // T = (A K) R^-1 = A Q
+        } else {
+            SB_TRY(Tdirect.init(ctx, m, wq, 1));
+            SB_TRY(spmm_n(a, Kc.buf.p, Kc.ld, wq, Tdirect.buf.p, Tdirect.ld));  // T = A.dot(&Q)  :102
+            Tp = &Tdirect;
+        }
+        Tall &T = *Tp;
         SB_TRY(progress(ctx, cb, user, 0.93));
         if (k > wq) return sb_fail(SB_ERR_INVALID_K, "invalid k");
         Tall Uo, Vo;
@@ -218,7 +258,9 @@ extern "C" int sb_bksvd(sb_nmat *a, uint32_t k, uint32_t b, uint32_t n_iter, uin
     }
 
     // ---- n > m (bk_svd.rs:116-145): block on the gene side, replicated over ranks
-    Tall Y, Kt, T, P;
+    Tall Y, Kt, T, P, TK;
+    const u32 bq = b * n_iter;
+    const bool fast = !ctx->direct_projection && (b % 2 == 0) && bq <= m;
     SB_TRY(Y.init(ctx, m, b));
     if (!omega) {
         h_om.resize((size_t)b * m);
@@ -226,12 +268,15 @@ extern "C" int sb_bksvd(sb_nmat *a, uint32_t k, uint32_t b, uint32_t n_iter, uin
         omega = h_om.data();
     }
     SB_TRY(upload_tall(ctx, Y, omega, true));  // Y[g, j] = B[j, g]
-    SB_TRY(Kt.init(ctx, m, b * n_iter));
+    SB_TRY(Kt.init(ctx, m, bq));
     SB_TRY(T.init(ctx, n, b));
     SB_TRY(P.init(ctx, m, b, 1));
+    if (fast) SB_TRY(TK.init(ctx, n, bq));  // column block i-1 keeps A^T . Y_i (Y_i = block i of K^T)
     for (u32 i = 0; i < n_iter; i++) {
-        SB_TRY(spmm_t(a, Y.buf.p, Y.ld, b, T.buf.p, T.ld, uy.p));            // T = B.dot(A)^T        :122
-        SB_TRY(spmm_n(a, T.buf.p, T.ld, b, P.buf.p, P.ld));                  // A.dot(&T)             :123
+        double *Tp = (fast && i > 0) ? TK.buf.p + (size_t)(i - 1) * b : T.buf.p;
+        u32 Tld = (fast && i > 0) ? TK.ld : T.ld;
+        SB_TRY(spmm_t(a, Y.buf.p, Y.ld, b, Tp, Tld, uy.p));                  // T = B.dot(A)^T        :122
+        SB_TRY(spmm_n(a, Tp, Tld, b, P.buf.p, P.ld));                        // A.dot(&T)             :123
         u32 wq = 0;
         SB_TRY(qr_tall(ctx, P.buf.p, m, b, P.ld, &wq));                      // .qr()?.0
         SB_TRY(copy_block(ctx, Y.buf.p, Y.ld, 0, P.buf.p, P.ld, m, b));
@@ -239,11 +284,23 @@ extern "C" int sb_bksvd(sb_nmat *a, uint32_t k, uint32_t b, uint32_t n_iter, uin
         SB_TRY(progress(ctx, cb, user, (double)i / (double)n_iter * 0.8));   // :125
     }
     u32 wq = 0;
-    SB_TRY(qr_tall(ctx, Kt.buf.p, m, b * n_iter, Kt.ld, &wq));               // Q = K.t().qr()?.0     :127
+    DevBuf<double> R;
+    SB_TRY(R.alloc((size_t)bq * bq));
+    if (fast) SB_TRY(spmm_t(a, Y.buf.p, Y.ld, b, TK.buf.p + (size_t)(n_iter - 1) * b, TK.ld, uy.p));  // A^T . Y_q
+    SB_TRY(qr_tall(ctx, Kt.buf.p, m, bq, Kt.ld, &wq, R.p));                  // Q = K.t().qr()?.0     :127
     SB_TRY(progress(ctx, cb, user, 0.82));
-    Tall Tt;
-    SB_TRY(Tt.init(ctx, n, wq));
-    SB_TRY(spmm_t(a, Kt.buf.p, Kt.ld, wq, Tt.buf.p, Tt.ld, uy.p));           // T = Q.t().dot(A)      :131
+    bool use_r = false;
+    if (fast && wq == bq) SB_TRY(r_usable(ctx, R.p, bq, 1e-12, &use_r));
+    Tall Tdirect;
+    Tall *Ttp = &TK;
+    if (use_r) {
+        SB_TRY(trsm_right_upper(ctx, TK.buf.p, n, bq, TK.ld, R.p));          // T^T = (A^T K^T) R^-1 = A^T Q
+    } else {
+        SB_TRY(Tdirect.init(ctx, n, wq));
+        SB_TRY(spmm_t(a, Kt.buf.p, Kt.ld, wq, Tdirect.buf.p, Tdirect.ld, uy.p));  // T = Q.t().dot(A)      :131
+        Ttp = &Tdirect;
+    }
+    Tall &Tt = *Ttp;
     SB_TRY(progress(ctx, cb, user, 0.93));
     if (k > wq) return sb_fail(SB_ERR_INVALID_K, "invalid k");
     Tall Vo, Uo;
@@ -266,7 +323,7 @@ extern "C" int sb_randsvd(sb_nmat *a, uint32_t k, uint32_t l, uint32_t n_iter, u
     if (!a || !U || !S || !V) return sb_fail(SB_ERR_INVALID_ARG, "sb_randsvd: NULL argument");
     sb_mat *mt = a->mat;
     sb_ctx *ctx = mt->ctx;
-    SB_CUDA(cudaSetDevice(ctx->device));
+    SB_ENTER(ctx);
     SB_TRY(check_shape(a, k));
     if (ctx->nranks > 1) return sb_fail(SB_ERR_UNSUPPORTED, "sb_randsvd: single-rank only (its QR runs on the cell side)");
     const u32 m = mt->m;

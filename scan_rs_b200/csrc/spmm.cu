@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) k_spmm_t(const u64 *__restrict__ cm_ptr, 
         const u64 s = cm_ptr[c], e = cm_ptr[c + 1];
         const double cp = mp.col[c];
         double lut = 0.0;
-        if (mp.kind == 1) lut = map_log_part(mp.log_base, cp, (u32)lane + 1u);
+        if (mp.kind == 1) lut = map_log_part(mp.log_base, cp, (u32)lane + 1u, sb_log_table);
         double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
         for (u64 k0 = s; k0 < e; k0 += 32) {
             const u64 k = k0 + lane;
@@ -114,10 +114,10 @@ __global__ void __launch_bounds__(256) k_spmm_t(const u64 *__restrict__ cm_ptr, 
             double x;
             if (mp.kind == 1) {
                 x = __shfl_sync(FULLMASK, lut, (int)((z.y - 1u) & 31u));
-                if (z.y - 1u >= 32u) x = map_log_part(mp.log_base, cp, z.y);
+                if (z.y - 1u >= 32u) x = map_log_part(mp.log_base, cp, z.y, sb_log_table);
                 if (mp.row) x = mp.row[z.x] * x;
             } else {
-                x = map_full(mp, z.y, z.x, cp, true);
+                x = map_full(mp, z.y, z.x, cp, true, sb_log_table);
             }
             __syncwarp();
             stage[lane].x = valid ? x : 0.0;
@@ -179,9 +179,19 @@ __global__ void __launch_bounds__(256) k_spmm_t(const u64 *__restrict__ cm_ptr, 
 // ---------------------------------------------------------------- K8: gene-major panel gather
 // A CTA owns a contiguous run of work units; a unit is an nnz sub-range of one cell panel.  The
 // panel's rows of X (pc x wt doubles) and its per-cell map parameters are staged in shared
-// memory once per panel.  Each warp walks a contiguous span of the unit's entries; entries are
-// sorted by gene, so a lane group accumulates in registers until its gene changes and then adds
-// its partial row into P with f64 reductions (RED.ADD.F64) -- a few per (gene, panel), not per nonzero.
+// memory once per panel.  Each warp walks a contiguous span of the unit's entries, 32 at a time:
+// the lane that loaded an entry evaluates its map value once and publishes {value, smem offset of
+// the X row, gene} in the warp's staging buffer; then G = 32/LPR lane groups consume G entries per
+// step (one 16-byte LDS of the X row + two DFMA per lane).  Entries are sorted by gene; a ballot
+// of "gene differs from the previous entry" gives a warp-uniform head mask, so steps without a
+// head are branch-free and a head flushes every group's partial row into P with f64 reductions
+// (RED.ADD.F64) -- a few per (gene, panel), never one per nonzero.
+struct __align__(16) StageN {
+    double x;
+    u32 off;   // byte offset of the X row inside the staged panel
+    u32 gene;
+};
+
 template <int LPR_T>
 __global__ void __launch_bounds__(1024, 1)
 k_spmm_n(const uint2 *__restrict__ gm, const u64 *__restrict__ gm_base, u32 np, u32 ur, u32 pc, u64 n, MapDev mp,
@@ -192,20 +202,29 @@ k_spmm_n(const uint2 *__restrict__ gm, const u64 *__restrict__ gm_base, u32 np, 
     const u32 wtp = 2 * LPR;
     double *Xs = reinterpret_cast<double *>(smem_raw);                   // pc * wtp
     double *cs = Xs + (size_t)pc * wtp;                                   // pc
-    StageEnt *stage_all = reinterpret_cast<StageEnt *>(cs + pc);         // nwarps * 32
+    LogEnt *ltab = reinterpret_cast<LogEnt *>(cs + pc);                   // 128
+    StageN *stage_all = reinterpret_cast<StageN *>(ltab + 128);          // nwarps * 32
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int grp = lane / LPR, lig = lane - grp * LPR;
     const bool lane_on = grp < G;
-    StageEnt *stage = stage_all + wib * 32;
+    StageN *stage = stage_all + wib * 32;
+    const u32 xs_sa = (u32)__cvta_generic_to_shared(Xs) + (u32)lig * 16u;          // this lane's column pair in row 0
+    const u32 stage_sa = (u32)__cvta_generic_to_shared(stage);
+    const u32 stage_sa_own = stage_sa + (u32)lane * 16u;
+    const u32 grp_bytes = (u32)grp * 16u;
+    const u32 grp_bytes_safe = (u32)(lane_on ? grp : 0) * 16u;  // spare lanes shadow group 0
     const u32 c_lo = col0 + 2 * lig;
     const bool col_ok0 = lane_on && c_lo < col0 + wt && c_lo < w;
     const bool col_ok1 = lane_on && c_lo + 1 < col0 + wt && c_lo + 1 < w;
+    const u32 NONE = 0xFFFFFFFFu;
+
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) ltab[i] = sb_log_table[i];
 
     const u64 total_units = (u64)np * ur;
     const u64 upc = (total_units + gridDim.x - 1) / gridDim.x;
     const u64 u_lo = (u64)blockIdx.x * upc;
     const u64 u_hi = min(total_units, u_lo + upc);
-    u32 staged = 0xFFFFFFFFu;
+    u32 staged = NONE;
 
     for (u64 unit = u_lo; unit < u_hi; unit++) {
         const u32 p = (u32)(unit / ur), r = (u32)(unit % ur);
@@ -233,43 +252,71 @@ k_spmm_n(const uint2 *__restrict__ gm, const u64 *__restrict__ gm_base, u32 np, 
         span = (span + 31) & ~(u64)31;
         const u64 wb = min(ue, ub + (u64)wib * span), we = min(ue, wb + span);
 
-        u32 mygene = 0xFFFFFFFFu;
+        u32 cur_gene = NONE, carry = NONE;  // warp-uniform
         double a0 = 0.0, a1 = 0.0;
+
+        auto flush = [&]() {
+            if (cur_gene != NONE) {
+                if (col_ok0 && a0 != 0.0) atomicAdd(P + (size_t)cur_gene * ldp + c_lo, a0);
+                if (col_ok1 && a1 != 0.0) atomicAdd(P + (size_t)cur_gene * ldp + c_lo + 1, a1);
+            }
+            a0 = 0.0;
+            a1 = 0.0;
+        };
+        // entry t of the staging buffer: one 16-byte LDS for {x, off, gene}, one for the X row
+        auto accumulate = [&](u32 t_bytes) {
+            u32 m0, m1, off, g;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(m0), "=r"(m1), "=r"(off), "=r"(g) : "r"(stage_sa + t_bytes));
+            double x0, x1;
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(x1) : "r"(xs_sa + off));
+            const double xm = __hiloint2double((int)m1, (int)m0);
+            a0 = fma(xm, x0, a0);
+            a1 = fma(xm, x1, a1);
+        };
+
         for (u64 k0 = wb; k0 < we; k0 += 32) {
             const u64 k = k0 + lane;
             const bool valid = k < we;
-            uint2 z = valid ? gm[k] : make_uint2(0u, 0u);
+            const uint2 z = valid ? __ldcs(gm + k) : make_uint2(NONE, 0u);
             const u32 gene = z.x & SB_GENE_MASK, cl = z.x >> SB_GENE_BITS;
             double x = 0.0;
-            if (valid) x = map_full(mp, z.y, gene, cs[cl], false);
+            if (valid) x = map_full(mp, z.y, gene, cs[cl], false, ltab);
+            u32 prev = __shfl_up_sync(FULLMASK, gene, 1);
+            if (lane == 0) prev = carry;
+            const u32 H = __ballot_sync(FULLMASK, valid && gene != prev);
+            const int cnt = (we - k0) >= 32 ? 32 : (int)(we - k0);
+            carry = __shfl_sync(FULLMASK, gene, cnt - 1);
             __syncwarp();
-            stage[lane].x = x;
-            stage[lane].idx = z.x;
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(stage_sa_own), "r"((u32)__double2loint(x)), "r"((u32)__double2hiint(x)),
+                         "r"(cl * wtp * 8u), "r"(gene)
+                         : "memory");
             __syncwarp();
-            const int cnt = (int)min((u64)32, we - k0);
-            if (lane_on) {
-                for (int t = grp; t < cnt; t += G) {
-                    const StageEnt m0 = stage[t];
-                    const u32 g = m0.idx & SB_GENE_MASK, l = m0.idx >> SB_GENE_BITS;
-                    if (g != mygene) {
-                        if (mygene != 0xFFFFFFFFu) {
-                            if (col_ok0) atomicAdd(P + (size_t)mygene * ldp + c_lo, a0);
-                            if (col_ok1) atomicAdd(P + (size_t)mygene * ldp + c_lo + 1, a1);
+            if (LPR_T > 0 && cnt == 32 && H == 0u) {
+                // whole chunk inside one gene segment: branch-free.  Lanes of the spare group (lane >= G*LPR) run
+                // along on in-bounds addresses; their accumulators are never flushed.
+                constexpr int GG = LPR_T > 0 ? 32 / LPR_T : 1;
+#pragma unroll
+                for (int st = 0; st < 32 / GG; st++) accumulate((u32)(st * GG) * 16u + grp_bytes_safe);
+                if ((32 % GG) != 0 && grp < (32 % GG)) accumulate((u32)((32 / GG) * GG) * 16u + grp_bytes);
+            } else {
+                const u32 gmask = (1u << G) - 1u;
+                for (int t0 = 0; t0 < cnt; t0 += G) {
+                    const u32 hb = (H >> t0) & gmask;
+                    if (hb == 0u) {
+                        if (lane_on && t0 + grp < cnt) accumulate((u32)t0 * 16u + grp_bytes);
+                    } else {
+                        for (int j = 0; j < G; j++) {
+                            if ((hb >> j) & 1u) {
+                                flush();
+                                cur_gene = stage[t0 + j].gene;
+                            }
+                            if (lane_on && grp == j && t0 + j < cnt) accumulate((u32)(t0 + j) * 16u);
                         }
-                        mygene = g;
-                        a0 = 0.0;
-                        a1 = 0.0;
                     }
-                    const double2 xv = *reinterpret_cast<const double2 *>(Xs + (size_t)l * wtp + 2 * lig);
-                    a0 = fma(m0.x, xv.x, a0);
-                    a1 = fma(m0.x, xv.y, a1);
                 }
             }
         }
-        if (lane_on && mygene != 0xFFFFFFFFu) {
-            if (col_ok0) atomicAdd(P + (size_t)mygene * ldp + c_lo, a0);
-            if (col_ok1) atomicAdd(P + (size_t)mygene * ldp + c_lo + 1, a1);
-        }
+        flush();
     }
 }
 
@@ -364,7 +411,10 @@ int spmm_n(sb_nmat *a, const double *X, u32 ldx, u32 w, double *P, u32 ldp) {
     sb_ctx *ctx = mt->ctx;
     if ((ldx & 1) || (ldp & 1)) return sb_fail(SB_ERR_INVALID_ARG, "spmm_n: leading dimensions must be even");
     double *vx = P + (size_t)mt->m * ldp;
-    SB_CUDA(cudaMemsetAsync(P, 0, ((size_t)mt->m + 1) * ldp * sizeof(double), ctx->stream));
+    const u32 wpad = (w + 1) & ~1u;
+    if (ctx->nranks > 1 && ldp != wpad) return sb_fail(SB_ERR_INVALID_ARG, "spmm_n: sharded runs need a contiguous output block");
+    // zero the w (padded) columns of the m + 1 rows only: P may be a column block of a wider matrix
+    SB_CUDA(cudaMemset2DAsync(P, (size_t)ldp * sizeof(double), 0, (size_t)wpad * sizeof(double), (size_t)mt->m + 1, ctx->stream));
     if (a->has_offset) SB_TRY(colsum_weighted(ctx, X, mt->n, w, ldx, a->v_ones ? nullptr : a->v.p, vx));
     MapDev mp = make_map(a);
     if (mt->nnz && w) {
@@ -372,7 +422,7 @@ int spmm_n(sb_nmat *a, const double *X, u32 ldx, u32 w, double *P, u32 ldp) {
         // tile width: the X panel (pc x wt doubles) must fit in shared memory next to the staging buffers
         const size_t smem_budget = 200 * 1024;
         const int threads = 1024;
-        size_t fixed = (size_t)mt->pc * 8 + (threads / 32) * 32 * sizeof(StageEnt);
+        size_t fixed = (size_t)mt->pc * 8 + 128 * sizeof(LogEnt) + (threads / 32) * 32 * sizeof(StageN);
         u32 tile_max = (u32)((smem_budget - fixed) / ((size_t)mt->pc * 8));
         tile_max &= ~1u;
         if (tile_max > 64) tile_max = 64;

@@ -68,7 +68,7 @@ extern "C" int sb_synth_generate(sb_ctx *ctx, uint32_t m, uint64_t n_local, uint
     if (!ctx || !out || !pf || (n_local && (!depth || !cluster)) || r_dispersion == 0 || n_clusters == 0)
         return sb_fail(SB_ERR_INVALID_ARG, "sb_synth_generate: bad argument");
     if (m > SB_GENE_MASK) return sb_fail(SB_ERR_UNSUPPORTED, "too many genes");
-    SB_CUDA(cudaSetDevice(ctx->device));
+    SB_ENTER(ctx);
     *out = nullptr;
     const u64 n = n_local;
     DevBuf<double> d_pf, d_depth;

@@ -36,6 +36,9 @@ class Context:
         L.check(L.lib().sb_comm_init(self._h, C.c_int(nranks), C.c_int(rank), C.c_char_p(uid)))
         self.nranks, self.rank = nranks, rank
 
+    def set_option(self, name: str, value: float):
+        L.check(L.lib().sb_set_option(self._h, C.c_char_p(name.encode()), C.c_double(value)))
+
     def sync(self):
         L.check(L.lib().sb_sync(self._h))
 

@@ -81,7 +81,9 @@ def test_golden_one_dim_no_nan(ctx):  # normalization.rs:477-516
     out = sb.normalize(sb.AdaptiveMat.from_dense(ctx, row), sb.Normalization.CellRanger).to_dense()
     assert not np.isnan(out).any()
     ref = orc.normalize(orc.CountMatrix.from_dense(row), orc.CELLRANGER).to_dense()
-    np.testing.assert_allclose(out, ref, rtol=0, atol=1e-9)
+    # a zero-variance gene: whether sq - mean^2 rounds to <= 0 (sd := 1, mat.rs:996) or to a tiny positive
+    # number depends on the summation order, so only the reference's own 1e-6 bar applies here
+    np.testing.assert_allclose(out, ref, rtol=0, atol=1e-6)
 
 
 def test_golden_sum_fns(ctx):  # sqz/src/mat.rs:1293-1325
@@ -174,6 +176,28 @@ def test_partition_and_select(ctx):
         np.testing.assert_array_equal(a, b)
 
 
+def test_device_log(ctx):
+    """The table-driven device log2 (csrc/map.cuh) against numpy's libm: <= 2 ulp over 6e5 arguments
+    spanning 1 + 1e-12 ... 1e9, for all three bases."""
+    rng = np.random.default_rng(0)
+    n = 200_000
+    counts = np.concatenate([rng.integers(1, 40, n), rng.integers(1, 2**31, n), np.ones(n, dtype=np.int64)]).astype(np.uint32)
+    n = counts.shape[0]
+    sf = rng.integers(1, 2**31, n).astype(np.uint32)
+    sf[-1000:] = 1
+    m = sb.AdaptiveMat.from_csr(ctx, 1, n, [0, n], np.arange(n, dtype=np.uint32), counts)
+    for base, fn in [(sb.LogBase.Two, np.log2), (sb.LogBase.E, np.log), (sb.LogBase.Ten, np.log10)]:
+        for target in (1.0, 1e-3, 7.0e8):
+            a = sb.log_normalize_with_size_factor(m, target, base, sf)
+            cs, _, _, _ = a.params()
+            np.testing.assert_array_equal(cs, target / sf.astype(np.float64))
+            y = cs * counts.astype(np.float64) + 1.0
+            got = a.rdot(np.ones((1, 1)))[0]
+            want = fn(y)
+            ulp = np.abs(got - want) / np.spacing(np.abs(want))
+            assert ulp.max() <= 2.5, (base, target, ulp.max())
+
+
 # ------------------------------------------------------------------ sparse products
 def _identity_nmat(dm):
     """log_base 0, target 1, size factors 1: the map is v as f64 (MatrixIntoMap) -- integer data"""
@@ -246,6 +270,24 @@ def test_bksvd_matches_oracle(ctx, n_cells, n_genes, k):
     assert orc.frobenius(a_g.dot(v) - u * s) < 1e-3
 
 
+@pytest.mark.parametrize("n_cells,n_genes", [(4000, 1500), (1200, 3000)])
+def test_projection_shortcut_and_direct_pass_agree(ctx, n_cells, n_genes):
+    """The wide projection T = Q^T A (bk_svd.rs:102,131) runs either as a sparse pass of width b*n_iter
+    ("direct_projection") or through Q^T A = R^-T (K^T A); both must meet the parity bar."""
+    cfg, cm, dm, _ = synth_pair(ctx, n_cells, n_genes, seed=36)
+    res_o = orc.BkSvd().run_pca(orc.normalize(cm, orc.CELLRANGER), 10)
+    a_g = sb.normalize(dm, sb.Normalization.CellRanger)
+    try:
+        ctx.set_option("direct_projection", 1)
+        res_direct = sb.BkSvd().run_pca(a_g, 10)
+    finally:
+        ctx.set_option("direct_projection", 0)
+    res_fast = sb.BkSvd().run_pca(a_g, 10)
+    check_pca_parity(res_direct, res_o)
+    check_pca_parity(res_fast, res_o)
+    check_pca_parity(res_fast, res_direct)
+
+
 def test_bksvd_seurat_and_binomial(ctx):
     cfg, cm, dm, _ = synth_pair(ctx, 3000, 1200, seed=32)
     check_pca_parity(sb.BkSvd().run_pca(sb.normalize(dm, sb.Normalization.SeuratLog), 8),
@@ -287,7 +329,7 @@ def test_errors_and_cancellation(ctx):  # bk_svd.rs:73-79, :96; snoop/src/lib.rs
     assert ei.value.code == L.SB_ERR_INVALID_K
     snoop = sb.AtomicSnoop()
     sb.BkSvd().run_pca_cancellable(a, 4, snoop)
-    assert snoop.history == [0.0, 0.16000000000000003, 0.32000000000000006, 0.48, 0.64, 0.82, 0.93, 1.0]
+    assert snoop.history == [i / 5 * 0.8 for i in range(5)] + [0.82, 0.93, 1.0]  # bk_svd.rs:125,128,132,143
 
     class CancelAfter(sb.AtomicSnoop):
         def set_progress(self, f):
@@ -329,8 +371,8 @@ def test_properties_at_scale(ctx):
     assert np.all(np.diff(s) <= 0) and s[-1] > 0
     assert np.abs(u.T.dot(u) - np.eye(10)).max() < 1e-10
     assert np.abs(v.T.dot(v) - np.eye(10)).max() < 1e-10
-    av = a.dot(v)
-    assert np.abs(av - u * s).max() < 1e-8 * s[0]
+    # n > m branch: T = Q^T A = U_T S V^T and U = Q U_T, so A^T u = v s is an identity of the method ...
     atu = a.rdot(u.T).T
-    # Ritz pairs of a 5-block Krylov space: residual small relative to sigma_1 but not at rounding level
-    assert np.linalg.norm(atu - v * s) < 2e-2 * s[0]
+    assert np.abs(atu - v * s).max() < 1e-9 * s[0]
+    # ... while A v = u s holds up to the Ritz residual: the reference's own bar (dim_red/test.rs:69-75, :107)
+    assert orc.frobenius(a.dot(v) - u * s) < 1e-3
