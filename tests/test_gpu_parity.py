@@ -376,3 +376,20 @@ def test_properties_at_scale(ctx):
     assert np.abs(atu - v * s).max() < 1e-9 * s[0]
     # ... while A v = u s holds up to the Ritz residual: the reference's own bar (dim_red/test.rs:69-75, :107)
     assert orc.frobenius(a.dot(v) - u * s) < 1e-3
+
+
+def test_two_gpu_cell_sharding_matches_oracle():
+    """One rank per GPU over NCCL (launched like the driver launches bench.py): cell-sharded normalize + PCA
+    equals the unsharded oracle.  Skipped on a single-GPU box."""
+    import subprocess
+    import sys
+    import ctypes
+    n = ctypes.c_int(0)
+    ctypes.CDLL("libcuda.so.1").cuDeviceGetCount(ctypes.byref(n))
+    if n.value < 2:
+        pytest.skip("needs 2 GPUs")
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29517", os.path.join(root, "tests", "mgpu_worker.py")], capture_output=True, text=True, timeout=600)
+    assert "MGPU_PARITY_OK world=2" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
