@@ -1,0 +1,101 @@
+// host_api_test.cpp -- the reference's own unit tests for this path, rewritten against the C++ host
+// layer (include/scanb200.hpp).  Reads like scan-rs/src/normalization.rs:539-575 and
+// scan-rs/src/dim_red/test.rs:58-110.  Exit code 0 = all passed.  Needs a GPU.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "scanb200.hpp"
+
+using namespace scanb200;
+using normalization::Normalization;
+
+static int failures = 0;
+#define EXPECT(cond)                                                  \
+    do {                                                              \
+        if (!(cond)) {                                                \
+            std::printf("FAIL %s:%d: %s\n", __FILE__, __LINE__, #cond); \
+            failures++;                                               \
+        }                                                             \
+    } while (0)
+
+static bool abs_diff_eq(const Array2 &a, const double *b, double eps) {
+    for (size_t i = 0; i < a.data.size(); i++)
+        if (std::fabs(a.data[i] - b[i]) > eps) return false;
+    return true;
+}
+
+static void test_cellranger_normalisation(Context &ctx) {  // normalization.rs:539-575
+    std::vector<uint32_t> dense = {136, 936, 0, 0, 264, 134, 682, 417, 8, 391, 0, 133, 780, 0, 0, 396, 76, 96, 198, 0};
+    const double expected[] = {0.61392149,  0.95459951, -1.21707302, -1.21707302, 0.86562504,  -0.11878431, 0.54279925,
+                               0.38607315,  -1.85660965, 1.04652156, -0.78758751, 0.76437149,  1.59839105,  -0.78758751,
+                               -0.78758751, 0.88718256, -0.25584717, -0.01048423, 1.09574143,  -1.71659259};
+    auto mtx = sqz::AdaptiveMat::from_dense(ctx, 4, 5, dense);
+    auto norm_mat = normalization::normalize_with_size_factor(mtx, Normalization::CellRanger, nullptr);
+    EXPECT(abs_diff_eq(norm_mat.to_dense(), expected, 1e-6));
+    auto sums = mtx.sum_axis0_u32();
+    EXPECT(sums[0] == 666 && sums[1] == 1827 && sums[4] == 655);
+}
+
+struct Recorder : snoop::CancelProgress {
+    std::vector<double> seen;
+    size_t cancel_after = 1000;
+    bool is_cancelled() const override { return seen.size() >= cancel_after; }
+    void set_progress(double f) override { seen.push_back(f); }
+};
+
+static void test_bksvd(Context &ctx) {  // dim_red/test.rs:58-110 on a sparse count matrix
+    const uint32_t m = 300;
+    const uint64_t n = 900;
+    std::vector<uint32_t> dense(m * n, 0);
+    uint64_t s = 12345;
+    for (auto &v : dense) {
+        s = s * 6364136223846793005ULL + 1442695040888963407ULL;
+        uint32_t r = (uint32_t)(s >> 40);
+        v = (r % 5 == 0) ? 1 + (r >> 8) % 7 : 0;
+    }
+    auto mtx = sqz::AdaptiveMat::from_dense(ctx, m, n, dense);
+    auto a = normalization::normalize(mtx, Normalization::CellRanger);
+    dim_red::BkSvd svd;
+    auto res = svd.run_pca(a, 10);
+    EXPECT(res.u.rows == m && res.u.cols == 10 && res.v.rows == n && res.v.cols == 10 && res.s.size() == 10);
+    for (size_t i = 1; i < 10; i++) EXPECT(res.s[i] <= res.s[i - 1]);
+    // ||A v - u s||_F / size < 1e-3 (test.rs:69-75, :107)
+    Array2 av = a.dot(res.v);
+    for (size_t r = 0; r < m; r++)
+        for (size_t j = 0; j < 10; j++) av(r, j) -= res.u(r, j) * res.s[j];
+    EXPECT(dim_red::frobenius(av) < 1e-3);
+    // error behaviour (bk_svd.rs:73-79)
+    try {
+        svd.run_pca(a, 301);
+        EXPECT(false);
+    } catch (const Error &e) {
+        EXPECT(std::strcmp(e.what(), "invalid k") == 0 && e.code == SB_ERR_INVALID_K);
+    }
+    // progress milestones and cancellation (bk_svd.rs:125-143, snoop/src/lib.rs:45-57)
+    Recorder rec;
+    svd.run_pca_cancellable(a, 4, rec);
+    EXPECT(rec.seen.size() == 8 && rec.seen[5] == 0.82 && rec.seen[6] == 0.93 && rec.seen[7] == 1.0);
+    Recorder rec2;
+    rec2.cancel_after = 2;
+    try {
+        svd.run_pca_cancellable(a, 4, rec2);
+        EXPECT(false);
+    } catch (const CancellationError &) {
+        EXPECT(rec2.seen.size() == 2);
+    }
+    EXPECT(normalization::from_str("seuratlog") == Normalization::SeuratLog);
+}
+
+int main() {
+    try {
+        Context ctx(0);
+        test_cellranger_normalisation(ctx);
+        test_bksvd(ctx);
+    } catch (const Error &e) {
+        std::printf("FAIL: exception %d: %s\n", e.code, e.what());
+        return 2;
+    }
+    std::printf(failures ? "%d FAILURES\n" : "ALL PASSED\n", failures);
+    return failures ? 1 : 0;
+}

@@ -393,3 +393,17 @@ def test_two_gpu_cell_sharding_matches_oracle():
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                           "--master-port", "29517", os.path.join(root, "tests", "mgpu_worker.py")], capture_output=True, text=True, timeout=600)
     assert "MGPU_PARITY_OK world=2" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+def test_cpp_host_layer():
+    """include/scanb200.hpp (the C++ mirror of the reference's interface) against the reference's own
+    unit-test expectations; the binary is built by __graft_entry__.build()."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "host_api_test")
+    if not os.path.exists(exe):
+        import __graft_entry__ as g
+        g.build()
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ALL PASSED" in out.stdout, out.stdout + out.stderr
