@@ -113,6 +113,8 @@ struct sb_ctx {
     cusolverDnHandle_t cusolver = nullptr;
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
+    int dense_cap = 2048;            // max genes in the dense hot panel (0 disables the hybrid layout)
+    double dense_min_density = 0.12; // a gene joins the panel only if nnz/n_global is at least this
     bool direct_projection = false;  // true: always run the wide Q^T A pass (bk_svd.rs:102,131) instead of the R^-T identity
     // profiling
     bool profile_on = false;
@@ -148,10 +150,25 @@ struct sb_mat {
     DevBuf<uint2> gm;
     DevBuf<u64> gm_base;
     DevBuf<u64> unit_ptr;
+    bool have_full_gm = false;  // gm / gm_base above cover ALL entries; built lazily when a dense panel exists
+    // Hybrid layout (log-normalization maps only): the `gd` most expressed genes live in a dense u8 panel
+    // D[n x gd] (counts 1..SB_DENSE_MAX_COUNT, 0 elsewhere); every other entry -- cold genes and the rare larger
+    // counts of hot genes -- stays in the sparse `cold_*` pair of layouts (same formats as cm / gm).
+    u32 gd = 0;
+    DevBuf<unsigned char> D;
+    DevBuf<u32> hot_idx;      // [gd] gene id of panel column j
+    DevBuf<u32> hot_of_gene;  // [m] panel column of a gene or 0xFFFFFFFF
+    u64 cold_nnz = 0;
+    DevBuf<u64> cold_cm_ptr;
+    DevBuf<uint2> cold_cm;
+    DevBuf<uint2> cold_gm;
+    DevBuf<u64> cold_gm_base;
     // cached integer reductions
     DevBuf<u32> cell_tot;
     bool have_cell_tot = false;
 };
+#define SB_DENSE_MAX_COUNT 15u
+#define SB_DENSE_LUT 16
 
 // device view of the per-nonzero map (sqz/src/matrix_map.rs): see MapDev in map.cuh
 struct sb_nmat {

@@ -92,6 +92,14 @@ extern "C" int sb_set_option(sb_ctx *ctx, const char *name, double value) {
         ctx->direct_projection = value != 0.0;
         return SB_OK;
     }
+    if (!strcmp(name, "dense_genes")) {  // applies to matrices uploaded afterwards
+        ctx->dense_cap = value < 0 ? 0 : (int)value;
+        return SB_OK;
+    }
+    if (!strcmp(name, "dense_min_density")) {
+        ctx->dense_min_density = value;
+        return SB_OK;
+    }
     return sb_fail(SB_ERR_INVALID_ARG, "sb_set_option: unknown option %s", name);
 }
 

@@ -265,26 +265,106 @@ static void choose_panels(sb_mat *mt) {
     mt->ur = ur;
 }
 
-// builds the gene-major panelled copy from the (complete) cell-major copy
-static int build_gene_major(sb_mat *mt) {
+// builds a gene-major panelled copy (gm, gm_base) from a cell-major pair (cm_ptr, cm) of the same matrix
+static int build_gene_major(sb_mat *mt, const u64 *cm_ptr, const uint2 *cm, u64 nnz, DevBuf<uint2> &gm, DevBuf<u64> &gm_base) {
     sb_ctx *ctx = mt->ctx;
-    choose_panels(mt);
-    SB_TRY(mt->gm_base.alloc((size_t)mt->np + 1));
-    k_panel_base<<<cdiv(mt->np + 1, 256), 256, 0, ctx->stream>>>(mt->cm_ptr.p, mt->n, mt->pc, mt->np, mt->gm_base.p);
+    SB_TRY(gm_base.alloc((size_t)mt->np + 1));
+    k_panel_base<<<cdiv(mt->np + 1, 256), 256, 0, ctx->stream>>>(cm_ptr, mt->n, mt->pc, mt->np, gm_base.p);
     count_launch(ctx);
-    SB_TRY(mt->gm.alloc(mt->nnz));
-    if (mt->nnz == 0) return SB_OK;
+    SB_TRY(gm.alloc(nnz));
+    if (nnz == 0) return SB_OK;
     if ((u64)mt->np * mt->m > 0xFFFFFFFFull) return sb_fail(SB_ERR_UNSUPPORTED, "panel x gene key exceeds 32 bits");
     DevBuf<u32> keys;
     DevBuf<u64> payload;
-    SB_TRY(keys.alloc(mt->nnz));
-    SB_TRY(payload.alloc(mt->nnz));
-    k_make_keys<<<grid_for(mt->n * 32, 256, ctx, 16), 256, 0, ctx->stream>>>(mt->cm_ptr.p, mt->cm.p, mt->n, 0, mt->m, mt->pc, keys.p, payload.p);
+    SB_TRY(keys.alloc(nnz));
+    SB_TRY(payload.alloc(nnz));
+    k_make_keys<<<grid_for(mt->n * 32, 256, ctx, 16), 256, 0, ctx->stream>>>(cm_ptr, cm, mt->n, 0, mt->m, mt->pc, keys.p, payload.p);
     count_launch(ctx);
-    SB_TRY(sort_pairs(ctx, keys, payload, mt->nnz, bits_for((u64)mt->np * mt->m - 1)));
-    k_unpack_payload<<<grid_for(mt->nnz, 256, ctx, 16), 256, 0, ctx->stream>>>(payload.p, mt->gm.p, mt->nnz);
+    SB_TRY(sort_pairs(ctx, keys, payload, nnz, bits_for((u64)mt->np * mt->m - 1)));
+    k_unpack_payload<<<grid_for(nnz, 256, ctx, 16), 256, 0, ctx->stream>>>(payload.p, gm.p, nnz);
     count_launch(ctx);
     SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+
+// the gene-major copy of ALL entries (binomial residual maps, which have no per-cell value table)
+int mat_ensure_full_gm(sb_mat *mt) {
+    if (mt->have_full_gm) return SB_OK;
+    SB_TRY(build_gene_major(mt, mt->cm_ptr.p, mt->cm.p, mt->nnz, mt->gm, mt->gm_base));
+    mt->have_full_gm = true;
+    return SB_OK;
+}
+
+// splits the cell-major stream into the dense panel D and the cold sparse entries (count / fill passes)
+__global__ void k_split_hot(const u64 *__restrict__ ptr, const uint2 *__restrict__ cm, u64 n, const u32 *__restrict__ hot_of_gene, u32 gd,
+                            const u64 *__restrict__ new_ptr, u32 *__restrict__ counts, uint2 *__restrict__ out, unsigned char *__restrict__ D) {
+    u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    int lane = threadIdx.x & 31;
+    for (u64 c = warp; c < n; c += nwarps) {
+        u64 s = ptr[c], e = ptr[c + 1];
+        u64 wpos = new_ptr ? new_ptr[c] : 0;
+        u32 total = 0;
+        for (u64 k0 = s; k0 < e; k0 += 32) {
+            u64 k = k0 + lane;
+            bool valid = k < e;
+            uint2 z = valid ? cm[k] : make_uint2(0, 0);
+            u32 h = valid ? hot_of_gene[z.x] : 0xFFFFFFFFu;
+            bool dense = valid && h != 0xFFFFFFFFu && z.y <= SB_DENSE_MAX_COUNT;
+            bool cold = valid && !dense;
+            if (D && dense) D[c * (u64)gd + h] = (unsigned char)z.y;
+            unsigned mask = __ballot_sync(0xffffffffu, cold);
+            if (out && cold) out[wpos + total + __popc(mask & ((1u << lane) - 1u))] = z;
+            total += __popc(mask);
+        }
+        if (counts && lane == 0) counts[c] = total;
+    }
+}
+
+int mat_gene_sums_dev(sb_mat *mat, int mode, const unsigned char *excl_cells, const unsigned char *excl_genes, u64 *d_out, bool allreduce);
+
+// picks the hot genes (most non-zeros, at least dense_min_density of the cells, at most dense_cap) and builds D + cold layouts
+static int build_hybrid(sb_mat *mt) {
+    sb_ctx *ctx = mt->ctx;
+    mt->gd = 0;
+    if (ctx->dense_cap < 64 || mt->m < 64 || mt->n == 0 || mt->n_global == 0) return SB_OK;
+    DevBuf<u64> d_nnz;
+    SB_TRY(d_nnz.alloc(mt->m));
+    SB_TRY(mat_gene_sums_dev(mt, 2, nullptr, nullptr, d_nnz.p, true));
+    std::vector<u64> h(mt->m);
+    SB_CUDA(cudaMemcpyAsync(h.data(), d_nnz.p, (size_t)mt->m * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<u32> order(mt->m);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 b) { return h[a] > h[b]; });
+    u32 gd = 0;
+    double thr = ctx->dense_min_density * (double)mt->n_global;
+    while (gd < mt->m && gd < (u32)ctx->dense_cap && (double)h[order[gd]] >= thr) gd++;
+    gd &= ~63u;  // whole 64-gene groups: 16-byte aligned panel rows, full thread tiles
+    if (gd == 0) return SB_OK;
+    std::vector<u32> hot(order.begin(), order.begin() + gd), hot_of(mt->m, 0xFFFFFFFFu);
+    std::sort(hot.begin(), hot.end());  // panel columns in ascending gene order
+    for (u32 j = 0; j < gd; j++) hot_of[hot[j]] = j;
+    SB_TRY(mt->hot_idx.alloc(gd));
+    SB_TRY(mt->hot_of_gene.alloc(mt->m));
+    SB_CUDA(cudaMemcpyAsync(mt->hot_idx.p, hot.data(), gd * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+    SB_CUDA(cudaMemcpyAsync(mt->hot_of_gene.p, hot_of.data(), (size_t)mt->m * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+    SB_TRY(mt->D.alloc((size_t)mt->n * gd));
+    SB_CUDA(cudaMemsetAsync(mt->D.p, 0, (size_t)mt->n * gd, ctx->stream));
+    DevBuf<u32> counts;
+    SB_TRY(counts.alloc(mt->n));
+    int grid = grid_for(mt->n * 32, 256, ctx, 16);
+    k_split_hot<<<grid, 256, 0, ctx->stream>>>(mt->cm_ptr.p, mt->cm.p, mt->n, mt->hot_of_gene.p, gd, nullptr, counts.p, nullptr, nullptr);
+    count_launch(ctx);
+    SB_TRY(mt->cold_cm_ptr.alloc(mt->n + 1));
+    SB_TRY(exclusive_scan_u32_to_u64(ctx, counts.p, mt->n, mt->cold_cm_ptr.p));
+    SB_CUDA(cudaMemcpyAsync(&mt->cold_nnz, mt->cold_cm_ptr.p + mt->n, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    SB_TRY(mt->cold_cm.alloc(mt->cold_nnz));
+    k_split_hot<<<grid, 256, 0, ctx->stream>>>(mt->cm_ptr.p, mt->cm.p, mt->n, mt->hot_of_gene.p, gd, mt->cold_cm_ptr.p, nullptr, mt->cold_cm.p, mt->D.p);
+    count_launch(ctx);
+    SB_TRY(build_gene_major(mt, mt->cold_cm_ptr.p, mt->cold_cm.p, mt->cold_nnz, mt->cold_gm, mt->cold_gm_base));
+    mt->gd = gd;
     return SB_OK;
 }
 
@@ -298,7 +378,10 @@ static int finish_matrix(sb_mat *mt) {
         if (r < ctx->rank) mt->cell_offset += all[r];
         mt->n_global += all[r];
     }
-    return build_gene_major(mt);
+    choose_panels(mt);
+    SB_TRY(build_hybrid(mt));
+    if (mt->gd == 0) SB_TRY(mat_ensure_full_gm(mt));
+    return SB_OK;
 }
 
 extern "C" int sb_upload(sb_ctx *ctx, int major, uint32_t m, uint64_t n_local, const uint64_t *indptr, const uint32_t *idx,

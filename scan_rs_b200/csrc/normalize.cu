@@ -10,6 +10,8 @@ int mat_median_total(sb_mat *mat, u32 *median, int *nonempty);
 int mat_gene_sums_dev(sb_mat *mat, int mode, const unsigned char *excl_cells, const unsigned char *excl_genes, u64 *d_out, bool allreduce);
 int spmm_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo, double *uy_scratch);
 int spmm_n(sb_nmat *a, const double *X, u32 ldx, u32 w, double *P, u32 ldp);
+int dense_moments(sb_nmat *a, double *S1, double *S2);
+int mat_ensure_full_gm(sb_mat *mt);
 
 #define FULLMASK 0xffffffffu
 
@@ -91,14 +93,21 @@ static int moments(sb_nmat *a, double *S /* 2m */) {
     sb_mat *mt = a->mat;
     sb_ctx *ctx = mt->ctx;
     SB_CUDA(cudaMemsetAsync(S, 0, 2 * (size_t)mt->m * sizeof(double), ctx->stream));
+    const bool hybrid = mt->gd > 0;  // moments are only taken of log-normalized (kind 1) matrices
+    if (!hybrid) SB_TRY(mat_ensure_full_gm(mt));
+    const uint2 *gm = hybrid ? mt->cold_gm.p : mt->gm.p;
+    const u64 *gm_base = hybrid ? mt->cold_gm_base.p : mt->gm_base.p;
     if (mt->nnz) {
         ProfScope ps(ctx, PH_MOMENTS);
         u32 gy = mt->np < 65535u ? mt->np : 65535u;
         u32 gx = (u32)((u64)ctx->sm_count * 16 / gy);
         if (gx < 1) gx = 1;
         dim3 grid(gx, gy);
-        k_moments<<<grid, 256, 0, ctx->stream>>>(mt->gm.p, mt->gm_base.p, mt->np, mt->pc, a->log_base, a->col_scale.p, S, S + mt->m);
-        count_launch(ctx);
+        if (hybrid ? mt->cold_nnz : mt->nnz) {
+            k_moments<<<grid, 256, 0, ctx->stream>>>(gm, gm_base, mt->np, mt->pc, a->log_base, a->col_scale.p, S, S + mt->m);
+            count_launch(ctx);
+        }
+        if (hybrid) SB_TRY(dense_moments(a, S, S + mt->m));
         SB_CUDA(cudaGetLastError());
     }
     SB_TRY(comm_allreduce_f64(ctx, S, 2 * (size_t)mt->m));

@@ -370,6 +370,10 @@ static void account(sb_ctx *ctx, const sb_mat *mt, u32 w, bool is_t) {
 }
 
 // K7 driver: out[n x w] (ld ldo) = A^T . Y[m x w] (ld ldy) + v (u^T Y).  uy_scratch: device vector of >= w doubles.
+int dense_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo);
+int dense_n(sb_nmat *a, const double *X, u32 ldx, u32 w, double *P, u32 ldp);
+int mat_ensure_full_gm(sb_mat *mt);
+
 int spmm_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo, double *uy_scratch) {
     sb_mat *mt = a->mat;
     sb_ctx *ctx = mt->ctx;
@@ -382,6 +386,10 @@ int spmm_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo, do
     if (mt->n == 0 || w == 0) return SB_OK;
     MapDev mp = make_map(a);
     ProfScope ps(ctx, PH_SPMM_T);
+    // hybrid layout: the sparse kernel sees the cold entries only, the dense panel kernel adds the rest
+    const bool hybrid = a->kind == 1 && mt->gd > 0;
+    const u64 *cm_ptr = hybrid ? mt->cold_cm_ptr.p : mt->cm_ptr.p;
+    const uint2 *cm = hybrid ? mt->cold_cm.p : mt->cm.p;
     const u32 tile_max = 64;
     u32 ntiles = (w + tile_max - 1) / tile_max;
     u32 tw = (w + ntiles - 1) / ntiles;
@@ -394,11 +402,12 @@ int spmm_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo, do
         int lpr = (int)((wt + 1) / 2);
         dispatch_lpr(lpr, [&](auto tag) {
             constexpr int L = decltype(tag)::value;
-            k_spmm_t<L><<<blocks, 256, 0, ctx->stream>>>(mt->cm_ptr.p, mt->cm.p, mt->n, mp, Y, ldy, col0, wt, w, uy,
+            k_spmm_t<L><<<blocks, 256, 0, ctx->stream>>>(cm_ptr, cm, mt->n, mp, Y, ldy, col0, wt, w, uy,
                                                          a->v_ones ? nullptr : a->v.p, out, ldo, lpr);
         });
         count_launch(ctx);
     }
+    if (hybrid) SB_TRY(dense_t(a, Y, ldy, w, out, ldo));
     account(ctx, mt, w, true);
     SB_CUDA(cudaGetLastError());
     return SB_OK;
@@ -417,6 +426,11 @@ int spmm_n(sb_nmat *a, const double *X, u32 ldx, u32 w, double *P, u32 ldp) {
     SB_CUDA(cudaMemset2DAsync(P, (size_t)ldp * sizeof(double), 0, (size_t)wpad * sizeof(double), (size_t)mt->m + 1, ctx->stream));
     if (a->has_offset) SB_TRY(colsum_weighted(ctx, X, mt->n, w, ldx, a->v_ones ? nullptr : a->v.p, vx));
     MapDev mp = make_map(a);
+    const bool hybrid = a->kind == 1 && mt->gd > 0;
+    if (!hybrid) SB_TRY(mat_ensure_full_gm(mt));
+    const uint2 *gm = hybrid ? mt->cold_gm.p : mt->gm.p;
+    const u64 *gm_base = hybrid ? mt->cold_gm_base.p : mt->gm_base.p;
+    const u64 sparse_nnz = hybrid ? mt->cold_nnz : mt->nnz;
     if (mt->nnz && w) {
         ProfScope ps(ctx, PH_SPMM_N);
         // tile width: the X panel (pc x wt doubles) must fit in shared memory next to the staging buffers
@@ -431,7 +445,7 @@ int spmm_n(sb_nmat *a, const double *X, u32 ldx, u32 w, double *P, u32 ldp) {
         u32 tw = (w + ntiles - 1) / ntiles;
         tw = (tw + 1) & ~1u;
         u64 total_units = (u64)mt->np * mt->ur;
-        for (u32 col0 = 0; col0 < w; col0 += tw) {
+        for (u32 col0 = 0; col0 < w && sparse_nnz; col0 += tw) {
             u32 wt = min(tw, w - col0);
             int lpr = (int)((wt + 1) / 2);
             size_t smem = (size_t)mt->pc * (2 * lpr) * 8 + fixed;
@@ -447,12 +461,13 @@ int spmm_n(sb_nmat *a, const double *X, u32 ldx, u32 w, double *P, u32 ldp) {
                     rc = sb_fail(SB_ERR_CUDA, "cudaFuncSetAttribute(%zu B smem): %s", smem, cudaGetErrorString(e));
                     return;
                 }
-                k_spmm_n<L><<<blocks, threads, smem, ctx->stream>>>(mt->gm.p, mt->gm_base.p, mt->np, mt->ur, mt->pc, mt->n, mp, X, ldx,
+                k_spmm_n<L><<<blocks, threads, smem, ctx->stream>>>(gm, gm_base, mt->np, mt->ur, mt->pc, mt->n, mp, X, ldx,
                                                                     col0, wt, w, P, ldp, lpr);
             });
             SB_TRY(rc);
             count_launch(ctx);
         }
+        if (hybrid) SB_TRY(dense_n(a, X, ldx, w, P, ldp));
         account(ctx, mt, w, false);
         SB_CUDA(cudaGetLastError());
     }

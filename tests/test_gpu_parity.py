@@ -288,6 +288,35 @@ def test_projection_shortcut_and_direct_pass_agree(ctx, n_cells, n_genes):
     check_pca_parity(res_fast, res_direct)
 
 
+def test_hybrid_dense_panel_matches_pure_sparse(ctx):
+    """The dense hot-gene panel (csrc/dense_panel.cu) and the pure sparse layout give the same products and
+    moments to rounding, and both match the oracle; counts above 15 in hot genes stay on the sparse side."""
+    cfg, cm, dm_h, (ip, g, c) = synth_pair(ctx, 3000, 2500, seed=37, n_dense=40, dense_mean=40.0)
+    try:
+        ctx.set_option("dense_genes", 0)
+        dm_s = sb.AdaptiveMat.from_csc(ctx, 2500, 3000, ip, g, c)
+    finally:
+        ctx.set_option("dense_genes", 2048)
+    a_o = orc.normalize(cm, orc.CELLRANGER)
+    a_h, a_s = sb.normalize(dm_h, sb.Normalization.CellRanger), sb.normalize(dm_s, sb.Normalization.CellRanger)
+    for p_h, p_s, p_o in zip(a_h.params(), a_s.params(), (a_o.mat.spec.col_scale, a_o.mat.spec.row_scale, a_o.u.ravel(), a_o.v.ravel())):
+        np.testing.assert_allclose(p_h, p_s, rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(p_h, p_o, rtol=1e-9, atol=1e-12)
+    rng = np.random.default_rng(5)
+    for w in (20, 7, 40):
+        x = rng.standard_normal((3000, w))
+        ref = a_o.dot(x)
+        for a in (a_h, a_s):
+            assert np.abs(a.dot(x) - ref).max() <= 1e-11 * np.abs(ref).max()
+        y = rng.standard_normal((w, 2500))
+        ref = a_o.rdot(y)
+        for a in (a_h, a_s):
+            assert np.abs(a.rdot(y) - ref).max() <= 1e-11 * np.abs(ref).max()
+    res_o = orc.BkSvd().run_pca(a_o, 10)
+    check_pca_parity(sb.BkSvd().run_pca(a_h, 10), res_o)
+    check_pca_parity(sb.BkSvd().run_pca(a_s, 10), res_o)
+
+
 def test_bksvd_seurat_and_binomial(ctx):
     cfg, cm, dm, _ = synth_pair(ctx, 3000, 1200, seed=32)
     check_pca_parity(sb.BkSvd().run_pca(sb.normalize(dm, sb.Normalization.SeuratLog), 8),
