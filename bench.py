@@ -243,12 +243,16 @@ def main():
         return r
 
     e2e_step()  # warm-up
+    ctx.profile_enable(True)
+    ctx.profile_reset()
     ctx.sync()
     barrier()
     ctx.timer_begin()
     for _ in range(args.e2e_steps):
         e2e_step()
     e_ms = max_over_ranks(ctx.timer_end()) / args.e2e_steps
+    eprof = ctx.profile()
+    ctx.profile_enable(False)
     barrier()
     h2d = int(h_ip.nbytes + h_g.nbytes + h_c.nbytes)
     d2h = int((N_GENES * K + K + n_loc * K) * 8)
@@ -269,7 +273,7 @@ def main():
                     "launches": int(d_launch), "avg_launch_ms": d_ms / max(1, d_launch),
                     "algorithmic_bytes_per_launch": d_bytes / max(1, d_launch),
                     "fp64_tflops": d_flops / (d_ms * 1e-3) / 1e12 if d_ms > 0 else 0.0,
-                    "phase_ms_per_step": {k: prof[k] / args.steps for k in ("spmm_t_ms", "spmm_n_ms", "moments_ms", "reduce_ms", "dense_ms", "comm_ms")},
+                    "phase_ms_per_step": {k: prof[k] / args.steps for k in ("spmm_t_ms", "spmm_n_ms", "moments_ms", "reduce_ms", "dense_ms", "comm_ms", "output_ms")},
                     "other": {"kernel": "k_spmm_n" if dom == "spmm_t" else "k_spmm_t",
                               "achieved": ((prof["spmm_n_bytes"] / (kn * 1e-3) / 1e9) if dom == "spmm_t" and kn > 0 else
                                            (prof["spmm_t_bytes"] / (kt * 1e-3) / 1e9) if kt > 0 else 0.0)}}
@@ -280,7 +284,8 @@ def main():
                                        f"(b=20, n_iter=5)", "nnz_rank0": int(nnz_local), "cell_sharding": f"{world} ranks, contiguous cell ranges",
                            "l2": "inputs (2 x 8 B/nnz device layouts) far larger than L2; no flush needed"},
                 "e2e": {"value": n_total / (e_ms * 1e-3), "unit": "cells/s", "ms_per_step": e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": args.e2e_steps},
+                        "steps": args.e2e_steps, "upload_ms": eprof["upload_ms"] / args.e2e_steps, "layout_build_ms": eprof["build_ms"] / args.e2e_steps,
+                        "output_ms": eprof["output_ms"] / args.e2e_steps},
                 "gpu_launches": int(prof["own_kernel_launches"]), "library_launches": int(prof["kernel_launches"] - prof["own_kernel_launches"]),
                 "roofline": roofline, "clocks": clocks, "wall_s_timed_region": wall}
         if world == 1 and not args.no_cpu_baseline:

@@ -97,6 +97,11 @@ SB_API int sb_sync(sb_ctx *ctx);
  * bk_svd.rs:102,131 to run as a sparse product; 0 lets the library use Q^T A = R^-T (K^T A) when R is usable. */
 SB_API int sb_set_option(sb_ctx *ctx, const char *name, double value);
 
+/* Page-locked host memory for inputs / outputs (optional): copies to and from pinned buffers run at PCIe
+ * speed and asynchronously; pageable buffers work too, several times slower for the large V block. */
+SB_API int sb_host_alloc(size_t bytes, void **out);
+SB_API void sb_host_free(void *p);
+
 /* ---------------------------------------------------------------- count matrix
  * sb_upload replaces AdaptiveMat::from_csmat / new (sqz/src/mat.rs:81-124): the Rust side
  * decodes each AdaptiveVec once (vec.rs `foreach` :1230-1273) into these arrays.  `major`
@@ -197,6 +202,9 @@ typedef struct {
     uint64_t spmm_n_launches;
     uint64_t kernel_launches; /* every kernel this library launched (own + library calls) */
     uint64_t own_kernel_launches;
+    double upload_ms;     /* sb_upload: host -> device copies */
+    double build_ms;      /* sb_upload: device-side layout build (sorts, dense panel) */
+    double output_ms;     /* device -> host copies of U, sigma, V */
 } sb_profile;
 SB_API int sb_profile_enable(sb_ctx *ctx, int on); /* on: record a CUDA-event pair around every phase */
 SB_API int sb_profile_reset(sb_ctx *ctx);

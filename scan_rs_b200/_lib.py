@@ -22,7 +22,8 @@ class SbProfile(C.Structure):
                 ("spmm_t_bytes", C.c_double), ("spmm_n_bytes", C.c_double),
                 ("spmm_t_flops", C.c_double), ("spmm_n_flops", C.c_double),
                 ("spmm_t_launches", C.c_uint64), ("spmm_n_launches", C.c_uint64),
-                ("kernel_launches", C.c_uint64), ("own_kernel_launches", C.c_uint64)]
+                ("kernel_launches", C.c_uint64), ("own_kernel_launches", C.c_uint64),
+                ("upload_ms", C.c_double), ("build_ms", C.c_double), ("output_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -40,7 +41,7 @@ class CancellationError(ScanB200Error):
 
 # every symbol include/scanb200.h declares (tests/test_host_abi.py checks the export list)
 SYMBOLS = [
-    "sb_version", "sb_last_error", "sb_init", "sb_shutdown", "sb_comm_unique_id", "sb_comm_init", "sb_sync", "sb_set_option",
+    "sb_version", "sb_last_error", "sb_init", "sb_shutdown", "sb_comm_unique_id", "sb_comm_init", "sb_sync", "sb_set_option", "sb_host_alloc", "sb_host_free",
     "sb_upload", "sb_mat_shape", "sb_download", "sb_free_mat", "sb_cell_totals", "sb_gene_totals", "sb_gene_nnz",
     "sb_median_cell_total", "sb_partition", "sb_select_rows", "sb_select_cols", "sb_hvg_select",
     "sb_normalize", "sb_log_normalize", "sb_normalize_fixed_point", "sb_nmat_params", "sb_nmat_to_dense",
@@ -63,11 +64,13 @@ def lib():
         _lib.sb_last_error.restype = C.c_char_p
         for name in SYMBOLS:
             fn = getattr(_lib, name)
-            if name not in ("sb_last_error", "sb_shutdown", "sb_free_mat", "sb_free_nmat"):
+            if name not in ("sb_last_error", "sb_shutdown", "sb_free_mat", "sb_free_nmat", "sb_host_free"):
                 fn.restype = C.c_int
         _lib.sb_shutdown.restype = None
         _lib.sb_free_mat.restype = None
         _lib.sb_free_nmat.restype = None
+        _lib.sb_host_free.restype = None
+        _lib.sb_host_free.argtypes = [C.c_void_p]
     return _lib
 
 
@@ -82,3 +85,31 @@ def check(rc: int):
 
 def vp(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class _Pinned:
+    """Owner of one page-locked allocation (freed when the last array view dies)."""
+
+    def __init__(self, nbytes):
+        self.ptr = C.c_void_p()
+        check(lib().sb_host_alloc(C.c_size_t(max(int(nbytes), 1)), C.byref(self.ptr)))
+        self.nbytes = int(nbytes)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().sb_host_free(self.ptr)
+                self.ptr = C.c_void_p()
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype):
+    """numpy array in page-locked host memory (sb_host_alloc); freed with its last view."""
+    import numpy as np
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape))
+    owner = _Pinned(n * dt.itemsize)
+    buf = (C.c_char * max(n * dt.itemsize, 1)).from_address(owner.ptr.value)
+    buf._owner = owner  # the ctypes buffer is the array's base object and keeps the allocation alive
+    return np.frombuffer(buf, dtype=dt, count=n).reshape(shape)

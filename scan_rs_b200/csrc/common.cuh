@@ -102,7 +102,7 @@ struct DevBuf {
 };
 
 // ---------------------------------------------------------------- profile phases
-enum Phase { PH_SPMM_T = 0, PH_SPMM_N, PH_MOMENTS, PH_REDUCE, PH_DENSE, PH_COMM, PH_COUNT };
+enum Phase { PH_SPMM_T = 0, PH_SPMM_N, PH_MOMENTS, PH_REDUCE, PH_DENSE, PH_COMM, PH_UPLOAD, PH_BUILD, PH_OUTPUT, PH_COUNT };
 
 struct sb_ctx {
     int device = 0;
@@ -211,5 +211,26 @@ int comm_allgather_u64_host(sb_ctx *ctx, u64 mine, std::vector<u64> &all);
         SB_CUDA(cudaSetDevice((ctx_ptr)->device)); \
         sb_set_alloc_stream((ctx_ptr)->stream);    \
     } while (0)
+
+// SCANB200_TRACE=1: host wall-clock trace of the upload / build stages (synchronising; diagnostics only)
+struct TraceScope {
+    sb_ctx *c;
+    const char *name;
+    double t0;
+    static bool on();
+    static double now();
+    TraceScope(sb_ctx *ctx, const char *n) : c(ctx), name(n), t0(0) {
+        if (on()) {
+            cudaStreamSynchronize(c->stream);
+            t0 = now();
+        }
+    }
+    ~TraceScope() {
+        if (on()) {
+            cudaStreamSynchronize(c->stream);
+            fprintf(stderr, "[scanb200] %-28s %8.2f ms\n", name, (now() - t0) * 1e3);
+        }
+    }
+};
 
 static inline unsigned cdiv(u64 a, u64 b) { return (unsigned)((a + b - 1) / b); }

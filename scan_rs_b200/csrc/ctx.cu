@@ -1,6 +1,9 @@
 // ctx.cu -- context, errors, communicator, timers and per-phase accounting.
 #include <dlfcn.h>
 
+#include <chrono>
+#include <cstdlib>
+
 #include "common.cuh"
 
 static thread_local char g_err[1024] = "";
@@ -22,6 +25,16 @@ int sb_fail(int code, const char *fmt, ...) {
     va_end(ap);
     return code;
 }
+
+bool TraceScope::on() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SCANB200_TRACE");
+        v = (e && *e && *e != '0') ? 1 : 0;
+    }
+    return v == 1;
+}
+double TraceScope::now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 extern "C" const char *sb_last_error(void) { return g_err; }
 extern "C" int sb_version(void) { return SB_VERSION; }
@@ -84,6 +97,16 @@ extern "C" void sb_shutdown(sb_ctx *ctx) {
     }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+extern "C" int sb_host_alloc(size_t bytes, void **out) {
+    if (!out) return sb_fail(SB_ERR_INVALID_ARG, "sb_host_alloc: out is NULL");
+    SB_CUDA(cudaMallocHost(out, bytes ? bytes : 1));
+    return SB_OK;
+}
+
+extern "C" void sb_host_free(void *p) {
+    if (p) cudaFreeHost(p);
 }
 
 extern "C" int sb_set_option(sb_ctx *ctx, const char *name, double value) {
@@ -278,6 +301,9 @@ void prof_collect(sb_ctx *ctx) {
             case PH_REDUCE: ctx->prof.reduce_ms += ms; break;
             case PH_DENSE: ctx->prof.dense_ms += ms; break;
             case PH_COMM: ctx->prof.comm_ms += ms; break;
+            case PH_UPLOAD: ctx->prof.upload_ms += ms; break;
+            case PH_BUILD: ctx->prof.build_ms += ms; break;
+            case PH_OUTPUT: ctx->prof.output_ms += ms; break;
             }
         }
         ctx->event_pool.push_back(p.second.first);

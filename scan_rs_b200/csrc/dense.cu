@@ -54,6 +54,7 @@ __global__ void k_extract_r(const double *__restrict__ cm, u64 rows, u32 w, doub
 // thin QR: A (row-major rows x w, ld) is replaced by Q (rows x min(rows, w)); returns the new width.
 // R_out (device, col-major w x w) optionally receives the triangular factor (needs rows >= w).
 int qr_tall(sb_ctx *ctx, double *A, u64 rows, u32 w, u32 ld, u32 *w_out, double *R_out) {
+    TraceScope trc(ctx, "dense: qr_tall");
     ProfScope ps(ctx, PH_DENSE);
     u32 kq = (u32)std::min<u64>(rows, w);
     *w_out = kq;
@@ -91,6 +92,7 @@ int qr_tall(sb_ctx *ctx, double *A, u64 rows, u32 w, u32 ld, u32 *w_out, double 
 
 // G (col-major w x w) = A^T A for A row-major rows x w (ld); all-reduced over ranks when `reduce`
 int gram(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 ld, double *G, bool reduce) {
+    TraceScope trc(ctx, "dense: gram");
     ProfScope ps(ctx, PH_DENSE);
     if (rows > 0x7FFFFFFFull) return sb_fail(SB_ERR_UNSUPPORTED, "gram: more than 2^31 rows");
     const double one = 1.0, zero = 0.0;
@@ -107,6 +109,7 @@ int gram(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 ld, double *G, bool 
 
 // symmetric eigendecomposition of G (col-major w x w, overwritten by eigenvectors); evals ascending
 int eigh(sb_ctx *ctx, double *G, u32 w, double *evals_dev) {
+    TraceScope trc(ctx, "dense: eigh");
     ProfScope ps(ctx, PH_DENSE);
     int lwork = 0;
     SB_CUSOLVER(cusolverDnDsyevd_bufferSize(ctx->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)w, G, (int)w, evals_dev, &lwork));
@@ -125,6 +128,7 @@ int eigh(sb_ctx *ctx, double *G, u32 w, double *evals_dev) {
 
 // Out (row-major rows x k, ldo) = A (row-major rows x w, lda) . S (col-major w x k, lds)
 int gemm_tall_small(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 lda, const double *S, u32 k, u32 lds, double *Out, u32 ldo) {
+    TraceScope trc(ctx, "dense: gemm_tall_small");
     ProfScope ps(ctx, PH_DENSE);
     if (rows == 0 || k == 0) return SB_OK;
     if (rows > 0x7FFFFFFFull) return sb_fail(SB_ERR_UNSUPPORTED, "gemm: more than 2^31 rows");
@@ -137,6 +141,7 @@ int gemm_tall_small(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 lda, cons
 // A (row-major rows x w, ld) <- A . R^-1 for upper-triangular R (col-major w x w): the column-major
 // view A_c = A^T (w x rows) gets R^-T applied from the left.
 int trsm_right_upper(sb_ctx *ctx, double *A, u64 rows, u32 w, u32 ld, const double *R) {
+    TraceScope trc(ctx, "dense: trsm");
     ProfScope ps(ctx, PH_DENSE);
     if (rows == 0 || w == 0) return SB_OK;
     if (rows > 0x7FFFFFFFull) return sb_fail(SB_ERR_UNSUPPORTED, "trsm: more than 2^31 rows");

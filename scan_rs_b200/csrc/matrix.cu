@@ -326,11 +326,15 @@ int mat_gene_sums_dev(sb_mat *mat, int mode, const unsigned char *excl_cells, co
 // picks the hot genes (most non-zeros, at least dense_min_density of the cells, at most dense_cap) and builds D + cold layouts
 static int build_hybrid(sb_mat *mt) {
     sb_ctx *ctx = mt->ctx;
+    TraceScope tr(ctx, "build: hybrid total");
     mt->gd = 0;
     if (ctx->dense_cap < 64 || mt->m < 64 || mt->n == 0 || mt->n_global == 0) return SB_OK;
     DevBuf<u64> d_nnz;
     SB_TRY(d_nnz.alloc(mt->m));
-    SB_TRY(mat_gene_sums_dev(mt, 2, nullptr, nullptr, d_nnz.p, true));
+    {
+        TraceScope t2(ctx, "build: gene nnz");
+        SB_TRY(mat_gene_sums_dev(mt, 2, nullptr, nullptr, d_nnz.p, true));
+    }
     std::vector<u64> h(mt->m);
     SB_CUDA(cudaMemcpyAsync(h.data(), d_nnz.p, (size_t)mt->m * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     SB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -349,6 +353,7 @@ static int build_hybrid(sb_mat *mt) {
     SB_TRY(mt->hot_of_gene.alloc(mt->m));
     SB_CUDA(cudaMemcpyAsync(mt->hot_idx.p, hot.data(), gd * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
     SB_CUDA(cudaMemcpyAsync(mt->hot_of_gene.p, hot_of.data(), (size_t)mt->m * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+    TraceScope t4(ctx, "build: split hot/cold");
     SB_TRY(mt->D.alloc((size_t)mt->n * gd));
     SB_CUDA(cudaMemsetAsync(mt->D.p, 0, (size_t)mt->n * gd, ctx->stream));
     DevBuf<u32> counts;
@@ -363,7 +368,10 @@ static int build_hybrid(sb_mat *mt) {
     SB_TRY(mt->cold_cm.alloc(mt->cold_nnz));
     k_split_hot<<<grid, 256, 0, ctx->stream>>>(mt->cm_ptr.p, mt->cm.p, mt->n, mt->hot_of_gene.p, gd, mt->cold_cm_ptr.p, nullptr, mt->cold_cm.p, mt->D.p);
     count_launch(ctx);
-    SB_TRY(build_gene_major(mt, mt->cold_cm_ptr.p, mt->cold_cm.p, mt->cold_nnz, mt->cold_gm, mt->cold_gm_base));
+    {
+        TraceScope t3(ctx, "build: cold gene-major sort");
+        SB_TRY(build_gene_major(mt, mt->cold_cm_ptr.p, mt->cold_cm.p, mt->cold_nnz, mt->cold_gm, mt->cold_gm_base));
+    }
     mt->gd = gd;
     return SB_OK;
 }
@@ -406,11 +414,17 @@ extern "C" int sb_upload(sb_ctx *ctx, int major, uint32_t m, uint64_t n_local, c
     SB_TRY(d_ptr.alloc(nvec + 1));
     SB_TRY(d_idx.alloc(nnz));
     SB_TRY(d_cnt.alloc(nnz));
+    TraceScope *tr_up = new TraceScope(ctx, "upload: H2D");
+    prof_begin(ctx, PH_UPLOAD);
     SB_CUDA(cudaMemcpyAsync(d_ptr.p, indptr, (nvec + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
     if (nnz) {
         SB_CUDA(cudaMemcpyAsync(d_idx.p, idx, nnz * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
         SB_CUDA(cudaMemcpyAsync(d_cnt.p, cnt, nnz * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
     }
+    prof_end(ctx, PH_UPLOAD);
+    delete tr_up;
+    ProfScope build_scope(ctx, PH_BUILD);
+    TraceScope tr_build(ctx, "upload: build total");
     // validation: pointers monotone, indices in range
     void *scr;
     SB_TRY(ctx_scratch(ctx, 256, &scr));
@@ -432,6 +446,7 @@ extern "C" int sb_upload(sb_ctx *ctx, int major, uint32_t m, uint64_t n_local, c
     u64 bound = major == SB_GENE_MAJOR ? n_local : (u64)m;
     if (nnz && (u64)(u32)h[1] >= bound) return sb_fail(SB_ERR_INVALID_ARG, "sb_upload: index %u out of range %llu", (u32)h[1], (unsigned long long)bound);
 
+    TraceScope *tr_cm = new TraceScope(ctx, "upload: cell-major copy");
     if (major == SB_CELL_MAJOR) {
         mt->cm_ptr.swap(d_ptr);
         SB_TRY(mt->cm.alloc(nnz));
@@ -466,6 +481,7 @@ extern "C" int sb_upload(sb_ctx *ctx, int major, uint32_t m, uint64_t n_local, c
         }
     }
     SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    delete tr_cm;
     d_idx.release();
     d_cnt.release();
     SB_TRY(finish_matrix(mt.get()));

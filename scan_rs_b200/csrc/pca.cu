@@ -133,6 +133,7 @@ static int finish_svd(sb_ctx *ctx, const Tall &Tt, const Tall &Q, u32 wq, u32 k,
 
 static int download_tall(sb_ctx *ctx, const Tall &t, double *host) {
     if (t.rows == 0 || t.w == 0) return SB_OK;
+    ProfScope ps(ctx, PH_OUTPUT);
     SB_CUDA(cudaMemcpy2DAsync(host, t.w * sizeof(double), t.buf.p, t.ld * sizeof(double), t.w * sizeof(double), t.rows, cudaMemcpyDeviceToHost,
                               ctx->stream));
     SB_CUDA(cudaStreamSynchronize(ctx->stream));

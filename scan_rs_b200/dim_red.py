@@ -11,6 +11,11 @@ from .snoop import NoOpSnoop
 from .sqz import LowRankOffset
 
 
+def _outputs(m, n, k):
+    """U, S, V result buffers in page-locked memory (the V block is n x k: pageable copies are several times slower)."""
+    return L.pinned_empty((m, k), np.float64), L.pinned_empty((k,), np.float64), L.pinned_empty((n, k), np.float64)
+
+
 def omega(seed: int, rows: int, cols: int) -> np.ndarray:
     """The start block: SmallRng::seed_from_u64(seed) + Uniform(-1, 1), row-major (bk_svd.rs:83-84)."""
     out = np.zeros((rows, cols))
@@ -31,7 +36,7 @@ def _make_cb(snoop):
 def svd_bk(A: LowRankOffset, k: int, b: int, n_iter: int, seed: int = 0, snoop=None, omega_block: Optional[np.ndarray] = None):
     """bk_svd.rs:57-146 -> (U m x k, sigma k, Va k x n_local)."""
     m, n = A.shape()
-    U, S, V = np.zeros((m, k)), np.zeros(k), np.zeros((n, k))
+    U, S, V = _outputs(m, n, k)
     cb = _make_cb(snoop or NoOpSnoop())
     om = None if omega_block is None else np.ascontiguousarray(omega_block, dtype=np.float64)
     L.check(L.lib().sb_bksvd(A._h, C.c_uint32(k), C.c_uint32(b), C.c_uint32(n_iter), C.c_uint64(seed), L.vp(om), cb, None,
@@ -42,7 +47,7 @@ def svd_bk(A: LowRankOffset, k: int, b: int, n_iter: int, seed: int = 0, snoop=N
 def svd_rand(A: LowRankOffset, k: int, l: int, n_iter: int, seed: int = 0, omega_block: Optional[np.ndarray] = None):
     """rand_svd.rs:54-129 -> (U, sigma, Va k x n)."""
     m, n = A.shape()
-    U, S, V = np.zeros((m, k)), np.zeros(k), np.zeros((n, k))
+    U, S, V = _outputs(m, n, k)
     om = None if omega_block is None else np.ascontiguousarray(omega_block, dtype=np.float64)
     L.check(L.lib().sb_randsvd(A._h, C.c_uint32(k), C.c_uint32(l), C.c_uint32(n_iter), C.c_uint64(seed), L.vp(om),
                                L.vp(U), L.vp(S), L.vp(V)))
@@ -58,7 +63,7 @@ class BkSvd:
     def run_pca_cancellable(self, array: LowRankOffset, k: int, snoop):
         """-> (u m x k, s k, v n x k): PcaResult with `vt.reversed_axes()` (bk_svd.rs:48-52)."""
         m, n = array.shape()
-        U, S, V = np.zeros((m, k)), np.zeros(k), np.zeros((n, k))
+        U, S, V = _outputs(m, n, k)
         cb = _make_cb(snoop)
         L.check(L.lib().sb_bksvd_run_pca(array._h, C.c_uint32(k), C.c_double(self.k_multiplier), C.c_uint32(self.n_iter), cb, None,
                                          L.vp(U), L.vp(S), L.vp(V)))
@@ -76,7 +81,7 @@ class RandSvd:
 
     def run_pca_cancellable(self, array: LowRankOffset, k: int, _snoop=None):
         m, n = array.shape()
-        U, S, V = np.zeros((m, k)), np.zeros(k), np.zeros((n, k))
+        U, S, V = _outputs(m, n, k)
         L.check(L.lib().sb_randsvd_run_pca(array._h, C.c_uint32(k), C.c_double(self.l_multiplier), C.c_uint32(self.n_iter),
                                            L.vp(U), L.vp(S), L.vp(V)))
         return U, S, V
