@@ -197,9 +197,11 @@ def main():
     dm = generate_device(ctx, cfg, lo, hi)
     nnz_local = dm.nnz()
 
+    out_bufs = sb.pinned_outputs(N_GENES, hi - lo, K)  # page-locked result buffers, allocated once
+
     def step(mat):
         a = sb.normalize(mat, sb.Normalization.CellRanger)
-        res = sb.BkSvd().run_pca(a, K)
+        res = sb.BkSvd().run_pca(a, K, out=out_bufs)
         a.free()
         return res
 

@@ -13,5 +13,5 @@ from .sqz import AdaptiveMat, Context, LowRankOffset  # noqa: F401
 from .normalization import (LogBase, Normalization, binom_deviance_resid, binom_pearson_resid,  # noqa: F401
                             log1p_normalize_fixed_point, log_normalize, log_normalize_with_size_factor,
                             normalize, normalize_with_size_factor)
-from .dim_red import BkSvd, RandSvd, omega, svd_bk, svd_rand  # noqa: F401
+from .dim_red import BkSvd, RandSvd, omega, pinned_outputs, svd_bk, svd_rand  # noqa: F401
 from .snoop import AtomicSnoop, NoOpSnoop  # noqa: F401

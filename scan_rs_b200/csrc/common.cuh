@@ -109,6 +109,7 @@ struct sb_ctx {
     int sm_count = 148;
     size_t l2_bytes = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // host -> device copies of the pipelined upload
     cublasHandle_t cublas = nullptr;
     cusolverDnHandle_t cusolver = nullptr;
     ncclComm_t comm = nullptr;
@@ -126,6 +127,8 @@ struct sb_ctx {
     // scratch reused by reductions / collectives
     DevBuf<char> scratch;
     void *pinned = nullptr;  // small pinned staging (4 KB)
+    std::vector<double> omega_cache;  // last generated start block (host)
+    u64 omega_seed = ~0ull, omega_rows = 0, omega_cols = 0;
 };
 
 // The packed gene-major entry: x = gene | (cell_local << SB_GENE_BITS), y = count.

@@ -95,6 +95,7 @@ extern "C" void sb_shutdown(sb_ctx *ctx) {
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
     }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

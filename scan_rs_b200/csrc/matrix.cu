@@ -265,37 +265,46 @@ static void choose_panels(sb_mat *mt) {
     mt->ur = ur;
 }
 
-// builds a gene-major panelled copy (gm, gm_base) from a cell-major pair (cm_ptr, cm) of the same matrix
-static int build_gene_major(sb_mat *mt, const u64 *cm_ptr, const uint2 *cm, u64 nnz, DevBuf<uint2> &gm, DevBuf<u64> &gm_base) {
+// ---- range-based building blocks (whole matrix or one upload chunk of whole cell panels) -------------------
+// gene-major panelled order of `nc` cells given their (range-local) cell-major pair: stable sort by (panel, gene)
+static int gene_major_range(sb_mat *mt, u64 nc, const u64 *ptr_local, const uint2 *ent, u64 nnz, DevBuf<uint2> &gm) {
     sb_ctx *ctx = mt->ctx;
-    SB_TRY(gm_base.alloc((size_t)mt->np + 1));
-    k_panel_base<<<cdiv(mt->np + 1, 256), 256, 0, ctx->stream>>>(cm_ptr, mt->n, mt->pc, mt->np, gm_base.p);
-    count_launch(ctx);
     SB_TRY(gm.alloc(nnz));
     if (nnz == 0) return SB_OK;
-    if ((u64)mt->np * mt->m > 0xFFFFFFFFull) return sb_fail(SB_ERR_UNSUPPORTED, "panel x gene key exceeds 32 bits");
+    const u64 npanels = (nc + mt->pc - 1) / mt->pc;
+    if (npanels * mt->m > 0xFFFFFFFFull) return sb_fail(SB_ERR_UNSUPPORTED, "panel x gene key exceeds 32 bits");
     DevBuf<u32> keys;
     DevBuf<u64> payload;
     SB_TRY(keys.alloc(nnz));
     SB_TRY(payload.alloc(nnz));
-    k_make_keys<<<grid_for(mt->n * 32, 256, ctx, 16), 256, 0, ctx->stream>>>(cm_ptr, cm, mt->n, 0, mt->m, mt->pc, keys.p, payload.p);
+    k_make_keys<<<grid_for(nc * 32, 256, ctx, 16), 256, 0, ctx->stream>>>(ptr_local, ent, nc, 0, mt->m, mt->pc, keys.p, payload.p);
     count_launch(ctx);
-    SB_TRY(sort_pairs(ctx, keys, payload, nnz, bits_for((u64)mt->np * mt->m - 1)));
+    SB_TRY(sort_pairs(ctx, keys, payload, nnz, bits_for(npanels * mt->m - 1)));
     k_unpack_payload<<<grid_for(nnz, 256, ctx, 16), 256, 0, ctx->stream>>>(payload.p, gm.p, nnz);
     count_launch(ctx);
     SB_CUDA(cudaStreamSynchronize(ctx->stream));
     return SB_OK;
 }
 
+static int panel_base(sb_mat *mt, const u64 *cm_ptr, DevBuf<u64> &gm_base) {
+    sb_ctx *ctx = mt->ctx;
+    SB_TRY(gm_base.alloc((size_t)mt->np + 1));
+    k_panel_base<<<cdiv(mt->np + 1, 256), 256, 0, ctx->stream>>>(cm_ptr, mt->n, mt->pc, mt->np, gm_base.p);
+    count_launch(ctx);
+    return SB_OK;
+}
+
 // the gene-major copy of ALL entries (binomial residual maps, which have no per-cell value table)
 int mat_ensure_full_gm(sb_mat *mt) {
     if (mt->have_full_gm) return SB_OK;
-    SB_TRY(build_gene_major(mt, mt->cm_ptr.p, mt->cm.p, mt->nnz, mt->gm, mt->gm_base));
+    SB_TRY(panel_base(mt, mt->cm_ptr.p, mt->gm_base));
+    SB_TRY(gene_major_range(mt, mt->n, mt->cm_ptr.p, mt->cm.p, mt->nnz, mt->gm));
     mt->have_full_gm = true;
     return SB_OK;
 }
 
-// splits the cell-major stream into the dense panel D and the cold sparse entries (count / fill passes)
+// splits the cell-major stream into the dense panel D and the cold sparse entries (count / fill passes).
+// ptr / D are already offset to the first cell of the range; new_ptr and out are range-local.
 __global__ void k_split_hot(const u64 *__restrict__ ptr, const uint2 *__restrict__ cm, u64 n, const u32 *__restrict__ hot_of_gene, u32 gd,
                             const u64 *__restrict__ new_ptr, u32 *__restrict__ counts, uint2 *__restrict__ out, unsigned char *__restrict__ D) {
     u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -321,30 +330,42 @@ __global__ void k_split_hot(const u64 *__restrict__ ptr, const uint2 *__restrict
     }
 }
 
-int mat_gene_sums_dev(sb_mat *mat, int mode, const unsigned char *excl_cells, const unsigned char *excl_genes, u64 *d_out, bool allreduce);
+__global__ void k_add_offset(const u64 *__restrict__ src, u64 n, u64 add, u64 *__restrict__ dst) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i] + add;
+}
 
-// picks the hot genes (most non-zeros, at least dense_min_density of the cells, at most dense_cap) and builds D + cold layouts
-static int build_hybrid(sb_mat *mt) {
+// Picks the hot genes from the non-zero counts of local cells [c0, c1) (the whole shard, or the first upload
+// chunk as a sample), summed over ranks: most non-zeros first, at least dense_min_density of the sampled
+// cells, at most dense_cap, whole groups of 64.  Allocates and zeroes the panel.
+static int select_hot_genes(sb_mat *mt, u64 c0, u64 c1) {
     sb_ctx *ctx = mt->ctx;
-    TraceScope tr(ctx, "build: hybrid total");
     mt->gd = 0;
-    if (ctx->dense_cap < 64 || mt->m < 64 || mt->n == 0 || mt->n_global == 0) return SB_OK;
+    if (ctx->dense_cap < 64 || mt->m < 64 || mt->n_global == 0) return SB_OK;
+    TraceScope tr(ctx, "build: hot gene selection");
     DevBuf<u64> d_nnz;
-    SB_TRY(d_nnz.alloc(mt->m));
-    {
-        TraceScope t2(ctx, "build: gene nnz");
-        SB_TRY(mat_gene_sums_dev(mt, 2, nullptr, nullptr, d_nnz.p, true));
+    SB_TRY(d_nnz.alloc((size_t)mt->m + 1));
+    SB_CUDA(cudaMemsetAsync(d_nnz.p, 0, ((size_t)mt->m + 1) * sizeof(u64), ctx->stream));
+    if (c1 > c0) {
+        ProfScope ps(ctx, PH_REDUCE);
+        k_gene_sums<<<grid_for((c1 - c0) * 32, 256, ctx, 16), 256, 0, ctx->stream>>>(mt->cm_ptr.p + c0, mt->cm.p, c1 - c0, 2, nullptr, nullptr,
+                                                                                    (unsigned long long *)d_nnz.p);
+        count_launch(ctx);
     }
-    std::vector<u64> h(mt->m);
-    SB_CUDA(cudaMemcpyAsync(h.data(), d_nnz.p, (size_t)mt->m * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    u64 sample = c1 - c0;
+    SB_CUDA(cudaMemcpyAsync(d_nnz.p + mt->m, &sample, sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    SB_TRY(comm_allreduce_u64(ctx, d_nnz.p, (size_t)mt->m + 1));
+    std::vector<u64> h((size_t)mt->m + 1);
+    SB_CUDA(cudaMemcpyAsync(h.data(), d_nnz.p, h.size() * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (h[mt->m] == 0) return SB_OK;
     std::vector<u32> order(mt->m);
     std::iota(order.begin(), order.end(), 0u);
     std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 b) { return h[a] > h[b]; });
     u32 gd = 0;
-    double thr = ctx->dense_min_density * (double)mt->n_global;
-    while (gd < mt->m && gd < (u32)ctx->dense_cap && (double)h[order[gd]] >= thr) gd++;
-    gd &= ~63u;  // whole 64-gene groups: 16-byte aligned panel rows, full thread tiles
+    double thr = ctx->dense_min_density * (double)h[mt->m];
+    while (gd < mt->m && gd < (u32)ctx->dense_cap && (double)h[order[gd]] >= thr && h[order[gd]] > 0) gd++;
+    gd &= ~63u;  // whole 64-gene groups: 16-byte aligned panel rows, full fragment tiles
     if (gd == 0) return SB_OK;
     std::vector<u32> hot(order.begin(), order.begin() + gd), hot_of(mt->m, 0xFFFFFFFFu);
     std::sort(hot.begin(), hot.end());  // panel columns in ascending gene order
@@ -353,30 +374,54 @@ static int build_hybrid(sb_mat *mt) {
     SB_TRY(mt->hot_of_gene.alloc(mt->m));
     SB_CUDA(cudaMemcpyAsync(mt->hot_idx.p, hot.data(), gd * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
     SB_CUDA(cudaMemcpyAsync(mt->hot_of_gene.p, hot_of.data(), (size_t)mt->m * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
-    TraceScope t4(ctx, "build: split hot/cold");
     SB_TRY(mt->D.alloc((size_t)mt->n * gd));
-    SB_CUDA(cudaMemsetAsync(mt->D.p, 0, (size_t)mt->n * gd, ctx->stream));
-    DevBuf<u32> counts;
-    SB_TRY(counts.alloc(mt->n));
-    int grid = grid_for(mt->n * 32, 256, ctx, 16);
-    k_split_hot<<<grid, 256, 0, ctx->stream>>>(mt->cm_ptr.p, mt->cm.p, mt->n, mt->hot_of_gene.p, gd, nullptr, counts.p, nullptr, nullptr);
-    count_launch(ctx);
-    SB_TRY(mt->cold_cm_ptr.alloc(mt->n + 1));
-    SB_TRY(exclusive_scan_u32_to_u64(ctx, counts.p, mt->n, mt->cold_cm_ptr.p));
-    SB_CUDA(cudaMemcpyAsync(&mt->cold_nnz, mt->cold_cm_ptr.p + mt->n, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
-    SB_CUDA(cudaStreamSynchronize(ctx->stream));
-    SB_TRY(mt->cold_cm.alloc(mt->cold_nnz));
-    k_split_hot<<<grid, 256, 0, ctx->stream>>>(mt->cm_ptr.p, mt->cm.p, mt->n, mt->hot_of_gene.p, gd, mt->cold_cm_ptr.p, nullptr, mt->cold_cm.p, mt->D.p);
-    count_launch(ctx);
-    {
-        TraceScope t3(ctx, "build: cold gene-major sort");
-        SB_TRY(build_gene_major(mt, mt->cold_cm_ptr.p, mt->cold_cm.p, mt->cold_nnz, mt->cold_gm, mt->cold_gm_base));
-    }
+    SB_CUDA(cudaMemsetAsync(mt->D.p, 0, std::max<size_t>(1, (size_t)mt->n * gd), ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));  // hot / hot_of are host temporaries
     mt->gd = gd;
     return SB_OK;
 }
 
-static int finish_matrix(sb_mat *mt) {
+// dense / cold split of local cells [c0, c1): fills their panel rows, returns the range-local cold pair
+static int split_range(sb_mat *mt, u64 c0, u64 c1, DevBuf<u64> &ptr_local, DevBuf<uint2> &cold, u64 *cold_nnz) {
+    sb_ctx *ctx = mt->ctx;
+    const u64 nc = c1 - c0;
+    DevBuf<u32> counts;
+    SB_TRY(counts.alloc(nc));
+    SB_TRY(ptr_local.alloc(nc + 1));
+    int grid = grid_for(nc * 32, 256, ctx, 16);
+    if (nc) {
+        k_split_hot<<<grid, 256, 0, ctx->stream>>>(mt->cm_ptr.p + c0, mt->cm.p, nc, mt->hot_of_gene.p, mt->gd, nullptr, counts.p, nullptr, nullptr);
+        count_launch(ctx);
+    }
+    SB_TRY(exclusive_scan_u32_to_u64(ctx, counts.p, nc, ptr_local.p));
+    SB_CUDA(cudaMemcpyAsync(cold_nnz, ptr_local.p + nc, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    SB_TRY(cold.alloc(*cold_nnz));
+    if (nc) {
+        k_split_hot<<<grid, 256, 0, ctx->stream>>>(mt->cm_ptr.p + c0, mt->cm.p, nc, mt->hot_of_gene.p, mt->gd, ptr_local.p, nullptr, cold.p,
+                                                   mt->D.p + c0 * (u64)mt->gd);
+        count_launch(ctx);
+    }
+    return SB_OK;
+}
+
+// whole-matrix hybrid build (matrices created on the device: generator, select, partition; gene-major uploads)
+static int build_hybrid(sb_mat *mt) {
+    sb_ctx *ctx = mt->ctx;
+    TraceScope tr(ctx, "build: hybrid total");
+    SB_TRY(select_hot_genes(mt, 0, mt->n));
+    if (mt->gd == 0) return SB_OK;
+    {
+        TraceScope t4(ctx, "build: split hot/cold");
+        SB_TRY(split_range(mt, 0, mt->n, mt->cold_cm_ptr, mt->cold_cm, &mt->cold_nnz));
+    }
+    TraceScope t3(ctx, "build: cold gene-major sort");
+    SB_TRY(panel_base(mt, mt->cold_cm_ptr.p, mt->cold_gm_base));
+    SB_TRY(gene_major_range(mt, mt->n, mt->cold_cm_ptr.p, mt->cold_cm.p, mt->cold_nnz, mt->cold_gm));
+    return SB_OK;
+}
+
+static int set_global_shape(sb_mat *mt) {
     sb_ctx *ctx = mt->ctx;
     std::vector<u64> all;
     SB_TRY(comm_allgather_u64_host(ctx, mt->n, all));
@@ -387,8 +432,88 @@ static int finish_matrix(sb_mat *mt) {
         mt->n_global += all[r];
     }
     choose_panels(mt);
+    return SB_OK;
+}
+
+static int finish_matrix(sb_mat *mt) {
+    SB_TRY(set_global_shape(mt));
     SB_TRY(build_hybrid(mt));
     if (mt->gd == 0) SB_TRY(mat_ensure_full_gm(mt));
+    return SB_OK;
+}
+
+// Cell-major upload as a pipeline: the host arrays are copied in chunks of whole cell panels on a second
+// stream while the library stream turns the previous chunk into the device layouts (interleave, dense /
+// cold split, per-chunk panel sort).  The hot genes are chosen from the first chunk (a sample of the cells).
+static int upload_pipelined(sb_mat *mt, const u64 *h_indptr, const u32 *h_idx, const u32 *h_cnt, DevBuf<u32> &d_idx, DevBuf<u32> &d_cnt,
+                            u32 *d_max) {
+    sb_ctx *ctx = mt->ctx;
+    const u64 n = mt->n;
+    const u32 nch = 8;
+    u64 cells_per = ((n + nch - 1) / nch + mt->pc - 1) / mt->pc * mt->pc;
+    std::vector<u64> cb;
+    for (u64 c = 0; c < n; c += cells_per) cb.push_back(c);
+    cb.push_back(n);
+    const size_t chunks = cb.size() - 1;
+    if (!ctx->copy_stream) SB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    std::vector<cudaEvent_t> ev(chunks);
+    cudaEvent_t ready;
+    SB_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    SB_CUDA(cudaEventRecord(ready, ctx->stream));  // the staging buffers exist (stream-ordered allocation)
+    SB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ready, 0));
+    prof_begin(ctx, PH_UPLOAD);
+    for (size_t i = 0; i < chunks; i++) {
+        const u64 e0 = h_indptr[cb[i]], e1 = h_indptr[cb[i + 1]];
+        if (e1 > e0) {
+            SB_CUDA(cudaMemcpyAsync(d_idx.p + e0, h_idx + e0, (e1 - e0) * sizeof(u32), cudaMemcpyHostToDevice, ctx->copy_stream));
+            SB_CUDA(cudaMemcpyAsync(d_cnt.p + e0, h_cnt + e0, (e1 - e0) * sizeof(u32), cudaMemcpyHostToDevice, ctx->copy_stream));
+        }
+        SB_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+        SB_CUDA(cudaEventRecord(ev[i], ctx->copy_stream));
+    }
+    std::vector<DevBuf<u64>> ptrs(chunks);
+    std::vector<DevBuf<uint2>> colds(chunks), gms(chunks);
+    std::vector<u64> cold_n(chunks, 0);
+    int rc = SB_OK;
+    for (size_t i = 0; i < chunks && rc == SB_OK; i++) {
+        const u64 c0 = cb[i], c1 = cb[i + 1], e0 = h_indptr[c0], e1 = h_indptr[c1];
+        cudaStreamWaitEvent(ctx->stream, ev[i], 0);
+        if (e1 > e0) {
+            k_max_u32<<<grid_for(e1 - e0, 256, ctx), 256, 0, ctx->stream>>>(d_idx.p + e0, e1 - e0, d_max);
+            k_interleave<<<grid_for(e1 - e0, 256, ctx, 16), 256, 0, ctx->stream>>>(d_idx.p + e0, d_cnt.p + e0, mt->cm.p + e0, e1 - e0);
+            count_launch(ctx); count_launch(ctx);
+        }
+        if (i == 0) rc = select_hot_genes(mt, c0, c1);
+        if (rc == SB_OK && mt->gd > 0) {
+            rc = split_range(mt, c0, c1, ptrs[i], colds[i], &cold_n[i]);
+            if (rc == SB_OK) rc = gene_major_range(mt, c1 - c0, ptrs[i].p, colds[i].p, cold_n[i], gms[i]);
+        }
+    }
+    cudaStreamSynchronize(ctx->copy_stream);
+    prof_end(ctx, PH_UPLOAD);  // spans the overlapped copies and builds
+    for (auto e : ev) cudaEventDestroy(e);
+    cudaEventDestroy(ready);
+    SB_TRY(rc);
+    if (mt->gd == 0) return SB_OK;
+    // concatenate the per-chunk cold layouts
+    mt->cold_nnz = 0;
+    for (u64 x : cold_n) mt->cold_nnz += x;
+    SB_TRY(mt->cold_cm_ptr.alloc(n + 1));
+    SB_TRY(mt->cold_cm.alloc(mt->cold_nnz));
+    SB_TRY(mt->cold_gm.alloc(mt->cold_nnz));
+    u64 base = 0;
+    for (size_t i = 0; i < chunks; i++) {
+        const u64 nc = cb[i + 1] - cb[i];
+        k_add_offset<<<cdiv(nc + 1, 256), 256, 0, ctx->stream>>>(ptrs[i].p, nc + 1, base, mt->cold_cm_ptr.p + cb[i]);
+        count_launch(ctx);
+        if (cold_n[i]) {
+            SB_CUDA(cudaMemcpyAsync(mt->cold_cm.p + base, colds[i].p, cold_n[i] * sizeof(uint2), cudaMemcpyDeviceToDevice, ctx->stream));
+            SB_CUDA(cudaMemcpyAsync(mt->cold_gm.p + base, gms[i].p, cold_n[i] * sizeof(uint2), cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        base += cold_n[i];
+    }
+    SB_TRY(panel_base(mt, mt->cold_cm_ptr.p, mt->cold_gm_base));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
     return SB_OK;
 }
 
@@ -414,6 +539,28 @@ extern "C" int sb_upload(sb_ctx *ctx, int major, uint32_t m, uint64_t n_local, c
     SB_TRY(d_ptr.alloc(nvec + 1));
     SB_TRY(d_idx.alloc(nnz));
     SB_TRY(d_cnt.alloc(nnz));
+    // large cell-major uploads take the pipelined path (copies overlapped with the layout build)
+    const bool pipelined = major == SB_CELL_MAJOR && nnz >= ((u64)1 << 22) && n_local >= 8 * (u64)SB_MAX_PANEL_CELLS && !TraceScope::on();
+    if (pipelined) {
+        SB_CUDA(cudaMemcpyAsync(d_ptr.p, indptr, (nvec + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+        void *scr0;
+        SB_TRY(ctx_scratch(ctx, 256, &scr0));
+        SB_CUDA(cudaMemsetAsync(scr0, 0, 256, ctx->stream));
+        k_check_ptr<<<cdiv(nvec, 256), 256, 0, ctx->stream>>>(d_ptr.p, nvec, (int *)scr0);
+        count_launch(ctx);
+        mt->cm_ptr.swap(d_ptr);
+        SB_TRY(mt->cm.alloc(nnz));
+        SB_TRY(set_global_shape(mt.get()));
+        SB_TRY(upload_pipelined(mt.get(), indptr, idx, cnt, d_idx, d_cnt, (u32 *)scr0 + 1));
+        int hchk[2] = {0, 0};
+        SB_CUDA(cudaMemcpyAsync(hchk, scr0, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        SB_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (hchk[0]) return sb_fail(SB_ERR_INVALID_ARG, "sb_upload: indptr is not monotone from 0");
+        if ((u64)(u32)hchk[1] >= (u64)m) return sb_fail(SB_ERR_INVALID_ARG, "sb_upload: index %u out of range %u", (u32)hchk[1], m);
+        if (mt->gd == 0) SB_TRY(mat_ensure_full_gm(mt.get()));
+        *out = mt.release();
+        return SB_OK;
+    }
     TraceScope *tr_up = new TraceScope(ctx, "upload: H2D");
     prof_begin(ctx, PH_UPLOAD);
     SB_CUDA(cudaMemcpyAsync(d_ptr.p, indptr, (nvec + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));

@@ -46,6 +46,18 @@ struct Xoshiro256pp {
     }
 };
 
+// the start block is a pure function of (seed, rows, cols): keep the last one (BkSvd always asks for seed 0)
+static const double *omega_cached(sb_ctx *ctx, u64 seed, u64 rows, u64 cols) {
+    if (ctx->omega_seed != seed || ctx->omega_rows != rows || ctx->omega_cols != cols || ctx->omega_cache.size() != rows * cols) {
+        ctx->omega_cache.resize(rows * cols);
+        sb_omega(seed, rows, cols, ctx->omega_cache.data());
+        ctx->omega_seed = seed;
+        ctx->omega_rows = rows;
+        ctx->omega_cols = cols;
+    }
+    return ctx->omega_cache.data();
+}
+
 extern "C" int sb_omega(uint64_t seed, uint64_t rows, uint64_t cols, double *out) {
     if (!out && rows * cols) return sb_fail(SB_ERR_INVALID_ARG, "sb_omega: out is NULL");
     Xoshiro256pp rng(seed);
@@ -211,9 +223,7 @@ extern "C" int sb_bksvd(sb_nmat *a, uint32_t k, uint32_t b, uint32_t n_iter, uin
         const bool fast = !ctx->direct_projection && (b % 2 == 0) && (u64)bq <= n;
         SB_TRY(B.init(ctx, n, b));
         if (!omega) {
-            h_om.resize((size_t)n * b);
-            SB_TRY(sb_omega(seed, n, b, h_om.data()));  // :90 (n x b, row-major fill)
-            omega = h_om.data();
+            omega = omega_cached(ctx, seed, n, b);  // :90 (n x b, row-major fill)
         }
         SB_TRY(upload_tall(ctx, B, omega, false));
         SB_TRY(Kc.init(ctx, n, bq));
@@ -259,25 +269,34 @@ extern "C" int sb_bksvd(sb_nmat *a, uint32_t k, uint32_t b, uint32_t n_iter, uin
     }
 
     // ---- n > m (bk_svd.rs:116-145): block on the gene side, replicated over ranks
+    TraceScope tr_all(ctx, "bksvd: total (n > m)");
     Tall Y, Kt, T, P, TK;
     const u32 bq = b * n_iter;
     const bool fast = !ctx->direct_projection && (b % 2 == 0) && bq <= m;
-    SB_TRY(Y.init(ctx, m, b));
-    if (!omega) {
-        h_om.resize((size_t)b * m);
-        SB_TRY(sb_omega(seed, b, m, h_om.data()));  // :118 (b x m, row-major fill)
-        omega = h_om.data();
+    {
+        TraceScope t0(ctx, "bksvd: omega + buffers");
+        SB_TRY(Y.init(ctx, m, b));
+        if (!omega) {
+            omega = omega_cached(ctx, seed, b, m);  // :118 (b x m, row-major fill)
+        }
+        SB_TRY(upload_tall(ctx, Y, omega, true));  // Y[g, j] = B[j, g]
+        SB_TRY(Kt.init(ctx, m, bq));
+        SB_TRY(T.init(ctx, n, b));
+        SB_TRY(P.init(ctx, m, b, 1));
+        if (fast) SB_TRY(TK.init(ctx, n, bq));  // column block i-1 keeps A^T . Y_i (Y_i = block i of K^T)
     }
-    SB_TRY(upload_tall(ctx, Y, omega, true));  // Y[g, j] = B[j, g]
-    SB_TRY(Kt.init(ctx, m, bq));
-    SB_TRY(T.init(ctx, n, b));
-    SB_TRY(P.init(ctx, m, b, 1));
-    if (fast) SB_TRY(TK.init(ctx, n, bq));  // column block i-1 keeps A^T . Y_i (Y_i = block i of K^T)
     for (u32 i = 0; i < n_iter; i++) {
         double *Tp = (fast && i > 0) ? TK.buf.p + (size_t)(i - 1) * b : T.buf.p;
         u32 Tld = (fast && i > 0) ? TK.ld : T.ld;
-        SB_TRY(spmm_t(a, Y.buf.p, Y.ld, b, Tp, Tld, uy.p));                  // T = B.dot(A)^T        :122
-        SB_TRY(spmm_n(a, Tp, Tld, b, P.buf.p, P.ld));                        // A.dot(&T)             :123
+        {
+            TraceScope t1(ctx, "bksvd: spmm_t");
+            SB_TRY(spmm_t(a, Y.buf.p, Y.ld, b, Tp, Tld, uy.p));              // T = B.dot(A)^T        :122
+        }
+        {
+            TraceScope t1(ctx, "bksvd: spmm_n");
+            SB_TRY(spmm_n(a, Tp, Tld, b, P.buf.p, P.ld));                    // A.dot(&T)             :123
+        }
+        TraceScope t2(ctx, "bksvd: qr + copies + progress");
         u32 wq = 0;
         SB_TRY(qr_tall(ctx, P.buf.p, m, b, P.ld, &wq));                      // .qr()?.0
         SB_TRY(copy_block(ctx, Y.buf.p, Y.ld, 0, P.buf.p, P.ld, m, b));
@@ -306,6 +325,7 @@ extern "C" int sb_bksvd(sb_nmat *a, uint32_t k, uint32_t b, uint32_t n_iter, uin
     if (k > wq) return sb_fail(SB_ERR_INVALID_K, "invalid k");
     Tall Vo, Uo;
     Kt.w = wq;
+    TraceScope t9(ctx, "bksvd: gram + eigh + outputs");
     SB_TRY(finish_svd(ctx, Tt, Kt, wq, k, true, S, Vo, Uo));                 // :134-142
     SB_TRY(download_tall(ctx, Uo, U));
     SB_TRY(download_tall(ctx, Vo, V));

@@ -11,9 +11,21 @@ from .snoop import NoOpSnoop
 from .sqz import LowRankOffset
 
 
-def _outputs(m, n, k):
-    """U, S, V result buffers in page-locked memory (the V block is n x k: pageable copies are several times slower)."""
+def pinned_outputs(m: int, n: int, k: int):
+    """(U, S, V) result buffers in page-locked memory, to be passed as `out=` and reused across calls: the V block is
+    n x k and a pageable device-to-host copy of it is several times slower (page-locking itself costs ~1 ms/MB, so
+    allocate once)."""
     return L.pinned_empty((m, k), np.float64), L.pinned_empty((k,), np.float64), L.pinned_empty((n, k), np.float64)
+
+
+def _outputs(m, n, k, out=None):
+    if out is None:
+        return np.zeros((m, k)), np.zeros(k), np.zeros((n, k))
+    U, S, V = out
+    for a, shape in ((U, (m, k)), (S, (k,)), (V, (n, k))):
+        if a.shape != shape or a.dtype != np.float64 or not a.flags["C_CONTIGUOUS"]:
+            raise ValueError(f"out buffer must be C-contiguous float64 of shape {shape}")
+    return U, S, V
 
 
 def omega(seed: int, rows: int, cols: int) -> np.ndarray:
@@ -33,10 +45,10 @@ def _make_cb(snoop):
     return L.PROGRESS_CB(_cb)
 
 
-def svd_bk(A: LowRankOffset, k: int, b: int, n_iter: int, seed: int = 0, snoop=None, omega_block: Optional[np.ndarray] = None):
+def svd_bk(A: LowRankOffset, k: int, b: int, n_iter: int, seed: int = 0, snoop=None, omega_block: Optional[np.ndarray] = None, out=None):
     """bk_svd.rs:57-146 -> (U m x k, sigma k, Va k x n_local)."""
     m, n = A.shape()
-    U, S, V = _outputs(m, n, k)
+    U, S, V = _outputs(m, n, k, out)
     cb = _make_cb(snoop or NoOpSnoop())
     om = None if omega_block is None else np.ascontiguousarray(omega_block, dtype=np.float64)
     L.check(L.lib().sb_bksvd(A._h, C.c_uint32(k), C.c_uint32(b), C.c_uint32(n_iter), C.c_uint64(seed), L.vp(om), cb, None,
@@ -44,10 +56,10 @@ def svd_bk(A: LowRankOffset, k: int, b: int, n_iter: int, seed: int = 0, snoop=N
     return U, S, V.T
 
 
-def svd_rand(A: LowRankOffset, k: int, l: int, n_iter: int, seed: int = 0, omega_block: Optional[np.ndarray] = None):
+def svd_rand(A: LowRankOffset, k: int, l: int, n_iter: int, seed: int = 0, omega_block: Optional[np.ndarray] = None, out=None):
     """rand_svd.rs:54-129 -> (U, sigma, Va k x n)."""
     m, n = A.shape()
-    U, S, V = _outputs(m, n, k)
+    U, S, V = _outputs(m, n, k, out)
     om = None if omega_block is None else np.ascontiguousarray(omega_block, dtype=np.float64)
     L.check(L.lib().sb_randsvd(A._h, C.c_uint32(k), C.c_uint32(l), C.c_uint32(n_iter), C.c_uint64(seed), L.vp(om),
                                L.vp(U), L.vp(S), L.vp(V)))
@@ -60,17 +72,17 @@ class BkSvd:
     def __init__(self, k_multiplier: float = 2.0, n_iter: int = 5):
         self.k_multiplier, self.n_iter = k_multiplier, n_iter
 
-    def run_pca_cancellable(self, array: LowRankOffset, k: int, snoop):
+    def run_pca_cancellable(self, array: LowRankOffset, k: int, snoop, out=None):
         """-> (u m x k, s k, v n x k): PcaResult with `vt.reversed_axes()` (bk_svd.rs:48-52)."""
         m, n = array.shape()
-        U, S, V = _outputs(m, n, k)
+        U, S, V = _outputs(m, n, k, out)
         cb = _make_cb(snoop)
         L.check(L.lib().sb_bksvd_run_pca(array._h, C.c_uint32(k), C.c_double(self.k_multiplier), C.c_uint32(self.n_iter), cb, None,
                                          L.vp(U), L.vp(S), L.vp(V)))
         return U, S, V
 
-    def run_pca(self, array: LowRankOffset, k: int):  # dim_red/mod.rs:108-110
-        return self.run_pca_cancellable(array, k, NoOpSnoop())
+    def run_pca(self, array: LowRankOffset, k: int, out=None):  # dim_red/mod.rs:108-110
+        return self.run_pca_cancellable(array, k, NoOpSnoop(), out)
 
 
 class RandSvd:
@@ -79,12 +91,12 @@ class RandSvd:
     def __init__(self, l_multiplier: float = 10.0, n_iter: int = 2):
         self.l_multiplier, self.n_iter = l_multiplier, n_iter
 
-    def run_pca_cancellable(self, array: LowRankOffset, k: int, _snoop=None):
+    def run_pca_cancellable(self, array: LowRankOffset, k: int, _snoop=None, out=None):
         m, n = array.shape()
-        U, S, V = _outputs(m, n, k)
+        U, S, V = _outputs(m, n, k, out)
         L.check(L.lib().sb_randsvd_run_pca(array._h, C.c_uint32(k), C.c_double(self.l_multiplier), C.c_uint32(self.n_iter),
                                            L.vp(U), L.vp(S), L.vp(V)))
         return U, S, V
 
-    def run_pca(self, array: LowRankOffset, k: int):
-        return self.run_pca_cancellable(array, k)
+    def run_pca(self, array: LowRankOffset, k: int, out=None):
+        return self.run_pca_cancellable(array, k, None, out)
