@@ -268,15 +268,21 @@ def main():
         achieved = d_bytes / (d_ms * 1e-3) / 1e9 if d_ms > 0 else 0.0
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(dom)
-        roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+        if os.path.exists(tpath):  # ncu DRAM bytes per pass, measured at 400k cells, scaled by nnz to this shard
+            tj = json.load(open(tpath))
+            if tj.get(dom):
+                traffic = float(tj[dom]) * nnz_local / float(tj["nnz_measured"])
+        names = {"spmm_t": "spmm_t = k_spmm_t (sparse gather over the cold entries) + k_dense_t (FP64 mma.sync over the dense hot-gene panel)",
+                 "spmm_n": "spmm_n = k_spmm_n (sparse panel gather over the cold entries) + k_dense_n (FP64 mma.sync over the dense hot-gene panel)"}
+        roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                     "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                     "launches": int(d_launch), "avg_launch_ms": d_ms / max(1, d_launch),
                     "algorithmic_bytes_per_launch": d_bytes / max(1, d_launch),
                     "fp64_tflops": d_flops / (d_ms * 1e-3) / 1e12 if d_ms > 0 else 0.0,
                     "phase_ms_per_step": {k: prof[k] / args.steps for k in ("spmm_t_ms", "spmm_n_ms", "moments_ms", "reduce_ms", "dense_ms", "comm_ms", "output_ms")},
-                    "other": {"kernel": "k_spmm_n" if dom == "spmm_t" else "k_spmm_t",
+                    "note": "achieved = algorithmic bytes of the u32/u32 sparse form (SURVEY 8d) / event-timed duration of the pass; f64 width-20 "
+                            "SpMM is bound by on-chip operand bandwidth and the FP64 pipe, not HBM (DESIGN.md 3)",
+                    "other": {"kernel": "spmm_n" if dom == "spmm_t" else "spmm_t",
                               "achieved": ((prof["spmm_n_bytes"] / (kn * 1e-3) / 1e9) if dom == "spmm_t" and kn > 0 else
                                            (prof["spmm_t_bytes"] / (kt * 1e-3) / 1e9) if kt > 0 else 0.0)}}
         line = {"metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
