@@ -176,6 +176,7 @@ struct sb_mat {
 // device view of the per-nonzero map (sqz/src/matrix_map.rs): see MapDev in map.cuh
 struct sb_nmat {
     sb_mat *mat = nullptr;
+    sb_ctx *ctx = nullptr;  // kept separately: freeing must not touch `mat` (a caller may free the matrix first)
     int kind = 1;      // 1 log chain, 2 binomial deviance, 3 binomial Pearson
     int log_base = 0;  // 0 none, 1 ln, 2 log2, 10 log10
     DevBuf<double> col_scale;  // [n] (kind 1) or binomial n[c]

@@ -126,6 +126,7 @@ extern "C" int sb_log_normalize(sb_mat *mat, int has_target, double target, int 
     *out = nullptr;
     std::unique_ptr<sb_nmat> a(new sb_nmat());
     a->mat = mat;
+    a->ctx = mat->ctx;
     a->kind = 1;
     a->log_base = log_base;
     // normalization.rs:148-168
@@ -197,6 +198,7 @@ static int normalize_binomial(sb_mat *mat, int deviance, sb_nmat **out) {
     sb_ctx *ctx = mat->ctx;
     std::unique_ptr<sb_nmat> a(new sb_nmat());
     a->mat = mat;
+    a->ctx = mat->ctx;
     a->kind = deviance ? 2 : 3;
     a->log_base = 0;
     SB_TRY(mat_cell_totals_dev(mat));
@@ -272,9 +274,9 @@ extern "C" int sb_normalize_fixed_point(sb_mat *mat, int log_base, uint32_t base
 
 extern "C" void sb_free_nmat(sb_nmat *a) {
     if (!a) return;
-    cudaSetDevice(a->mat->ctx->device);
-    sb_set_alloc_stream(a->mat->ctx->stream);
-    cudaStreamSynchronize(a->mat->ctx->stream);
+    cudaSetDevice(a->ctx->device);
+    sb_set_alloc_stream(a->ctx->stream);
+    cudaStreamSynchronize(a->ctx->stream);
     delete a;
 }
 

@@ -85,6 +85,7 @@ class AdaptiveMat:
 
     def __init__(self, ctx: Context, handle):
         self.ctx, self._h = ctx, handle
+        self._views = weakref.WeakSet()  # LowRankOffsets borrowing this matrix: freed before it
         ctx._mats.add(self)
 
     # ---- constructors
@@ -244,6 +245,8 @@ class AdaptiveMat:
 
     def free(self):
         if self._h:
+            for a in list(self._views):
+                a.free()
             L.lib().sb_free_mat(self._h)
             self._h = C.c_void_p()
 
@@ -260,6 +263,7 @@ class LowRankOffset:
     def __init__(self, mat: AdaptiveMat, handle):
         self.mat, self._h = mat, handle
         mat.ctx._nmats.add(self)
+        mat._views.add(self)
 
     def rows(self) -> int:
         return self.mat.rows()
