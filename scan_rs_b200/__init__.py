@@ -5,6 +5,7 @@ The package mirrors the reference's module layout for this path only:
   normalization  Normalization, normalize, normalize_with_size_factor, ...
   dim_red        BkSvd, RandSvd, svd_bk, svd_rand
   snoop          NoOpSnoop, AtomicSnoop
+  mtx            load_mtx (gz MatrixMarket -> device matrix)
   synth          synthetic workloads (test / bench utility)
 All compute runs in scan_rs_b200/libscanb200.so (hand-written sm_100a CUDA + cuSOLVER/cuBLAS for the
 small dense steps); there is no CPU fallback."""
@@ -15,3 +16,4 @@ from .normalization import (LogBase, Normalization, binom_deviance_resid, binom_
                             normalize, normalize_with_size_factor)
 from .dim_red import BkSvd, RandSvd, omega, pinned_outputs, svd_bk, svd_rand  # noqa: F401
 from .snoop import AtomicSnoop, NoOpSnoop  # noqa: F401
+from .mtx import load_mtx  # noqa: F401

@@ -459,3 +459,20 @@ def test_cpp_host_layer():
         g.build()
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "ALL PASSED" in out.stdout, out.stdout + out.stderr
+
+
+def test_load_mtx(ctx, tmp_path):
+    """scan_rs::mtx::load_mtx mirror: gz MatrixMarket -> device matrix == the matrix it was written from."""
+    import gzip
+    from scan_rs_b200.mtx import load_mtx
+    cfg, cm, dm, _ = synth_pair(ctx, 300, 400, seed=39)
+    path = tmp_path / "m.mtx.gz"
+    with gzip.open(path, "wt") as f:
+        f.write("%%MatrixMarket matrix coordinate integer general\n%\n")
+        f.write(f"{cm.rows} {cm.cols} {cm.nnz}\n")
+        for r in range(cm.rows):
+            for kk in range(int(cm.indptr[r]), int(cm.indptr[r + 1])):
+                f.write(f"{r + 1} {int(cm.idx[kk]) + 1} {int(cm.val[kk])}\n")
+    lm = load_mtx(ctx, str(path))
+    for a, b in zip(lm.to_csr(), dm.to_csr()):
+        np.testing.assert_array_equal(a, b)
