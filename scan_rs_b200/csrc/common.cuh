@@ -110,6 +110,12 @@ struct sb_ctx {
     size_t l2_bytes = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // host -> device copies of the pipelined upload
+    cudaStream_t aux_stream = nullptr;   // the dense panel kernels when overlapped with the sparse kernels
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // Experimental (default off, measured slower -- DESIGN.md 3): run the sparse and the DMMA panel kernel of a product on two
+    // streams with CTAs of both resident on every SM.
+    bool overlap = false;    // A.X
+    bool overlap_t = false;  // A^T.Y
     cublasHandle_t cublas = nullptr;
     cusolverDnHandle_t cusolver = nullptr;
     ncclComm_t comm = nullptr;

@@ -67,6 +67,9 @@ extern "C" int sb_init(int device, sb_ctx **out) {
     SB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
     SB_CUSOLVER(cusolverDnCreate(&ctx->cusolver));
     SB_CUSOLVER(cusolverDnSetStream(ctx->cusolver, ctx->stream));
+    SB_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    SB_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    SB_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     SB_CUDA(cudaEventCreate(&ctx->t0));
     SB_CUDA(cudaEventCreate(&ctx->t1));
     SB_CUDA(cudaMallocHost(&ctx->pinned, 4096));
@@ -96,6 +99,12 @@ extern "C" void sb_shutdown(sb_ctx *ctx) {
         if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
     }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->aux_stream) {
+        cudaStreamSynchronize(ctx->aux_stream);
+        cudaStreamDestroy(ctx->aux_stream);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -114,6 +123,14 @@ extern "C" int sb_set_option(sb_ctx *ctx, const char *name, double value) {
     if (!ctx || !name) return sb_fail(SB_ERR_INVALID_ARG, "sb_set_option: NULL argument");
     if (!strcmp(name, "direct_projection")) {
         ctx->direct_projection = value != 0.0;
+        return SB_OK;
+    }
+    if (!strcmp(name, "overlap")) {  // A.X: run the sparse and the dense-panel kernel concurrently
+        ctx->overlap = value != 0.0;
+        return SB_OK;
+    }
+    if (!strcmp(name, "overlap_t")) {  // same for A^T.Y
+        ctx->overlap_t = value != 0.0;
         return SB_OK;
     }
     if (!strcmp(name, "dense_genes")) {  // applies to matrices uploaded afterwards

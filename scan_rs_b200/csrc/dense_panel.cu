@@ -24,15 +24,14 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
 }
 
 // ---------------------------------------------------------------- dense_t
-#define DT_THREADS 512
-#define DT_MC 4                          // m-tiles (8 cells) per warp
-#define DT_CELLS (DT_THREADS / 32 * 8 * DT_MC)  // 512 cells per CTA tile
+#define DT_MC 4  // m-tiles (8 cells) per warp: a CTA of T threads works on tiles of T cells
 
-template <int NT>
-__global__ void __launch_bounds__(DT_THREADS, 1)
+template <int NT, int DT_THREADS>
+__global__ void __launch_bounds__(DT_THREADS, 512 / DT_THREADS)  // <= 128 registers in both configurations
 k_dense_t(const unsigned char *__restrict__ D, u32 gd, u64 n, const double *__restrict__ cs, int log_base, const u32 *__restrict__ hot_idx,
           const double *__restrict__ row_scale, const double *__restrict__ Y, u32 ldy, u32 col0, u32 w, u32 gchunk, double *__restrict__ out,
-          u32 ldo) {
+          u32 ldo, int atomic_out) {
+    constexpr int DT_CELLS = DT_THREADS / 32 * 8 * DT_MC;
     constexpr int YS = NT * 8 + 1;  // row stride of the staged Y chunk (== 1 mod 4: conflict-free B fragments)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *Ys = reinterpret_cast<double *>(smem_raw);            // gchunk x YS
@@ -107,7 +106,10 @@ k_dense_t(const unsigned char *__restrict__ D, u32 gd, u64 n, const double *__re
             for (int nt = 0; nt < NT; nt++) {
                 const u32 col = col0 + nt * 8 + 2 * k;
                 double *o = out + cell * (size_t)ldo + col;
-                if (col + 1 < w) {
+                if (atomic_out) {  // overlapped with the sparse kernel: both add into the zeroed block
+                    if (col < w) atomicAdd(o, c[mt][nt][0]);
+                    if (col + 1 < w) atomicAdd(o + 1, c[mt][nt][1]);
+                } else if (col + 1 < w) {
                     double2 cur = *reinterpret_cast<double2 *>(o);
                     cur.x += c[mt][nt][0];
                     cur.y += c[mt][nt][1];
@@ -121,15 +123,14 @@ k_dense_t(const unsigned char *__restrict__ D, u32 gd, u64 n, const double *__re
 }
 
 // ---------------------------------------------------------------- dense_n
-#define DN_THREADS 512
-#define DN_MG 4                                   // m-tiles (8 genes) per warp
-#define DN_GENES (DN_THREADS / 32 * 8 * DN_MG)    // 512 genes per CTA
-#define DN_GROUP 32                               // cells staged per synchronisation (8 k-steps)
+#define DN_MG 4  // m-tiles (8 genes) per warp: a CTA of T threads covers T panel columns and stages T/16 cells per sync
 
-template <int NT>
-__global__ void __launch_bounds__(DN_THREADS, 1)
+template <int NT, int DN_THREADS>
+__global__ void __launch_bounds__(DN_THREADS, 512 / DN_THREADS)  // <= 128 registers in both configurations
 k_dense_n(const unsigned char *__restrict__ D, u32 gd, u64 n, const double *__restrict__ cs, int log_base, const u32 *__restrict__ hot_idx,
           const double *__restrict__ X, u32 ldx, u32 col0, u32 w, double *__restrict__ P, u32 ldp) {
+    constexpr int DN_GENES = DN_THREADS / 32 * 8 * DN_MG;
+    constexpr int DN_GROUP = DN_THREADS / SB_DENSE_LUT;  // one table entry per thread per staged group
     constexpr int XS = NT * 8 + 4;  // row stride of the staged X rows (== 4 mod 16: conflict-free B fragments)
     __shared__ __align__(16) double Xs[2][DN_GROUP][XS];
     __shared__ __align__(16) double lut[2][DN_GROUP][LUT_STRIDE];
@@ -251,29 +252,37 @@ k_dense_moments(const unsigned char *__restrict__ D, u32 gd, u64 n, const double
 // columns are processed in passes of at most 24 (three n-tiles); w = 20 is one pass with 4 padded columns
 static inline u32 pass_width(u32 remaining) { return remaining >= 24 ? 24u : remaining; }
 
-int dense_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo) {
+// `overlap`: half-size CTAs (256 threads, 32 K registers, < 190 KB shared) so that two CTAs of the sparse kernel stay
+// resident beside each of them, atomic epilogue, launched on `stream` (the auxiliary stream)
+int dense_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo, cudaStream_t stream, bool overlap) {
     sb_mat *mt = a->mat;
     sb_ctx *ctx = mt->ctx;
     if (mt->gd == 0 || mt->n == 0 || w == 0) return SB_OK;
-    const size_t lut_bytes = (size_t)DT_CELLS * LUT_STRIDE * sizeof(double);
-    u64 ntiles = (mt->n + DT_CELLS - 1) / DT_CELLS;
+    const int threads = overlap ? 256 : 512;
+    const size_t lut_bytes = (size_t)threads * LUT_STRIDE * sizeof(double);
+    u64 ntiles = (mt->n + threads - 1) / threads;
     int blocks = (int)std::min<u64>(ntiles, (u64)ctx->sm_count);
     const double *rs = a->has_row_scale ? a->row_scale.p : nullptr;
     for (u32 col0 = 0; col0 < w;) {
         const u32 pw = pass_width(w - col0);
         const int nt = (int)((pw + 7) / 8);
         const u32 ys = nt * 8 + 1;
-        u32 gchunk = (u32)((size_t)(220 * 1024 - lut_bytes) / (ys * sizeof(double)));
+        const size_t budget = overlap ? 184 * 1024 : 220 * 1024;
+        u32 gchunk = (u32)((budget - lut_bytes) / (ys * sizeof(double)));
         gchunk &= ~15u;
         if (gchunk > mt->gd) gchunk = mt->gd;
         const size_t smem = (size_t)gchunk * ys * sizeof(double) + lut_bytes;
         cudaError_t e = cudaSuccess;
-#define LAUNCH_DT(NTV)                                                                                                                         \
-    e = cudaFuncSetAttribute(k_dense_t<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                          \
+#define LAUNCH_DT(NTV, THR)                                                                                                                    \
+    e = cudaFuncSetAttribute(k_dense_t<NTV, THR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                     \
     if (e == cudaSuccess)                                                                                                                      \
-        k_dense_t<NTV><<<blocks, DT_THREADS, smem, ctx->stream>>>(mt->D.p, mt->gd, mt->n, a->col_scale.p, a->log_base, mt->hot_idx.p, rs, Y, ldy, col0, \
-                                                                   w, gchunk, out, ldo);
-        if (nt == 3) { LAUNCH_DT(3) } else if (nt == 2) { LAUNCH_DT(2) } else { LAUNCH_DT(1) }
+        k_dense_t<NTV, THR><<<blocks, THR, smem, stream>>>(mt->D.p, mt->gd, mt->n, a->col_scale.p, a->log_base, mt->hot_idx.p, rs, Y, ldy, col0, w,   \
+                                                            gchunk, out, ldo, overlap ? 1 : 0);
+        if (overlap) {
+            if (nt == 3) { LAUNCH_DT(3, 256) } else if (nt == 2) { LAUNCH_DT(2, 256) } else { LAUNCH_DT(1, 256) }
+        } else {
+            if (nt == 3) { LAUNCH_DT(3, 512) } else if (nt == 2) { LAUNCH_DT(2, 512) } else { LAUNCH_DT(1, 512) }
+        }
 #undef LAUNCH_DT
         if (e != cudaSuccess) return sb_fail(SB_ERR_CUDA, "dense_t: %s", cudaGetErrorString(e));
         count_launch(ctx);
@@ -283,24 +292,30 @@ int dense_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo) {
     return SB_OK;
 }
 
-int dense_n(sb_nmat *a, const double *X, u32 ldx, u32 w, double *P, u32 ldp) {
+// `overlap`: 256-thread CTAs (28 K registers, 12 KB shared) that fit beside a 512-thread CTA of the sparse kernel
+int dense_n(sb_nmat *a, const double *X, u32 ldx, u32 w, double *P, u32 ldp, cudaStream_t stream, bool overlap) {
     sb_mat *mt = a->mat;
     sb_ctx *ctx = mt->ctx;
     if (mt->gd == 0 || mt->n == 0 || w == 0) return SB_OK;
-    u32 gblocks = (mt->gd + DN_GENES - 1) / DN_GENES;
+    const u32 threads = overlap ? 256 : 512;
+    const u32 genes_per_cta = threads;  // threads / 32 warps x 32 genes
+    const u32 group = threads / SB_DENSE_LUT;
+    u32 gblocks = (mt->gd + genes_per_cta - 1) / genes_per_cta;
     u32 ranges = std::max<u32>(1, (u32)ctx->sm_count / gblocks);
-    u64 max_ranges = (mt->n + DN_GROUP - 1) / DN_GROUP;
+    u64 max_ranges = (mt->n + group - 1) / group;
     if (ranges > max_ranges) ranges = (u32)max_ranges;
     dim3 grid(gblocks, ranges);
     for (u32 col0 = 0; col0 < w;) {
         const u32 pw = pass_width(w - col0);
         const int nt = (int)((pw + 7) / 8);
-        if (nt == 3)
-            k_dense_n<3><<<grid, DN_THREADS, 0, ctx->stream>>>(mt->D.p, mt->gd, mt->n, a->col_scale.p, a->log_base, mt->hot_idx.p, X, ldx, col0, w, P, ldp);
-        else if (nt == 2)
-            k_dense_n<2><<<grid, DN_THREADS, 0, ctx->stream>>>(mt->D.p, mt->gd, mt->n, a->col_scale.p, a->log_base, mt->hot_idx.p, X, ldx, col0, w, P, ldp);
-        else
-            k_dense_n<1><<<grid, DN_THREADS, 0, ctx->stream>>>(mt->D.p, mt->gd, mt->n, a->col_scale.p, a->log_base, mt->hot_idx.p, X, ldx, col0, w, P, ldp);
+#define LAUNCH_DN(NTV, THR) \
+    k_dense_n<NTV, THR><<<grid, THR, 0, stream>>>(mt->D.p, mt->gd, mt->n, a->col_scale.p, a->log_base, mt->hot_idx.p, X, ldx, col0, w, P, ldp);
+        if (overlap) {
+            if (nt == 3) { LAUNCH_DN(3, 256) } else if (nt == 2) { LAUNCH_DN(2, 256) } else { LAUNCH_DN(1, 256) }
+        } else {
+            if (nt == 3) { LAUNCH_DN(3, 512) } else if (nt == 2) { LAUNCH_DN(2, 512) } else { LAUNCH_DN(1, 512) }
+        }
+#undef LAUNCH_DN
         count_launch(ctx);
         col0 += nt * 8;
     }
