@@ -3,7 +3,7 @@ usage: python profiles/ncu_extract.py raw.csv"""
 import csv, sys
 rows=list(csv.reader(open(sys.argv[1])))
 hdr=rows[0]; units=rows[1]
-want=['Kernel Name','gpu__time_duration.sum','dram__bytes_read.sum','dram__bytes_write.sum','dram__throughput.avg.pct_of_peak_sustained_elapsed','lts__t_bytes.sum','lts__t_sector_hit_rate.pct','l1tex__t_sector_hit_rate.pct','l1tex__data_pipe_lsu_wavefronts_mem_shared.sum','l1tex__data_pipe_lsu_wavefronts.sum','sm__throughput.avg.pct_of_peak_sustained_elapsed','sm__warps_active.avg.pct_of_peak_sustained_active','launch__registers_per_thread','smsp__inst_executed.sum','sm__inst_executed_pipe_fp64.sum','sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active','l1tex__throughput.avg.pct_of_peak_sustained_elapsed','lts__throughput.avg.pct_of_peak_sustained_elapsed','sm__cycles_elapsed.max','l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum','smsp__issue_active.avg.pct_of_peak_sustained_active','l1tex__t_bytes_pipe_lsu_mem_global_op_ld.sum','launch__grid_size','launch__block_size','sm__inst_executed_pipe_lsu.sum','smsp__inst_executed_op_shared_ld.sum','smsp__inst_executed_op_global_ld.sum','smsp__inst_executed_op_global_red.sum','lts__t_sectors_op_red.sum','lts__t_sectors_op_atom.sum']
+want=['Kernel Name','gpu__time_duration.sum','dram__bytes_read.sum','dram__bytes_write.sum','dram__throughput.avg.pct_of_peak_sustained_elapsed','lts__t_bytes.sum','lts__t_sector_hit_rate.pct','l1tex__t_sector_hit_rate.pct','l1tex__data_pipe_lsu_wavefronts_mem_shared.sum','l1tex__data_pipe_lsu_wavefronts.sum','sm__throughput.avg.pct_of_peak_sustained_elapsed','sm__warps_active.avg.pct_of_peak_sustained_active','launch__registers_per_thread','smsp__inst_executed.sum','sm__inst_executed_pipe_fp64.sum','sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active','l1tex__throughput.avg.pct_of_peak_sustained_elapsed','lts__throughput.avg.pct_of_peak_sustained_elapsed','sm__cycles_elapsed.max','sm__cycles_active.avg','sm__cycles_active.max','sm__cycles_active.min','l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum','smsp__issue_active.avg.pct_of_peak_sustained_active','l1tex__t_bytes_pipe_lsu_mem_global_op_ld.sum','launch__grid_size','launch__block_size','sm__inst_executed_pipe_lsu.sum','smsp__inst_executed_op_shared_ld.sum','smsp__inst_executed_op_global_ld.sum','smsp__inst_executed_op_global_red.sum','lts__t_sectors_op_red.sum','lts__t_sectors_op_atom.sum']
 idx={h:i for i,h in enumerate(hdr)}
 for r in rows[2:]:
     print('-----')

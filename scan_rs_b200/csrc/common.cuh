@@ -122,6 +122,7 @@ struct sb_ctx {
     int nranks = 1, rank = 0;
     int dense_cap = 2048;            // max genes in the dense hot panel (0 disables the hybrid layout)
     double dense_min_density = 0.12; // a gene joins the panel only if nnz/n_global is at least this
+    bool use_gather = true;          // panelled gather kernels (gather.cu); false: the first-generation K7 / K8 of spmm.cu
     bool direct_projection = false;  // true: always run the wide Q^T A pass (bk_svd.rs:102,131) instead of the R^-T identity
     // profiling
     bool profile_on = false;
@@ -141,6 +142,29 @@ struct sb_ctx {
 #define SB_GENE_BITS 22
 #define SB_GENE_MASK 0x3FFFFFu
 #define SB_MAX_PANEL_CELLS 1024
+#define GA_TBLOCK 16384  // cells per block of the T-side gather order (gather.cu)
+
+// A work unit of the panelled gather (gather.cu): entries [begin, end) of a stream, all of one panel.
+struct __align__(16) GUnit {
+    u64 begin, end;
+    u32 panel, pad0;
+    u64 pad1;
+};
+
+// One side of the panelled gather: the entry stream, its work units and (T side) the gene of every panel slot.
+struct GatherLayout {
+    bool ready = false;
+    u32 rows = 0;     // rows per panel: cells (N side) or gene slots (T side)
+    u32 npanels = 0;
+    u64 nnz = 0;
+    const uint2 *ent = nullptr;  // N side: aliases gm / cold_gm; T side: ent_own
+    DevBuf<uint2> ent_own;
+    DevBuf<GUnit> units;
+    u32 n_units = 0;
+    u32 grid = 0;
+    DevBuf<u32> cta_first;  // N side: [grid + 1] first unit of every CTA (contiguous, nnz-balanced)
+    DevBuf<u32> slot_gene;  // T side: [npanels * rows] gene of a slot or 0xFFFFFFFF
+};
 
 struct sb_mat {
     sb_ctx *ctx = nullptr;
@@ -172,6 +196,9 @@ struct sb_mat {
     DevBuf<uint2> cold_cm;
     DevBuf<uint2> cold_gm;
     DevBuf<u64> cold_gm_base;
+    // panelled gather layouts over the sparse set the products use (the cold entries when gd > 0, else all entries)
+    GatherLayout gn, gt;
+    DevBuf<u32> slot_of_gene;  // [m] T-side slot (rank by expression) of a gene
     // cached integer reductions
     DevBuf<u32> cell_tot;
     bool have_cell_tot = false;
@@ -186,6 +213,7 @@ struct sb_nmat {
     int kind = 1;      // 1 log chain, 2 binomial deviance, 3 binomial Pearson
     int log_base = 0;  // 0 none, 1 ln, 2 log2, 10 log10
     DevBuf<double> col_scale;  // [n] (kind 1) or binomial n[c]
+    DevBuf<double> l1c, inv_l1c;  // [n] kind 1: L_c(1) = log_b(col_scale[c] + 1) and its reciprocal (gather.cu)
     DevBuf<double> row_scale;  // [m] 1/sd (kind 1; may be empty) or binomial pi[r]
     bool has_row_scale = false;
     bool has_offset = false;

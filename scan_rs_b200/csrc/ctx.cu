@@ -133,6 +133,10 @@ extern "C" int sb_set_option(sb_ctx *ctx, const char *name, double value) {
         ctx->overlap_t = value != 0.0;
         return SB_OK;
     }
+    if (!strcmp(name, "gather")) {  // 1 (default): panelled gather kernels; 0: first-generation sparse kernels
+        ctx->use_gather = value != 0.0;
+        return SB_OK;
+    }
     if (!strcmp(name, "dense_genes")) {  // applies to matrices uploaded afterwards
         ctx->dense_cap = value < 0 ? 0 : (int)value;
         return SB_OK;

@@ -20,6 +20,8 @@ struct MapDev {
     int log_base;
     const double *col;  // kind 1: col_scale[c]; kinds 2/3: n[c]
     const double *row;  // kind 1: row_scale[r] or nullptr; kinds 2/3: pi[r]
+    const double *l1;      // kind 1: L_c(1) = log_b(col_scale[c] + 1) per cell (the value of a count of 1); else nullptr
+    const double *inv_l1;  // kind 1: 1 / L_c(1) (0 where that is not finite); else nullptr
 };
 
 struct __align__(16) LogEnt {

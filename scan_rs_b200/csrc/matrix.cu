@@ -14,6 +14,14 @@
 
 #include "common.cuh"
 
+// gather.cu
+int gather_build_n(sb_mat *mt, GatherLayout &L, const uint2 *gm, const u64 *gm_base_dev, u64 nnz);
+int gather_build_t(sb_mat *mt, const u64 *ptr, const uint2 *ent, u64 nnz);
+int gather_assign_slots(sb_mat *mt, const uint2 *ent, u64 nnz);
+int gather_build_t_range(sb_mat *mt, u64 c0, u64 nc, const u64 *ptr_local, const uint2 *ent, u64 nnz, DevBuf<uint2> &out, std::vector<u64> &seg_len,
+                         std::vector<u64> &seg_runs);
+int gather_finish_t(sb_mat *mt, const std::vector<u64> &seg_len, const std::vector<u64> &seg_runs);
+
 // ---------------------------------------------------------------- small kernels
 __global__ void k_interleave(const u32 *__restrict__ idx, const u32 *__restrict__ cnt, uint2 *__restrict__ out, u64 nnz) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -435,10 +443,22 @@ static int set_global_shape(sb_mat *mt) {
     return SB_OK;
 }
 
+// panelled gather layouts (gather.cu) over the sparse set the products use; whatever the upload pipeline has not built yet
+static int finish_gather(sb_mat *mt) {
+    TraceScope tr(mt->ctx, "build: gather layouts");
+    const bool cold = mt->gd > 0;
+    if (!mt->gn.ready)
+        SB_TRY(gather_build_n(mt, mt->gn, cold ? mt->cold_gm.p : mt->gm.p, cold ? mt->cold_gm_base.p : mt->gm_base.p, cold ? mt->cold_nnz : mt->nnz));
+    if (!mt->gt.ready)
+        SB_TRY(gather_build_t(mt, cold ? mt->cold_cm_ptr.p : mt->cm_ptr.p, cold ? mt->cold_cm.p : mt->cm.p, cold ? mt->cold_nnz : mt->nnz));
+    return SB_OK;
+}
+
 static int finish_matrix(sb_mat *mt) {
     SB_TRY(set_global_shape(mt));
     SB_TRY(build_hybrid(mt));
     if (mt->gd == 0) SB_TRY(mat_ensure_full_gm(mt));
+    SB_TRY(finish_gather(mt));
     return SB_OK;
 }
 
@@ -450,7 +470,8 @@ static int upload_pipelined(sb_mat *mt, const u64 *h_indptr, const u32 *h_idx, c
     sb_ctx *ctx = mt->ctx;
     const u64 n = mt->n;
     const u32 nch = 8;
-    u64 cells_per = ((n + nch - 1) / nch + mt->pc - 1) / mt->pc * mt->pc;
+    const u64 calign = std::max<u64>(mt->pc, GA_TBLOCK);  // whole cell panels and whole T-side cell blocks (pc divides GA_TBLOCK)
+    u64 cells_per = ((n + nch - 1) / nch + calign - 1) / calign * calign;
     std::vector<u64> cb;
     for (u64 c = 0; c < n; c += cells_per) cb.push_back(c);
     cb.push_back(n);
@@ -472,8 +493,10 @@ static int upload_pipelined(sb_mat *mt, const u64 *h_indptr, const u32 *h_idx, c
         SB_CUDA(cudaEventRecord(ev[i], ctx->copy_stream));
     }
     std::vector<DevBuf<u64>> ptrs(chunks);
-    std::vector<DevBuf<uint2>> colds(chunks), gms(chunks);
+    std::vector<DevBuf<uint2>> colds(chunks), gms(chunks), tps(chunks);
     std::vector<u64> cold_n(chunks, 0);
+    std::vector<u64> seg_all, seg, runs_all, runs;
+    const bool build_t = n <= SB_GENE_MASK;
     int rc = SB_OK;
     for (size_t i = 0; i < chunks && rc == SB_OK; i++) {
         const u64 c0 = cb[i], c1 = cb[i + 1], e0 = h_indptr[c0], e1 = h_indptr[c1];
@@ -487,6 +510,12 @@ static int upload_pipelined(sb_mat *mt, const u64 *h_indptr, const u32 *h_idx, c
         if (rc == SB_OK && mt->gd > 0) {
             rc = split_range(mt, c0, c1, ptrs[i], colds[i], &cold_n[i]);
             if (rc == SB_OK) rc = gene_major_range(mt, c1 - c0, ptrs[i].p, colds[i].p, cold_n[i], gms[i]);
+            if (rc == SB_OK && build_t) {
+                if (i == 0) rc = gather_assign_slots(mt, colds[0].p, cold_n[0]);
+                if (rc == SB_OK) rc = gather_build_t_range(mt, c0, c1 - c0, ptrs[i].p, colds[i].p, cold_n[i], tps[i], seg, runs);
+                seg_all.insert(seg_all.end(), seg.begin(), seg.end());
+                runs_all.insert(runs_all.end(), runs.begin(), runs.end());
+            }
         }
     }
     cudaStreamSynchronize(ctx->copy_stream);
@@ -501,6 +530,7 @@ static int upload_pipelined(sb_mat *mt, const u64 *h_indptr, const u32 *h_idx, c
     SB_TRY(mt->cold_cm_ptr.alloc(n + 1));
     SB_TRY(mt->cold_cm.alloc(mt->cold_nnz));
     SB_TRY(mt->cold_gm.alloc(mt->cold_nnz));
+    if (build_t) SB_TRY(mt->gt.ent_own.alloc(mt->cold_nnz));
     u64 base = 0;
     for (size_t i = 0; i < chunks; i++) {
         const u64 nc = cb[i + 1] - cb[i];
@@ -509,11 +539,14 @@ static int upload_pipelined(sb_mat *mt, const u64 *h_indptr, const u32 *h_idx, c
         if (cold_n[i]) {
             SB_CUDA(cudaMemcpyAsync(mt->cold_cm.p + base, colds[i].p, cold_n[i] * sizeof(uint2), cudaMemcpyDeviceToDevice, ctx->stream));
             SB_CUDA(cudaMemcpyAsync(mt->cold_gm.p + base, gms[i].p, cold_n[i] * sizeof(uint2), cudaMemcpyDeviceToDevice, ctx->stream));
+            if (build_t)
+                SB_CUDA(cudaMemcpyAsync(mt->gt.ent_own.p + base, tps[i].p, cold_n[i] * sizeof(uint2), cudaMemcpyDeviceToDevice, ctx->stream));
         }
         base += cold_n[i];
     }
     SB_TRY(panel_base(mt, mt->cold_cm_ptr.p, mt->cold_gm_base));
     SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (build_t) SB_TRY(gather_finish_t(mt, seg_all, runs_all));
     return SB_OK;
 }
 
@@ -558,6 +591,7 @@ extern "C" int sb_upload(sb_ctx *ctx, int major, uint32_t m, uint64_t n_local, c
         if (hchk[0]) return sb_fail(SB_ERR_INVALID_ARG, "sb_upload: indptr is not monotone from 0");
         if ((u64)(u32)hchk[1] >= (u64)m) return sb_fail(SB_ERR_INVALID_ARG, "sb_upload: index %u out of range %u", (u32)hchk[1], m);
         if (mt->gd == 0) SB_TRY(mat_ensure_full_gm(mt.get()));
+        SB_TRY(finish_gather(mt.get()));
         *out = mt.release();
         return SB_OK;
     }

@@ -21,6 +21,19 @@ __global__ void k_col_scale(const u32 *__restrict__ counts, u64 n, double target
     if (i < n) out[i] = target / (double)counts[i];
 }
 
+// L_c(1) = log_b(cs_c * 1 + 1), the map value of a count of 1, and its reciprocal: the panelled gather stages operand
+// rows pre-multiplied by it (N side) or applies it once per run (T side) instead of once per entry.  Same function of
+// the same inputs as the per-entry evaluation, so the bits agree.
+__global__ void k_l1_tables(const double *__restrict__ cs, u64 n, int log_base, double *__restrict__ l1, double *__restrict__ inv) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const double v = map_log_part(log_base, cs[i], 1u, sb_log_table);
+        l1[i] = v;
+        const double r = 1.0 / v;
+        inv[i] = (v != 0.0 && r == r && r - r == 0.0) ? r : 0.0;
+    }
+}
+
 __global__ void k_fill(double *p, u64 n, double v) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -147,7 +160,10 @@ extern "C" int sb_log_normalize(sb_mat *mat, int has_target, double target, int 
             counts = d_sf.p;
         }
         k_col_scale<<<cdiv(mat->n, 256), 256, 0, ctx->stream>>>(counts, mat->n, target, a->col_scale.p);
-        count_launch(ctx);
+        SB_TRY(a->l1c.alloc(mat->n));
+        SB_TRY(a->inv_l1c.alloc(mat->n));
+        k_l1_tables<<<cdiv(mat->n, 256), 256, 0, ctx->stream>>>(a->col_scale.p, mat->n, log_base, a->l1c.p, a->inv_l1c.p);
+        count_launch(ctx); count_launch(ctx);
         SB_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     if (center_scale) {

@@ -347,6 +347,8 @@ static MapDev make_map(const sb_nmat *a) {
     mp.log_base = a->log_base;
     mp.col = a->col_scale.p;
     mp.row = (a->kind == 1) ? (a->has_row_scale ? a->row_scale.p : nullptr) : a->row_scale.p;
+    mp.l1 = a->kind == 1 ? a->l1c.p : nullptr;
+    mp.inv_l1 = a->kind == 1 ? a->inv_l1c.p : nullptr;
     return mp;
 }
 
@@ -380,6 +382,15 @@ static void account(sb_ctx *ctx, const sb_mat *mt, u32 w, bool is_t) {
 int dense_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo, cudaStream_t stream, bool overlap);
 int dense_n(sb_nmat *a, const double *X, u32 ldx, u32 w, double *P, u32 ldp, cudaStream_t stream, bool overlap);
 int mat_ensure_full_gm(sb_mat *mt);
+// gather.cu
+int gather_run(sb_ctx *ctx, const GatherLayout &L, int mode, const MapDev &mp, u64 n_cells, const double *B, u32 ldb, u32 w, double *out, u32 ldo);
+int gather_t_init(sb_ctx *ctx, double *out, u64 n, u32 w, u32 ldo, const double *uy, const double *v);
+
+// the panelled gather layouts cover the cold entries of a hybrid matrix, or every entry of a matrix without a dense panel
+static bool gather_usable(const sb_nmat *a, const GatherLayout &L) {
+    const sb_mat *mt = a->mat;
+    return mt->ctx->use_gather && L.ready && ((a->kind == 1 && mt->gd > 0) || mt->gd == 0);
+}
 
 int spmm_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo, double *uy_scratch) {
     sb_mat *mt = a->mat;
@@ -395,6 +406,14 @@ int spmm_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo, do
     ProfScope ps(ctx, PH_SPMM_T);
     // hybrid layout: the sparse kernel sees the cold entries only, the dense panel kernel adds the rest
     const bool hybrid = a->kind == 1 && mt->gd > 0;
+    if (gather_usable(a, mt->gt)) {
+        // T = v (u^T Y)  ->  += dense panel (DMMA)  ->  += panelled gather of the sparse set (f64 reductions)
+        SB_TRY(gather_t_init(ctx, out, mt->n, w, ldo, uy, a->v_ones ? nullptr : a->v.p));
+        if (hybrid) SB_TRY(dense_t(a, Y, ldy, w, out, ldo, ctx->stream, false));
+        SB_TRY(gather_run(ctx, mt->gt, 1, mp, mt->n, Y, ldy, w, out, ldo));
+        account(ctx, mt, w, true);
+        return SB_OK;
+    }
     const u64 *cm_ptr = hybrid ? mt->cold_cm_ptr.p : mt->cm_ptr.p;
     const uint2 *cm = hybrid ? mt->cold_cm.p : mt->cm.p;
     const u32 tile_max = 64;
@@ -456,6 +475,12 @@ int spmm_n(sb_nmat *a, const double *X, u32 ldx, u32 w, double *P, u32 ldp) {
         // tile width: the X panel (pc x wt doubles) must fit in shared memory next to the staging buffers
         // Overlap: this kernel is bound by the shared-memory pipe, the panel kernel by the FP64 tensor pipe and it needs
         // little shared memory; with 512-thread CTAs here and 256-thread CTAs there both are resident on every SM.
+        if (gather_usable(a, mt->gn)) {
+            SB_TRY(gather_run(ctx, mt->gn, 0, mp, mt->n, X, ldx, w, P, ldp));
+            if (hybrid) SB_TRY(dense_n(a, X, ldx, w, P, ldp, ctx->stream, false));
+            account(ctx, mt, w, false);
+            SB_CUDA(cudaGetLastError());
+        } else {
         const bool overlap = hybrid && ctx->overlap && ctx->aux_stream != nullptr && sparse_nnz > 0;
         if (overlap) {
             SB_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
@@ -503,6 +528,7 @@ int spmm_n(sb_nmat *a, const double *X, u32 ldx, u32 w, double *P, u32 ldp) {
         else if (hybrid) SB_TRY(dense_n(a, X, ldx, w, P, ldp, ctx->stream, false));
         account(ctx, mt, w, false);
         SB_CUDA(cudaGetLastError());
+        }
     }
     SB_TRY(comm_allreduce_f64(ctx, P, ((size_t)mt->m + 1) * ldp));
     const bool need_row = mp.kind == 1 && mp.row != nullptr;

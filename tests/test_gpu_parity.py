@@ -317,6 +317,39 @@ def test_hybrid_dense_panel_matches_pure_sparse(ctx):
     check_pca_parity(sb.BkSvd().run_pca(a_s, 10), res_o)
 
 
+@pytest.mark.parametrize("n_cells,n_genes,norm", [(3000, 2500, "log"), (40000, 1500, "log"), (2000, 1300, "deviance"), (600, 90, "log")])
+def test_panelled_gather_matches_first_generation_kernels(ctx, n_cells, n_genes, norm):
+    """The panelled gather kernels (csrc/gather.cu; default) against the first-generation cell-major / gene-major
+    kernels (csrc/spmm.cu; option gather=0) and the oracle, on both products: several cell blocks and gene panels,
+    ragged panels, widths that need 1-3 column passes with and without the 4-column tail."""
+    cfg, cm, dm, (ip, g, c) = synth_pair(ctx, n_cells, n_genes, seed=41, depth=600.0)
+    if norm == "log":
+        a_o, a_g = orc.normalize(cm, orc.CELLRANGER), sb.normalize(dm, sb.Normalization.CellRanger)
+    else:  # the binomial maps take the panelled gather only on a matrix without a dense panel
+        try:
+            ctx.set_option("dense_genes", 0)
+            dm = sb.AdaptiveMat.from_csc(ctx, n_genes, n_cells, ip, g, c)
+        finally:
+            ctx.set_option("dense_genes", 2048)
+        a_o, a_g = orc.binom_deviance_resid(cm), sb.binom_deviance_resid(dm)
+    rng = np.random.default_rng(6)
+    for w in (20, 16, 9, 45):
+        x = rng.standard_normal((n_cells, w))
+        y = rng.standard_normal((w, n_genes))
+        ref_n, ref_t = a_o.dot(x), a_o.rdot(y)
+        got = {}
+        for g in (1, 0):
+            try:
+                ctx.set_option("gather", g)
+                got[g] = (a_g.dot(x), a_g.rdot(y))
+            finally:
+                ctx.set_option("gather", 1)
+            assert np.abs(got[g][0] - ref_n).max() <= 1e-10 * np.abs(ref_n).max(), (g, w)
+            assert np.abs(got[g][1] - ref_t).max() <= 1e-10 * np.abs(ref_t).max(), (g, w)
+        assert np.abs(got[0][0] - got[1][0]).max() <= 1e-11 * np.abs(ref_n).max()
+        assert np.abs(got[0][1] - got[1][1]).max() <= 1e-11 * np.abs(ref_t).max()
+
+
 def test_pipelined_upload_matches_plain_upload(ctx):
     """Large cell-major uploads are chunked and overlapped with the layout build (hot genes picked from the first
     chunk); the result must be the same matrix as the unpipelined gene-major upload and match the oracle."""
