@@ -6,8 +6,9 @@
 One "step" = normalize(CellRanger) + BkSvd::run_pca(k=10) over the whole synthetic
 1.3M-cell x 33,538-gene count matrix (BASELINE.json configs[2]; cells sharded over the N ranks,
 strong scaling).  `value`: counts already device-resident (both device layouts built) -> U, sigma, V
-on the host.  `e2e`: the same call sequence starting from pinned HOST CSC buffers (sb_upload's
-H2D copies and the device-side layout build are inside the timed region) -> U, sigma, V on the host.
+on the host.  `e2e`: the same call sequence starting from pinned HOST CSC buffers in the C ABI's narrow form
+(sb_upload_compact: u16 gene index + u8 count, 3 B per entry; the H2D copies and the device-side layout build are
+inside the timed region) -> U, sigma, V on the host.
 Timing is on the device (CUDA events on the library's stream), max over ranks.
 
 `--impl reference` times the CPU restatement of the reference (oracle/, all host threads) on a
@@ -231,15 +232,17 @@ def main():
 
     # ---------------- end-to-end arm: pinned host CSC buffers -> results on host
     ip, g, c = dm.to_csc()
+    # the narrow host form of the C ABI (sb_upload_compact: u16 gene + u8 count, counts >= 255 in a side list)
+    g16, c8, big_pos, big_cnt = sb.AdaptiveMat.compact_csc(g, c)
     h_ip, k1 = pinned_u(len(ip), np.uint64)
-    h_g, k2 = pinned_u(len(g), np.uint32)
-    h_c, k3 = pinned_u(len(c), np.uint32)
-    h_ip[:], h_g[:], h_c[:] = ip, g, c
-    del ip, g, c
+    h_g, k2 = pinned_u(len(g16), np.uint16)
+    h_c, k3 = pinned_u(len(c8), np.uint8)
+    h_ip[:], h_g[:], h_c[:] = ip, g16, c8
+    del ip, g, c, g16, c8
     n_loc = hi - lo
 
     def e2e_step():
-        m2 = sb.AdaptiveMat.from_csc(ctx, N_GENES, n_loc, h_ip, h_g, h_c)
+        m2 = sb.AdaptiveMat.from_csc_compact(ctx, N_GENES, n_loc, h_ip, h_g, h_c, big_pos, big_cnt)
         r = step(m2)
         m2.free()
         return r
@@ -256,7 +259,7 @@ def main():
     eprof = ctx.profile()
     ctx.profile_enable(False)
     barrier()
-    h2d = int(h_ip.nbytes + h_g.nbytes + h_c.nbytes)
+    h2d = int(h_ip.nbytes + h_g.nbytes + h_c.nbytes + big_pos.nbytes + big_cnt.nbytes)
     d2h = int((N_GENES * K + K + n_loc * K) * 8)
 
     if rank == 0:
@@ -272,8 +275,8 @@ def main():
             tj = json.load(open(tpath))
             if tj.get(dom):
                 traffic = float(tj[dom]) * nnz_local / float(tj["nnz_measured"])
-        names = {"spmm_t": "spmm_t = k_spmm_t (sparse gather over the cold entries) + k_dense_t (FP64 mma.sync over the dense hot-gene panel)",
-                 "spmm_n": "spmm_n = k_spmm_n (sparse panel gather over the cold entries) + k_dense_n (FP64 mma.sync over the dense hot-gene panel)"}
+        names = {"spmm_t": "spmm_t = k_t_init + k_dense_t (FP64 mma.sync over the dense hot-gene panel) + k_gather<T> (panelled gather over the cold entries)",
+                 "spmm_n": "spmm_n = k_gather<N> (panelled gather over the cold entries) + k_dense_n (FP64 mma.sync over the dense hot-gene panel)"}
         roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                     "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                     "launches": int(d_launch), "avg_launch_ms": d_ms / max(1, d_launch),
@@ -292,7 +295,7 @@ def main():
                                        f"(b=20, n_iter=5)", "nnz_rank0": int(nnz_local), "cell_sharding": f"{world} ranks, contiguous cell ranges",
                            "l2": "inputs (2 x 8 B/nnz device layouts) far larger than L2; no flush needed"},
                 "e2e": {"value": n_total / (e_ms * 1e-3), "unit": "cells/s", "ms_per_step": e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": args.e2e_steps, "upload_ms": eprof["upload_ms"] / args.e2e_steps, "layout_build_ms": eprof["build_ms"] / args.e2e_steps,
+                        "steps": args.e2e_steps, "host_format": "cell-major u64 indptr + u16 gene + u8 count (sb_upload_compact)", "upload_ms": eprof["upload_ms"] / args.e2e_steps, "layout_build_ms": eprof["build_ms"] / args.e2e_steps,
                         "output_ms": eprof["output_ms"] / args.e2e_steps},
                 "gpu_launches": int(prof["own_kernel_launches"]), "library_launches": int(prof["kernel_launches"] - prof["own_kernel_launches"]),
                 "roofline": roofline, "clocks": clocks, "wall_s_timed_region": wall}

@@ -110,6 +110,12 @@ SB_API void sb_host_free(void *p);
  * counts non-zero (what AdaptiveVec guarantees); zeros are dropped. */
 SB_API int sb_upload(sb_ctx *ctx, int major, uint32_t m, uint64_t n_local, const uint64_t *indptr,
               const uint32_t *idx, const uint32_t *cnt, sb_mat **out);
+/* The same constructor for a cell-major matrix in a narrow host form, for m <= 65536: u16 gene index + u8 count per entry
+ * (3 bytes over PCIe instead of 8 -- the host-to-device copy is the largest part of an end-to-end call).  Counts >= 255
+ * are written as 255 in cnt8 and listed in the side arrays: entry big_pos[i] (ascending stream positions) has count
+ * big_cnt[i].  The Rust side fills these from the same AdaptiveVec `foreach` walk (vec.rs:1230-1273) as sb_upload's. */
+SB_API int sb_upload_compact(sb_ctx *ctx, uint32_t m, uint64_t n_local, const uint64_t *indptr, const uint16_t *idx16,
+                      const uint8_t *cnt8, uint64_t n_big, const uint64_t *big_pos, const uint32_t *big_cnt, sb_mat **out);
 /* rows(), cols(), shape() (mat.rs:160-176) + nnz() (:155-157); n_global == n_local without a communicator */
 SB_API int sb_mat_shape(const sb_mat *mat, uint32_t *m, uint64_t *n_local, uint64_t *n_global, uint64_t *nnz_local);
 /* to_csmat (mat.rs:207-239): sizes from sb_mat_shape; indptr has m+1 or n_local+1 entries */

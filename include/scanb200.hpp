@@ -13,6 +13,7 @@
 //   scan_rs::dim_red::{Pca,BkSvd,..} scan-rs/src/dim_red/*.rs     scanb200::dim_red::*
 //   snoop::{CancelProgress,NoOpSnoop} snoop/src/lib.rs            scanb200::snoop::*
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cmath>
 #include <cstdint>
@@ -116,6 +117,25 @@ class AdaptiveMat {
                                 const std::vector<uint32_t> &val) {
         sb_mat *h = nullptr;
         check(sb_upload(ctx.raw(), SB_CELL_MAJOR, rows, cols, indptr.data(), idx.data(), val.data(), &h));
+        return AdaptiveMat(h);
+    }
+    // CSC arrays in the narrow host form of sb_upload_compact (rows <= 65536): counts >= 255 go to the side list
+    static AdaptiveMat from_csc_compact(Context &ctx, uint32_t rows, uint64_t cols, const std::vector<uint64_t> &indptr,
+                                        const std::vector<uint32_t> &idx, const std::vector<uint32_t> &val) {
+        std::vector<uint16_t> idx16(idx.size());
+        std::vector<uint8_t> cnt8(val.size());
+        std::vector<uint64_t> big_pos;
+        std::vector<uint32_t> big_cnt;
+        for (size_t i = 0; i < idx.size(); i++) {
+            idx16[i] = (uint16_t)idx[i];
+            cnt8[i] = (uint8_t)std::min<uint32_t>(val[i], 255u);
+            if (val[i] >= 255u) {
+                big_pos.push_back(i);
+                big_cnt.push_back(val[i]);
+            }
+        }
+        sb_mat *h = nullptr;
+        check(sb_upload_compact(ctx.raw(), rows, cols, indptr.data(), idx16.data(), cnt8.data(), big_pos.size(), big_pos.data(), big_cnt.data(), &h));
         return AdaptiveMat(h);
     }
     // from_dense (mat.rs:586-609); dense is row-major rows x cols

@@ -124,6 +124,32 @@ class AdaptiveMat:
                                   L.vp(val), C.byref(h)))
         return cls(ctx, h)
 
+    @staticmethod
+    def compact_csc(idx, val):
+        """Cell-major u32 index / count arrays -> the narrow host form of sb_upload_compact:
+        (idx16, cnt8, big_pos, big_cnt); counts >= 255 go to the side list."""
+        idx = np.asarray(idx)
+        val = np.asarray(val)
+        if idx.size and int(idx.max()) > 0xFFFF:
+            raise ValueError("compact form needs gene indices below 65536")
+        big_pos = np.flatnonzero(val >= 255).astype(np.uint64)
+        return (idx.astype(np.uint16), np.minimum(val, 255).astype(np.uint8), big_pos, val[big_pos].astype(np.uint32))
+
+    @classmethod
+    def from_csc_compact(cls, ctx: Context, rows: int, cols: int, indptr, idx16, cnt8, big_pos=None, big_cnt=None) -> "AdaptiveMat":
+        """Cell-major upload in the narrow host form (3 B per entry over PCIe instead of 8); rows <= 65536."""
+        indptr = np.ascontiguousarray(indptr, dtype=np.uint64)
+        idx16 = np.ascontiguousarray(idx16, dtype=np.uint16)
+        cnt8 = np.ascontiguousarray(cnt8, dtype=np.uint8)
+        big_pos = np.ascontiguousarray(big_pos if big_pos is not None else [], dtype=np.uint64)
+        big_cnt = np.ascontiguousarray(big_cnt if big_cnt is not None else [], dtype=np.uint32)
+        if indptr.shape != (cols + 1,) or idx16.shape != cnt8.shape or idx16.shape[0] != int(indptr[-1]) or big_pos.shape != big_cnt.shape:
+            raise ValueError("inconsistent compact CSC arrays")
+        h = C.c_void_p()
+        L.check(L.lib().sb_upload_compact(ctx._h, C.c_uint32(rows), C.c_uint64(cols), L.vp(indptr), L.vp(idx16), L.vp(cnt8),
+                                          C.c_uint64(big_pos.shape[0]), L.vp(big_pos), L.vp(big_cnt), C.byref(h)))
+        return cls(ctx, h)
+
     @classmethod
     def _synth(cls, ctx, m, n_local, cell_offset, seed, pf, depth, cluster, r):
         h = C.c_void_p()

@@ -373,6 +373,28 @@ def test_pipelined_upload_matches_plain_upload(ctx):
         assert np.abs(a.rdot(y) - ref).max() <= 1e-11 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("n_cells,n_genes", [(1500, 900), (20000, 3000)])
+def test_compact_upload_matches_plain_upload(ctx, n_cells, n_genes):
+    """sb_upload_compact (u16 index + u8 count + side list of the counts >= 255) builds the same matrix as sb_upload,
+    on the plain and on the pipelined path; the antibody-style dense features supply the large counts."""
+    cfg, cm, dm, (ip, g, c) = synth_pair(ctx, n_cells, n_genes, seed=43, n_dense=12, dense_mean=400.0)
+    idx16, cnt8, big_pos, big_cnt = sb.AdaptiveMat.compact_csc(g, c)
+    assert big_pos.size > 0 and int(c.max()) >= 255
+    dm_c = sb.AdaptiveMat.from_csc_compact(ctx, n_genes, n_cells, ip, idx16, cnt8, big_pos, big_cnt)
+    for a, b in zip(dm_c.to_csc(), (ip, g, c)):
+        np.testing.assert_array_equal(a, b)
+    for a, b in zip(dm_c.to_csr(), dm.to_csr()):
+        np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(dm_c.sum_axis_u32(0), cm.sum_axis_u32(0))
+    a_c, a_p = sb.normalize(dm_c, sb.Normalization.CellRanger), sb.normalize(dm, sb.Normalization.CellRanger)
+    x = np.random.default_rng(2).standard_normal((n_cells, 20))
+    np.testing.assert_allclose(a_c.dot(x), a_p.dot(x), rtol=0, atol=1e-11 * np.abs(a_p.dot(x)).max())
+    with pytest.raises(L.ScanB200Error):  # an index past the gene count is rejected
+        bad = idx16.copy()
+        bad[0] = n_genes
+        sb.AdaptiveMat.from_csc_compact(ctx, n_genes, n_cells, ip, bad, cnt8, big_pos, big_cnt)
+
+
 def test_bksvd_seurat_and_binomial(ctx):
     cfg, cm, dm, _ = synth_pair(ctx, 3000, 1200, seed=32)
     check_pca_parity(sb.BkSvd().run_pca(sb.normalize(dm, sb.Normalization.SeuratLog), 8),
