@@ -84,6 +84,33 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa(local_rank):
+    """Host plumbing: run this rank (and first-touch its pinned buffers) on the CPUs local to its GPU, so the host -> device
+    copies of the end-to-end arm do not cross the socket interconnect.  Returns a short description for the result line."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = open(base + "/numa_node").read().strip()
+        cpus = open(base + "/local_cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                ids.update(range(int(a), int(b) + 1))
+            elif part:
+                ids.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        use = ids & allowed
+        if use and node not in ("-1", ""):
+            os.sched_setaffinity(0, use)
+            return f"numa node {node}, {len(use)} local cpus"
+        return f"numa node {node} (no binding)"
+    except Exception as e:  # sysfs layout differs in some containers: binding is an optimisation only
+        return f"unbound ({type(e).__name__})"
+
+
 def pinned_u(n, dtype):
     """Pinned host buffer as a numpy array (torch is plumbing: page-locked allocation only)."""
     import torch
@@ -185,7 +212,10 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    numa = bind_to_gpu_numa(local_rank)
     ctx = sb.Context(local_rank)
+    if os.environ.get("SCANB200_UPLOAD_SYNC"):  # diagnostics: A/B of the per-chunk synchronisation of the pipelined upload
+        ctx.set_option("upload_sync", float(os.environ["SCANB200_UPLOAD_SYNC"]))
     if world > 1:
         obj = [sb.Context.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(obj, src=0)
@@ -253,8 +283,11 @@ def main():
     ctx.sync()
     barrier()
     ctx.timer_begin()
+    e_wall = []
     for _ in range(args.e2e_steps):
-        e2e_step()
+        t_s = time.perf_counter()
+        e2e_step()  # returns with U, sigma, V on the host
+        e_wall.append(round((time.perf_counter() - t_s) * 1e3, 1))
     e_ms = max_over_ranks(ctx.timer_end()) / args.e2e_steps
     eprof = ctx.profile()
     ctx.profile_enable(False)
@@ -295,7 +328,7 @@ def main():
                                        f"(b=20, n_iter=5)", "nnz_rank0": int(nnz_local), "cell_sharding": f"{world} ranks, contiguous cell ranges",
                            "l2": "inputs (2 x 8 B/nnz device layouts) far larger than L2; no flush needed"},
                 "e2e": {"value": n_total / (e_ms * 1e-3), "unit": "cells/s", "ms_per_step": e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": args.e2e_steps, "host_format": "cell-major u64 indptr + u16 gene + u8 count (sb_upload_compact)", "upload_ms": eprof["upload_ms"] / args.e2e_steps, "layout_build_ms": eprof["build_ms"] / args.e2e_steps,
+                        "steps": args.e2e_steps, "step_ms_host_clock": e_wall, "host_format": "cell-major u64 indptr + u16 gene + u8 count (sb_upload_compact)", "host_binding": numa, "upload_ms": eprof["upload_ms"] / args.e2e_steps, "layout_build_ms": eprof["build_ms"] / args.e2e_steps,
                         "output_ms": eprof["output_ms"] / args.e2e_steps},
                 "gpu_launches": int(prof["own_kernel_launches"]), "library_launches": int(prof["kernel_launches"] - prof["own_kernel_launches"]),
                 "roofline": roofline, "clocks": clocks, "wall_s_timed_region": wall}

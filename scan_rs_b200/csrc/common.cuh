@@ -122,6 +122,7 @@ struct sb_ctx {
     int nranks = 1, rank = 0;
     int dense_cap = 2048;            // max genes in the dense hot panel (0 disables the hybrid layout)
     double dense_min_density = 0.12; // a gene joins the panel only if nnz/n_global is at least this
+    bool upload_sync = true;         // pipelined upload: synchronise the build stream after every chunk (matrix.cu)
     bool use_gather = true;          // panelled gather kernels (gather.cu); false: the first-generation K7 / K8 of spmm.cu
     bool direct_projection = false;  // true: always run the wide Q^T A pass (bk_svd.rs:102,131) instead of the R^-T identity
     // profiling
@@ -256,6 +257,7 @@ struct TraceScope {
     const char *name;
     double t0;
     static bool on();
+    static int level();
     static double now();
     TraceScope(sb_ctx *ctx, const char *n) : c(ctx), name(n), t0(0) {
         if (on()) {

@@ -26,13 +26,17 @@ int sb_fail(int code, const char *fmt, ...) {
     return code;
 }
 
-bool TraceScope::on() {
+// SCANB200_TRACE=1: synchronising stage trace, uploads take the unpipelined path; =2: same trace, pipelined uploads kept
+int TraceScope::level() {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("SCANB200_TRACE");
-        v = (e && *e && *e != '0') ? 1 : 0;
+        v = (e && *e && *e != '0') ? (*e == '2' ? 2 : 1) : 0;
     }
-    return v == 1;
+    return v;
+}
+bool TraceScope::on() {
+    return level() > 0;
 }
 double TraceScope::now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
@@ -131,6 +135,10 @@ extern "C" int sb_set_option(sb_ctx *ctx, const char *name, double value) {
     }
     if (!strcmp(name, "overlap_t")) {  // same for A^T.Y
         ctx->overlap_t = value != 0.0;
+        return SB_OK;
+    }
+    if (!strcmp(name, "upload_sync")) {
+        ctx->upload_sync = value != 0.0;
         return SB_OK;
     }
     if (!strcmp(name, "gather")) {  // 1 (default): panelled gather kernels; 0: first-generation sparse kernels

@@ -572,12 +572,19 @@ static int upload_pipelined(sb_mat *mt, const u64 *h_indptr, const HostEntries &
     SB_CUDA(cudaEventRecord(ready, ctx->stream));  // the staging buffers exist (stream-ordered allocation)
     SB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ready, 0));
     prof_begin(ctx, PH_UPLOAD);
-    for (size_t i = 0; i < chunks; i++) {
-        const u64 e0 = h_indptr[cb[i]], e1 = h_indptr[cb[i + 1]];
-        SB_TRY(copy_entries(he, de, e0, e1, ctx->copy_stream));
-        SB_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
-        SB_CUDA(cudaEventRecord(ev[i], ctx->copy_stream));
-    }
+    // The first chunk's build makes small host -> device copies of its own (hot-gene and slot tables); they queue on the
+    // copy engine behind every bulk copy already issued, so only two chunks are in flight until that build is done.
+    for (size_t i = 0; i < chunks; i++) SB_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    size_t issued = 0;
+    auto issue_copies = [&](size_t upto) -> int {
+        for (; issued < std::min(upto, chunks); issued++) {
+            const u64 e0 = h_indptr[cb[issued]], e1 = h_indptr[cb[issued + 1]];
+            SB_TRY(copy_entries(he, de, e0, e1, ctx->copy_stream));
+            SB_CUDA(cudaEventRecord(ev[issued], ctx->copy_stream));
+        }
+        return SB_OK;
+    };
+    SB_TRY(issue_copies(2));
     std::vector<DevBuf<u64>> ptrs(chunks);
     std::vector<DevBuf<uint2>> colds(chunks), gms(chunks), tps(chunks);
     std::vector<u64> cold_n(chunks, 0);
@@ -587,18 +594,37 @@ static int upload_pipelined(sb_mat *mt, const u64 *h_indptr, const HostEntries &
     for (size_t i = 0; i < chunks && rc == SB_OK; i++) {
         const u64 c0 = cb[i], c1 = cb[i + 1], e0 = h_indptr[c0], e1 = h_indptr[c1];
         cudaStreamWaitEvent(ctx->stream, ev[i], 0);
-        rc = expand_entries(ctx, he, de, e0, e1, mt->cm.p, d_max);
+        // Drain the build stream after every stage (the copies run on their own stream and are not held up).  Measured at
+        // 1.3M cells: letting the host run ahead of the device makes the whole upload take ~390-510 ms instead of ~125 ms
+        // (stream-ordered allocations issued long before the frees they could reuse have executed grow the pool).
+        auto drain = [&]() { if (ctx->upload_sync) cudaStreamSynchronize(ctx->stream); };
+        {
+            TraceScope t0(ctx, "chunk: wait copy + expand");
+            rc = expand_entries(ctx, he, de, e0, e1, mt->cm.p, d_max);
+            drain();
+        }
         if (rc == SB_OK && i == 0) rc = select_hot_genes(mt, c0, c1);
         if (rc == SB_OK && mt->gd > 0) {
-            rc = split_range(mt, c0, c1, ptrs[i], colds[i], &cold_n[i]);
-            if (rc == SB_OK) rc = gene_major_range(mt, c1 - c0, ptrs[i].p, colds[i].p, cold_n[i], gms[i]);
+            {
+                TraceScope t1(ctx, "chunk: split hot/cold");
+                rc = split_range(mt, c0, c1, ptrs[i], colds[i], &cold_n[i]);
+                drain();
+            }
+            if (rc == SB_OK) {
+                TraceScope t2(ctx, "chunk: cold gene-major sort");
+                rc = gene_major_range(mt, c1 - c0, ptrs[i].p, colds[i].p, cold_n[i], gms[i]);
+                drain();
+            }
             if (rc == SB_OK && build_t) {
+                TraceScope t3(ctx, "chunk: T-side order");
                 if (i == 0) rc = gather_assign_slots(mt, colds[0].p, cold_n[0]);
                 if (rc == SB_OK) rc = gather_build_t_range(mt, c0, c1 - c0, ptrs[i].p, colds[i].p, cold_n[i], tps[i], seg, runs);
                 seg_all.insert(seg_all.end(), seg.begin(), seg.end());
                 runs_all.insert(runs_all.end(), runs.begin(), runs.end());
+                drain();
             }
         }
+        if (rc == SB_OK) rc = issue_copies(chunks);  // after the first chunk: everything else
     }
     cudaStreamSynchronize(ctx->copy_stream);
     prof_end(ctx, PH_UPLOAD);  // spans the overlapped copies and builds
@@ -606,6 +632,7 @@ static int upload_pipelined(sb_mat *mt, const u64 *h_indptr, const HostEntries &
     cudaEventDestroy(ready);
     SB_TRY(rc);
     if (mt->gd == 0) return SB_OK;
+    TraceScope tcat(ctx, "upload: concatenate chunks");
     // concatenate the per-chunk cold layouts
     mt->cold_nnz = 0;
     for (u64 x : cold_n) mt->cold_nnz += x;
@@ -648,7 +675,7 @@ static int upload_impl(sb_ctx *ctx, int major, uint32_t m, uint64_t n_local, con
     SB_TRY(d_ptr.alloc(nvec + 1));
     SB_TRY(de.alloc(he, nnz, ctx->stream));
     // large cell-major uploads take the pipelined path (copies overlapped with the layout build)
-    const bool pipelined = major == SB_CELL_MAJOR && nnz >= ((u64)1 << 22) && n_local >= 8 * (u64)SB_MAX_PANEL_CELLS && !TraceScope::on();
+    const bool pipelined = major == SB_CELL_MAJOR && nnz >= ((u64)1 << 22) && n_local >= 8 * (u64)SB_MAX_PANEL_CELLS && TraceScope::level() != 1;
     if (pipelined) {
         SB_CUDA(cudaMemcpyAsync(d_ptr.p, indptr, (nvec + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
         void *scr0;
