@@ -146,8 +146,11 @@ static int finish_svd(sb_ctx *ctx, const Tall &Tt, const Tall &Q, u32 wq, u32 k,
 static int download_tall(sb_ctx *ctx, const Tall &t, double *host) {
     if (t.rows == 0 || t.w == 0) return SB_OK;
     ProfScope ps(ctx, PH_OUTPUT);
-    SB_CUDA(cudaMemcpy2DAsync(host, t.w * sizeof(double), t.buf.p, t.ld * sizeof(double), t.w * sizeof(double), t.rows, cudaMemcpyDeviceToHost,
-                              ctx->stream));
+    if (t.ld == t.w)  // contiguous block: one linear copy (the pitched copy of a 1.3M x 10 block runs at under half the PCIe rate)
+        SB_CUDA(cudaMemcpyAsync(host, t.buf.p, t.rows * (size_t)t.w * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    else
+        SB_CUDA(cudaMemcpy2DAsync(host, t.w * sizeof(double), t.buf.p, t.ld * sizeof(double), t.w * sizeof(double), t.rows, cudaMemcpyDeviceToHost,
+                                  ctx->stream));
     SB_CUDA(cudaStreamSynchronize(ctx->stream));
     return SB_OK;
 }

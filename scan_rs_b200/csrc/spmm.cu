@@ -26,10 +26,11 @@ struct __align__(16) StageEnt {
 };
 
 // ---------------------------------------------------------------- column sums:  out[j] = sum_r wgt[r] * A[r, j]
-#define CS_ROWS_PER_BLOCK 2048
+#define CS_ROWS_PER_BLOCK 512
+#define CS_FINAL_THREADS 256
 __global__ void k_colsum_partial(const double *__restrict__ A, u64 rows, u32 w, u32 ld, const double *__restrict__ wgt,
                                  double *__restrict__ partial) {
-    // block b sums rows [b*CS, (b+1)*CS); thread t handles column t % ldw for rows t / ldw + k * (blockDim/ldw)
+    // block b sums rows [b*CS, (b+1)*CS); thread t handles column t % w for rows t / w + k * (blockDim / w)
     extern __shared__ double sh[];
     u32 tpr = w;  // threads per row
     u32 rows_par = blockDim.x / tpr;
@@ -51,13 +52,19 @@ __global__ void k_colsum_partial(const double *__restrict__ A, u64 rows, u32 w, 
     }
 }
 
-__global__ void k_colsum_final(const double *__restrict__ partial, u32 nblocks, u32 w, double *__restrict__ out) {
-    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < w) {
-        double s = 0.0;
-        for (u32 b = 0; b < nblocks; b++) s += partial[(u64)b * w + j];
-        out[j] = s;
+// one block per column: strided sums of the partials, then a fixed-order tree (deterministic)
+__global__ void __launch_bounds__(CS_FINAL_THREADS) k_colsum_final(const double *__restrict__ partial, u32 nblocks, u32 w, double *__restrict__ out) {
+    __shared__ double sh[CS_FINAL_THREADS];
+    const u32 j = blockIdx.x;
+    double s = 0.0;
+    for (u32 b = threadIdx.x; b < nblocks; b += CS_FINAL_THREADS) s += partial[(u64)b * w + j];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (u32 o = CS_FINAL_THREADS / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
     }
+    if (threadIdx.x == 0) out[j] = sh[0];
 }
 
 // deterministic two-stage weighted column sum; out is a device vector of w doubles
@@ -75,7 +82,7 @@ int colsum_weighted(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 ld, const
     if (rows_par < 1) rows_par = 1;
     int threads = rows_par * (int)w;
     k_colsum_partial<<<nblocks, threads, threads * sizeof(double), ctx->stream>>>(A, rows, w, ld, wgt, (double *)scr);
-    k_colsum_final<<<cdiv(w, 128), 128, 0, ctx->stream>>>((double *)scr, nblocks, w, out);
+    k_colsum_final<<<w, CS_FINAL_THREADS, 0, ctx->stream>>>((double *)scr, nblocks, w, out);
     count_launch(ctx); count_launch(ctx);
     return SB_OK;
 }
