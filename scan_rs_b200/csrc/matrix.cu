@@ -369,7 +369,7 @@ static int select_hot_genes(sb_mat *mt, u64 c0, u64 c1) {
     sb_ctx *ctx = mt->ctx;
     mt->gd = 0;
     if (ctx->dense_cap < 64 || mt->m < 64 || mt->n_global == 0) return SB_OK;
-    TraceScope tr(ctx, "build: hot gene selection");
+    SyncScope tr(ctx, "build: hot gene selection");
     DevBuf<u64> d_nnz;
     SB_TRY(d_nnz.alloc((size_t)mt->m + 1));
     SB_CUDA(cudaMemsetAsync(d_nnz.p, 0, ((size_t)mt->m + 1) * sizeof(u64), ctx->stream));
@@ -435,14 +435,14 @@ static int split_range(sb_mat *mt, u64 c0, u64 c1, DevBuf<u64> &ptr_local, DevBu
 // whole-matrix hybrid build (matrices created on the device: generator, select, partition; gene-major uploads)
 static int build_hybrid(sb_mat *mt) {
     sb_ctx *ctx = mt->ctx;
-    TraceScope tr(ctx, "build: hybrid total");
+    SyncScope tr(ctx, "build: hybrid total");
     SB_TRY(select_hot_genes(mt, 0, mt->n));
     if (mt->gd == 0) return SB_OK;
     {
-        TraceScope t4(ctx, "build: split hot/cold");
+        SyncScope t4(ctx, "build: split hot/cold");
         SB_TRY(split_range(mt, 0, mt->n, mt->cold_cm_ptr, mt->cold_cm, &mt->cold_nnz));
     }
-    TraceScope t3(ctx, "build: cold gene-major sort");
+    SyncScope t3(ctx, "build: cold gene-major sort");
     SB_TRY(panel_base(mt, mt->cold_cm_ptr.p, mt->cold_gm_base));
     SB_TRY(gene_major_range(mt, mt->n, mt->cold_cm_ptr.p, mt->cold_cm.p, mt->cold_nnz, mt->cold_gm));
     return SB_OK;
@@ -464,7 +464,7 @@ static int set_global_shape(sb_mat *mt) {
 
 // panelled gather layouts (gather.cu) over the sparse set the products use; whatever the upload pipeline has not built yet
 static int finish_gather(sb_mat *mt) {
-    TraceScope tr(mt->ctx, "build: gather layouts");
+    SyncScope tr(mt->ctx, "build: gather layouts");
     const bool cold = mt->gd > 0;
     if (!mt->gn.ready)
         SB_TRY(gather_build_n(mt, mt->gn, cold ? mt->cold_gm.p : mt->gm.p, cold ? mt->cold_gm_base.p : mt->gm_base.p, cold ? mt->cold_nnz : mt->nnz));
@@ -599,24 +599,29 @@ static int upload_pipelined(sb_mat *mt, const u64 *h_indptr, const HostEntries &
         // (stream-ordered allocations issued long before the frees they could reuse have executed grow the pool).
         auto drain = [&]() { if (ctx->upload_sync) cudaStreamSynchronize(ctx->stream); };
         {
-            TraceScope t0(ctx, "chunk: wait copy + expand");
+            SyncScope t0(ctx, "chunk: wait copy + expand");
             rc = expand_entries(ctx, he, de, e0, e1, mt->cm.p, d_max);
             drain();
+            // indices are validated before any kernel uses them as table offsets
+            u32 hmax = 0;
+            if (rc == SB_OK && cudaMemcpyAsync(&hmax, d_max, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess &&
+                cudaStreamSynchronize(ctx->stream) == cudaSuccess && hmax >= mt->m)
+                rc = sb_fail(SB_ERR_INVALID_ARG, "sb_upload: index %u out of range %u", hmax, mt->m);
         }
         if (rc == SB_OK && i == 0) rc = select_hot_genes(mt, c0, c1);
         if (rc == SB_OK && mt->gd > 0) {
             {
-                TraceScope t1(ctx, "chunk: split hot/cold");
+                SyncScope t1(ctx, "chunk: split hot/cold");
                 rc = split_range(mt, c0, c1, ptrs[i], colds[i], &cold_n[i]);
                 drain();
             }
             if (rc == SB_OK) {
-                TraceScope t2(ctx, "chunk: cold gene-major sort");
+                SyncScope t2(ctx, "chunk: cold gene-major sort");
                 rc = gene_major_range(mt, c1 - c0, ptrs[i].p, colds[i].p, cold_n[i], gms[i]);
                 drain();
             }
             if (rc == SB_OK && build_t) {
-                TraceScope t3(ctx, "chunk: T-side order");
+                SyncScope t3(ctx, "chunk: T-side order");
                 if (i == 0) rc = gather_assign_slots(mt, colds[0].p, cold_n[0]);
                 if (rc == SB_OK) rc = gather_build_t_range(mt, c0, c1 - c0, ptrs[i].p, colds[i].p, cold_n[i], tps[i], seg, runs);
                 seg_all.insert(seg_all.end(), seg.begin(), seg.end());
@@ -632,7 +637,7 @@ static int upload_pipelined(sb_mat *mt, const u64 *h_indptr, const HostEntries &
     cudaEventDestroy(ready);
     SB_TRY(rc);
     if (mt->gd == 0) return SB_OK;
-    TraceScope tcat(ctx, "upload: concatenate chunks");
+    SyncScope tcat(ctx, "upload: concatenate chunks");
     // concatenate the per-chunk cold layouts
     mt->cold_nnz = 0;
     for (u64 x : cold_n) mt->cold_nnz += x;
@@ -659,9 +664,22 @@ static int upload_pipelined(sb_mat *mt, const u64 *h_indptr, const HostEntries &
     return SB_OK;
 }
 
+// SCANB200_TRACE: state of the stream-ordered pool (reserved = held from the driver, used = handed out)
+static void trace_pool(sb_ctx *ctx, const char *label) {
+    if (!TraceScope::on()) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) != cudaSuccess) return;
+    unsigned long long reserved = 0, used = 0;
+    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+    fprintf(stderr, "[scanb200] pool %-22s reserved %7.2f GB used %7.2f GB\n", label, reserved / 1e9, used / 1e9);
+}
+
 static int upload_impl(sb_ctx *ctx, int major, uint32_t m, uint64_t n_local, const uint64_t *indptr, const HostEntries &he, sb_mat **out) {
     *out = nullptr;
     SB_ENTER(ctx);
+    trace_pool(ctx, "at upload start");
+    SyncScope tr_total(ctx, "upload: whole call");
     u64 nvec = major == SB_GENE_MAJOR ? m : n_local;
     u64 nnz = indptr[nvec];
     std::unique_ptr<sb_mat> mt(new sb_mat());
@@ -672,8 +690,11 @@ static int upload_impl(sb_ctx *ctx, int major, uint32_t m, uint64_t n_local, con
 
     DevBuf<u64> d_ptr;
     DevEntries de;
-    SB_TRY(d_ptr.alloc(nvec + 1));
-    SB_TRY(de.alloc(he, nnz, ctx->stream));
+    {
+        SyncScope tr_a(ctx, "upload: staging allocations");
+        SB_TRY(d_ptr.alloc(nvec + 1));
+        SB_TRY(de.alloc(he, nnz, ctx->stream));
+    }
     // large cell-major uploads take the pipelined path (copies overlapped with the layout build)
     const bool pipelined = major == SB_CELL_MAJOR && nnz >= ((u64)1 << 22) && n_local >= 8 * (u64)SB_MAX_PANEL_CELLS && TraceScope::level() != 1;
     if (pipelined) {
@@ -684,9 +705,16 @@ static int upload_impl(sb_ctx *ctx, int major, uint32_t m, uint64_t n_local, con
         k_check_ptr<<<cdiv(nvec, 256), 256, 0, ctx->stream>>>(d_ptr.p, nvec, (int *)scr0);
         count_launch(ctx);
         mt->cm_ptr.swap(d_ptr);
-        SB_TRY(mt->cm.alloc(nnz));
+        {
+            SyncScope tr_b(ctx, "upload: cm allocation");
+            SB_TRY(mt->cm.alloc(nnz));
+        }
         SB_TRY(set_global_shape(mt.get()));
-        SB_TRY(upload_pipelined(mt.get(), indptr, he, de, (u32 *)scr0 + 1));
+        {
+            SyncScope tr_c(ctx, "upload: pipeline");
+            SB_TRY(upload_pipelined(mt.get(), indptr, he, de, (u32 *)scr0 + 1));
+        }
+        trace_pool(ctx, "after pipeline");
         int hchk[2] = {0, 0};
         SB_CUDA(cudaMemcpyAsync(hchk, scr0, 8, cudaMemcpyDeviceToHost, ctx->stream));
         SB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -697,14 +725,14 @@ static int upload_impl(sb_ctx *ctx, int major, uint32_t m, uint64_t n_local, con
         *out = mt.release();
         return SB_OK;
     }
-    TraceScope *tr_up = new TraceScope(ctx, "upload: H2D");
+    SyncScope *tr_up = new SyncScope(ctx, "upload: H2D");
     prof_begin(ctx, PH_UPLOAD);
     SB_CUDA(cudaMemcpyAsync(d_ptr.p, indptr, (nvec + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
     SB_TRY(copy_entries(he, de, 0, nnz, ctx->stream));
     prof_end(ctx, PH_UPLOAD);
     delete tr_up;
     ProfScope build_scope(ctx, PH_BUILD);
-    TraceScope tr_build(ctx, "upload: build total");
+    SyncScope tr_build(ctx, "upload: build total");
     // interleave into {index, count} pairs; validation: pointers monotone, indices in range
     void *scr;
     SB_TRY(ctx_scratch(ctx, 256, &scr));
@@ -726,7 +754,7 @@ static int upload_impl(sb_ctx *ctx, int major, uint32_t m, uint64_t n_local, con
     u64 bound = major == SB_GENE_MAJOR ? n_local : (u64)m;
     if (nnz && (u64)(u32)h[1] >= bound) return sb_fail(SB_ERR_INVALID_ARG, "sb_upload: index %u out of range %llu", (u32)h[1], (unsigned long long)bound);
 
-    TraceScope *tr_cm = new TraceScope(ctx, "upload: cell-major copy");
+    SyncScope *tr_cm = new SyncScope(ctx, "upload: cell-major copy");
     if (major == SB_CELL_MAJOR) {
         mt->cm_ptr.swap(d_ptr);
         mt->cm.swap(ent);
