@@ -699,8 +699,11 @@ static int upload_impl(sb_ctx *ctx, int major, uint32_t m, uint64_t n_local, con
     const bool pipelined = major == SB_CELL_MAJOR && nnz >= ((u64)1 << 22) && n_local >= 8 * (u64)SB_MAX_PANEL_CELLS && TraceScope::level() != 1;
     if (pipelined) {
         SB_CUDA(cudaMemcpyAsync(d_ptr.p, indptr, (nvec + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
-        void *scr0;
-        SB_TRY(ctx_scratch(ctx, 256, &scr0));
+        // private flags {pointer check, largest index}: the context scratch is also the staging buffer of the collectives
+        // that set_global_shape / select_hot_genes run on a sharded context
+        DevBuf<int> flags;
+        SB_TRY(flags.alloc(64));
+        void *scr0 = flags.p;
         SB_CUDA(cudaMemsetAsync(scr0, 0, 256, ctx->stream));
         k_check_ptr<<<cdiv(nvec, 256), 256, 0, ctx->stream>>>(d_ptr.p, nvec, (int *)scr0);
         count_launch(ctx);
@@ -734,8 +737,9 @@ static int upload_impl(sb_ctx *ctx, int major, uint32_t m, uint64_t n_local, con
     ProfScope build_scope(ctx, PH_BUILD);
     SyncScope tr_build(ctx, "upload: build total");
     // interleave into {index, count} pairs; validation: pointers monotone, indices in range
-    void *scr;
-    SB_TRY(ctx_scratch(ctx, 256, &scr));
+    DevBuf<int> flags;
+    SB_TRY(flags.alloc(64));
+    void *scr = flags.p;
     SB_CUDA(cudaMemsetAsync(scr, 0, 256, ctx->stream));
     int *d_bad = (int *)scr;
     u32 *d_max = (u32 *)scr + 1;
