@@ -94,7 +94,12 @@ SB_API int sb_comm_unique_id(char id[128]);
 SB_API int sb_comm_init(sb_ctx *ctx, int nranks, int rank, const char id[128]);
 SB_API int sb_sync(sb_ctx *ctx);
 /* Options: "direct_projection" (0/1, default 0): 1 forces the wide projection pass T = Q^T A of
- * bk_svd.rs:102,131 to run as a sparse product; 0 lets the library use Q^T A = R^-T (K^T A) when R is usable. */
+ * bk_svd.rs:102,131 to run as a sparse product; 0 lets the library use Q^T A = R^-T (K^T A) when R is usable.
+ * "gather" (default 1): 1 = panelled gather kernels for the sparse halves of both products, 0 = the first-generation
+ * cell-major / gene-major kernels (A/B and accuracy reference).  "dense_genes" (default 2048) / "dense_min_density"
+ * (default 0.12): size of the dense hot-gene panel of matrices uploaded afterwards (0 disables it).
+ * "upload_sync" (default 1): drain the build stream after every stage of a pipelined upload.
+ * "overlap" / "overlap_t" (default 0): experimental concurrent sparse + panel kernels. */
 SB_API int sb_set_option(sb_ctx *ctx, const char *name, double value);
 
 /* Page-locked host memory for inputs / outputs (optional): copies to and from pinned buffers run at PCIe

@@ -72,3 +72,27 @@ def test_synth_cpu_is_deterministic_and_shardable():
     np.testing.assert_array_equal(ga, g[s:e])
     np.testing.assert_array_equal(ca, c[s:e])
     assert (c > 0).all() and (np.diff(ip.astype(np.int64)) > 0).all()
+
+
+def test_compact_host_form_round_trip():
+    """AdaptiveMat.compact_csc (the narrow host form sb_upload_compact takes): u16 index + u8 count + side list of the
+    counts >= 255 reproduces the u32 arrays; indices past 65535 are refused."""
+    import numpy as np
+    import pytest
+    from scan_rs_b200.sqz import AdaptiveMat
+    rng = np.random.default_rng(0)
+    idx = rng.integers(0, 65536, 5000).astype(np.uint32)
+    val = rng.integers(1, 40, 5000).astype(np.uint32)
+    val[rng.integers(0, 5000, 60)] = rng.integers(255, 2**31, 60)
+    val[7] = 255
+    val[8] = 254
+    idx16, cnt8, big_pos, big_cnt = AdaptiveMat.compact_csc(idx, val)
+    assert idx16.dtype == np.uint16 and cnt8.dtype == np.uint8 and big_pos.dtype == np.uint64 and big_cnt.dtype == np.uint32
+    back = cnt8.astype(np.uint32)
+    assert (back[big_pos.astype(np.int64)] == 255).all() and (np.diff(big_pos.astype(np.int64)) > 0).all()
+    back[big_pos.astype(np.int64)] = big_cnt
+    np.testing.assert_array_equal(back, val)
+    np.testing.assert_array_equal(idx16.astype(np.uint32), idx)
+    assert 7 in big_pos and 8 not in big_pos
+    with pytest.raises(ValueError):
+        AdaptiveMat.compact_csc(np.array([70000], dtype=np.uint32), np.array([1], dtype=np.uint32))
