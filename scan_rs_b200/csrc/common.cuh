@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/scanb200.h"
+#include "gather_units.h"  // GUnit + the host-side cutting of the gather streams into work units
 
 typedef uint32_t u32;
 typedef uint64_t u64;
@@ -144,13 +145,6 @@ struct sb_ctx {
 #define SB_GENE_MASK 0x3FFFFFu
 #define SB_MAX_PANEL_CELLS 1024
 #define GA_TBLOCK 16384  // cells per block of the T-side gather order (gather.cu)
-
-// A work unit of the panelled gather (gather.cu): entries [begin, end) of a stream, all of one panel.
-struct __align__(16) GUnit {
-    u64 begin, end;
-    u32 panel, pad0;
-    u64 pad1;
-};
 
 // One side of the panelled gather: the entry stream, its work units and (T side) the gene of every panel slot.
 struct GatherLayout {

@@ -295,27 +295,8 @@ int gather_build_n(sb_mat *mt, GatherLayout &L, const uint2 *gm, const u64 *gm_b
     SB_CUDA(cudaStreamSynchronize(ctx->stream));
     const u32 G = (u32)ctx->sm_count;
     std::vector<GUnit> units;
-    std::vector<u32> first(G + 1, 0);
-    u32 p = 0;
-    for (u32 b = 0; b < G; b++) {
-        first[b] = (u32)units.size();
-        u64 lo = nnz / G * b + std::min<u64>(b, nnz % G), hi = nnz / G * (b + 1) + std::min<u64>(b + 1, nnz % G);
-        lo &= ~(u64)7;
-        hi = b + 1 == G ? nnz : hi & ~(u64)7;
-        while (lo < hi) {
-            while (p + 1 <= mt->np && base[p + 1] <= lo) p++;
-            const u64 e = std::min(hi, base[p + 1]);
-            GUnit u;
-            u.begin = lo;
-            u.end = e;
-            u.panel = p;
-            u.pad0 = 0;
-            u.pad1 = 0;
-            units.push_back(u);
-            lo = e;
-        }
-    }
-    first[G] = (u32)units.size();
+    std::vector<u32> first;
+    gather_units_n(base, nnz, G, units, first);
     L.n_units = (u32)units.size();
     L.grid = G;
     SB_TRY(L.units.alloc(units.size()));
@@ -485,65 +466,13 @@ int gather_build_t_range(sb_mat *mt, u64 c0, u64 nc, const u64 *ptr_local, const
 int gather_finish_t(sb_mat *mt, const std::vector<u64> &seg_len, const std::vector<u64> &seg_runs) {
     sb_ctx *ctx = mt->ctx;
     GatherLayout &L = mt->gt;
-    const u32 np = L.npanels;
-    const size_t nblk = np ? seg_len.size() / np : 0;
-    std::vector<u64> seg_pos(seg_len.size() + 1, 0);
-    std::vector<double> pn(np, 0.0);  // cost of a panel
-    double total = 0.0;
-    for (size_t k = 0; k < seg_len.size(); k++) {
-        seg_pos[k + 1] = seg_pos[k] + seg_len[k];
-        const double cost = (double)seg_len[k] + GA_FLUSH_COST * (double)seg_runs[k];
-        pn[k % np] += cost;
-        total += cost;
-    }
-    L.nnz = seg_pos[seg_len.size()];
-    const u32 G = (u32)ctx->sm_count;
-    // Panel-major cost line cut into G equal intervals: a CTA gets the fraction [f0, f1) of every segment of a panel
-    // (and, where an interval crosses a panel boundary, a fraction of the next panel: one more staging).
+    u64 total_nnz = 0;
+    for (u64 x : seg_len) total_nnz += x;
+    L.nnz = total_nnz;
     std::vector<GUnit> units;
     std::vector<u32> first;
-    auto add_units = [&](u32 p, double f0, double f1) {
-        for (size_t b = 0; b < nblk; b++) {
-            const size_t k = b * np + p;
-            const u64 len = seg_len[k];
-            if (len == 0) continue;
-            GUnit u;
-            u.begin = seg_pos[k] + (f0 <= 0.0 ? 0 : std::min<u64>(len, (u64)((double)len * f0)) & ~(u64)7);
-            u.end = seg_pos[k] + (f1 >= 1.0 ? len : std::min<u64>(len, (u64)((double)len * f1)) & ~(u64)7);
-            u.panel = p;
-            u.pad0 = 0;
-            u.pad1 = 0;
-            if (u.end > u.begin) units.push_back(u);
-        }
-    };
-    if (total > 0.0) {
-        const double per_cta = total / G;
-        u32 p = 0;
-        double used = 0.0;  // cost of panel p already handed out
-        for (u32 b = 0; b < G; b++) {
-            first.push_back((u32)units.size());
-            double need = per_cta;
-            while (p < np && need > 1e-9 * per_cta) {
-                const double left = pn[p] - used;
-                if (left <= 1e-9 * per_cta) {
-                    p++;
-                    used = 0.0;
-                    continue;
-                }
-                const bool last_cta = b + 1 == G;
-                const double take = last_cta ? left : std::min(left, need);
-                const double f0 = used / pn[p];
-                const double f1 = (take >= left) ? 1.0 : (used + take) / pn[p];
-                add_units(p, f0, f1);
-                used += take;
-                need -= take;
-                if (last_cta) need = per_cta;  // the last CTA sweeps up whatever rounding left behind
-            }
-        }
-    }
-    if (first.empty()) first.push_back(0);
-    L.grid = (u32)first.size();
-    first.push_back((u32)units.size());
+    gather_units_t(seg_len, seg_runs, L.npanels, (u32)ctx->sm_count, GA_FLUSH_COST, units, first);
+    L.grid = (u32)first.size() - 1;
     L.n_units = (u32)units.size();
     SB_TRY(L.units.alloc(units.size()));
     SB_TRY(L.cta_first.alloc(first.size()));

@@ -96,3 +96,18 @@ def test_compact_host_form_round_trip():
     assert 7 in big_pos and 8 not in big_pos
     with pytest.raises(ValueError):
         AdaptiveMat.compact_csc(np.array([70000], dtype=np.uint32), np.array([1], dtype=np.uint32))
+
+
+def test_gather_work_units_cover_every_entry_once():
+    """scan_rs_b200/csrc/gather_units.h (how the sparse streams are cut into work units and handed to CTAs) fuzzed on the
+    CPU: exact tiling of the stream, units inside their panel / segment, sweep order, balanced CTA loads."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "tests", "cpp", "gather_units_test.cpp")
+    exe = os.path.join(root, "tests", "cpp", "gather_units_test")
+    hdr = os.path.join(root, "scan_rs_b200", "csrc", "gather_units.h")
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-std=c++17", "-O1", src, "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ALL PASSED" in out.stdout, out.stdout + out.stderr
