@@ -99,7 +99,10 @@ SB_API int sb_sync(sb_ctx *ctx);
  * cell-major / gene-major kernels (A/B and accuracy reference).  "dense_genes" (default 2048) / "dense_min_density"
  * (default 0.12): size of the dense hot-gene panel of matrices uploaded afterwards (0 disables it).
  * "upload_sync" (default 1): drain the build stream after every stage of a pipelined upload.
- * "overlap" / "overlap_t" (default 0): experimental concurrent sparse + panel kernels. */
+ * "overlap" / "overlap_t" (default 0): experimental concurrent sparse + panel kernels.
+ * "dense_max_count" (default 15, 1..15): largest count kept in the dense panel of matrices uploaded afterwards.
+ * "panel_i8" (default 0): EXPERIMENTAL tcgen05 int8 contraction of the T-side panel (needs dense_max_count <= 3, a
+ * 2,048-gene panel and width <= 20); written without hardware access, off until validated. */
 SB_API int sb_set_option(sb_ctx *ctx, const char *name, double value);
 
 /* Page-locked host memory for inputs / outputs (optional): copies to and from pinned buffers run at PCIe

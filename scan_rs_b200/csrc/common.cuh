@@ -123,6 +123,8 @@ struct sb_ctx {
     int nranks = 1, rank = 0;
     int dense_cap = 2048;            // max genes in the dense hot panel (0 disables the hybrid layout)
     double dense_min_density = 0.12; // a gene joins the panel only if nnz/n_global is at least this
+    bool panel_i8 = false;           // EXPERIMENTAL (panel_i8.cu): T-side dense panel on tcgen05 int8 instead of FP64 mma.sync
+    int dense_max_count = 15;        // largest count kept in the dense panel of matrices uploaded afterwards (<= 15)
     bool upload_sync = true;         // pipelined upload: synchronise the build stream after every chunk (matrix.cu)
     bool use_gather = true;          // panelled gather kernels (gather.cu); false: the first-generation K7 / K8 of spmm.cu
     bool direct_projection = false;  // true: always run the wide Q^T A pass (bk_svd.rs:102,131) instead of the R^-T identity
@@ -183,6 +185,7 @@ struct sb_mat {
     // D[n x gd] (counts 1..SB_DENSE_MAX_COUNT, 0 elsewhere); every other entry -- cold genes and the rare larger
     // counts of hot genes -- stays in the sparse `cold_*` pair of layouts (same formats as cm / gm).
     u32 gd = 0;
+    u32 dense_max_count = 15;  // counts 1..dense_max_count live in D
     DevBuf<unsigned char> D;
     DevBuf<u32> hot_idx;      // [gd] gene id of panel column j
     DevBuf<u32> hot_of_gene;  // [m] panel column of a gene or 0xFFFFFFFF

@@ -137,6 +137,15 @@ extern "C" int sb_set_option(sb_ctx *ctx, const char *name, double value) {
         ctx->overlap_t = value != 0.0;
         return SB_OK;
     }
+    if (!strcmp(name, "panel_i8")) {  // experimental, see panel_i8.cu
+        ctx->panel_i8 = value != 0.0;
+        return SB_OK;
+    }
+    if (!strcmp(name, "dense_max_count")) {  // applies to matrices uploaded afterwards
+        if (value < 1 || value > 15) return sb_fail(SB_ERR_INVALID_ARG, "sb_set_option: dense_max_count must be 1..15");
+        ctx->dense_max_count = (int)value;
+        return SB_OK;
+    }
     if (!strcmp(name, "upload_sync")) {
         ctx->upload_sync = value != 0.0;
         return SB_OK;

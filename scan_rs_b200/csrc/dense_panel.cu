@@ -254,10 +254,15 @@ static inline u32 pass_width(u32 remaining) { return remaining >= 24 ? 24u : rem
 
 // `overlap`: half-size CTAs (256 threads, 32 K registers, < 190 KB shared) so that two CTAs of the sparse kernel stay
 // resident beside each of them, atomic epilogue, launched on `stream` (the auxiliary stream)
+// panel_i8.cu (experimental, default off)
+bool dense_t_i8_usable(const sb_nmat *a, u32 w);
+int dense_t_i8(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo);
+
 int dense_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo, cudaStream_t stream, bool overlap) {
     sb_mat *mt = a->mat;
     sb_ctx *ctx = mt->ctx;
     if (mt->gd == 0 || mt->n == 0 || w == 0) return SB_OK;
+    if (!overlap && stream == ctx->stream && dense_t_i8_usable(a, w)) return dense_t_i8(a, Y, ldy, w, out, ldo);
     const int threads = overlap ? 256 : 512;
     const size_t lut_bytes = (size_t)threads * LUT_STRIDE * sizeof(double);
     u64 ntiles = (mt->n + threads - 1) / threads;

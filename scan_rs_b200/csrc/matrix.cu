@@ -333,7 +333,8 @@ int mat_ensure_full_gm(sb_mat *mt) {
 // splits the cell-major stream into the dense panel D and the cold sparse entries (count / fill passes).
 // ptr / D are already offset to the first cell of the range; new_ptr and out are range-local.
 __global__ void k_split_hot(const u64 *__restrict__ ptr, const uint2 *__restrict__ cm, u64 n, const u32 *__restrict__ hot_of_gene, u32 gd,
-                            const u64 *__restrict__ new_ptr, u32 *__restrict__ counts, uint2 *__restrict__ out, unsigned char *__restrict__ D) {
+                            u32 max_count, const u64 *__restrict__ new_ptr, u32 *__restrict__ counts, uint2 *__restrict__ out,
+                            unsigned char *__restrict__ D) {
     u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
     int lane = threadIdx.x & 31;
@@ -346,7 +347,7 @@ __global__ void k_split_hot(const u64 *__restrict__ ptr, const uint2 *__restrict
             bool valid = k < e;
             uint2 z = valid ? cm[k] : make_uint2(0, 0);
             u32 h = valid ? hot_of_gene[z.x] : 0xFFFFFFFFu;
-            bool dense = valid && h != 0xFFFFFFFFu && z.y <= SB_DENSE_MAX_COUNT;
+            bool dense = valid && h != 0xFFFFFFFFu && z.y <= max_count;
             bool cold = valid && !dense;
             if (D && dense) D[c * (u64)gd + h] = (unsigned char)z.y;
             unsigned mask = __ballot_sync(0xffffffffu, cold);
@@ -368,6 +369,7 @@ __global__ void k_add_offset(const u64 *__restrict__ src, u64 n, u64 add, u64 *_
 static int select_hot_genes(sb_mat *mt, u64 c0, u64 c1) {
     sb_ctx *ctx = mt->ctx;
     mt->gd = 0;
+    mt->dense_max_count = (u32)std::min(std::max(ctx->dense_max_count, 1), (int)SB_DENSE_MAX_COUNT);
     if (ctx->dense_cap < 64 || mt->m < 64 || mt->n_global == 0) return SB_OK;
     SyncScope tr(ctx, "build: hot gene selection");
     DevBuf<u64> d_nnz;
@@ -417,7 +419,7 @@ static int split_range(sb_mat *mt, u64 c0, u64 c1, DevBuf<u64> &ptr_local, DevBu
     SB_TRY(ptr_local.alloc(nc + 1));
     int grid = grid_for(nc * 32, 256, ctx, 16);
     if (nc) {
-        k_split_hot<<<grid, 256, 0, ctx->stream>>>(mt->cm_ptr.p + c0, mt->cm.p, nc, mt->hot_of_gene.p, mt->gd, nullptr, counts.p, nullptr, nullptr);
+        k_split_hot<<<grid, 256, 0, ctx->stream>>>(mt->cm_ptr.p + c0, mt->cm.p, nc, mt->hot_of_gene.p, mt->gd, mt->dense_max_count, nullptr, counts.p, nullptr, nullptr);
         count_launch(ctx);
     }
     SB_TRY(exclusive_scan_u32_to_u64(ctx, counts.p, nc, ptr_local.p));
@@ -425,7 +427,7 @@ static int split_range(sb_mat *mt, u64 c0, u64 c1, DevBuf<u64> &ptr_local, DevBu
     SB_CUDA(cudaStreamSynchronize(ctx->stream));
     SB_TRY(cold.alloc(*cold_nnz));
     if (nc) {
-        k_split_hot<<<grid, 256, 0, ctx->stream>>>(mt->cm_ptr.p + c0, mt->cm.p, nc, mt->hot_of_gene.p, mt->gd, ptr_local.p, nullptr, cold.p,
+        k_split_hot<<<grid, 256, 0, ctx->stream>>>(mt->cm_ptr.p + c0, mt->cm.p, nc, mt->hot_of_gene.p, mt->gd, mt->dense_max_count, ptr_local.p, nullptr, cold.p,
                                                    mt->D.p + c0 * (u64)mt->gd);
         count_launch(ctx);
     }

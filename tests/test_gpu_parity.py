@@ -359,6 +359,36 @@ def test_panelled_gather_matches_first_generation_kernels(ctx, n_cells, n_genes,
         assert np.abs(got[0][1] - got[1][1]).max() <= 1e-11 * np.abs(ref_t).max()
 
 
+@pytest.mark.skipif(__import__("os").environ.get("SCANB200_TEST_EXPERIMENTAL") != "1",
+                    reason="experimental tcgen05 int8 panel kernel (csrc/panel_i8.cu): default off, not yet validated on hardware; "
+                           "set SCANB200_TEST_EXPERIMENTAL=1 to run")
+def test_experimental_int8_panel_matches_fp64_panel(ctx):
+    """T-side dense panel on the integer tensor cores (option panel_i8) against the FP64 mma.sync panel and the oracle,
+    on a panel restricted to counts 1..3 (option dense_max_count)."""
+    n_cells, n_genes = 6000, 33538
+    cfg, cm, _, (ip, g, c) = synth_pair(ctx, n_cells, n_genes, seed=44)
+    try:
+        ctx.set_option("dense_max_count", 3)
+        dm = sb.AdaptiveMat.from_csc(ctx, n_genes, n_cells, ip, g, c)
+    finally:
+        ctx.set_option("dense_max_count", 15)
+    a_o, a_g = orc.normalize(cm, orc.CELLRANGER), sb.normalize(dm, sb.Normalization.CellRanger)
+    rng = np.random.default_rng(8)
+    for w in (20, 7):
+        y = rng.standard_normal((w, n_genes))
+        ref = a_o.rdot(y)
+        got = {}
+        for on in (0, 1):
+            try:
+                ctx.set_option("panel_i8", on)
+                got[on] = a_g.rdot(y)
+            finally:
+                ctx.set_option("panel_i8", 0)
+            assert np.abs(got[on] - ref).max() <= 1e-10 * np.abs(ref).max(), (on, w)
+        assert np.abs(got[0] - got[1]).max() <= 1e-11 * np.abs(ref).max()
+        assert np.abs(got[0] - got[1]).max() > 0.0  # the two paths really are different kernels
+
+
 def test_pipelined_upload_matches_plain_upload(ctx):
     """Large cell-major uploads are chunked and overlapped with the layout build (hot genes picked from the first
     chunk); the result must be the same matrix as the unpipelined gene-major upload and match the oracle."""
