@@ -76,3 +76,34 @@ for S in (6, 7, 8):
         else:
             frac = 0.0
         report(f"int8 slices S={S}, counts 1..{kmax} (rest {frac:.1%} in f64)", T)
+
+# ---------------------------------------------------------------- N side: P[hot_j,:] = sum_c L_c(D[c,j]) * X[c,:]
+# The contraction runs over the cells, so the digit planes are those of the B operand L_c(k) * X[c,:] (one fixed-point
+# scale per column and count level, taken over all cells) and the 0/1 operand is [D == k]^T.  X is a realistic block:
+# A^T . Y of the normalized matrix (what the Krylov loop feeds to A . X).
+print("\nN side (contraction over cells)")
+X = a.rdot(Y.T[:w]).T if hasattr(a, "rdot") else None      # n x w
+Lval_T = Lval.T                                            # gd x n
+truth_n = Lval_T.astype(ld) @ X.astype(ld)
+scale_n = np.abs(Lval_T) @ np.abs(X)
+
+def report_n(name, P):
+    err = np.abs(P.astype(ld) - truth_n).astype(np.float64)
+    print(f"{name:44s} max err / (eps*sum|terms|) = {np.max(err / (eps * scale_n)):9.3f}   max rel to |P| = {np.max(err / np.abs(truth_n).astype(np.float64).max()):.2e}")
+
+report_n("f64 contraction (numpy dot, as the DMMA kernel)", Lval_T @ X)
+for S in (7, 8):
+    P = np.zeros((gd, w))
+    for k in range(1, 4):
+        Bk = L[:, k][:, None] * X                          # n x w, the level's B operand in f64
+        digs, e = digits(Bk, S)
+        Mk = (D == k).astype(np.int32).T                   # gd x n
+        acc = np.zeros((gd, w))
+        for s in range(S):
+            p = Mk @ digs[s].astype(np.int32)
+            assert np.abs(p).max() < 2 ** 31
+            acc += p.astype(np.float64) * 2.0 ** (7 * s)
+        P += acc * 2.0 ** (e - (7 * S - 1))[None, :]
+    rest = np.where(D > 3, Lval, 0.0).T
+    P += rest @ X
+    report_n(f"int8 slices S={S}, counts 1..3 (rest in f64)", P)
