@@ -101,6 +101,8 @@ SB_API int sb_sync(sb_ctx *ctx);
  * "upload_sync" (default 1): drain the build stream after every stage of a pipelined upload.
  * "overlap" / "overlap_t" (default 0): experimental concurrent sparse + panel kernels.
  * "dense_max_count" (default 15, 1..15): largest count kept in the dense panel of matrices uploaded afterwards.
+ * "gather_split" (default 0): EXPERIMENTAL separate 4-byte stream for the sparse entries with a count of 1 (gather_split.cu);
+ * written without hardware access, off until validated.
  * "panel_i8" (default 0): EXPERIMENTAL tcgen05 int8 contraction of the T-side panel (needs dense_max_count <= 3, a
  * 2,048-gene panel and width <= 20); written without hardware access, off until validated. */
 SB_API int sb_set_option(sb_ctx *ctx, const char *name, double value);

@@ -123,6 +123,7 @@ struct sb_ctx {
     int nranks = 1, rank = 0;
     int dense_cap = 2048;            // max genes in the dense hot panel (0 disables the hybrid layout)
     double dense_min_density = 0.12; // a gene joins the panel only if nnz/n_global is at least this
+    bool gather_split = false;       // EXPERIMENTAL (gather_split.cu): separate 4-byte stream for the entries with a count of 1
     bool panel_i8 = false;           // EXPERIMENTAL (panel_i8.cu): T-side dense panel on tcgen05 int8 instead of FP64 mma.sync
     int dense_max_count = 15;        // largest count kept in the dense panel of matrices uploaded afterwards (<= 15)
     bool upload_sync = true;         // pipelined upload: synchronise the build stream after every chunk (matrix.cu)
@@ -163,6 +164,14 @@ struct GatherLayout {
     DevBuf<u32> slot_gene;  // T side: [npanels * rows] gene of a slot or 0xFFFFFFFF
 };
 
+// EXPERIMENTAL (gather_split.cu, default off): each side's stream split into a 4-byte "count == 1" stream and a general one
+struct GatherSplit {
+    bool tried = false, ready = false;
+    DevBuf<u32> n_ones, t_ones;
+    DevBuf<uint2> n_gen, t_gen;
+    GatherLayout n1, ng, t1, tg;  // units of the four streams (n1 / t1: ones, walked by k_gather_ones)
+};
+
 struct sb_mat {
     sb_ctx *ctx = nullptr;
     u32 m = 0;            // genes
@@ -197,6 +206,8 @@ struct sb_mat {
     // panelled gather layouts over the sparse set the products use (the cold entries when gd > 0, else all entries)
     GatherLayout gn, gt;
     DevBuf<u32> slot_of_gene;  // [m] T-side slot (rank by expression) of a gene
+    std::vector<u64> t_seg_len, t_seg_runs;  // T side: entries / runs of every (block, panel) segment, in stream order
+    GatherSplit split;
     // cached integer reductions
     DevBuf<u32> cell_tot;
     bool have_cell_tot = false;

@@ -137,6 +137,10 @@ extern "C" int sb_set_option(sb_ctx *ctx, const char *name, double value) {
         ctx->overlap_t = value != 0.0;
         return SB_OK;
     }
+    if (!strcmp(name, "gather_split")) {  // experimental, see gather_split.cu
+        ctx->gather_split = value != 0.0;
+        return SB_OK;
+    }
     if (!strcmp(name, "panel_i8")) {  // experimental, see panel_i8.cu
         ctx->panel_i8 = value != 0.0;
         return SB_OK;

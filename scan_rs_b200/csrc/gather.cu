@@ -469,6 +469,8 @@ int gather_finish_t(sb_mat *mt, const std::vector<u64> &seg_len, const std::vect
     u64 total_nnz = 0;
     for (u64 x : seg_len) total_nnz += x;
     L.nnz = total_nnz;
+    mt->t_seg_len = seg_len;  // kept for gather_split.cu
+    mt->t_seg_runs = seg_runs;
     std::vector<GUnit> units;
     std::vector<u32> first;
     gather_units_t(seg_len, seg_runs, L.npanels, (u32)ctx->sm_count, GA_FLUSH_COST, units, first);
