@@ -126,9 +126,19 @@ struct sb_ctx {
     bool gather_split = false;       // EXPERIMENTAL (gather_split.cu): separate 4-byte stream for the entries with a count of 1
     bool panel_i8 = false;           // EXPERIMENTAL (panel_i8.cu): T-side dense panel on tcgen05 int8 instead of FP64 mma.sync
     int dense_max_count = 15;        // largest count kept in the dense panel of matrices uploaded afterwards (<= 15)
+    // dense half of the hybrid layout of matrices built afterwards: 0 none, 1 u8 panel on the FP64 mma.sync path (dense_panel.cu),
+    // 2 bit planes on the int8 tensor cores (planes.cu)
+    int panel_mode = 2;
+    int plane_cap = 12288;           // most ranks a plane may cover
+    int plane_levels = 6;            // most count levels kept as planes (<= PL_MAX_LEVELS)
+    double plane_min_density = 0.01; // a 128-rank block joins level k only if this fraction of the cells has exactly that count
     bool upload_sync = true;         // pipelined upload: synchronise the build stream after every chunk (matrix.cu)
     bool use_gather = true;          // panelled gather kernels (gather.cu); false: the first-generation K7 / K8 of spmm.cu
     bool direct_projection = false;  // true: always run the wide Q^T A pass (bk_svd.rs:102,131) instead of the R^-T identity
+    bool verify_projection = false;  // true: always check the R^-T identity a posteriori (default: only when cond(R) > 1e9)
+    bool own_dense = true;           // QR / Gram / projections on the repo's kernels (dense_own.cu); false: cuSOLVER / cuBLAS (dense.cu)
+    double last_cond_r = 0.0, last_probe_resid = 0.0;  // diagnostics of the last sb_bksvd
+    int last_fallbacks = 0;
     // profiling
     bool profile_on = false;
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending;  // phase, (start, stop)
@@ -148,6 +158,28 @@ struct sb_ctx {
 #define SB_GENE_MASK 0x3FFFFFu
 #define SB_MAX_PANEL_CELLS 1024
 #define GA_TBLOCK 16384  // cells per block of the T-side gather order (gather.cu)
+
+// Bit planes of the dense half on the int8 tensor cores (planes.cu)
+#define PL_MAX_LEVELS 6
+struct PlUnitT {  // T side: a block of 1,024 ranks x up to three levels; CTAs [cta0, cta0 + nctas) stride over the cell tiles
+    u32 g0, nlev;
+    u32 lev[3], nkb[3];  // level index; 64-gene K blocks of the level inside the block (non-increasing)
+    u32 cta0, nctas;
+};
+struct PlUnitN {  // N side: a group of 384 ranks; levels 0..nlev-1; CTAs split the cell tiles into contiguous ranges
+    u32 g0, nlev;
+    u32 mt[PL_MAX_LEVELS];  // 128-gene M tiles of each level inside the group (non-increasing)
+    u32 cta0, nctas;
+};
+struct PlaneSet {
+    bool active = false;
+    u32 L = 0;
+    u32 G[PL_MAX_LEVELS] = {0, 0, 0, 0, 0, 0};  // ranks covered by level k + 1: multiples of 128, non-increasing
+    u64 ntiles = 0;                              // cell tiles of 128
+    DevBuf<u32> bits[PL_MAX_LEVELS];             // [ntiles][G / 32][128] words
+    DevBuf<char> units_t, units_n;
+    u32 n_units_t = 0, n_units_n = 0, t_grid = 0, n_grid = 0;
+};
 
 // One side of the panelled gather: the entry stream, its work units and (T side) the gene of every panel slot.
 struct GatherLayout {
@@ -198,6 +230,7 @@ struct sb_mat {
     DevBuf<unsigned char> D;
     DevBuf<u32> hot_idx;      // [gd] gene id of panel column j
     DevBuf<u32> hot_of_gene;  // [m] panel column of a gene or 0xFFFFFFFF
+    PlaneSet pl;  // panel_mode 2: bit planes instead of D (gd = ranks of level 1; hot_idx / hot_of_gene are in rank order)
     u64 cold_nnz = 0;
     DevBuf<u64> cold_cm_ptr;
     DevBuf<uint2> cold_cm;

@@ -129,6 +129,14 @@ extern "C" int sb_set_option(sb_ctx *ctx, const char *name, double value) {
         ctx->direct_projection = value != 0.0;
         return SB_OK;
     }
+    if (!strcmp(name, "verify_projection")) {
+        ctx->verify_projection = value != 0.0;
+        return SB_OK;
+    }
+    if (!strcmp(name, "own_dense")) {  // 1 (default): dense_own.cu kernels; 0: cuSOLVER / cuBLAS
+        ctx->own_dense = value != 0.0;
+        return SB_OK;
+    }
     if (!strcmp(name, "overlap")) {  // A.X: run the sparse and the dense-panel kernel concurrently
         ctx->overlap = value != 0.0;
         return SB_OK;
@@ -164,6 +172,25 @@ extern "C" int sb_set_option(sb_ctx *ctx, const char *name, double value) {
     }
     if (!strcmp(name, "dense_min_density")) {
         ctx->dense_min_density = value;
+        return SB_OK;
+    }
+    // dense half of matrices built afterwards: 0 none, 1 u8 panel / FP64 mma.sync (dense_panel.cu), 2 bit planes / int8 tcgen05 (planes.cu)
+    if (!strcmp(name, "panel_mode")) {
+        if (value != 0.0 && value != 1.0 && value != 2.0) return sb_fail(SB_ERR_INVALID_ARG, "sb_set_option: panel_mode must be 0, 1 or 2");
+        ctx->panel_mode = (int)value;
+        return SB_OK;
+    }
+    if (!strcmp(name, "plane_cap")) {
+        ctx->plane_cap = value < 0 ? 0 : (int)value;
+        return SB_OK;
+    }
+    if (!strcmp(name, "plane_levels")) {
+        if (value < 1 || value > PL_MAX_LEVELS) return sb_fail(SB_ERR_INVALID_ARG, "sb_set_option: plane_levels must be 1..%d", PL_MAX_LEVELS);
+        ctx->plane_levels = (int)value;
+        return SB_OK;
+    }
+    if (!strcmp(name, "plane_min_density")) {
+        ctx->plane_min_density = value;
         return SB_OK;
     }
     return sb_fail(SB_ERR_INVALID_ARG, "sb_set_option: unknown option %s", name);

@@ -107,22 +107,17 @@ int gram(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 ld, double *G, bool 
     return SB_OK;
 }
 
-// symmetric eigendecomposition of G (col-major w x w, overwritten by eigenvectors); evals ascending
-int eigh(sb_ctx *ctx, double *G, u32 w, double *evals_dev) {
+// symmetric eigendecomposition of G (col-major w x w, overwritten by eigenvectors); evals ascending.  The solver's status
+// goes to info_dev (device) and is read by the caller with its outputs: no host synchronisation here.
+int eigh(sb_ctx *ctx, double *G, u32 w, double *evals_dev, int *info_dev) {
     TraceScope trc(ctx, "dense: eigh");
     ProfScope ps(ctx, PH_DENSE);
     int lwork = 0;
     SB_CUSOLVER(cusolverDnDsyevd_bufferSize(ctx->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)w, G, (int)w, evals_dev, &lwork));
     DevBuf<double> work;
-    DevBuf<int> info;
     SB_TRY(work.alloc(lwork));
-    SB_TRY(info.alloc(1));
-    SB_CUSOLVER(cusolverDnDsyevd(ctx->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)w, G, (int)w, evals_dev, work.p, lwork, info.p));
+    SB_CUSOLVER(cusolverDnDsyevd(ctx->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)w, G, (int)w, evals_dev, work.p, lwork, info_dev));
     count_launch(ctx, false);
-    int h_info = 0;
-    SB_CUDA(cudaMemcpyAsync(&h_info, info.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    SB_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (h_info != 0) return sb_fail(SB_ERR_LINALG, "eigendecomposition failed: info = %d", h_info);
     return SB_OK;
 }
 

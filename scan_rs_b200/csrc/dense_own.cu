@@ -1,0 +1,377 @@
+// dense_own.cu -- the repo's own kernels for the tall-skinny dense steps of the Krylov loop, replacing
+// the cuSOLVER / cuBLAS calls of dense.cu on the common path:
+//   syrk_tall      G = A^T A for a tall row-major block (FP64 mma.sync m8n8k4, shared-memory staged, symmetric blocks once)
+//   gemm_tall      Out = A . S for a tall block and a small matrix (same tensor path)
+//   chol_inv       Cholesky of a small SPD matrix (optionally shifted) and the inverse of its factor, one CTA
+//   qr_chol        thin QR of a tall block by shifted CholeskyQR3 (Fukaya et al. 2020): three rounds of Gram -> Cholesky -> A R^-1.
+//                  Replaces LAPACK dgeqrf + dorgqr at bk_svd.rs:94,98,123,127.  The Krylov basis K is ill-conditioned by
+//                  construction (cond 1e8..1e9): plain CholeskyQR fails there, the shifted first round brings the
+//                  condition number down to ~1e5 and two more rounds restore orthogonality to rounding.  Everything is a GEMM-shaped
+//                  kernel or a one-CTA kernel on a b x b matrix: no host synchronisation, no Householder panel latency, and nothing
+//                  that has to be replicated at length over ranks.  Breakdown (a non-positive pivot: exactly rank-deficient input)
+//                  raises a device flag that the PCA driver reads with its outputs; it then reruns with the Householder path.
+#include "common.cuh"
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// ---------------------------------------------------------------- G += A^T A
+#define SY_THREADS 512
+#define SY_BLK 128
+#define SY_RC 16
+#define SY_STRIDE 136  // == 8 mod 32 doubles: the four k rows of a fragment land in disjoint bank groups
+
+// grid (row chunks, block pairs bi <= bj).  G: column-major w x w, zeroed by the caller; only blocks with bi <= bj are written.
+__global__ void __launch_bounds__(SY_THREADS, 1)
+k_syrk_tall(const double *__restrict__ A, u64 rows, u32 w, u32 ld, double *__restrict__ G, u32 nb) {
+    extern __shared__ __align__(16) double sy_smem[];
+    double(*sI)[SY_RC][SY_STRIDE] = reinterpret_cast<double(*)[SY_RC][SY_STRIDE]>(sy_smem);
+    double(*sJ)[SY_RC][SY_STRIDE] = reinterpret_cast<double(*)[SY_RC][SY_STRIDE]>(sy_smem + 2 * SY_RC * SY_STRIDE);
+    // decode the block pair
+    u32 bi = 0, bj = 0;
+    {
+        u32 p = blockIdx.y;
+        for (bi = 0; bi < nb; bi++) {
+            const u32 cnt = nb - bi;
+            if (p < cnt) {
+                bj = bi + p;
+                break;
+            }
+            p -= cnt;
+        }
+    }
+    const bool diag = bi == bj;
+    const u32 I0 = bi * SY_BLK, J0 = bj * SY_BLK;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int wr = warp >> 2, wc = warp & 3;
+    const int fr = lane >> 2, fk = lane & 3;
+    u64 per = (rows + gridDim.x - 1) / gridDim.x;
+    per = (per + SY_RC - 1) / SY_RC * SY_RC;
+    const u64 r_lo = min(rows, (u64)blockIdx.x * per), r_hi = min(rows, r_lo + per);
+    if (r_lo >= r_hi) return;
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+    // each thread moves 4 doubles per operand per stage: row = t / 32, columns 4 (t % 32) .. + 3
+    const int lrow = t >> 5, lcol = (t & 31) * 4;
+    double ri[4], rj[4];
+    auto gload = [&](u64 r0) {
+        const u64 r = r0 + lrow;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const u32 ci = I0 + lcol + i, cj = J0 + lcol + i;
+            ri[i] = (r < r_hi && ci < w) ? A[r * (size_t)ld + ci] : 0.0;
+            rj[i] = (!diag && r < r_hi && cj < w) ? A[r * (size_t)ld + cj] : 0.0;
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            sI[buf][lrow][lcol + i] = ri[i];
+            if (!diag) sJ[buf][lrow][lcol + i] = rj[i];
+        }
+    };
+    gload(r_lo);
+    sstore(0);
+    __syncthreads();
+    int buf = 0;
+    for (u64 r0 = r_lo; r0 < r_hi; r0 += SY_RC, buf ^= 1) {
+        const bool more = r0 + SY_RC < r_hi;
+        if (more) gload(r0 + SY_RC);
+        double(*sB)[SY_STRIDE] = diag ? sI[buf] : sJ[buf];
+#pragma unroll
+        for (int ks = 0; ks < SY_RC / 4; ks++) {
+            double a[4], b[4];
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++) a[mt] = sI[buf][ks * 4 + fk][(wr * 4 + mt) * 8 + fr];
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) b[nt] = sB[ks * 4 + fk][(wc * 4 + nt) * 8 + fr];
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+        }
+        if (more) sstore(buf ^ 1);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+            const u32 i = I0 + (wr * 4 + mt) * 8 + fr;
+            const u32 j = J0 + (wc * 4 + nt) * 8 + 2 * fk;
+            if (i < w && j < w) atomicAdd(G + (size_t)j * w + i, acc[mt][nt][0]);
+            if (i < w && j + 1 < w) atomicAdd(G + (size_t)(j + 1) * w + i, acc[mt][nt][1]);
+        }
+}
+
+// fills the blocks below the block diagonal from their transposes
+__global__ void k_symmetrize_blocks(double *__restrict__ G, u32 w) {
+    const u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (u64)w * w) return;
+    const u32 j = (u32)(idx / w), i = (u32)(idx - (u64)j * w);  // element (i, j)
+    if (i / SY_BLK > j / SY_BLK) G[idx] = G[(size_t)i * w + j];
+}
+
+int syrk_tall(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 ld, double *G) {
+    SB_CUDA(cudaMemsetAsync(G, 0, (size_t)w * w * sizeof(double), ctx->stream));
+    if (rows == 0 || w == 0) return SB_OK;
+    const u32 nb = (w + SY_BLK - 1) / SY_BLK;
+    const u32 pairs = nb * (nb + 1) / 2;
+    u32 chunks = std::max<u32>(1, (u32)std::min<u64>((rows + 4 * SY_RC - 1) / (4 * SY_RC), std::max<u32>(1, (u32)ctx->sm_count * 2 / pairs)));
+    const size_t smem = (size_t)4 * SY_RC * SY_STRIDE * sizeof(double);
+    SB_CUDA(cudaFuncSetAttribute(k_syrk_tall, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_syrk_tall<<<dim3(chunks, pairs), SY_THREADS, smem, ctx->stream>>>(A, rows, w, ld, G, nb);
+    count_launch(ctx);
+    if (nb > 1) {
+        k_symmetrize_blocks<<<cdiv((u64)w * w, 256), 256, 0, ctx->stream>>>(G, w);
+        count_launch(ctx);
+    }
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
+// ---------------------------------------------------------------- Out = A . S
+#define GM_THREADS 512
+#define GM_KC 16
+#define GM_ASTRIDE 20   // == 4 mod 32 doubles: eight rows x four k land in 32 distinct doubles
+#define GM_SSTRIDE 136
+
+// A row-major rows x w (lda); S column-major w x k (lds); Out row-major rows x k (ldo; pad columns k..ldo-1 are zeroed)
+__global__ void __launch_bounds__(GM_THREADS, 1)
+k_gemm_tall(const double *__restrict__ A, u64 rows, u32 w, u32 lda, const double *__restrict__ S, u32 k, u32 lds, double *__restrict__ Out, u32 ldo) {
+    extern __shared__ __align__(16) double gm_smem[];
+    double(*sA)[128][GM_ASTRIDE] = reinterpret_cast<double(*)[128][GM_ASTRIDE]>(gm_smem);
+    double(*sS)[GM_KC][GM_SSTRIDE] = reinterpret_cast<double(*)[GM_KC][GM_SSTRIDE]>(gm_smem + 2 * 128 * GM_ASTRIDE);
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int wr = warp >> 2, wc = warp & 3;
+    const int fr = lane >> 2, fk = lane & 3;
+    const u64 r0 = (u64)blockIdx.x * 128;
+    const u32 c0 = blockIdx.y * 128;
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+    // staging: A chunk 128 rows x 16 k: thread -> row t / 4, k 4 (t % 4) .. + 3; S chunk 16 k x 128 cols: thread -> col t / 4, k 4 (t % 4) .. + 3
+    const int arow = t >> 2, ak = (t & 3) * 4;
+    double ra[4], rs[4];
+    auto gload = [&](u32 k0) {
+        const u64 r = r0 + arow;
+        const u32 c = c0 + arow;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const u32 kk = k0 + ak + i;
+            ra[i] = (r < rows && kk < w) ? A[r * (size_t)lda + kk] : 0.0;
+            rs[i] = (c < k && kk < w) ? S[(size_t)c * lds + kk] : 0.0;
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            sA[buf][arow][ak + i] = ra[i];
+            sS[buf][ak + i][arow] = rs[i];
+        }
+    };
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    int buf = 0;
+    for (u32 k0 = 0; k0 < w; k0 += GM_KC, buf ^= 1) {
+        const bool more = k0 + GM_KC < w;
+        if (more) gload(k0 + GM_KC);
+#pragma unroll
+        for (int ks = 0; ks < GM_KC / 4; ks++) {
+            double a[4], b[4];
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++) a[mt] = sA[buf][(wr * 4 + mt) * 8 + fr][ks * 4 + fk];
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) b[nt] = sS[buf][ks * 4 + fk][(wc * 4 + nt) * 8 + fr];
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+        }
+        if (more) sstore(buf ^ 1);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++) {
+        const u64 r = r0 + (wr * 4 + mt) * 8 + fr;
+        if (r >= rows) continue;
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+            const u32 c = c0 + (wc * 4 + nt) * 8 + 2 * fk;  // even; ldo is even
+            if (c + 1 < ldo) *reinterpret_cast<double2 *>(Out + r * (size_t)ldo + c) = make_double2(c < k ? acc[mt][nt][0] : 0.0, c + 1 < k ? acc[mt][nt][1] : 0.0);
+        }
+    }
+}
+
+int gemm_tall(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 lda, const double *S, u32 k, u32 lds, double *Out, u32 ldo) {
+    if (rows == 0 || k == 0) return SB_OK;
+    if (ldo & 1) return sb_fail(SB_ERR_INVALID_ARG, "gemm_tall: odd leading dimension");
+    const u32 cols = (std::max(k, ldo) + 127) / 128;  // also zero the pad columns
+    const size_t smem = (size_t)(2 * 128 * GM_ASTRIDE + 2 * GM_KC * GM_SSTRIDE) * sizeof(double);
+    SB_CUDA(cudaFuncSetAttribute(k_gemm_tall, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_gemm_tall<<<dim3(cdiv(rows, 128), cols), GM_THREADS, smem, ctx->stream>>>(A, rows, w, lda, S, k, lds, Out, ldo);
+    count_launch(ctx);
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
+// ---------------------------------------------------------------- small SPD: Cholesky + inverse of the factor (one CTA)
+// G: column-major w x w symmetric (upper triangle read).  On return the upper triangle of G holds R (G + shift I = R^T R) and
+// Rinv (column-major, upper, zero below) its inverse.  shift = shift_coef * trace(G).  flag |= 1 on a non-positive pivot.
+#define CH_THREADS 1024
+__global__ void __launch_bounds__(CH_THREADS, 1) k_chol_inv(double *__restrict__ G, u32 w, double shift_coef, double *__restrict__ Rinv, int *__restrict__ flag) {
+    extern __shared__ __align__(16) double ch_smem[];
+    __shared__ double s_red[32];
+    __shared__ double s_piv;
+    __shared__ double s_row[1024];  // row j of R (w <= 1024)
+    const u32 t = threadIdx.x;
+    const bool in_smem = (size_t)w * w * sizeof(double) <= 160 * 1024;
+    double *M = in_smem ? ch_smem : G;
+    if (in_smem)
+        for (u32 i = t; i < w * w; i += CH_THREADS) M[i] = G[i];
+    // trace
+    double tr = 0.0;
+    for (u32 i = t; i < w; i += CH_THREADS) tr += G[(size_t)i * w + i];
+    for (int o = 16; o > 0; o >>= 1) tr += __shfl_xor_sync(0xffffffffu, tr, o);
+    if ((t & 31) == 0) s_red[t >> 5] = tr;
+    __syncthreads();
+    if (t < 32) {
+        double v = s_red[t];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (t == 0) s_red[0] = v;
+    }
+    __syncthreads();
+    const double shift = shift_coef * s_red[0];
+    __syncthreads();
+    for (u32 i = t; i < w; i += CH_THREADS) M[(size_t)i * w + i] += shift;
+    __syncthreads();
+    // right-looking Cholesky on the upper triangle: element (r, c), r <= c, at M[c * w + r]
+    for (u32 j = 0; j < w; j++) {
+        if (t == 0) {
+            double d = M[(size_t)j * w + j];
+            if (!(d > 0.0)) {
+                atomicOr(flag, 1);
+                d = 1.0;
+            }
+            s_piv = sqrt(d);
+            M[(size_t)j * w + j] = s_piv;
+        }
+        __syncthreads();
+        const double inv = 1.0 / s_piv;
+        for (u32 c = j + 1 + t; c < w; c += CH_THREADS) {
+            const double v = M[(size_t)c * w + j] * inv;
+            M[(size_t)c * w + j] = v;
+            s_row[c] = v;
+        }
+        __syncthreads();
+        // trailing update: M(r, c) -= R(j, r) R(j, c) for j < r <= c: a warp per column c, lanes along r (contiguous)
+        for (u32 c = j + 1 + (t >> 5); c < w; c += CH_THREADS / 32) {
+            const double rc = s_row[c];
+            for (u32 r = j + 1 + (t & 31); r <= c; r += 32) M[(size_t)c * w + r] -= s_row[r] * rc;
+        }
+        __syncthreads();
+    }
+    // inverse of the upper factor, one column per thread: R x = e_c
+    for (u32 c = t; c < w; c += CH_THREADS) {
+        double *x = Rinv + (size_t)c * w;
+        for (u32 i = c + 1; i < w; i++) x[i] = 0.0;
+        x[c] = 1.0 / M[(size_t)c * w + c];
+        for (u32 ii = c; ii-- > 0;) {
+            double s = 0.0;
+            for (u32 kk = ii + 1; kk <= c; kk++) s += M[(size_t)kk * w + ii] * x[kk];
+            x[ii] = -s / M[(size_t)ii * w + ii];
+        }
+    }
+    __syncthreads();
+    if (in_smem)
+        for (u32 i = t; i < w * w; i += CH_THREADS) G[i] = M[i];
+}
+
+int chol_inv(sb_ctx *ctx, double *G, u32 w, double shift_coef, double *Rinv, int *flag) {
+    if (w == 0) return SB_OK;
+    if (w > 1024) return sb_fail(SB_ERR_UNSUPPORTED, "chol_inv: more than 1024 columns");
+    const size_t bytes = (size_t)w * w * sizeof(double);
+    const size_t smem = bytes <= 160 * 1024 ? bytes : 0;
+    SB_CUDA(cudaFuncSetAttribute(k_chol_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    k_chol_inv<<<1, CH_THREADS, smem, ctx->stream>>>(G, w, shift_coef, Rinv, flag);
+    count_launch(ctx);
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
+// C (w x w, column-major) = A . B for upper-triangular A, B (small; one thread per output element)
+__global__ void k_tri_mul(const double *__restrict__ A, const double *__restrict__ B, double *__restrict__ C, u32 w) {
+    const u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (u64)w * w) return;
+    const u32 j = (u32)(idx / w), i = (u32)(idx - (u64)j * w);
+    double s = 0.0;
+    if (i <= j)
+        for (u32 kk = i; kk <= j; kk++) s += A[(size_t)kk * w + i] * B[(size_t)j * w + kk];
+    C[idx] = s;
+}
+
+// ---------------------------------------------------------------- thin QR by shifted CholeskyQR3
+// A (row-major rows x w, ld) is replaced by Q; Rinv_out (device, column-major w x w, may be NULL) receives R^-1 with A_in = Q R.
+// tmp: a scratch block of the same shape as A.  Needs rows >= w.  *flag is raised on breakdown (the caller falls back).
+int qr_chol(sb_ctx *ctx, double *A, double *tmp, u64 rows, u32 w, u32 ld, double *Rinv_out, int *flag) {
+    ProfScope ps(ctx, PH_DENSE);
+    DevBuf<double> G, Ri, Racc, Rtmp;
+    SB_TRY(G.alloc((size_t)w * w));
+    SB_TRY(Ri.alloc((size_t)w * w));
+    if (Rinv_out) SB_TRY(Rtmp.alloc((size_t)w * w));
+    // shift of the first round: 11 (m n + n (n + 1)) u ||A||_2^2, with the trace as the bound on ||A||_2^2
+    const double u = 1.1102230246251565e-16;
+    const double coef0 = 11.0 * ((double)rows * w + (double)w * (w + 1)) * u;
+    double *src = A, *dst = tmp;
+    for (int pass = 0; pass < 3; pass++) {
+        SB_TRY(syrk_tall(ctx, src, rows, w, ld, G.p));
+        SB_TRY(chol_inv(ctx, G.p, w, pass == 0 ? coef0 : 0.0, Ri.p, flag));
+        SB_TRY(gemm_tall(ctx, src, rows, w, ld, Ri.p, w, w, dst, ld));
+        if (Rinv_out) {
+            if (pass == 0) {
+                SB_CUDA(cudaMemcpyAsync(Rinv_out, Ri.p, (size_t)w * w * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+            } else {
+                k_tri_mul<<<cdiv((u64)w * w, 256), 256, 0, ctx->stream>>>(Rinv_out, Ri.p, Rtmp.p, w);
+                count_launch(ctx);
+                SB_CUDA(cudaMemcpyAsync(Rinv_out, Rtmp.p, (size_t)w * w * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+        }
+        std::swap(src, dst);
+    }
+    // three swaps: the result is in `tmp`
+    SB_CUDA(cudaMemcpyAsync(A, tmp, rows * (size_t)ld * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    return SB_OK;
+}
+
+// ---------------------------------------------------------------- top-k eigenpairs -> projection matrices (device resident)
+// W: eigenvectors, column-major wq x wq, eigenvalues ascending.  Wsel[i] = eigenvector of the i-th largest eigenvalue,
+// Wsc[i] = Wsel[i] / sigma_i, S[i] = sigma_i = sqrt(max(lambda, 0)).
+__global__ void k_topk(const double *__restrict__ W, const double *__restrict__ ev, u32 wq, u32 k, double *__restrict__ Wsel, double *__restrict__ Wsc,
+                       double *__restrict__ S) {
+    const u32 idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= wq * k) return;
+    const u32 i = idx / wq, r = idx - i * wq;
+    const u32 src = wq - 1 - i;
+    const double lam = ev[src];
+    const double sig = lam > 0.0 ? sqrt(lam) : 0.0;
+    const double x = W[(size_t)src * wq + r];
+    Wsel[idx] = x;
+    Wsc[idx] = sig > 0.0 ? x * (1.0 / sig) : 0.0;
+    if (r == 0) S[i] = sig;
+}
+
+int topk_select(sb_ctx *ctx, const double *W, const double *ev, u32 wq, u32 k, double *Wsel, double *Wsc, double *S) {
+    if (wq == 0 || k == 0) return SB_OK;
+    k_topk<<<cdiv((u64)wq * k, 256), 256, 0, ctx->stream>>>(W, ev, wq, k, Wsel, Wsc, S);
+    count_launch(ctx);
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}

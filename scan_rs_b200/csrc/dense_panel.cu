@@ -258,10 +258,19 @@ static inline u32 pass_width(u32 remaining) { return remaining >= 24 ? 24u : rem
 bool dense_t_i8_usable(const sb_nmat *a, u32 w);
 int dense_t_i8(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo);
 
+// planes.cu: the same three products over the bit planes (panel_mode 2)
+int planes_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo);
+int planes_n(sb_nmat *a, const double *X, u32 ldx, u32 w, double *P, u32 ldp);
+int planes_moments(sb_nmat *a, double *S1, double *S2);
+
 int dense_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo, cudaStream_t stream, bool overlap) {
     sb_mat *mt = a->mat;
     sb_ctx *ctx = mt->ctx;
     if (mt->gd == 0 || mt->n == 0 || w == 0) return SB_OK;
+    if (mt->pl.active) {
+        if (stream != ctx->stream) return sb_fail(SB_ERR_UNSUPPORTED, "dense_t: the plane kernels run on the library stream only");
+        return planes_t(a, Y, ldy, w, out, ldo);
+    }
     if (!overlap && stream == ctx->stream && dense_t_i8_usable(a, w)) return dense_t_i8(a, Y, ldy, w, out, ldo);
     const int threads = overlap ? 256 : 512;
     const size_t lut_bytes = (size_t)threads * LUT_STRIDE * sizeof(double);
@@ -302,6 +311,10 @@ int dense_n(sb_nmat *a, const double *X, u32 ldx, u32 w, double *P, u32 ldp, cud
     sb_mat *mt = a->mat;
     sb_ctx *ctx = mt->ctx;
     if (mt->gd == 0 || mt->n == 0 || w == 0) return SB_OK;
+    if (mt->pl.active) {
+        if (stream != ctx->stream) return sb_fail(SB_ERR_UNSUPPORTED, "dense_n: the plane kernels run on the library stream only");
+        return planes_n(a, X, ldx, w, P, ldp);
+    }
     const u32 threads = overlap ? 256 : 512;
     const u32 genes_per_cta = threads;  // threads / 32 warps x 32 genes
     const u32 group = threads / SB_DENSE_LUT;
@@ -332,6 +345,7 @@ int dense_moments(sb_nmat *a, double *S1, double *S2) {
     sb_mat *mt = a->mat;
     sb_ctx *ctx = mt->ctx;
     if (mt->gd == 0 || mt->n == 0) return SB_OK;
+    if (mt->pl.active) return planes_moments(a, S1, S2);
     u32 gblocks = (mt->gd + DM_GENES - 1) / DM_GENES;
     u32 ranges = std::max<u32>(1, (u32)ctx->sm_count * 2 / gblocks);
     u64 max_ranges = (mt->n + DM_GROUP - 1) / DM_GROUP;

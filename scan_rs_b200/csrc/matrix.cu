@@ -21,6 +21,9 @@ int gather_assign_slots(sb_mat *mt, const uint2 *ent, u64 nnz);
 int gather_build_t_range(sb_mat *mt, u64 c0, u64 nc, const u64 *ptr_local, const uint2 *ent, u64 nnz, DevBuf<uint2> &out, std::vector<u64> &seg_len,
                          std::vector<u64> &seg_runs);
 int gather_finish_t(sb_mat *mt, const std::vector<u64> &seg_len, const std::vector<u64> &seg_runs);
+// planes.cu
+int planes_select(sb_mat *mt, u64 c0, u64 c1);
+int planes_split_launch(sb_mat *mt, u64 c0, u64 nc, const u64 *new_ptr, u32 *counts, uint2 *out);
 
 // ---------------------------------------------------------------- small kernels
 __global__ void k_interleave(const u32 *__restrict__ idx, const u32 *__restrict__ cnt, uint2 *__restrict__ out, u64 nnz) {
@@ -369,6 +372,9 @@ __global__ void k_add_offset(const u64 *__restrict__ src, u64 n, u64 add, u64 *_
 static int select_hot_genes(sb_mat *mt, u64 c0, u64 c1) {
     sb_ctx *ctx = mt->ctx;
     mt->gd = 0;
+    mt->pl.active = false;
+    if (ctx->panel_mode == 0) return SB_OK;
+    if (ctx->panel_mode == 2) return ctx->dense_cap >= 64 ? planes_select(mt, c0, c1) : SB_OK;  // sets gd = ranks of level 1 when planes are built
     mt->dense_max_count = (u32)std::min(std::max(ctx->dense_max_count, 1), (int)SB_DENSE_MAX_COUNT);
     if (ctx->dense_cap < 64 || mt->m < 64 || mt->n_global == 0) return SB_OK;
     SyncScope tr(ctx, "build: hot gene selection");
@@ -418,7 +424,8 @@ static int split_range(sb_mat *mt, u64 c0, u64 c1, DevBuf<u64> &ptr_local, DevBu
     SB_TRY(counts.alloc(nc));
     SB_TRY(ptr_local.alloc(nc + 1));
     int grid = grid_for(nc * 32, 256, ctx, 16);
-    if (nc) {
+    if (mt->pl.active) SB_TRY(planes_split_launch(mt, c0, nc, nullptr, counts.p, nullptr));
+    else if (nc) {
         k_split_hot<<<grid, 256, 0, ctx->stream>>>(mt->cm_ptr.p + c0, mt->cm.p, nc, mt->hot_of_gene.p, mt->gd, mt->dense_max_count, nullptr, counts.p, nullptr, nullptr);
         count_launch(ctx);
     }
@@ -426,7 +433,8 @@ static int split_range(sb_mat *mt, u64 c0, u64 c1, DevBuf<u64> &ptr_local, DevBu
     SB_CUDA(cudaMemcpyAsync(cold_nnz, ptr_local.p + nc, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     SB_CUDA(cudaStreamSynchronize(ctx->stream));
     SB_TRY(cold.alloc(*cold_nnz));
-    if (nc) {
+    if (mt->pl.active) SB_TRY(planes_split_launch(mt, c0, nc, ptr_local.p, nullptr, cold.p));
+    else if (nc) {
         k_split_hot<<<grid, 256, 0, ctx->stream>>>(mt->cm_ptr.p + c0, mt->cm.p, nc, mt->hot_of_gene.p, mt->gd, mt->dense_max_count, ptr_local.p, nullptr, cold.p,
                                                    mt->D.p + c0 * (u64)mt->gd);
         count_launch(ctx);

@@ -12,8 +12,14 @@ int spmm_n(sb_nmat *a, const double *X, u32 ldx, u32 w, double *P, u32 ldp);
 int qr_tall(sb_ctx *ctx, double *A, u64 rows, u32 w, u32 ld, u32 *w_out, double *R_out = nullptr);
 int trsm_right_upper(sb_ctx *ctx, double *A, u64 rows, u32 w, u32 ld, const double *R);
 int gram(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 ld, double *G, bool reduce);
-int eigh(sb_ctx *ctx, double *G, u32 w, double *evals_dev);
+int eigh(sb_ctx *ctx, double *G, u32 w, double *evals_dev, int *info_dev);
 int gemm_tall_small(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 lda, const double *S, u32 k, u32 lds, double *Out, u32 ldo);
+// dense_own.cu: the repo's own tall-skinny kernels (FP64 mma.sync) and the CholeskyQR3 factorisation
+int syrk_tall(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 ld, double *G);
+int gemm_tall(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 lda, const double *S, u32 k, u32 lds, double *Out, u32 ldo);
+int qr_chol(sb_ctx *ctx, double *A, double *tmp, u64 rows, u32 w, u32 ld, double *Rinv_out, int *flag);
+int topk_select(sb_ctx *ctx, const double *W, const double *ev, u32 wq, u32 k, double *Wsel, double *Wsc, double *S);
+int comm_allreduce_f64(sb_ctx *ctx, double *buf, size_t count);
 
 // ---------------------------------------------------------------- start block
 // rand 0.10.1 SmallRng on 64-bit targets = Xoshiro256++, seeded from a u64 through SplitMix64;
@@ -96,8 +102,9 @@ static int copy_block(sb_ctx *ctx, double *dst, u32 ldd, u32 c0, const double *s
 }
 
 static int progress(sb_ctx *ctx, sb_progress_cb cb, void *user, double frac) {
-    int cancel = 0;
-    if (cb) cancel = cb(frac, user) != 0;
+    // Without a callback nothing can cancel: no collective, no host synchronisation (every rank must pass a callback or none).
+    if (!cb) return SB_OK;
+    int cancel = cb(frac, user) != 0;
     if (ctx->nranks > 1) SB_TRY(comm_allreduce_max_i32(ctx, &cancel));
     if (cancel) return sb_fail(SB_ERR_CANCELLED, "cancelled at progress %.3f", frac);
     return SB_OK;
@@ -106,40 +113,33 @@ static int progress(sb_ctx *ctx, sb_progress_cb cb, void *user, double frac) {
 // From the projected tall block Tt (rows_t x wq, the cell side when n > m, the gene side when
 // m >= n) and the orthonormal basis Q (rows_q x wq): Gram -> eigh -> top-k triplets.
 //   left  (rows_t x k) = Tt . W_k . diag(1/sigma)      right (rows_q x k) = Q . W_k
-// `reduce_gram` all-reduces the Gram matrix (cell-sharded Tt).
-static int finish_svd(sb_ctx *ctx, const Tall &Tt, const Tall &Q, u32 wq, u32 k, bool reduce_gram, double *S_host, Tall &from_t, Tall &from_q) {
+// `reduce_gram` all-reduces the Gram matrix (cell-sharded Tt).  Nothing returns to the host here: S_dev (k values) and the
+// eigensolver's status (info_dev) are read by the caller together with the outputs.
+static int finish_svd(sb_ctx *ctx, const Tall &Tt, const Tall &Q, u32 wq, u32 k, bool reduce_gram, double *S_dev, int *info_dev, Tall &from_t, Tall &from_q) {
     DevBuf<double> G, ev, Wk;
     SB_TRY(G.alloc((size_t)wq * wq));
     SB_TRY(ev.alloc(wq));
     SB_TRY(Wk.alloc((size_t)wq * k * 2));
-    SB_TRY(gram(ctx, Tt.buf.p, Tt.rows, wq, Tt.ld, G.p, reduce_gram));
-    SB_TRY(eigh(ctx, G.p, wq, ev.p));
-    std::vector<double> h_ev(wq), h_W((size_t)wq * wq);
-    SB_CUDA(cudaMemcpyAsync(h_ev.data(), ev.p, wq * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    SB_CUDA(cudaMemcpyAsync(h_W.data(), G.p, (size_t)wq * wq * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    SB_CUDA(cudaStreamSynchronize(ctx->stream));
-    // eigenvalues ascending -> take the k largest, descending
-    std::vector<double> Wsel((size_t)wq * k), Wscaled((size_t)wq * k);
-    for (u32 i = 0; i < k; i++) {
-        u32 src = wq - 1 - i;
-        double lam = h_ev[src];
-        double sig = lam > 0.0 ? std::sqrt(lam) : 0.0;
-        S_host[i] = sig;
-        double inv = sig > 0.0 ? 1.0 / sig : 0.0;
-        for (u32 r = 0; r < wq; r++) {
-            double x = h_W[(size_t)src * wq + r];
-            Wsel[(size_t)i * wq + r] = x;
-            Wscaled[(size_t)i * wq + r] = x * inv;
-        }
+    if (ctx->own_dense) {
+        ProfScope ps(ctx, PH_DENSE);
+        SB_TRY(syrk_tall(ctx, Tt.buf.p, Tt.rows, wq, Tt.ld, G.p));
+        if (reduce_gram) SB_TRY(comm_allreduce_f64(ctx, G.p, (size_t)wq * wq));
+    } else {
+        SB_TRY(gram(ctx, Tt.buf.p, Tt.rows, wq, Tt.ld, G.p, reduce_gram));
     }
+    SB_TRY(eigh(ctx, G.p, wq, ev.p, info_dev));
     double *dWsel = Wk.p, *dWsc = Wk.p + (size_t)wq * k;
-    SB_CUDA(cudaMemcpyAsync(dWsel, Wsel.data(), Wsel.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    SB_CUDA(cudaMemcpyAsync(dWsc, Wscaled.data(), Wscaled.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    SB_TRY(topk_select(ctx, G.p, ev.p, wq, k, dWsel, dWsc, S_dev));
     SB_TRY(from_t.init(ctx, Tt.rows, k));
     SB_TRY(from_q.init(ctx, Q.rows, k));
-    SB_TRY(gemm_tall_small(ctx, Tt.buf.p, Tt.rows, wq, Tt.ld, dWsc, k, wq, from_t.buf.p, from_t.ld));
-    SB_TRY(gemm_tall_small(ctx, Q.buf.p, Q.rows, wq, Q.ld, dWsel, k, wq, from_q.buf.p, from_q.ld));
-    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_dense) {
+        ProfScope ps(ctx, PH_DENSE);
+        SB_TRY(gemm_tall(ctx, Tt.buf.p, Tt.rows, wq, Tt.ld, dWsc, k, wq, from_t.buf.p, from_t.ld));
+        SB_TRY(gemm_tall(ctx, Q.buf.p, Q.rows, wq, Q.ld, dWsel, k, wq, from_q.buf.p, from_q.ld));
+    } else {
+        SB_TRY(gemm_tall_small(ctx, Tt.buf.p, Tt.rows, wq, Tt.ld, dWsc, k, wq, from_t.buf.p, from_t.ld));
+        SB_TRY(gemm_tall_small(ctx, Q.buf.p, Q.rows, wq, Q.ld, dWsel, k, wq, from_q.buf.p, from_q.ld));
+    }
     return SB_OK;
 }
 
@@ -175,22 +175,118 @@ static int upload_tall(sb_ctx *ctx, Tall &t, const double *host, bool transpose_
 
 // The projection T = Q^T A (bk_svd.rs:102,131) costs a sparse pass of width b*n_iter.  With K = Q R,
 // Q^T A = R^-T (K^T A), and the blocks of K^T A are the products the Krylov loop forms anyway (plus one
-// more width-b pass for the last block), so the wide pass becomes a triangular solve on the tall block.
-// R is ill-conditioned by construction (Krylov blocks are nearly dependent); the solve is used only when
-// min|r_ii| / max|r_ii| stays above `min_ratio`, otherwise the direct wide pass runs ("Projection").
-static int r_usable(sb_ctx *ctx, const double *R_dev, u32 w, double min_ratio, bool *ok) {
-    std::vector<double> h((size_t)w * w);
-    SB_CUDA(cudaMemcpyAsync(h.data(), R_dev, h.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    SB_CUDA(cudaStreamSynchronize(ctx->stream));
-    double mn = INFINITY, mx = 0.0;
+// more width-b pass for the last block), so the wide pass becomes a product with R^-1 on the tall block.
+// R is ill-conditioned by construction (Krylov blocks are nearly dependent) and the rounding error already
+// in K^T A is amplified by cond(R) in the directions R squeezes.  Guard ("Projection"): a 2-norm
+// condition estimate of the triangular factor (power + inverse iteration on the host, O(w^2) each):
+//   cond <= SB_COND_TRUST   : the identity is used as is (measured margin >= 30x on the sigma / angle bars at 1e9)
+//   cond <= SB_COND_VERIFY  : used, then verified a posteriori: || A^T u_i - sigma_i v_i || <= SB_RESID_TOL sigma_1 on
+//                             a few of the k triplets (one narrow sparse pass); on failure the direct wide pass reruns
+//   otherwise               : the direct wide pass
+#define SB_COND_TRUST 1.0e9
+#define SB_COND_VERIFY 1.0e12
+#define SB_RESID_TOL 1.0e-8
+
+// 2-norm condition estimate of an upper-triangular matrix (column-major w x w, host)
+static double cond_upper(const std::vector<double> &M, u32 w) {
+    if (w == 0) return 1.0;
     for (u32 i = 0; i < w; i++) {
-        double d = std::fabs(h[(size_t)i * w + i]);
-        if (!(d == d)) { *ok = false; return SB_OK; }
-        mn = std::min(mn, d);
-        mx = std::max(mx, d);
+        const double d = M[(size_t)i * w + i];
+        if (!(d == d) || d == 0.0 || std::fabs(d) > 1e300) return INFINITY;
     }
-    *ok = mx > 0.0 && mn / mx >= min_ratio;
-    return SB_OK;
+    std::vector<double> x(w), y(w), z(w);
+    auto normalize = [&](std::vector<double> &v) {
+        double s = 0.0;
+        for (double t : v) s += t * t;
+        s = std::sqrt(s);
+        if (s > 0.0 && s == s && s < 1e300)
+            for (double &t : v) t /= s;
+        return s;
+    };
+    // sigma_max: power iteration on M^T M
+    for (u32 i = 0; i < w; i++) x[i] = 1.0 + 0.37 * std::sin(1.7 * (double)i);
+    normalize(x);
+    double smax2 = 0.0;
+    for (int it = 0; it < 12; it++) {
+        for (u32 i = 0; i < w; i++) {  // y = M x
+            double t = 0.0;
+            for (u32 j = i; j < w; j++) t += M[(size_t)j * w + i] * x[j];
+            y[i] = t;
+        }
+        for (u32 j = 0; j < w; j++) {  // z = M^T y
+            double t = 0.0;
+            for (u32 i = 0; i <= j; i++) t += M[(size_t)j * w + i] * y[i];
+            z[j] = t;
+        }
+        smax2 = normalize(z);
+        x = z;
+    }
+    // sigma_min: inverse iteration, M^T y = x (forward), M z = y (backward)
+    for (u32 i = 0; i < w; i++) x[i] = 1.0 + 0.41 * std::cos(2.3 * (double)i);
+    normalize(x);
+    double inv_smin2 = 0.0;
+    for (int it = 0; it < 12; it++) {
+        for (u32 j = 0; j < w; j++) {
+            double t = x[j];
+            for (u32 i = 0; i < j; i++) t -= M[(size_t)j * w + i] * y[i];
+            y[j] = t / M[(size_t)j * w + j];
+        }
+        for (u32 ii = w; ii-- > 0;) {
+            double t = y[ii];
+            for (u32 j = ii + 1; j < w; j++) t -= M[(size_t)j * w + ii] * z[j];
+            z[ii] = t / M[(size_t)ii * w + ii];
+        }
+        inv_smin2 = normalize(z);
+        if (!(inv_smin2 == inv_smin2) || inv_smin2 > 1e300) return INFINITY;
+        x = z;
+    }
+    const double c = std::sqrt(smax2 * inv_smin2);
+    return c == c ? c : INFINITY;
+}
+
+// 0: direct pass, 1: identity trusted, 2: identity + a-posteriori verification
+static int projection_mode(sb_ctx *ctx, const double *tri_dev, u32 w, double *cond_out) {
+    std::vector<double> h((size_t)w * w);
+    if (cudaMemcpyAsync(h.data(), tri_dev, h.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        *cond_out = INFINITY;
+        return 0;
+    }
+    const double c = cond_upper(h, w);  // cond(R) = cond(R^-1): either factor serves
+    *cond_out = c;
+    ctx->last_cond_r = c;
+    if (TraceScope::on()) fprintf(stderr, "[scanb200] projection: cond(R) ~ %.3e\n", c);
+    if (ctx->verify_projection && c <= SB_COND_VERIFY) return 2;
+    if (c <= SB_COND_TRUST) return 1;
+    if (c <= SB_COND_VERIFY) return 2;
+    return 0;
+}
+
+// sum over cells of (T2[c, j] - sigma_sel[j] * V[c, sel[j]])^2 for up to 4 probe columns
+__global__ void k_probe_resid(const double *__restrict__ T2, u32 ld2, const double *__restrict__ V, u32 ldv, u64 n, const double *__restrict__ S,
+                              int4 sel, u32 nsel, double *__restrict__ out) {
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    const int se[4] = {sel.x, sel.y, sel.z, sel.w};
+    for (u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (u64)gridDim.x * blockDim.x)
+        for (u32 j = 0; j < nsel; j++) {
+            const double d = T2[c * (size_t)ld2 + j] - S[se[j]] * V[c * (size_t)ldv + se[j]];
+            acc[j] = fma(d, d, acc[j]);
+        }
+    for (u32 j = 0; j < nsel; j++) {
+        double v = acc[j];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(out + j, v);
+    }
+}
+
+// copies columns sel[] of src (rows x *, ld lds) into the leading columns of dst (ld ldd)
+__global__ void k_pick_cols(const double *__restrict__ src, u32 lds, u64 rows, int4 sel, u32 nsel, double *__restrict__ dst, u32 ldd) {
+    const int se[4] = {sel.x, sel.y, sel.z, sel.w};
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < rows * nsel; i += (u64)gridDim.x * blockDim.x) {
+        const u64 r = i / nsel;
+        const u32 j = (u32)(i - r * nsel);
+        dst[r * ldd + j] = src[r * (size_t)lds + se[j]];
+    }
 }
 
 static int check_shape(const sb_nmat *a, u32 k) {
@@ -202,35 +298,64 @@ static int check_shape(const sb_nmat *a, u32 k) {
 }
 
 // ---------------------------------------------------------------- block Krylov SVD
-extern "C" int sb_bksvd(sb_nmat *a, uint32_t k, uint32_t b, uint32_t n_iter, uint64_t seed, const double *omega, sb_progress_cb cb, void *user,
-                        double *U, double *S, double *V) {
-    if (!a || !U || !S || !V) return sb_fail(SB_ERR_INVALID_ARG, "sb_bksvd: NULL argument");
+// Thin QR of a tall block in place.  own: shifted CholeskyQR3 on the repo's kernels (dense_own.cu), no host synchronisation,
+// Rinv_out (optional) = R^-1; otherwise LAPACK-style Householder through cuSOLVER (dense.cu), R_out (optional) = R.
+static int qr_block(sb_ctx *ctx, bool own, Tall &A, Tall &tmp, u32 *wq, double *tri_out, int *flag_dev) {
+    if (own) {
+        *wq = A.w;
+        return qr_chol(ctx, A.buf.p, tmp.buf.p, A.rows, A.w, A.ld, tri_out, flag_dev);
+    }
+    return qr_tall(ctx, A.buf.p, A.rows, A.w, A.ld, wq, tri_out);
+}
+
+// T <- T . R^-1 (own: product with the explicit inverse on the tensor path; else cuBLAS trsm with R)
+static int apply_rinv(sb_ctx *ctx, bool own, Tall &T, Tall &tmp, const double *tri) {
+    if (!own) return trsm_right_upper(ctx, T.buf.p, T.rows, T.w, T.ld, tri);
+    ProfScope ps(ctx, PH_DENSE);
+    if (T.w <= 128) return gemm_tall(ctx, T.buf.p, T.rows, T.w, T.ld, tri, T.w, T.w, T.buf.p, T.ld);  // one column block per CTA: in place is safe
+    SB_TRY(tmp.init(ctx, T.rows, T.w));
+    SB_TRY(gemm_tall(ctx, T.buf.p, T.rows, T.w, T.ld, tri, T.w, T.w, tmp.buf.p, tmp.ld));
+    T.buf.swap(tmp.buf);
+    tmp.buf.release();
+    return SB_OK;
+}
+
+struct PcaStatus {  // read back once, with the outputs
+    int chol_flag;   // CholeskyQR breakdown (rank-deficient block)
+    int eig_info;    // syevd status
+    int pad[2];
+};
+
+static int bksvd_impl(sb_nmat *a, uint32_t k, uint32_t b, uint32_t n_iter, uint64_t seed, const double *omega, sb_progress_cb cb, void *user,
+                      double *U, double *S, double *V, bool own_qr, bool force_direct, bool *retry_householder, bool *retry_direct) {
     sb_mat *mt = a->mat;
     sb_ctx *ctx = mt->ctx;
-    SB_ENTER(ctx);
-    SB_TRY(check_shape(a, k));
-    if (n_iter == 0) return sb_fail(SB_ERR_INVALID_ARG, "sb_bksvd: n_iter must be >= 1");
     const u32 m = mt->m;
     const u64 n = mt->n, ng = mt->n_global;
-    b = (u32)std::min<u64>(std::min<u64>(m, ng), b);  // bk_svd.rs:81
-    if (b < k) return sb_fail(SB_ERR_INVALID_K, "invalid k");
-    DevBuf<double> uy;
+    DevBuf<double> uy, S_dev, resid;
+    DevBuf<int> status;
     SB_TRY(uy.alloc(even_up(b * n_iter) + 2));
-    std::vector<double> h_om;
+    SB_TRY(S_dev.alloc(k));
+    SB_TRY(resid.alloc(4));
+    SB_TRY(status.alloc(4));
+    SB_CUDA(cudaMemsetAsync(status.p, 0, 4 * sizeof(int), ctx->stream));
+    int *chol_flag = status.p, *eig_info = status.p + 1;
+    const u32 bq = b * n_iter;
+    PcaStatus hst = {0, 0, {0, 0}};
+    double cond = 0.0;
 
     if ((u64)m >= ng) {
         // ---- m >= n (bk_svd.rs:89-115): block on the cell side; single rank only
         if (ctx->nranks > 1) return sb_fail(SB_ERR_UNSUPPORTED, "sb_bksvd: the m >= n branch is single-rank");
-        Tall B, Kc, W, WK;
-        const u32 bq = b * n_iter;
-        const bool fast = !ctx->direct_projection && (b % 2 == 0) && (u64)bq <= n;
+        Tall B, Kc, W, WK, tmpB, tmpK;
+        const bool fast = !ctx->direct_projection && !force_direct && (b % 2 == 0) && (u64)bq <= n;
+        const bool own_b = own_qr && n >= 4ull * b, own_k = own_qr && n >= 4ull * bq;
         SB_TRY(B.init(ctx, n, b));
-        if (!omega) {
-            omega = omega_cached(ctx, seed, n, b);  // :90 (n x b, row-major fill)
-        }
+        if (!omega) omega = omega_cached(ctx, seed, n, b);  // :90 (n x b, row-major fill)
         SB_TRY(upload_tall(ctx, B, omega, false));
         SB_TRY(Kc.init(ctx, n, bq));
         SB_TRY(W.init(ctx, m, b, 1));
+        if (own_b) SB_TRY(tmpB.init(ctx, n, b));
         if (fast) SB_TRY(WK.init(ctx, m, bq, 1));  // column block i-1 keeps A . B_i (B_i = block i of K)
         for (u32 i = 0; i < n_iter; i++) {
             double *Wp = (fast && i > 0) ? WK.buf.p + (size_t)(i - 1) * b : W.buf.p;
@@ -238,22 +363,27 @@ extern "C" int sb_bksvd(sb_nmat *a, uint32_t k, uint32_t b, uint32_t n_iter, uin
             SB_TRY(spmm_n(a, B.buf.p, B.ld, b, Wp, Wld));                   // A.dot(&B)
             SB_TRY(spmm_t(a, Wp, Wld, b, B.buf.p, B.ld, uy.p));              // (.)^T.dot(A) ^T
             u32 wq = 0;
-            SB_TRY(qr_tall(ctx, B.buf.p, n, b, B.ld, &wq));                  // .qr()?.0   :94
+            SB_TRY(qr_block(ctx, own_b, B, tmpB, &wq, nullptr, chol_flag));  // .qr()?.0   :94
             SB_TRY(copy_block(ctx, Kc.buf.p, Kc.ld, i * b, B.buf.p, B.ld, n, b));  // :95
             SB_TRY(progress(ctx, cb, user, (double)i / (double)n_iter * 0.8));     // :96
         }
         u32 wq = 0;
-        DevBuf<double> R;
-        SB_TRY(R.alloc((size_t)bq * bq));
+        DevBuf<double> tri;
+        SB_TRY(tri.alloc((size_t)bq * bq));
         if (fast) SB_TRY(spmm_n(a, B.buf.p, B.ld, b, WK.buf.p + (size_t)(n_iter - 1) * b, WK.ld));  // A . B_q
-        SB_TRY(qr_tall(ctx, Kc.buf.p, n, bq, Kc.ld, &wq, R.p));              // :98
+        if (own_k) SB_TRY(tmpK.init(ctx, n, bq));
+        SB_TRY(qr_block(ctx, own_k, Kc, tmpK, &wq, tri.p, chol_flag));       // :98
+        tmpK.buf.release();
         SB_TRY(progress(ctx, cb, user, 0.82));
-        bool use_r = false;
-        if (fast && wq == bq) SB_TRY(r_usable(ctx, R.p, bq, 1e-12, &use_r));
+        int mode = 0;
+        if (fast && wq == bq) mode = projection_mode(ctx, tri.p, bq, &cond);
+        if (mode == 2) mode = 0;  // this branch has no a-posteriori check: past the trusted range the direct pass runs
         Tall Tdirect;
         Tall *Tp = &WK;
-        if (use_r) {
-            SB_TRY(trsm_right_upper(ctx, WK.buf.p, m, bq, WK.ld, R.p));      // T = (A K) R^-1 = A Q
+        if (mode == 1) {
+            Tall tmpT;
+            WK.rows = m;
+            SB_TRY(apply_rinv(ctx, own_k, WK, tmpT, tri.p));                 // T = (A K) R^-1 = A Q
         } else {
             SB_TRY(Tdirect.init(ctx, m, wq, 1));
             SB_TRY(spmm_n(a, Kc.buf.p, Kc.ld, wq, Tdirect.buf.p, Tdirect.ld));  // T = A.dot(&Q)  :102
@@ -264,28 +394,31 @@ extern "C" int sb_bksvd(sb_nmat *a, uint32_t k, uint32_t b, uint32_t n_iter, uin
         if (k > wq) return sb_fail(SB_ERR_INVALID_K, "invalid k");
         Tall Uo, Vo;
         Kc.w = wq;
-        SB_TRY(finish_svd(ctx, T, Kc, wq, k, false, S, Uo, Vo));             // :105-113
+        SB_TRY(finish_svd(ctx, T, Kc, wq, k, false, S_dev.p, eig_info, Uo, Vo));  // :105-113
+        SB_CUDA(cudaMemcpyAsync(S, S_dev.p, k * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        SB_CUDA(cudaMemcpyAsync(&hst, status.p, sizeof(hst), cudaMemcpyDeviceToHost, ctx->stream));
         SB_TRY(download_tall(ctx, Uo, U));
         SB_TRY(download_tall(ctx, Vo, V));
+        if (hst.chol_flag) { *retry_householder = true; return SB_OK; }
+        if (hst.eig_info != 0) return sb_fail(SB_ERR_LINALG, "eigendecomposition failed: info = %d", hst.eig_info);
         SB_TRY(progress(ctx, cb, user, 1.0));
         return SB_OK;
     }
 
     // ---- n > m (bk_svd.rs:116-145): block on the gene side, replicated over ranks
     TraceScope tr_all(ctx, "bksvd: total (n > m)");
-    Tall Y, Kt, T, P, TK;
-    const u32 bq = b * n_iter;
-    const bool fast = !ctx->direct_projection && (b % 2 == 0) && bq <= m;
+    Tall Y, Kt, T, P, TK, tmpP, tmpK;
+    const bool fast = !ctx->direct_projection && !force_direct && (b % 2 == 0) && bq <= m;
+    const bool own_b = own_qr && m >= 4u * b, own_k = own_qr && m >= 4u * bq;
     {
         TraceScope t0(ctx, "bksvd: omega + buffers");
         SB_TRY(Y.init(ctx, m, b));
-        if (!omega) {
-            omega = omega_cached(ctx, seed, b, m);  // :118 (b x m, row-major fill)
-        }
+        if (!omega) omega = omega_cached(ctx, seed, b, m);  // :118 (b x m, row-major fill)
         SB_TRY(upload_tall(ctx, Y, omega, true));  // Y[g, j] = B[j, g]
         SB_TRY(Kt.init(ctx, m, bq));
         SB_TRY(T.init(ctx, n, b));
         SB_TRY(P.init(ctx, m, b, 1));
+        if (own_b) SB_TRY(tmpP.init(ctx, m, b));
         if (fast) SB_TRY(TK.init(ctx, n, bq));  // column block i-1 keeps A^T . Y_i (Y_i = block i of K^T)
     }
     for (u32 i = 0; i < n_iter; i++) {
@@ -301,23 +434,26 @@ extern "C" int sb_bksvd(sb_nmat *a, uint32_t k, uint32_t b, uint32_t n_iter, uin
         }
         TraceScope t2(ctx, "bksvd: qr + copies + progress");
         u32 wq = 0;
-        SB_TRY(qr_tall(ctx, P.buf.p, m, b, P.ld, &wq));                      // .qr()?.0
+        SB_TRY(qr_block(ctx, own_b, P, tmpP, &wq, nullptr, chol_flag));      // .qr()?.0
         SB_TRY(copy_block(ctx, Y.buf.p, Y.ld, 0, P.buf.p, P.ld, m, b));
         SB_TRY(copy_block(ctx, Kt.buf.p, Kt.ld, i * b, P.buf.p, P.ld, m, b));  // K rows i*b..   :124
         SB_TRY(progress(ctx, cb, user, (double)i / (double)n_iter * 0.8));   // :125
     }
     u32 wq = 0;
-    DevBuf<double> R;
-    SB_TRY(R.alloc((size_t)bq * bq));
+    DevBuf<double> tri;
+    SB_TRY(tri.alloc((size_t)bq * bq));
     if (fast) SB_TRY(spmm_t(a, Y.buf.p, Y.ld, b, TK.buf.p + (size_t)(n_iter - 1) * b, TK.ld, uy.p));  // A^T . Y_q
-    SB_TRY(qr_tall(ctx, Kt.buf.p, m, bq, Kt.ld, &wq, R.p));                  // Q = K.t().qr()?.0     :127
+    if (own_k) SB_TRY(tmpK.init(ctx, m, bq));
+    SB_TRY(qr_block(ctx, own_k, Kt, tmpK, &wq, tri.p, chol_flag));           // Q = K.t().qr()?.0     :127
+    tmpK.buf.release();
     SB_TRY(progress(ctx, cb, user, 0.82));
-    bool use_r = false;
-    if (fast && wq == bq) SB_TRY(r_usable(ctx, R.p, bq, 1e-12, &use_r));
+    int mode = 0;
+    if (fast && wq == bq) mode = projection_mode(ctx, tri.p, bq, &cond);
     Tall Tdirect;
     Tall *Ttp = &TK;
-    if (use_r) {
-        SB_TRY(trsm_right_upper(ctx, TK.buf.p, n, bq, TK.ld, R.p));          // T^T = (A^T K^T) R^-1 = A^T Q
+    if (mode >= 1) {
+        Tall tmpT;
+        SB_TRY(apply_rinv(ctx, own_k, TK, tmpT, tri.p));                     // T^T = (A^T K^T) R^-1 = A^T Q
     } else {
         SB_TRY(Tdirect.init(ctx, n, wq));
         SB_TRY(spmm_t(a, Kt.buf.p, Kt.ld, wq, Tdirect.buf.p, Tdirect.ld, uy.p));  // T = Q.t().dot(A)      :131
@@ -329,11 +465,71 @@ extern "C" int sb_bksvd(sb_nmat *a, uint32_t k, uint32_t b, uint32_t n_iter, uin
     Tall Vo, Uo;
     Kt.w = wq;
     TraceScope t9(ctx, "bksvd: gram + eigh + outputs");
-    SB_TRY(finish_svd(ctx, Tt, Kt, wq, k, true, S, Vo, Uo));                 // :134-142
+    SB_TRY(finish_svd(ctx, Tt, Kt, wq, k, true, S_dev.p, eig_info, Vo, Uo)); // :134-142
+    u32 nsel = 0;
+    if (mode == 2) {
+        // a-posteriori check of the identity on a few triplets: A^T u_i against sigma_i v_i (shard-local rows, summed over ranks)
+        nsel = std::min<u32>(k, 4);
+        int4 sel = make_int4(0, (int)(k - 1), (int)(k / 2), (int)(k / 4));
+        if (nsel < 4) sel = make_int4(0, nsel > 1 ? 1 : 0, nsel > 2 ? 2 : 0, 0);
+        Tall Us, Ts;
+        SB_TRY(Us.init(ctx, m, nsel));
+        SB_TRY(Ts.init(ctx, n, nsel));
+        SB_CUDA(cudaMemsetAsync(resid.p, 0, 4 * sizeof(double), ctx->stream));
+        k_pick_cols<<<std::max(1u, std::min<u32>(cdiv((u64)m * nsel, 256), 1024u)), 256, 0, ctx->stream>>>(Uo.buf.p, Uo.ld, m, sel, nsel, Us.buf.p, Us.ld);
+        count_launch(ctx);
+        SB_TRY(spmm_t(a, Us.buf.p, Us.ld, nsel, Ts.buf.p, Ts.ld, uy.p));
+        if (n) {
+            k_probe_resid<<<(unsigned)std::max<u64>(1, std::min<u64>((n + 255) / 256, (u64)ctx->sm_count * 8)), 256, 0, ctx->stream>>>(
+                Ts.buf.p, Ts.ld, Vo.buf.p, Vo.ld, n, S_dev.p, sel, nsel, resid.p);
+            count_launch(ctx);
+        }
+        SB_TRY(comm_allreduce_f64(ctx, resid.p, 4));
+    }
+    double h_res[4] = {0, 0, 0, 0};
+    SB_CUDA(cudaMemcpyAsync(S, S_dev.p, k * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(cudaMemcpyAsync(&hst, status.p, sizeof(hst), cudaMemcpyDeviceToHost, ctx->stream));
+    if (mode == 2) SB_CUDA(cudaMemcpyAsync(h_res, resid.p, sizeof(h_res), cudaMemcpyDeviceToHost, ctx->stream));
     SB_TRY(download_tall(ctx, Uo, U));
-    SB_TRY(download_tall(ctx, Vo, V));
+    SB_TRY(download_tall(ctx, Vo, V));  // synchronises
+    if (hst.chol_flag) { *retry_householder = true; return SB_OK; }
+    if (hst.eig_info != 0) return sb_fail(SB_ERR_LINALG, "eigendecomposition failed: info = %d", hst.eig_info);
+    if (mode == 2) {
+        double worst = 0.0;
+        for (u32 j = 0; j < nsel; j++) worst = std::max(worst, std::sqrt(std::max(h_res[j], 0.0)));
+        const double rel = S[0] > 0.0 ? worst / S[0] : (worst > 0.0 ? INFINITY : 0.0);
+        ctx->last_probe_resid = rel;
+        if (TraceScope::on()) fprintf(stderr, "[scanb200] projection: probe residual %.3e sigma_1 (cond %.3e)\n", rel, cond);
+        if (!(rel <= SB_RESID_TOL)) { *retry_direct = true; return SB_OK; }
+    }
     SB_TRY(progress(ctx, cb, user, 1.0));
     return SB_OK;
+}
+
+extern "C" int sb_bksvd(sb_nmat *a, uint32_t k, uint32_t b, uint32_t n_iter, uint64_t seed, const double *omega, sb_progress_cb cb, void *user,
+                        double *U, double *S, double *V) {
+    if (!a || !U || !S || !V) return sb_fail(SB_ERR_INVALID_ARG, "sb_bksvd: NULL argument");
+    sb_mat *mt = a->mat;
+    sb_ctx *ctx = mt->ctx;
+    SB_ENTER(ctx);
+    SB_TRY(check_shape(a, k));
+    if (n_iter == 0) return sb_fail(SB_ERR_INVALID_ARG, "sb_bksvd: n_iter must be >= 1");
+    b = (u32)std::min<u64>(std::min<u64>(mt->m, mt->n_global), b);  // bk_svd.rs:81
+    if (b < k) return sb_fail(SB_ERR_INVALID_K, "invalid k");
+    bool own_qr = ctx->own_dense, force_direct = false;
+    ctx->last_cond_r = 0.0;
+    ctx->last_probe_resid = 0.0;
+    ctx->last_fallbacks = 0;
+    for (int attempt = 0; attempt < 3; attempt++) {
+        bool retry_h = false, retry_d = false;
+        SB_TRY(bksvd_impl(a, k, b, n_iter, seed, omega, cb, user, U, S, V, own_qr, force_direct, &retry_h, &retry_d));
+        if (!retry_h && !retry_d) return SB_OK;
+        // Both decisions derive from all-reduced (Gram, residual) or replicated (gene-side blocks) data: every rank takes the same turn.
+        if (retry_h) own_qr = false;       // CholeskyQR broke down (rank-deficient block): Householder handles it
+        if (retry_d) force_direct = true;  // the projection identity failed its check: the reference's wide pass
+        ctx->last_fallbacks += 1;
+    }
+    return sb_fail(SB_ERR_LINALG, "sb_bksvd: no stable path");
 }
 
 extern "C" int sb_bksvd_run_pca(sb_nmat *a, uint32_t k, double k_multiplier, uint32_t n_iter, sb_progress_cb cb, void *user, double *U, double *S,
@@ -357,6 +553,12 @@ extern "C" int sb_randsvd(sb_nmat *a, uint32_t k, uint32_t l, uint32_t n_iter, u
     DevBuf<double> uy;
     SB_TRY(uy.alloc(even_up(l) + 2));
     std::vector<double> h_om;
+    DevBuf<double> S_dev;
+    DevBuf<int> einfo;
+    int h_info = 0;
+    SB_TRY(S_dev.alloc(k));
+    SB_TRY(einfo.alloc(1));
+    SB_CUDA(cudaMemsetAsync(einfo.p, 0, sizeof(int), ctx->stream));
     Tall Qm, Qn;  // gene-side (m x l, +1 row for spmm_n) and cell-side (n x l) blocks
     SB_TRY(Qm.init(ctx, m, l, 1));
     SB_TRY(Qn.init(ctx, n, l));
@@ -378,7 +580,9 @@ extern "C" int sb_randsvd(sb_nmat *a, uint32_t k, uint32_t l, uint32_t n_iter, u
         }
         SB_TRY(spmm_t(a, Qm.buf.p, Qm.ld, l, Qn.buf.p, Qn.ld, uy.p));         // B = Q.t().dot(A)        :96  (stored as B^T)
         Tall Vo, Uo;
-        SB_TRY(finish_svd(ctx, Qn, Qm, l, k, false, S, Vo, Uo));              // U = Q.U_B               :104
+        SB_TRY(finish_svd(ctx, Qn, Qm, l, k, false, S_dev.p, einfo.p, Vo, Uo)); // U = Q.U_B               :104
+        SB_CUDA(cudaMemcpyAsync(S, S_dev.p, k * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        SB_CUDA(cudaMemcpyAsync(&h_info, einfo.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         SB_TRY(download_tall(ctx, Uo, U));
         SB_TRY(download_tall(ctx, Vo, V));
     } else {  // rand_svd.rs:106-128
@@ -398,10 +602,13 @@ extern "C" int sb_randsvd(sb_nmat *a, uint32_t k, uint32_t l, uint32_t n_iter, u
         }
         SB_TRY(spmm_n(a, Qn.buf.p, Qn.ld, l, Qm.buf.p, Qm.ld));              // B = A.dot(&Q)           :118
         Tall Uo, Vo;
-        SB_TRY(finish_svd(ctx, Qm, Qn, l, k, false, S, Uo, Vo));              // Va = Vt[:k].Q^T         :126
+        SB_TRY(finish_svd(ctx, Qm, Qn, l, k, false, S_dev.p, einfo.p, Uo, Vo)); // Va = Vt[:k].Q^T         :126
+        SB_CUDA(cudaMemcpyAsync(S, S_dev.p, k * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        SB_CUDA(cudaMemcpyAsync(&h_info, einfo.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         SB_TRY(download_tall(ctx, Uo, U));
         SB_TRY(download_tall(ctx, Vo, V));
     }
+    if (h_info != 0) return sb_fail(SB_ERR_LINALG, "eigendecomposition failed: info = %d", h_info);
     return SB_OK;
 }
 

@@ -1,0 +1,899 @@
+// planes.cu -- the dense half of the hybrid SpMM on the INTEGER tensor cores (tcgen05.mma kind::i8, accumulators in TMEM).
+//
+// Where the count matrix is dense enough, a sparse f64 gather (160 B of operand per 8-byte entry) is the wrong
+// tool.  Counts are small integers, so for each count level k = 1..L the indicator [v_gc == k] is a 0/1 matrix M_k, and
+//     A^T.Y  :  T[c,:] += sum_k L_c(k) * ( M_k^T-slice . Ys )[c,:]          Ys = row_scale * Y      (restates the products of
+//     A.X    :  P[g,:] += sum_k ( M_k . (L_c(k) X) )[g,:]                                           low_rank_offset.rs:68-96)
+// with L_c(k) = log_b(col_scale_c * k + 1) the only cell-dependent factor (map.cuh).  The dense f64 operand is cut per column
+// into 7 balanced base-256 digits of a 54-bit fixed-point number (Ozaki splitting): every M_k . digit-plane product is an
+// EXACT int8 x int8 -> int32 tensor-core product, and the digits are recombined in the epilogue (two int64 halves -> f64,
+// one rounding).  The error is that of one rounding to 54 bits of the column maximum per operand entry -- measured against
+// the oracle at the same level as the f64 DMMA panel it replaces (tests/test_gpu_parity.py).
+//
+// Layout ("bit planes"): genes are ranked by how many cells express them; level k keeps the first G_k ranks (multiples of
+// 128, G_1 >= G_2 >= ...), chosen so that a (gene, level) pair lives here only if at least `plane_min_density` of the cells
+// have exactly that count.  plane_k is bit-packed and tile-transposed: word (tile, gw, cell) = 32 genes [32 gw, 32 gw + 32) of
+// cell 128 tile + cell, stored at ((tile * G_k/32) + gw) * 128 + cell -- both products read 128-cell x 32-gene blocks as
+// 512 contiguous bytes.  Every entry not covered by a plane stays in the sparse streams (gather.cu).
+//
+// Kernels (one CTA per SM, warp-specialised: warps 0-3 epilogue, warp 4 MMA issue, warps 5-12 producers):
+//   k_planes_t : a CTA keeps the digit planes of 1,024 ranks resident in shared memory as the B operand (K-major, 144 KB),
+//                walks cell tiles; producers expand plane words into 0/1 int8 A tiles (K-major core matrices) through an
+//                8-stage mbarrier ring; up to three levels accumulate into three TMEM accumulators (3 x 144 columns).
+//   k_planes_n : a CTA owns 384 ranks (three 128-gene accumulators) and a range of cell tiles; per 32-cell K step and level
+//                the producers expand the plane words into an MN-major A tile and copy the digit rows of L_c(k).X[c,:]
+//                (written once per product by k_pl_digits_n) as the MN-major B tile; all levels share the accumulators.
+#include <numeric>
+
+#include "common.cuh"
+#include "map.cuh"
+#include "tc05.cuh"
+
+using namespace tc05;
+
+#define PL_TILE 128u
+#define PL_COLS 20u
+#define PL_DIG 7u
+#define PL_NCOL 144u  // 7 x 20 = 140 digit columns, padded to a multiple of 16 (UMMA N for M = 128)
+#define PL_FIX 54
+#define PL_NONE 0xFFFFFFFFu
+
+#define PT_RANGE 1024u                          // ranks per resident B block (T side)
+#define PT_B_BYTES (PT_RANGE * PL_NCOL)         // 147,456
+#define PT_KCHUNK_BYTES (PL_NCOL / 8 * 128)     // 2,304: one 16-gene K chunk of B (18 core matrices)
+#define PT_STAGE_BYTES (PL_TILE * 64u)          // 8,192: 128 cells x 64 genes of one level
+#define PT_NSTAGES 8u
+#define PL_EPI_WARPS 4u
+#define PL_PROD_WARPS 8u
+#define PL_THREADS ((PL_EPI_WARPS + 1 + PL_PROD_WARPS) * 32)  // 416
+
+#define PN_GROUP 384u                           // ranks per CTA (N side): three M tiles
+#define PN_A_BYTES (3u * 4096u)
+#define PN_B_BYTES (32u * PL_NCOL)              // 4,608
+#define PN_STAGE_BYTES (PN_A_BYTES + PN_B_BYTES)  // 16,896
+#define PN_NSTAGES 8u
+#define PN_CELLGRP_BYTES (PL_NCOL / 16 * 128)   // 1,152: digit rows of 8 cells (9 core matrices)
+
+struct PlDev {
+    u32 *bits[PL_MAX_LEVELS];
+    u32 G[PL_MAX_LEVELS];
+    u32 L;
+    u64 ntiles;
+    u64 n;
+};
+
+static PlDev make_pldev(const sb_mat *mt) {
+    PlDev d;
+    memset(&d, 0, sizeof(d));
+    d.L = mt->pl.L;
+    d.ntiles = mt->pl.ntiles;
+    d.n = mt->n;
+    for (u32 k = 0; k < mt->pl.L; k++) {
+        d.bits[k] = mt->pl.bits[k].p;
+        d.G[k] = mt->pl.G[k];
+    }
+    return d;
+}
+
+// ---------------------------------------------------------------- selection of the planes
+// hist[k * m + g] += 1 for every entry of the sampled cells with count k + 1 <= L
+__global__ void k_pl_level_hist(const u64 *__restrict__ ptr, const uint2 *__restrict__ cm, u64 n, u32 m, u32 L, unsigned long long *__restrict__ hist) {
+    u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    int lane = threadIdx.x & 31;
+    for (u64 c = warp; c < n; c += nwarps) {
+        const u64 s = ptr[c], e = ptr[c + 1];
+        for (u64 k = s + lane; k < e; k += 32) {
+            const uint2 z = cm[k];
+            if (z.y >= 1 && z.y <= L) atomicAdd(&hist[(size_t)(z.y - 1) * m + z.x], 1ull);
+        }
+    }
+}
+
+static void units_round(std::vector<u32> &nctas, const std::vector<double> &cost, u32 total) {
+    // largest-remainder apportionment with at least one CTA per unit
+    const size_t U = cost.size();
+    nctas.assign(U, 1);
+    if (U == 0) return;
+    double sum = 0.0;
+    for (double c : cost) sum += c;
+    if (U >= total || sum <= 0.0) return;
+    std::vector<double> ideal(U);
+    u32 used = 0;
+    for (size_t i = 0; i < U; i++) {
+        ideal[i] = cost[i] / sum * total;
+        nctas[i] = std::max<u32>(1, (u32)ideal[i]);
+        used += nctas[i];
+    }
+    while (used > total) {  // ones forced up to 1 may overshoot: take from the most over-served
+        size_t best = 0;
+        double worst = -1e300;
+        for (size_t i = 0; i < U; i++)
+            if (nctas[i] > 1 && (double)nctas[i] - ideal[i] > worst) { worst = (double)nctas[i] - ideal[i]; best = i; }
+        nctas[best]--;
+        used--;
+    }
+    while (used < total) {
+        size_t best = 0;
+        double worst = -1e300;
+        for (size_t i = 0; i < U; i++)
+            if (ideal[i] - (double)nctas[i] > worst) { worst = ideal[i] - (double)nctas[i]; best = i; }
+        nctas[best]++;
+        used++;
+    }
+}
+
+// Chooses the planes from the entry counts of local cells [c0, c1) (the whole shard or the first upload chunk), summed
+// over ranks.  Allocates and zeroes the planes, fills hot_idx (rank -> gene), hot_of_gene (gene -> rank) and the unit tables.
+int planes_select(sb_mat *mt, u64 c0, u64 c1) {
+    sb_ctx *ctx = mt->ctx;
+    PlaneSet &pl = mt->pl;
+    pl.active = false;
+    pl.L = 0;
+    const u32 m = mt->m;
+    const u32 Lmax = (u32)std::min<int>(std::max(ctx->plane_levels, 1), PL_MAX_LEVELS);
+    if (m < 128 || mt->n_global == 0 || ctx->plane_cap < 128) return SB_OK;
+    SyncScope tr(ctx, "build: plane selection");
+    DevBuf<u64> d_hist;
+    const size_t hn = (size_t)Lmax * m + 1;
+    SB_TRY(d_hist.alloc(hn));
+    SB_CUDA(cudaMemsetAsync(d_hist.p, 0, hn * sizeof(u64), ctx->stream));
+    if (c1 > c0) {
+        ProfScope ps(ctx, PH_REDUCE);
+        u64 blocks = std::min<u64>(((c1 - c0) * 32 + 255) / 256, (u64)ctx->sm_count * 16);
+        k_pl_level_hist<<<(unsigned)std::max<u64>(1, blocks), 256, 0, ctx->stream>>>(mt->cm_ptr.p + c0, mt->cm.p, c1 - c0, m, Lmax,
+                                                                                     (unsigned long long *)d_hist.p);
+        count_launch(ctx);
+    }
+    const u64 sample = c1 - c0;
+    SB_CUDA(cudaMemcpyAsync(d_hist.p + (hn - 1), &sample, sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    SB_TRY(comm_allreduce_u64(ctx, d_hist.p, hn));
+    std::vector<u64> h(hn);
+    SB_CUDA(cudaMemcpyAsync(h.data(), d_hist.p, hn * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    const double cells = (double)h[hn - 1];
+    if (cells <= 0.0) return SB_OK;
+    // rank by the number of entries with a count of 1..Lmax (ties: lower gene index)
+    std::vector<u64> tot(m, 0);
+    for (u32 k = 0; k < Lmax; k++)
+        for (u32 g = 0; g < m; g++) tot[g] += h[(size_t)k * m + g];
+    std::vector<u32> order(m);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 b) { return tot[a] > tot[b]; });
+    const u32 cap = std::min<u32>((u32)ctx->plane_cap, m) & ~127u;
+    const double thr = ctx->plane_min_density * cells;
+    u32 prev = cap;
+    u32 L = 0;
+    for (u32 k = 0; k < Lmax; k++) {
+        u32 G = 0;
+        for (u32 b0 = 0; b0 + 128 <= prev; b0 += 128) {  // leading 128-rank blocks whose mean level density clears the bar
+            double s = 0.0;
+            for (u32 r = b0; r < b0 + 128; r++) s += (double)h[(size_t)k * m + order[r]];
+            if (s / 128.0 < thr) break;
+            G = b0 + 128;
+        }
+        if (G == 0) break;
+        pl.G[k] = G;
+        prev = G;
+        L = k + 1;
+    }
+    if (L == 0) return SB_OK;
+    pl.L = L;
+    pl.ntiles = (mt->n + PL_TILE - 1) / PL_TILE;
+    const u32 G1 = pl.G[0];
+    std::vector<u32> hot(order.begin(), order.begin() + G1), hot_of(m, PL_NONE);
+    for (u32 r = 0; r < G1; r++) hot_of[hot[r]] = r;
+    SB_TRY(mt->hot_idx.alloc(G1));
+    SB_TRY(mt->hot_of_gene.alloc(m));
+    SB_CUDA(cudaMemcpyAsync(mt->hot_idx.p, hot.data(), G1 * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+    SB_CUDA(cudaMemcpyAsync(mt->hot_of_gene.p, hot_of.data(), (size_t)m * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+    for (u32 k = 0; k < L; k++) {
+        const size_t words = std::max<size_t>(1, (size_t)pl.ntiles * (pl.G[k] / 32) * PL_TILE);
+        SB_TRY(pl.bits[k].alloc(words));
+        SB_CUDA(cudaMemsetAsync(pl.bits[k].p, 0, words * sizeof(u32), ctx->stream));
+    }
+    // ---- T-side units: (range of 1,024 ranks) x (up to three levels)
+    std::vector<PlUnitT> ut;
+    std::vector<double> cost;
+    for (u32 g0 = 0; g0 < G1; g0 += PT_RANGE) {
+        std::vector<u32> lv;
+        for (u32 k = 0; k < L; k++)
+            if (pl.G[k] > g0) lv.push_back(k);
+        for (size_t i = 0; i < lv.size(); i += 3) {
+            PlUnitT u;
+            memset(&u, 0, sizeof(u));
+            u.g0 = g0;
+            double c = 0.0;
+            for (size_t j = i; j < std::min(lv.size(), i + 3); j++) {
+                const u32 genes = std::min(pl.G[lv[j]], g0 + PT_RANGE) - g0;  // multiple of 128
+                u.lev[u.nlev] = lv[j];
+                u.nkb[u.nlev] = genes / 64;
+                u.nlev++;
+                c += genes;
+            }
+            c += 160.0 * u.nlev;  // the epilogue of a tile costs about as much as 160 ranks of MMA per level
+            ut.push_back(u);
+            cost.push_back(c);
+        }
+    }
+    std::vector<u32> nc;
+    units_round(nc, cost, (u32)ctx->sm_count);
+    u32 at = 0;
+    for (size_t i = 0; i < ut.size(); i++) {
+        ut[i].cta0 = at;
+        ut[i].nctas = nc[i];
+        at += nc[i];
+    }
+    pl.t_grid = at;
+    pl.n_units_t = (u32)ut.size();
+    SB_TRY(pl.units_t.alloc(ut.size() * sizeof(PlUnitT)));
+    SB_CUDA(cudaMemcpyAsync(pl.units_t.p, ut.data(), ut.size() * sizeof(PlUnitT), cudaMemcpyHostToDevice, ctx->stream));
+    // ---- N-side units: groups of 384 ranks; the active levels of a group are a prefix
+    std::vector<PlUnitN> un;
+    cost.clear();
+    for (u32 g0 = 0; g0 < G1; g0 += PN_GROUP) {
+        PlUnitN u;
+        memset(&u, 0, sizeof(u));
+        u.g0 = g0;
+        double c = 0.0;
+        for (u32 k = 0; k < L && pl.G[k] > g0; k++) {
+            u.mt[k] = (std::min(pl.G[k], g0 + PN_GROUP) - g0) / 128;
+            u.nlev = k + 1;
+            c += u.mt[k] + 0.5;  // a stage costs its production (A words + the B copy) as well as its MMAs
+        }
+        un.push_back(u);
+        cost.push_back(c);
+    }
+    units_round(nc, cost, (u32)ctx->sm_count);
+    at = 0;
+    for (size_t i = 0; i < un.size(); i++) {
+        // int32 accumulators: at most 2^24 cells per CTA range (|digit| <= 128)
+        const u32 need = (u32)((mt->n + (1u << 24) - 1) >> 24);
+        un[i].cta0 = at;
+        un[i].nctas = std::max(nc[i], std::max<u32>(1, need));
+        at += un[i].nctas;
+    }
+    pl.n_grid = at;
+    pl.n_units_n = (u32)un.size();
+    SB_TRY(pl.units_n.alloc(un.size() * sizeof(PlUnitN)));
+    SB_CUDA(cudaMemcpyAsync(pl.units_n.p, un.data(), un.size() * sizeof(PlUnitN), cudaMemcpyHostToDevice, ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));  // host temporaries
+    pl.active = true;
+    mt->gd = G1;
+    if (TraceScope::on()) {
+        fprintf(stderr, "[scanb200] planes: L=%u G =", L);
+        for (u32 k = 0; k < L; k++) fprintf(stderr, " %u", pl.G[k]);
+        fprintf(stderr, "  (T units %u / %u CTAs, N units %u / %u CTAs)\n", pl.n_units_t, pl.t_grid, pl.n_units_n, pl.n_grid);
+    }
+    return SB_OK;
+}
+
+// Splits the cell-major stream of a cell range into plane bits and the cold sparse entries (count pass when `out` is NULL,
+// fill pass otherwise).  ptr is offset to the first cell of the range; cbase = its local cell index (a multiple of 128).
+__global__ void k_split_planes(const u64 *__restrict__ ptr, const uint2 *__restrict__ cm, u64 n, u64 cbase, const u32 *__restrict__ rank_of_gene,
+                               PlDev pl, const u64 *__restrict__ new_ptr, u32 *__restrict__ counts, uint2 *__restrict__ out) {
+    u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    int lane = threadIdx.x & 31;
+    for (u64 c = warp; c < n; c += nwarps) {
+        const u64 s = ptr[c], e = ptr[c + 1];
+        const u64 wpos = new_ptr ? new_ptr[c] : 0;
+        const u64 cell = cbase + c, tile = cell / PL_TILE;
+        const u32 cl = (u32)(cell % PL_TILE);
+        u32 total = 0;
+        for (u64 k0 = s; k0 < e; k0 += 32) {
+            const u64 k = k0 + lane;
+            const bool valid = k < e;
+            const uint2 z = valid ? cm[k] : make_uint2(0, 0);
+            const u32 r = valid ? rank_of_gene[z.x] : PL_NONE;
+            const bool dense = valid && r != PL_NONE && z.y >= 1 && z.y <= pl.L && r < pl.G[z.y - 1];
+            const bool cold = valid && !dense;
+            if (out && dense) {
+                const u32 lv = z.y - 1;
+                atomicOr(pl.bits[lv] + ((tile * (pl.G[lv] / 32) + (r >> 5)) * PL_TILE + cl), 1u << (r & 31));
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, cold);
+            if (out && cold) out[wpos + total + __popc(mask & ((1u << lane) - 1u))] = z;
+            total += __popc(mask);
+        }
+        if (counts && lane == 0) counts[c] = total;
+    }
+}
+
+int planes_split_launch(sb_mat *mt, u64 c0, u64 nc, const u64 *new_ptr, u32 *counts, uint2 *out) {
+    sb_ctx *ctx = mt->ctx;
+    if (nc == 0) return SB_OK;
+    if (c0 % PL_TILE) return sb_fail(SB_ERR_UNSUPPORTED, "planes_split: range start %llu is not a multiple of 128", (unsigned long long)c0);
+    u64 blocks = std::min<u64>((nc * 32 + 255) / 256, (u64)ctx->sm_count * 16);
+    k_split_planes<<<(unsigned)std::max<u64>(1, blocks), 256, 0, ctx->stream>>>(mt->cm_ptr.p + c0, mt->cm.p, nc, c0, mt->hot_of_gene.p, make_pldev(mt),
+                                                                                new_ptr, counts, out);
+    count_launch(ctx);
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
+// ---------------------------------------------------------------- digit helpers
+__device__ __forceinline__ double finite_or_zero(double x) { return (x == x && fabs(x) < 1.0e300) ? x : 0.0; }
+
+// q (|q| <= 2^54) -> 7 balanced base-256 digits in [-128, 127]
+__device__ __forceinline__ void digits7(long long q, signed char (&d)[PL_DIG]) {
+#pragma unroll
+    for (u32 s = 0; s < PL_DIG; s++) {
+        const long long t = ((q + 128) & 255) - 128;
+        d[s] = (signed char)t;
+        q = (q - t) >> 8;
+    }
+}
+
+__device__ __forceinline__ void atomic_max_abs(unsigned long long *slot, double v) {
+    atomicMax(slot, (unsigned long long)__double_as_longlong(fabs(v)));  // non-negative doubles order like their bits
+}
+
+// scale2[c] = 2^(e_c - PL_FIX) with |x| < 2^e_c for every entry of column c; ex[c] = PL_FIX - e_c
+__global__ void k_pl_scales(const unsigned long long *__restrict__ colmax_bits, double *__restrict__ scale2, int *__restrict__ ex) {
+    const u32 c = threadIdx.x;
+    if (c >= PL_COLS) return;
+    const double mx = __longlong_as_double((long long)colmax_bits[c]);
+    int e = 0;
+    if (mx > 0.0) frexp(mx, &e);
+    scale2[c] = ldexp(1.0, e - PL_FIX);
+    ex[c] = PL_FIX - e;
+}
+
+// ---------------------------------------------------------------- T side: digit planes of Ys
+__global__ void k_pl_colmax_t(const double *__restrict__ Y, u32 ldy, const u32 *__restrict__ hot_idx, const double *__restrict__ rs, u32 G1, u32 col0,
+                              u32 wt, unsigned long long *__restrict__ colmax_bits) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G1 * PL_COLS) return;
+    const u32 r = i / PL_COLS, c = i - r * PL_COLS;
+    if (c >= wt) return;
+    const u32 g = hot_idx[r];
+    double v = Y[(size_t)g * ldy + col0 + c];
+    if (rs) v *= rs[g];
+    atomic_max_abs(&colmax_bits[c], finite_or_zero(v));
+}
+
+// Bd[range][k / 16][n / 8][n % 8][k % 16], k = rank % 1024, n = 7 c + s (digit s of column c)
+__global__ void k_pl_digits_t(const double *__restrict__ Y, u32 ldy, const u32 *__restrict__ hot_idx, const double *__restrict__ rs, u32 G1, u32 col0,
+                              u32 wt, const int *__restrict__ ex, signed char *__restrict__ Bd) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G1 * PL_COLS) return;
+    const u32 r = i / PL_COLS, c = i - r * PL_COLS;
+    const u32 g = hot_idx[r];
+    double v = c < wt ? Y[(size_t)g * ldy + col0 + c] : 0.0;
+    if (rs) v *= rs[g];
+    const long long q = __double2ll_rn(ldexp(finite_or_zero(v), ex[c]));
+    signed char d[PL_DIG];
+    digits7(q, d);
+    const u32 range = r / PT_RANGE, k = r - range * PT_RANGE;
+    signed char *base = Bd + (size_t)range * PT_B_BYTES + (size_t)(k >> 4) * PT_KCHUNK_BYTES + (k & 15);
+#pragma unroll
+    for (u32 s = 0; s < PL_DIG; s++) {
+        const u32 n = c * PL_DIG + s;
+        base[(size_t)(n >> 3) * 128 + (n & 7) * 16] = d[s];
+    }
+}
+
+// ---------------------------------------------------------------- shared epilogue arithmetic
+// acc[n], n = 7 c + s: digit s of column c.  value_c = sum_s acc * 256^s, as two int64 halves -> one f64 rounding.
+struct Recombine {
+    long long lo, hi;
+    __device__ __forceinline__ void reset() { lo = 0; hi = 0; }
+    __device__ __forceinline__ void add(u32 s, int a) {
+        if (s < 4) lo += (long long)a << (8 * s);
+        else hi += (long long)a << (8 * (s - 4));
+    }
+    __device__ __forceinline__ double value() const { return (double)lo + (double)hi * 4294967296.0; }
+};
+
+// reads the 144 accumulator columns of this thread's TMEM lane starting at `taddr` and returns the 20 recombined values
+__device__ __forceinline__ void read_acc(u32 taddr, double (&val)[PL_COLS]) {
+    Recombine rc;
+    rc.reset();
+#pragma unroll
+    for (u32 cb = 0; cb < PL_NCOL; cb += 16) {
+        u32 r[16];
+        tmem_ld16(taddr + cb, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (u32 i = 0; i < 16; i++) {
+            const u32 n = cb + i;  // compile-time after unrolling
+            if (n < PL_COLS * PL_DIG) {
+                const u32 c = n / PL_DIG, s = n - c * PL_DIG;
+                rc.add(s, (int)r[i]);
+                if (s == PL_DIG - 1) {
+                    val[c] = rc.value();
+                    rc.reset();
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- k_planes_t
+struct PtShared {
+    unsigned long long full[PT_NSTAGES], empty[PT_NSTAGES], tfull[3], tempty[3];
+    u32 tmem;
+    u32 pad;
+    double scale2[PL_COLS];
+};
+
+__global__ void __launch_bounds__(PL_THREADS, 1)
+k_planes_t(PlDev pl, const PlUnitT *__restrict__ units, u32 n_units, const signed char *__restrict__ Bd, const double *__restrict__ scale2_g,
+           const double *__restrict__ cs, int log_base, u32 col0, u32 wt, double *__restrict__ out, u32 ldo) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char *sB = smem;
+    unsigned char *sA = sB + PT_B_BYTES;
+    PtShared *sh = reinterpret_cast<PtShared *>(sA + PT_NSTAGES * PT_STAGE_BYTES);
+
+    const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // this CTA's unit
+    PlUnitT un;
+    bool have = false;
+    for (u32 i = 0; i < n_units; i++) {
+        const PlUnitT u = units[i];
+        if (blockIdx.x >= u.cta0 && blockIdx.x < u.cta0 + u.nctas) {
+            un = u;
+            have = true;
+        }
+    }
+    const u32 sub = have ? blockIdx.x - un.cta0 : 0, stride = have ? un.nctas : 1;
+    const u32 nlev = have ? un.nlev : 0;
+    const u32 nslots = nlev == 1 ? 3u : 1u;
+    const u32 full0 = smem_u32(sh->full), empty0 = smem_u32(sh->empty), tfull0 = smem_u32(sh->tfull), tempty0 = smem_u32(sh->tempty);
+
+    if (tid == 0) {
+        for (u32 i = 0; i < PT_NSTAGES; i++) {
+            mbar_init(full0 + 8 * i, 1);
+            mbar_init(empty0 + 8 * i, 1);
+        }
+        for (u32 i = 0; i < 3; i++) {
+            mbar_init(tfull0 + 8 * i, 1);
+            mbar_init(tempty0 + 8 * i, PL_EPI_WARPS);
+        }
+        mbar_init_fence();
+    }
+    if (warp == 0) tmem_alloc_512(smem_u32(&sh->tmem));
+    if (have) {  // resident B operand: the digit planes of this unit's 1,024 ranks
+        const uint4 *src = reinterpret_cast<const uint4 *>(Bd + (size_t)(un.g0 / PT_RANGE) * PT_B_BYTES);
+        uint4 *dst = reinterpret_cast<uint4 *>(sB);
+        for (u32 i = tid; i < PT_B_BYTES / 16; i += PL_THREADS) dst[i] = src[i];
+    }
+    if (tid < PL_COLS) sh->scale2[tid] = scale2_g[tid];
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const u32 tmem = sh->tmem;
+    const u32 sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+
+    if (have && warp < PL_EPI_WARPS) {
+        // ===== epilogue: TMEM -> registers -> f64 -> T (one thread per cell row)
+        const u32 row = warp * 32 + lane;
+        u64 it = 0;
+        for (u64 tile = sub; tile < pl.ntiles; tile += stride, it++) {
+            const u32 slot = (u32)(it % nslots);
+            const u32 use = (u32)(it / nslots);
+            const u64 cell = tile * PL_TILE + row;
+            double res[PL_COLS];
+#pragma unroll
+            for (u32 j = 0; j < PL_COLS; j++) res[j] = 0.0;
+            double Lv[3] = {0.0, 0.0, 0.0};
+            if (cell < pl.n) {
+                const double s = cs[cell];
+                for (u32 a = 0; a < nlev; a++) Lv[a] = finite_or_zero(map_log_part(log_base, s, un.lev[a] + 1, sb_log_table));
+            }
+            mbar_wait(tfull0 + 8 * slot, use & 1u);
+            fence_after_sync();
+            for (u32 a = 0; a < nlev; a++) {
+                double val[PL_COLS];
+                read_acc(tmem + ((warp * 32u) << 16) + (slot * nlev + a) * PL_NCOL, val);
+                const double lk = Lv[a];
+#pragma unroll
+                for (u32 j = 0; j < PL_COLS; j++) res[j] = fma(lk, val[j], res[j]);
+            }
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * slot);  // this warp's quarter of the accumulators is free
+            if (cell < pl.n) {
+                double *o = out + cell * (size_t)ldo + col0;
+#pragma unroll
+                for (u32 j = 0; j < PL_COLS; j++)
+                    if (j < wt) atomicAdd(o + j, res[j] * sh->scale2[j]);  // other units (gene ranges, level triples) add into the same row
+            }
+        }
+    } else if (have && warp == PL_EPI_WARPS) {
+        // ===== MMA issue (one thread)
+        if (lane == 0) {
+            const u32 idesc = instr_desc_i8(PL_TILE, PL_NCOL, false, false);
+            u64 it = 0;
+            u32 q = 0;
+            for (u64 tile = sub; tile < pl.ntiles; tile += stride, it++) {
+                const u32 slot = (u32)(it % nslots);
+                const u32 use = (u32)(it / nslots);
+                if (use > 0) {
+                    mbar_wait(tempty0 + 8 * slot, (use - 1) & 1u);
+                    fence_after_sync();
+                }
+                for (u32 kb = 0; kb < un.nkb[0]; kb++) {
+                    for (u32 a = 0; a < nlev; a++) {
+                        if (kb >= un.nkb[a]) continue;
+                        const u32 s = q % PT_NSTAGES;
+                        mbar_wait(full0 + 8 * s, (q / PT_NSTAGES) & 1u);
+                        fence_after_sync();
+#pragma unroll
+                        for (u32 j = 0; j < 2; j++) {  // K = 32 per MMA: two 16-gene core-matrix columns
+                            const uint64_t da = smem_desc(sA_addr + s * PT_STAGE_BYTES + 2 * j * (PL_TILE * 16), PL_TILE * 16, 128);
+                            const uint64_t db = smem_desc(sB_addr + (kb * 4 + 2 * j) * PT_KCHUNK_BYTES, PT_KCHUNK_BYTES, 128);
+                            mma_i8(tmem + (slot * nlev + a) * PL_NCOL, da, db, idesc, (kb | j) ? 1u : 0u);
+                        }
+                        commit(empty0 + 8 * s);  // the stage is reusable once these MMAs have read it
+                        q++;
+                    }
+                }
+                commit(tfull0 + 8 * slot);  // accumulators of this tile complete
+            }
+        }
+    } else if (have) {
+        // ===== producers: plane words -> 0/1 int8 A tiles (K-major core matrices: [16-gene chunk][cell / 8][cell % 8][16 B])
+        const u32 p = warp - (PL_EPI_WARPS + 1);  // stage slot owned by this warp
+        u32 q = 0, fills = 0;
+        // iterator over the stage sequence (tile, kb, level), identical to the MMA thread's
+        u64 tile = sub;
+        u32 kb = 0, a = 0;
+        bool done = tile >= pl.ntiles;
+        auto advance = [&]() {  // to the next stage of the sequence
+            for (;;) {
+                a++;
+                if (a >= nlev) {
+                    a = 0;
+                    kb++;
+                    if (kb >= un.nkb[0]) {
+                        kb = 0;
+                        tile += stride;
+                        if (tile >= pl.ntiles) {
+                            done = true;
+                            return;
+                        }
+                    }
+                }
+                if (kb < un.nkb[a]) return;
+            }
+        };
+        auto seek_mine = [&]() {  // position on the next stage with q % 8 == p (the current one counts)
+            while (!done && (q % PT_NSTAGES) != p) {
+                advance();
+                q++;
+            }
+        };
+        auto load_words = [&](u32 (&w)[8]) {
+            const u32 lv = un.lev[a];
+            const u32 gw0 = (un.g0 + kb * 64) / 32;
+            const u32 *base = pl.bits[lv] + ((size_t)tile * (pl.G[lv] / 32) + gw0) * PL_TILE + lane;
+#pragma unroll
+            for (u32 j = 0; j < 2; j++)
+#pragma unroll
+                for (u32 i = 0; i < 4; i++) w[j * 4 + i] = __ldg(base + (size_t)j * PL_TILE + i * 32);
+        };
+        u32 cur[8], nxt[8];
+        seek_mine();
+        if (!done) load_words(cur);
+        while (!done) {
+            // prefetch the words of my next stage before expanding the current one
+            advance();
+            q++;
+            seek_mine();
+            const bool more = !done;
+            if (more) load_words(nxt);
+            if (fills > 0) mbar_wait(empty0 + 8 * p, (fills - 1) & 1u);
+            const u32 st = sA_addr + p * PT_STAGE_BYTES + lane * 16;
+#pragma unroll
+            for (u32 j = 0; j < 2; j++)
+#pragma unroll
+                for (u32 i = 0; i < 4; i++) {
+                    uint4 lo, hi;
+                    expand_bits32(cur[j * 4 + i], lo, hi);
+                    st_shared_v4(st + (2 * j) * (PL_TILE * 16) + i * 512, lo);
+                    st_shared_v4(st + (2 * j + 1) * (PL_TILE * 16) + i * 512, hi);
+                }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full0 + 8 * p);
+            fills++;
+            if (more) {
+#pragma unroll
+                for (u32 i = 0; i < 8; i++) cur[i] = nxt[i];
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc_512(tmem);
+}
+
+// ---------------------------------------------------------------- N side: digit rows of L_c(k) . X[c,:]
+// mode 0: value_j = L_c(k) * X[c, col0 + j]; mode 1 (moments): value_0 = L_c(k), value_1 = L_c(k)^2
+__global__ void k_pl_colmax_n(const double *__restrict__ X, u32 ldx, u64 n, const double *__restrict__ cs, int log_base, u32 Ltop, u32 col0, u32 wt,
+                              int mode, unsigned long long *__restrict__ colmax_bits) {
+    double mx[PL_COLS];
+#pragma unroll
+    for (u32 j = 0; j < PL_COLS; j++) mx[j] = 0.0;
+    for (u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (u64)gridDim.x * blockDim.x) {
+        const double l = finite_or_zero(map_log_part(log_base, cs[c], Ltop, sb_log_table));  // L_c(k) grows with k: the top level bounds all
+        if (mode == 1) {
+            mx[0] = fmax(mx[0], fabs(l));
+            mx[1] = fmax(mx[1], l * l);
+        } else {
+#pragma unroll
+            for (u32 j = 0; j < PL_COLS; j++)
+                if (j < wt) mx[j] = fmax(mx[j], fabs(finite_or_zero(l * X[c * (size_t)ldx + col0 + j])));
+        }
+    }
+#pragma unroll
+    for (u32 j = 0; j < PL_COLS; j++) {
+        double v = mx[j];
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if ((threadIdx.x & 31) == 0 && v > 0.0) atomic_max_abs(&colmax_bits[j], v);
+    }
+}
+
+// Bn[level][cell / 8][n / 16][cell % 8][n % 16] over the padded cells (zero rows beyond n): one thread per (cell, level)
+__global__ void k_pl_digits_n(const double *__restrict__ X, u32 ldx, u64 n, u64 n_pad, const double *__restrict__ cs, int log_base, u32 L, u32 col0,
+                              u32 wt, int mode, const int *__restrict__ ex, signed char *__restrict__ Bn) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad * L) return;
+    const u32 lv = (u32)(i / n_pad);
+    const u64 c = i - (u64)lv * n_pad;
+    u32 pk[PL_NCOL / 4];
+#pragma unroll
+    for (u32 t = 0; t < PL_NCOL / 4; t++) pk[t] = 0u;
+    if (c < n) {
+        const double l = finite_or_zero(map_log_part(log_base, cs[c], lv + 1, sb_log_table));
+#pragma unroll
+        for (u32 j = 0; j < PL_COLS; j++) {
+            double v = 0.0;
+            if (mode == 1) v = j == 0 ? l : (j == 1 ? l * l : 0.0);
+            else if (j < wt) v = finite_or_zero(l * X[c * (size_t)ldx + col0 + j]);
+            const long long q = __double2ll_rn(ldexp(v, ex[j]));
+            signed char d[PL_DIG];
+            digits7(q, d);
+#pragma unroll
+            for (u32 s = 0; s < PL_DIG; s++) {
+                const u32 nn = j * PL_DIG + s;  // compile-time
+                pk[nn >> 2] |= (u32)(unsigned char)d[s] << (8 * (nn & 3));
+            }
+        }
+    }
+    uint4 *dst = reinterpret_cast<uint4 *>(Bn + ((size_t)lv * (n_pad / 8) + (c >> 3)) * PN_CELLGRP_BYTES + (c & 7) * 16);
+#pragma unroll
+    for (u32 t = 0; t < PL_NCOL / 16; t++) dst[t * 8] = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);  // chunks are 128 B apart
+}
+
+// ---------------------------------------------------------------- k_planes_n
+struct PnShared {
+    unsigned long long full[PN_NSTAGES], empty[PN_NSTAGES], tfull;
+    u32 tmem;
+    u32 pad;
+    double scale2[PL_COLS];
+};
+
+// out[gene * row_stride + (col0 + j) * col_stride] += value
+__global__ void __launch_bounds__(PL_THREADS, 1)
+k_planes_n(PlDev pl, const PlUnitN *__restrict__ units, u32 n_units, const signed char *__restrict__ Bn, u64 n_pad, const double *__restrict__ scale2_g,
+           const u32 *__restrict__ hot_idx, u32 col0, u32 wt, double *__restrict__ out, u64 row_stride, u64 col_stride) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char *sS = smem;  // PN_NSTAGES stages: [A: 3 M tiles x 4,096 | B: 4,608]
+    PnShared *sh = reinterpret_cast<PnShared *>(sS + PN_NSTAGES * PN_STAGE_BYTES);
+    const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    PlUnitN un;
+    bool have = false;
+    for (u32 i = 0; i < n_units; i++) {
+        const PlUnitN u = units[i];
+        if (blockIdx.x >= u.cta0 && blockIdx.x < u.cta0 + u.nctas) {
+            un = u;
+            have = true;
+        }
+    }
+    const u32 sub = have ? blockIdx.x - un.cta0 : 0;
+    const u64 t_begin = have ? pl.ntiles * sub / un.nctas : 0, t_end = have ? pl.ntiles * (sub + 1) / un.nctas : 0;
+    have = have && t_end > t_begin;
+    const u32 nlev = have ? un.nlev : 0;
+    const u32 full0 = smem_u32(sh->full), empty0 = smem_u32(sh->empty), tfull0 = smem_u32(&sh->tfull);
+    if (tid == 0) {
+        for (u32 i = 0; i < PN_NSTAGES; i++) {
+            mbar_init(full0 + 8 * i, 1);
+            mbar_init(empty0 + 8 * i, 1);
+        }
+        mbar_init(tfull0, 1);
+        mbar_init_fence();
+    }
+    if (warp == 0) tmem_alloc_512(smem_u32(&sh->tmem));
+    if (tid < PL_COLS) sh->scale2[tid] = scale2_g[tid];
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const u32 tmem = sh->tmem;
+    const u32 sS_addr = smem_u32(sS);
+
+    if (have && warp < PL_EPI_WARPS) {
+        // ===== epilogue (once per CTA): TMEM lanes = gene rows of an M tile
+        mbar_wait(tfull0, 0);
+        fence_after_sync();
+        const u32 row = warp * 32 + lane;
+        for (u32 mtile = 0; mtile < un.mt[0]; mtile++) {
+            double val[PL_COLS];
+            read_acc(tmem + ((warp * 32u) << 16) + mtile * PL_NCOL, val);
+            const u32 g = hot_idx[un.g0 + mtile * 128 + row];
+            double *o = out + (size_t)g * row_stride;
+#pragma unroll
+            for (u32 j = 0; j < PL_COLS; j++)
+                if (j < wt && val[j] != 0.0) atomicAdd(o + (size_t)(col0 + j) * col_stride, val[j] * sh->scale2[j]);
+        }
+    } else if (have && warp == PL_EPI_WARPS) {
+        // ===== MMA issue
+        if (lane == 0) {
+            const u32 idesc = instr_desc_i8(128, PL_NCOL, true, true);
+            u32 q = 0;
+            u32 started = 0;  // bit mtile: the accumulator has been written
+            for (u64 tile = t_begin; tile < t_end; tile++)
+                for (u32 ks = 0; ks < 4; ks++)
+                    for (u32 k = 0; k < nlev; k++) {
+                        const u32 s = q % PN_NSTAGES;
+                        mbar_wait(full0 + 8 * s, (q / PN_NSTAGES) & 1u);
+                        fence_after_sync();
+                        const u32 st = sS_addr + s * PN_STAGE_BYTES;
+                        const uint64_t db = smem_desc(st + PN_A_BYTES, PN_CELLGRP_BYTES, 128);  // MN-major: lbo = next 8 cells, sbo = next 16 digit columns
+                        for (u32 mtile = 0; mtile < un.mt[k]; mtile++) {
+                            const uint64_t da = smem_desc(st + mtile * 4096, 128, 512);  // MN-major: lbo = next 8 cells, sbo = next 16 genes
+                            mma_i8(tmem + mtile * PL_NCOL, da, db, idesc, (started >> mtile) & 1u);
+                            started |= 1u << mtile;
+                        }
+                        commit(empty0 + 8 * s);
+                        q++;
+                    }
+            commit(tfull0);
+        }
+    } else if (have) {
+        // ===== producers: stage = (32-cell K step, level): A tiles [M tile][16-gene chunk (8)][cell / 8 (4)][cell % 8][16 B] + B digit rows
+        const u32 p = warp - (PL_EPI_WARPS + 1);
+        const u64 per_tile = 4ull * nlev;
+        const u64 total = (t_end - t_begin) * per_tile;
+        u32 fills = 0;
+        u32 cur[12], nxt[12];
+        auto coords = [&](u64 q, u64 &tile, u32 &ks, u32 &k) {
+            tile = t_begin + q / per_tile;
+            const u32 r = (u32)(q % per_tile);
+            ks = r / nlev;
+            k = r - ks * nlev;
+        };
+        auto load_words = [&](u64 q, u32 (&w)[12]) {
+            u64 tile;
+            u32 ks, k;
+            coords(q, tile, ks, k);
+            const u32 *base = pl.bits[k] + ((size_t)tile * (pl.G[k] / 32) + un.g0 / 32) * PL_TILE + ks * 32 + lane;
+#pragma unroll
+            for (u32 j = 0; j < 12; j++) w[j] = (j < un.mt[k] * 4) ? __ldg(base + (size_t)j * PL_TILE) : 0u;
+        };
+        u64 q = p;
+        if (q < total) load_words(q, cur);
+        for (; q < total; q += PN_NSTAGES) {
+            const bool more = q + PN_NSTAGES < total;
+            if (more) load_words(q + PN_NSTAGES, nxt);
+            u64 tile;
+            u32 ks, k;
+            coords(q, tile, ks, k);
+            // B rows of these 32 cells at level k (contiguous 4,608 bytes in Bn)
+            const uint4 *bsrc = reinterpret_cast<const uint4 *>(Bn + ((size_t)k * (n_pad / 8) + (tile * PL_TILE + ks * 32) / 8) * PN_CELLGRP_BYTES);
+            uint4 bv[PN_B_BYTES / 16 / 32];
+#pragma unroll
+            for (u32 t = 0; t < PN_B_BYTES / 16 / 32; t++) bv[t] = __ldg(bsrc + lane + 32 * t);
+            if (fills > 0) mbar_wait(empty0 + 8 * p, (fills - 1) & 1u);
+            const u32 st = sS_addr + p * PN_STAGE_BYTES;
+#pragma unroll
+            for (u32 j = 0; j < 12; j++) {
+                if (j < un.mt[k] * 4) {
+                    uint4 lo, hi;
+                    expand_bits32(cur[j], lo, hi);
+                    const u32 a0 = st + (j >> 2) * 4096 + (2 * (j & 3)) * 512 + lane * 16;
+                    st_shared_v4(a0, lo);
+                    st_shared_v4(a0 + 512, hi);
+                }
+            }
+#pragma unroll
+            for (u32 t = 0; t < PN_B_BYTES / 16 / 32; t++) st_shared_v4(st + PN_A_BYTES + (lane + 32 * t) * 16, bv[t]);
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full0 + 8 * p);
+            fills++;
+            if (more) {
+#pragma unroll
+                for (u32 j = 0; j < 12; j++) cur[j] = nxt[j];
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc_512(tmem);
+}
+
+// ---------------------------------------------------------------- launchers
+static int scales_from_colmax(sb_ctx *ctx, DevBuf<unsigned long long> &colmax, DevBuf<double> &scale2, DevBuf<int> &ex) {
+    SB_TRY(scale2.alloc(PL_COLS));
+    SB_TRY(ex.alloc(PL_COLS));
+    k_pl_scales<<<1, 32, 0, ctx->stream>>>(colmax.p, scale2.p, ex.p);
+    count_launch(ctx);
+    return SB_OK;
+}
+
+// T[c, :] += the plane part of A^T . Y   (out already holds the offset term; the sparse gather adds the rest)
+int planes_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo) {
+    sb_mat *mt = a->mat;
+    sb_ctx *ctx = mt->ctx;
+    const PlaneSet &pl = mt->pl;
+    if (!pl.active || mt->n == 0 || w == 0) return SB_OK;
+    const u32 G1 = pl.G[0];
+    const u32 nranges = (G1 + PT_RANGE - 1) / PT_RANGE;
+    DevBuf<unsigned long long> colmax;
+    DevBuf<signed char> Bd;
+    DevBuf<double> scale2;
+    DevBuf<int> ex;
+    SB_TRY(colmax.alloc(PL_COLS));
+    SB_TRY(Bd.alloc((size_t)nranges * PT_B_BYTES));
+    const double *rs = a->has_row_scale ? a->row_scale.p : nullptr;
+    const size_t smem = (size_t)PT_B_BYTES + PT_NSTAGES * PT_STAGE_BYTES + sizeof(PtShared);
+    cudaError_t e = cudaFuncSetAttribute(k_planes_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return sb_fail(SB_ERR_CUDA, "planes_t: %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+    const u32 items = G1 * PL_COLS;
+    for (u32 col0 = 0; col0 < w; col0 += PL_COLS) {
+        const u32 wt = std::min(PL_COLS, w - col0);
+        SB_CUDA(cudaMemsetAsync(colmax.p, 0, PL_COLS * sizeof(unsigned long long), ctx->stream));
+        if (col0 == 0) SB_CUDA(cudaMemsetAsync(Bd.p, 0, (size_t)nranges * PT_B_BYTES, ctx->stream));  // padding columns / ranks stay zero
+        k_pl_colmax_t<<<cdiv(items, 256), 256, 0, ctx->stream>>>(Y, ldy, mt->hot_idx.p, rs, G1, col0, wt, colmax.p);
+        SB_TRY(scales_from_colmax(ctx, colmax, scale2, ex));
+        k_pl_digits_t<<<cdiv(items, 256), 256, 0, ctx->stream>>>(Y, ldy, mt->hot_idx.p, rs, G1, col0, wt, ex.p, Bd.p);
+        k_planes_t<<<pl.t_grid, PL_THREADS, smem, ctx->stream>>>(make_pldev(mt), (const PlUnitT *)pl.units_t.p, pl.n_units_t, Bd.p, scale2.p,
+                                                                 a->col_scale.p, a->log_base, col0, wt, out, ldo);
+        count_launch(ctx); count_launch(ctx); count_launch(ctx);
+    }
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
+static int planes_n_impl(sb_nmat *a, const double *X, u32 ldx, u32 w, int mode, double *out, u64 row_stride, u64 col_stride) {
+    sb_mat *mt = a->mat;
+    sb_ctx *ctx = mt->ctx;
+    const PlaneSet &pl = mt->pl;
+    if (!pl.active || mt->n == 0 || w == 0) return SB_OK;
+    const u64 n_pad = pl.ntiles * PL_TILE;
+    DevBuf<unsigned long long> colmax;
+    DevBuf<signed char> Bn;
+    DevBuf<double> scale2;
+    DevBuf<int> ex;
+    SB_TRY(colmax.alloc(PL_COLS));
+    SB_TRY(Bn.alloc((size_t)pl.L * (n_pad / 8) * PN_CELLGRP_BYTES));
+    const size_t smem = (size_t)PN_NSTAGES * PN_STAGE_BYTES + sizeof(PnShared);
+    cudaError_t e = cudaFuncSetAttribute(k_planes_n, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return sb_fail(SB_ERR_CUDA, "planes_n: %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+    const int cm_blocks = (int)std::max<u64>(1, std::min<u64>((mt->n + 255) / 256, (u64)ctx->sm_count * 4));
+    for (u32 col0 = 0; col0 < w; col0 += PL_COLS) {
+        const u32 wt = std::min(PL_COLS, w - col0);
+        SB_CUDA(cudaMemsetAsync(colmax.p, 0, PL_COLS * sizeof(unsigned long long), ctx->stream));
+        k_pl_colmax_n<<<cm_blocks, 256, 0, ctx->stream>>>(X, ldx, mt->n, a->col_scale.p, a->log_base, pl.L, col0, wt, mode, colmax.p);
+        SB_TRY(scales_from_colmax(ctx, colmax, scale2, ex));
+        k_pl_digits_n<<<cdiv(n_pad * pl.L, 128), 128, 0, ctx->stream>>>(X, ldx, mt->n, n_pad, a->col_scale.p, a->log_base, pl.L, col0, wt, mode, ex.p, Bn.p);
+        k_planes_n<<<pl.n_grid, PL_THREADS, smem, ctx->stream>>>(make_pldev(mt), (const PlUnitN *)pl.units_n.p, pl.n_units_n, Bn.p, n_pad, scale2.p,
+                                                                 mt->hot_idx.p, col0, wt, out, row_stride, col_stride);
+        count_launch(ctx); count_launch(ctx); count_launch(ctx);
+    }
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
+// P[g, :] += the plane part of sum_c L_c(v_gc) X[c, :]   (row scale and offset are applied by k_spmm_n_finalize)
+int planes_n(sb_nmat *a, const double *X, u32 ldx, u32 w, double *P, u32 ldp) { return planes_n_impl(a, X, ldx, w, 0, P, ldp, 1); }
+
+// S1[g] += sum_c L, S2[g] += sum_c L^2 over the plane entries
+int planes_moments(sb_nmat *a, double *S1, double *S2) {
+    if (S2 < S1) return sb_fail(SB_ERR_UNSUPPORTED, "planes_moments: S2 must follow S1");
+    return planes_n_impl(a, nullptr, 0, 2, 1, S1, 1, (u64)(S2 - S1));
+}

@@ -449,7 +449,7 @@ int spmm_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo, do
     // Overlap: the sparse gather is bound by the L1 / shared-memory pipe, the panel kernel by the FP64 tensor pipe.
     // Run them on two streams with CTAs of both resident on every SM; both add into the zeroed output block
     // (0 + a + b is the same in either order, so the result stays deterministic).
-    const bool overlap = hybrid && ctx->overlap_t && ctx->aux_stream != nullptr;
+    const bool overlap = hybrid && !mt->pl.active && ctx->overlap_t && ctx->aux_stream != nullptr;
     if (overlap) {
         const u32 wpad = (w + 1) & ~1u;
         SB_CUDA(cudaMemset2DAsync(out, (size_t)ldo * sizeof(double), 0, (size_t)wpad * sizeof(double), (size_t)mt->n, ctx->stream));
@@ -507,7 +507,7 @@ int spmm_n(sb_nmat *a, const double *X, u32 ldx, u32 w, double *P, u32 ldp) {
             account(ctx, mt, w, false);
             SB_CUDA(cudaGetLastError());
         } else {
-        const bool overlap = hybrid && ctx->overlap && ctx->aux_stream != nullptr && sparse_nnz > 0;
+        const bool overlap = hybrid && !mt->pl.active && ctx->overlap && ctx->aux_stream != nullptr && sparse_nnz > 0;
         if (overlap) {
             SB_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
             SB_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
