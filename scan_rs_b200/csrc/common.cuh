@@ -171,14 +171,18 @@ struct PlUnitN {  // N side: a group of 384 ranks; levels 0..nlev-1; CTAs split 
     u32 mt[PL_MAX_LEVELS];  // 128-gene M tiles of each level inside the group (non-increasing)
     u32 cta0, nctas;
 };
+struct PlItem {  // T side work item: tiles [t0, t1) of a unit
+    u32 unit, t0, t1;
+};
 struct PlaneSet {
     bool active = false;
     u32 L = 0;
     u32 G[PL_MAX_LEVELS] = {0, 0, 0, 0, 0, 0};  // ranks covered by level k + 1: multiples of 128, non-increasing
     u64 ntiles = 0;                              // cell tiles of 128
     DevBuf<u32> bits[PL_MAX_LEVELS];             // [ntiles][G / 32][128] words
-    DevBuf<char> units_t, units_n;
-    u32 n_units_t = 0, n_units_n = 0, t_grid = 0, n_grid = 0;
+    DevBuf<char> units_t, units_n, items_t;
+    DevBuf<u32> counter;  // work-queue head of the T-side kernel
+    u32 n_units_t = 0, n_units_n = 0, n_items_t = 0, t_grid = 0, n_grid = 0;
 };
 
 // One side of the panelled gather: the entry stream, its work units and (T side) the gene of every panel slot.

@@ -1024,33 +1024,117 @@ extern "C" int sb_median_cell_total(sb_mat *mat, uint32_t *median, int *nonempty
 }
 
 // ---------------------------------------------------------------- selection
+// general form of the row selection: gene g is wanted at positions inv_list[inv_ptr[g] .. inv_ptr[g+1]) of the output
+__global__ void k_select_rows_multi(const u64 *__restrict__ ptr, const uint2 *__restrict__ cm, u64 n, const u32 *__restrict__ inv_ptr,
+                                    const u32 *__restrict__ inv_list, const u64 *__restrict__ new_ptr, u32 *__restrict__ counts,
+                                    u32 *__restrict__ out_gene, u32 *__restrict__ out_cnt) {
+    u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    int lane = threadIdx.x & 31;
+    for (u64 c = warp; c < n; c += nwarps) {
+        const u64 s = ptr[c], e = ptr[c + 1];
+        const u64 wpos = new_ptr ? new_ptr[c] : 0;
+        u32 total = 0;
+        for (u64 k0 = s; k0 < e; k0 += 32) {
+            const u64 k = k0 + lane;
+            const uint2 z = k < e ? cm[k] : make_uint2(0, 0);
+            const u32 a = k < e ? inv_ptr[z.x] : 0, b = k < e ? inv_ptr[z.x + 1] : 0;
+            const u32 mine = b - a;
+            u32 incl = mine;  // inclusive warp scan of the copies each lane emits
+            for (int o = 1; o < 32; o <<= 1) {
+                const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (out_gene)
+                for (u32 i = 0; i < mine; i++) {
+                    out_gene[wpos + total + incl - mine + i] = inv_list[a + i];
+                    out_cnt[wpos + total + incl - mine + i] = z.y;
+                }
+            total += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (counts && lane == 0) counts[c] = total;
+    }
+}
+
+__global__ void k_zip_entries(const u32 *__restrict__ gene, const u32 *__restrict__ cnt, u64 nnz, uint2 *__restrict__ out) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (u64)gridDim.x * blockDim.x) out[i] = make_uint2(gene[i], cnt[i]);
+}
+
+// select_rows (sqz/src/mat.rs:1040-1071): the output's row j is a clone of row rows[j] -- any order, duplicates allowed.
 static int select_rows_dev(sb_mat *mat, const u32 *h_rows, u32 count, sb_mat **out) {
     sb_ctx *ctx = mat->ctx;
-    std::vector<u32> map(mat->m, 0xFFFFFFFFu);
+    bool ascending = true;
     for (u32 j = 0; j < count; j++) {
         if (h_rows[j] >= mat->m) return sb_fail(SB_ERR_INVALID_ARG, "select_rows: row %u out of range", h_rows[j]);
-        if (map[h_rows[j]] != 0xFFFFFFFFu) return sb_fail(SB_ERR_UNSUPPORTED, "select_rows: duplicate row %u", h_rows[j]);
-        map[h_rows[j]] = j;
+        if (j && h_rows[j] <= h_rows[j - 1]) ascending = false;
     }
-    DevBuf<u32> d_map, d_counts;
-    SB_TRY(d_map.alloc(mat->m));
-    SB_TRY(d_counts.alloc(mat->n));
-    if (mat->m) SB_CUDA(cudaMemcpyAsync(d_map.p, map.data(), (size_t)mat->m * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+    DevBuf<u32> d_counts;
     DevBuf<u64> new_ptr;
+    DevBuf<uint2> new_cm;
+    SB_TRY(d_counts.alloc(mat->n));
     SB_TRY(new_ptr.alloc(mat->n + 1));
     int grid = grid_for(mat->n * 32, 256, ctx, 16);
+    u64 new_nnz = 0;
+    if (ascending) {  // one output position per gene and the cells' entries stay in ascending order
+        std::vector<u32> map(mat->m, 0xFFFFFFFFu);
+        for (u32 j = 0; j < count; j++) map[h_rows[j]] = j;
+        DevBuf<u32> d_map;
+        SB_TRY(d_map.alloc(mat->m));
+        if (mat->m) SB_CUDA(cudaMemcpyAsync(d_map.p, map.data(), (size_t)mat->m * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+        if (mat->n) {
+            k_select_rows<<<grid, 256, 0, ctx->stream>>>(mat->cm_ptr.p, mat->cm.p, mat->n, d_map.p, nullptr, d_counts.p, nullptr);
+            count_launch(ctx);
+        }
+        SB_TRY(exclusive_scan_u32_to_u64(ctx, d_counts.p, mat->n, new_ptr.p));
+        SB_CUDA(cudaMemcpyAsync(&new_nnz, new_ptr.p + mat->n, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+        SB_CUDA(cudaStreamSynchronize(ctx->stream));  // also: `map` is a host temporary
+        SB_TRY(new_cm.alloc(new_nnz));
+        if (mat->n) {
+            k_select_rows<<<grid, 256, 0, ctx->stream>>>(mat->cm_ptr.p, mat->cm.p, mat->n, d_map.p, new_ptr.p, nullptr, new_cm.p);
+            count_launch(ctx);
+        }
+        SB_CUDA(cudaStreamSynchronize(ctx->stream));
+        return mat_from_device_cm(ctx, count, mat->n, new_ptr, new_cm, new_nnz, out);
+    }
+    // general order: every wanted copy of a gene is emitted, then each cell's entries are sorted by their new row
+    std::vector<u32> inv_ptr((size_t)mat->m + 1, 0), inv_list(count ? count : 1, 0);
+    for (u32 j = 0; j < count; j++) inv_ptr[h_rows[j] + 1]++;
+    for (u32 g = 0; g < mat->m; g++) inv_ptr[g + 1] += inv_ptr[g];
+    {
+        std::vector<u32> fill(inv_ptr.begin(), inv_ptr.end() - 1);
+        for (u32 j = 0; j < count; j++) inv_list[fill[h_rows[j]]++] = j;
+    }
+    DevBuf<u32> d_iptr, d_ilist, g_in, c_in, g_out, c_out;
+    SB_TRY(d_iptr.alloc(inv_ptr.size()));
+    SB_TRY(d_ilist.alloc(inv_list.size()));
+    SB_CUDA(cudaMemcpyAsync(d_iptr.p, inv_ptr.data(), inv_ptr.size() * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+    SB_CUDA(cudaMemcpyAsync(d_ilist.p, inv_list.data(), inv_list.size() * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
     if (mat->n) {
-        k_select_rows<<<grid, 256, 0, ctx->stream>>>(mat->cm_ptr.p, mat->cm.p, mat->n, d_map.p, nullptr, d_counts.p, nullptr);
+        k_select_rows_multi<<<grid, 256, 0, ctx->stream>>>(mat->cm_ptr.p, mat->cm.p, mat->n, d_iptr.p, d_ilist.p, nullptr, d_counts.p, nullptr, nullptr);
         count_launch(ctx);
     }
     SB_TRY(exclusive_scan_u32_to_u64(ctx, d_counts.p, mat->n, new_ptr.p));
-    u64 new_nnz = 0;
     SB_CUDA(cudaMemcpyAsync(&new_nnz, new_ptr.p + mat->n, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     SB_CUDA(cudaStreamSynchronize(ctx->stream));
-    DevBuf<uint2> new_cm;
+    SB_TRY(g_in.alloc(new_nnz));
+    SB_TRY(c_in.alloc(new_nnz));
+    SB_TRY(g_out.alloc(new_nnz));
+    SB_TRY(c_out.alloc(new_nnz));
     SB_TRY(new_cm.alloc(new_nnz));
-    if (mat->n) {
-        k_select_rows<<<grid, 256, 0, ctx->stream>>>(mat->cm_ptr.p, mat->cm.p, mat->n, d_map.p, new_ptr.p, nullptr, new_cm.p);
+    if (mat->n && new_nnz) {
+        k_select_rows_multi<<<grid, 256, 0, ctx->stream>>>(mat->cm_ptr.p, mat->cm.p, mat->n, d_iptr.p, d_ilist.p, new_ptr.p, nullptr, g_in.p, c_in.p);
+        count_launch(ctx);
+        if (new_nnz > 0x7FFFFFFFull) return sb_fail(SB_ERR_UNSUPPORTED, "select_rows: more than 2^31 entries in a reordering selection");
+        size_t tmp_bytes = 0;
+        const int end_bit = bits_for(count ? count - 1 : 0);
+        SB_CUDA(cub::DeviceSegmentedRadixSort::SortPairs(nullptr, tmp_bytes, g_in.p, g_out.p, c_in.p, c_out.p, (int)new_nnz, (int)mat->n, new_ptr.p,
+                                                         new_ptr.p + 1, 0, end_bit, ctx->stream));
+        DevBuf<char> tmp;
+        SB_TRY(tmp.alloc(tmp_bytes));
+        SB_CUDA(cub::DeviceSegmentedRadixSort::SortPairs(tmp.p, tmp_bytes, g_in.p, g_out.p, c_in.p, c_out.p, (int)new_nnz, (int)mat->n, new_ptr.p,
+                                                         new_ptr.p + 1, 0, end_bit, ctx->stream));
+        count_launch(ctx, false);
+        k_zip_entries<<<grid_for(new_nnz, 256, ctx, 16), 256, 0, ctx->stream>>>(g_out.p, c_out.p, new_nnz, new_cm.p);
         count_launch(ctx);
     }
     SB_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -211,23 +211,45 @@ int planes_select(sb_mat *mt, u64 c0, u64 c1) {
                 u.nlev++;
                 c += genes;
             }
-            c += 160.0 * u.nlev;  // the epilogue of a tile costs about as much as 160 ranks of MMA per level
+            // the epilogue of a tile costs about as much as 100 ranks of MMA per level; with several levels it cannot overlap the
+            // next tile's MMAs (one accumulator set)
+            c += (u.nlev > 1 ? 250.0 : 100.0) * u.nlev;
             ut.push_back(u);
             cost.push_back(c);
         }
     }
-    std::vector<u32> nc;
-    units_round(nc, cost, (u32)ctx->sm_count);
-    u32 at = 0;
-    for (size_t i = 0; i < ut.size(); i++) {
-        ut[i].cta0 = at;
-        ut[i].nctas = nc[i];
-        at += nc[i];
+    // work items: every unit's tiles in chunks of about equal cost, heaviest units first (the queue is drained in order by
+    // persistent CTAs, so a long item never starts last); ~16 items per CTA keep the tail short
+    {
+        double total = 0.0;
+        for (double c : cost) total += c * (double)pl.ntiles;
+        const double target = std::max(1.0, total / ((double)ctx->sm_count * 16.0));
+        std::vector<u32> uo(ut.size());
+        std::iota(uo.begin(), uo.end(), 0u);
+        std::stable_sort(uo.begin(), uo.end(), [&](u32 x, u32 y) { return cost[x] > cost[y]; });
+        std::vector<PlItem> items;
+        for (u32 ui : uo) {
+            const u64 per = std::max<u64>(1, (u64)(target / cost[ui] + 0.5));
+            for (u64 t0 = 0; t0 < pl.ntiles; t0 += per) {
+                PlItem it;
+                it.unit = ui;
+                it.t0 = (u32)t0;
+                it.t1 = (u32)std::min<u64>(pl.ntiles, t0 + per);
+                items.push_back(it);
+            }
+        }
+        pl.n_units_t = (u32)ut.size();
+        SB_TRY(pl.units_t.alloc(std::max<size_t>(1, ut.size()) * sizeof(PlUnitT)));
+        if (!ut.empty()) SB_CUDA(cudaMemcpyAsync(pl.units_t.p, ut.data(), ut.size() * sizeof(PlUnitT), cudaMemcpyHostToDevice, ctx->stream));
+        pl.n_items_t = (u32)items.size();
+        pl.t_grid = (u32)std::min<size_t>((size_t)ctx->sm_count, std::max<size_t>(1, items.size()));
+        SB_TRY(pl.items_t.alloc(std::max<size_t>(1, items.size()) * sizeof(PlItem)));
+        if (!items.empty()) SB_CUDA(cudaMemcpyAsync(pl.items_t.p, items.data(), items.size() * sizeof(PlItem), cudaMemcpyHostToDevice, ctx->stream));
+        SB_TRY(pl.counter.alloc(4));
+        SB_CUDA(cudaStreamSynchronize(ctx->stream));  // `items` is a host temporary
     }
-    pl.t_grid = at;
-    pl.n_units_t = (u32)ut.size();
-    SB_TRY(pl.units_t.alloc(ut.size() * sizeof(PlUnitT)));
-    SB_CUDA(cudaMemcpyAsync(pl.units_t.p, ut.data(), ut.size() * sizeof(PlUnitT), cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<u32> nc;
+    u32 at = 0;
     // ---- N-side units: groups of 384 ranks; the active levels of a group are a prefix
     std::vector<PlUnitN> un;
     cost.clear();
@@ -375,21 +397,16 @@ __global__ void k_pl_digits_t(const double *__restrict__ Y, u32 ldy, const u32 *
 }
 
 // ---------------------------------------------------------------- shared epilogue arithmetic
-// acc[n], n = 7 c + s: digit s of column c.  value_c = sum_s acc * 256^s, as two int64 halves -> one f64 rounding.
-struct Recombine {
-    long long lo, hi;
-    __device__ __forceinline__ void reset() { lo = 0; hi = 0; }
-    __device__ __forceinline__ void add(u32 s, int a) {
-        if (s < 4) lo += (long long)a << (8 * s);
-        else hi += (long long)a << (8 * (s - 4));
-    }
-    __device__ __forceinline__ double value() const { return (double)lo + (double)hi * 4294967296.0; }
-};
+// acc[n], n = 7 c + s: digit s of column c.  value_c = sum_s acc_s 256^s.  Done on the FP64 pipe: int32 -> f64 by the
+// exponent trick (one LOP3 + one DADD), digits 0..3 and 4..6 are summed exactly (both halves stay below 2^53 for
+// |acc| <= 2^28), then hi * 2^32 + lo is the single rounding.
+__device__ __forceinline__ double i32_to_f64(u32 r) {
+    return __hiloint2double(0x43300000, (int)(r ^ 0x80000000u)) - 4503601774854144.0;  // 2^52 + 2^31
+}
 
 // reads the 144 accumulator columns of this thread's TMEM lane starting at `taddr` and returns the 20 recombined values
 __device__ __forceinline__ void read_acc(u32 taddr, double (&val)[PL_COLS]) {
-    Recombine rc;
-    rc.reset();
+    double lo = 0.0, hi = 0.0;
 #pragma unroll
     for (u32 cb = 0; cb < PL_NCOL; cb += 16) {
         u32 r[16];
@@ -400,11 +417,12 @@ __device__ __forceinline__ void read_acc(u32 taddr, double (&val)[PL_COLS]) {
             const u32 n = cb + i;  // compile-time after unrolling
             if (n < PL_COLS * PL_DIG) {
                 const u32 c = n / PL_DIG, s = n - c * PL_DIG;
-                rc.add(s, (int)r[i]);
-                if (s == PL_DIG - 1) {
-                    val[c] = rc.value();
-                    rc.reset();
-                }
+                const double d = i32_to_f64(r[i]);
+                if (s == 0) lo = d;
+                else if (s < 4) lo = fma(d, (double)(1u << (8 * s)), lo);
+                else if (s == 4) hi = d;
+                else hi = fma(d, (double)(1u << (8 * (s - 4))), hi);
+                if (s == PL_DIG - 1) val[c] = fma(hi, 4294967296.0, lo);
             }
         }
     }
@@ -414,32 +432,24 @@ __device__ __forceinline__ void read_acc(u32 taddr, double (&val)[PL_COLS]) {
 struct PtShared {
     unsigned long long full[PT_NSTAGES], empty[PT_NSTAGES], tfull[3], tempty[3];
     u32 tmem;
+    u32 item[2];  // work item fetched for this round (double buffered)
     u32 pad;
     double scale2[PL_COLS];
+    u32 stage_tab[48];  // stage i of a tile -> (kb << 2 | level slot); at most 3 x 16 stages per tile
 };
 
+// Persistent CTAs pull work items {unit, tile range} from a global queue (items are sized to ~equal cost and ordered by
+// unit, so the resident B block is reloaded only when the unit changes).  A CTA-wide barrier separates items; the
+// pipeline state (stage counter, barrier phases, accumulator slots) carries across them.
 __global__ void __launch_bounds__(PL_THREADS, 1)
-k_planes_t(PlDev pl, const PlUnitT *__restrict__ units, u32 n_units, const signed char *__restrict__ Bd, const double *__restrict__ scale2_g,
-           const double *__restrict__ cs, int log_base, u32 col0, u32 wt, double *__restrict__ out, u32 ldo) {
+k_planes_t(PlDev pl, const PlUnitT *__restrict__ units, const PlItem *__restrict__ items, u32 n_items, u32 *__restrict__ counter,
+           const signed char *__restrict__ Bd, const double *__restrict__ scale2_g, const double *__restrict__ cs, int log_base, u32 col0, u32 wt,
+           double *__restrict__ out, u32 ldo) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *sB = smem;
     unsigned char *sA = sB + PT_B_BYTES;
     PtShared *sh = reinterpret_cast<PtShared *>(sA + PT_NSTAGES * PT_STAGE_BYTES);
-
     const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // this CTA's unit
-    PlUnitT un;
-    bool have = false;
-    for (u32 i = 0; i < n_units; i++) {
-        const PlUnitT u = units[i];
-        if (blockIdx.x >= u.cta0 && blockIdx.x < u.cta0 + u.nctas) {
-            un = u;
-            have = true;
-        }
-    }
-    const u32 sub = have ? blockIdx.x - un.cta0 : 0, stride = have ? un.nctas : 1;
-    const u32 nlev = have ? un.nlev : 0;
-    const u32 nslots = nlev == 1 ? 3u : 1u;
     const u32 full0 = smem_u32(sh->full), empty0 = smem_u32(sh->empty), tfull0 = smem_u32(sh->tfull), tempty0 = smem_u32(sh->tempty);
 
     if (tid == 0) {
@@ -452,159 +462,204 @@ k_planes_t(PlDev pl, const PlUnitT *__restrict__ units, u32 n_units, const signe
             mbar_init(tempty0 + 8 * i, PL_EPI_WARPS);
         }
         mbar_init_fence();
+        sh->item[0] = atomicAdd(counter, 1u);
     }
     if (warp == 0) tmem_alloc_512(smem_u32(&sh->tmem));
-    if (have) {  // resident B operand: the digit planes of this unit's 1,024 ranks
-        const uint4 *src = reinterpret_cast<const uint4 *>(Bd + (size_t)(un.g0 / PT_RANGE) * PT_B_BYTES);
-        uint4 *dst = reinterpret_cast<uint4 *>(sB);
-        for (u32 i = tid; i < PT_B_BYTES / 16; i += PL_THREADS) dst[i] = src[i];
-    }
     if (tid < PL_COLS) sh->scale2[tid] = scale2_g[tid];
-    fence_async_smem();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const u32 tmem = sh->tmem;
     const u32 sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+    const u32 idesc = instr_desc_i8(PL_TILE, PL_NCOL, false, false);
+    const uint64_t da_hi = smem_desc(0, PL_TILE * 16, 128), db_hi = smem_desc(0, PT_KCHUNK_BYTES, 128);
 
-    if (have && warp < PL_EPI_WARPS) {
-        // ===== epilogue: TMEM -> registers -> f64 -> T (one thread per cell row)
-        const u32 row = warp * 32 + lane;
-        u64 it = 0;
-        for (u64 tile = sub; tile < pl.ntiles; tile += stride, it++) {
-            const u32 slot = (u32)(it % nslots);
-            const u32 use = (u32)(it / nslots);
-            const u64 cell = tile * PL_TILE + row;
-            double res[PL_COLS];
-#pragma unroll
-            for (u32 j = 0; j < PL_COLS; j++) res[j] = 0.0;
-            double Lv[3] = {0.0, 0.0, 0.0};
-            if (cell < pl.n) {
-                const double s = cs[cell];
-                for (u32 a = 0; a < nlev; a++) Lv[a] = finite_or_zero(map_log_part(log_base, s, un.lev[a] + 1, sb_log_table));
-            }
-            mbar_wait(tfull0 + 8 * slot, use & 1u);
-            fence_after_sync();
-            for (u32 a = 0; a < nlev; a++) {
-                double val[PL_COLS];
-                read_acc(tmem + ((warp * 32u) << 16) + (slot * nlev + a) * PL_NCOL, val);
-                const double lk = Lv[a];
-#pragma unroll
-                for (u32 j = 0; j < PL_COLS; j++) res[j] = fma(lk, val[j], res[j]);
-            }
-            fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty0 + 8 * slot);  // this warp's quarter of the accumulators is free
-            if (cell < pl.n) {
-                double *o = out + cell * (size_t)ldo + col0;
-#pragma unroll
-                for (u32 j = 0; j < PL_COLS; j++)
-                    if (j < wt) atomicAdd(o + j, res[j] * sh->scale2[j]);  // other units (gene ranges, level triples) add into the same row
-            }
-        }
-    } else if (have && warp == PL_EPI_WARPS) {
-        // ===== MMA issue (one thread)
-        if (lane == 0) {
-            const u32 idesc = instr_desc_i8(PL_TILE, PL_NCOL, false, false);
-            u64 it = 0;
-            u32 q = 0;
-            for (u64 tile = sub; tile < pl.ntiles; tile += stride, it++) {
-                const u32 slot = (u32)(it % nslots);
-                const u32 use = (u32)(it / nslots);
-                if (use > 0) {
-                    mbar_wait(tempty0 + 8 * slot, (use - 1) & 1u);
-                    fence_after_sync();
+    // pipeline state carried across items (each role uses its own part; all advance identically)
+    u32 q = 0;                    // stages issued / consumed so far (MMA thread), or before this item (producers)
+    u32 fills = 0;                // producer: fills of my stage slot
+    u32 rr = 0;                   // round-robin accumulator slot of single-level units
+    u32 u0 = 0, u1 = 0, u2 = 0;   // completed uses of accumulator slots 0..2
+    u32 cur_unit = 0xFFFFFFFFu;
+    u32 g0 = 0, nlev = 0, nkb0 = 0, nkb1 = 0, nkb2 = 0, lev0 = 0, lev1 = 0, lev2 = 0, S = 1;
+
+    for (u32 round = 0;; round++) {
+        const u32 it = sh->item[round & 1];
+        if (it >= n_items) break;
+        if (tid == 0) sh->item[(round + 1) & 1] = atomicAdd(counter, 1u);  // visible after the barrier that ends this round
+        const PlItem item = items[it];
+        if (item.unit != cur_unit) {
+            // every role is past the barrier of the previous round: all MMAs that read the old B block have completed
+            const PlUnitT un = units[item.unit];
+            cur_unit = item.unit;
+            g0 = un.g0;
+            nlev = un.nlev;
+            nkb0 = un.nkb[0];
+            nkb1 = nlev > 1 ? un.nkb[1] : 0;
+            nkb2 = nlev > 2 ? un.nkb[2] : 0;
+            lev0 = un.lev[0];
+            lev1 = nlev > 1 ? un.lev[1] : 0;
+            lev2 = nlev > 2 ? un.lev[2] : 0;
+            S = nkb0 + nkb1 + nkb2;
+            const uint4 *src = reinterpret_cast<const uint4 *>(Bd + (size_t)(g0 / PT_RANGE) * PT_B_BYTES);
+            uint4 *dst = reinterpret_cast<uint4 *>(sB);
+            for (u32 i = tid; i < PT_B_BYTES / 16; i += PL_THREADS) dst[i] = src[i];
+            for (u32 i = tid; i < S; i += PL_THREADS) {  // stage i of a tile -> (kb, level slot), in the MMA thread's order
+                u32 cnt = 0;
+                for (u32 kb = 0; kb < nkb0; kb++) {
+                    if (cnt == i) { sh->stage_tab[i] = kb << 2; break; }
+                    cnt++;
+                    if (kb < nkb1) { if (cnt == i) { sh->stage_tab[i] = (kb << 2) | 1u; break; } cnt++; }
+                    if (kb < nkb2) { if (cnt == i) { sh->stage_tab[i] = (kb << 2) | 2u; break; } cnt++; }
                 }
-                for (u32 kb = 0; kb < un.nkb[0]; kb++) {
-                    for (u32 a = 0; a < nlev; a++) {
-                        if (kb >= un.nkb[a]) continue;
-                        const u32 s = q % PT_NSTAGES;
-                        mbar_wait(full0 + 8 * s, (q / PT_NSTAGES) & 1u);
-                        fence_after_sync();
-#pragma unroll
-                        for (u32 j = 0; j < 2; j++) {  // K = 32 per MMA: two 16-gene core-matrix columns
-                            const uint64_t da = smem_desc(sA_addr + s * PT_STAGE_BYTES + 2 * j * (PL_TILE * 16), PL_TILE * 16, 128);
-                            const uint64_t db = smem_desc(sB_addr + (kb * 4 + 2 * j) * PT_KCHUNK_BYTES, PT_KCHUNK_BYTES, 128);
-                            mma_i8(tmem + (slot * nlev + a) * PL_NCOL, da, db, idesc, (kb | j) ? 1u : 0u);
-                        }
-                        commit(empty0 + 8 * s);  // the stage is reusable once these MMAs have read it
-                        q++;
-                    }
-                }
-                commit(tfull0 + 8 * slot);  // accumulators of this tile complete
             }
-        }
-    } else if (have) {
-        // ===== producers: plane words -> 0/1 int8 A tiles (K-major core matrices: [16-gene chunk][cell / 8][cell % 8][16 B])
-        const u32 p = warp - (PL_EPI_WARPS + 1);  // stage slot owned by this warp
-        u32 q = 0, fills = 0;
-        // iterator over the stage sequence (tile, kb, level), identical to the MMA thread's
-        u64 tile = sub;
-        u32 kb = 0, a = 0;
-        bool done = tile >= pl.ntiles;
-        auto advance = [&]() {  // to the next stage of the sequence
-            for (;;) {
-                a++;
-                if (a >= nlev) {
-                    a = 0;
-                    kb++;
-                    if (kb >= un.nkb[0]) {
-                        kb = 0;
-                        tile += stride;
-                        if (tile >= pl.ntiles) {
-                            done = true;
-                            return;
-                        }
-                    }
-                }
-                if (kb < un.nkb[a]) return;
-            }
-        };
-        auto seek_mine = [&]() {  // position on the next stage with q % 8 == p (the current one counts)
-            while (!done && (q % PT_NSTAGES) != p) {
-                advance();
-                q++;
-            }
-        };
-        auto load_words = [&](u32 (&w)[8]) {
-            const u32 lv = un.lev[a];
-            const u32 gw0 = (un.g0 + kb * 64) / 32;
-            const u32 *base = pl.bits[lv] + ((size_t)tile * (pl.G[lv] / 32) + gw0) * PL_TILE + lane;
-#pragma unroll
-            for (u32 j = 0; j < 2; j++)
-#pragma unroll
-                for (u32 i = 0; i < 4; i++) w[j * 4 + i] = __ldg(base + (size_t)j * PL_TILE + i * 32);
-        };
-        u32 cur[8], nxt[8];
-        seek_mine();
-        if (!done) load_words(cur);
-        while (!done) {
-            // prefetch the words of my next stage before expanding the current one
-            advance();
-            q++;
-            seek_mine();
-            const bool more = !done;
-            if (more) load_words(nxt);
-            if (fills > 0) mbar_wait(empty0 + 8 * p, (fills - 1) & 1u);
-            const u32 st = sA_addr + p * PT_STAGE_BYTES + lane * 16;
-#pragma unroll
-            for (u32 j = 0; j < 2; j++)
-#pragma unroll
-                for (u32 i = 0; i < 4; i++) {
-                    uint4 lo, hi;
-                    expand_bits32(cur[j * 4 + i], lo, hi);
-                    st_shared_v4(st + (2 * j) * (PL_TILE * 16) + i * 512, lo);
-                    st_shared_v4(st + (2 * j + 1) * (PL_TILE * 16) + i * 512, hi);
-                }
             fence_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full0 + 8 * p);
-            fills++;
-            if (more) {
-#pragma unroll
-                for (u32 i = 0; i < 8; i++) cur[i] = nxt[i];
-            }
+            __syncthreads();
         }
+        const u64 t0 = item.t0, t1 = item.t1;
+
+        if (warp < PL_EPI_WARPS) {
+            // ===== epilogue: TMEM -> registers -> f64 -> T (one thread per cell row)
+            const u32 row = warp * 32 + lane;
+            for (u64 tile = t0; tile < t1; tile++) {
+                const u32 slot = nlev == 1 ? rr : 0u;
+                const u32 use = slot == 0 ? u0 : (slot == 1 ? u1 : u2);
+                const u64 cell = tile * PL_TILE + row;
+                double res[PL_COLS];
+#pragma unroll
+                for (u32 j = 0; j < PL_COLS; j++) res[j] = 0.0;
+                double L0 = 0.0, L1 = 0.0, L2 = 0.0;
+                if (cell < pl.n) {
+                    const double sc = cs[cell];
+                    L0 = finite_or_zero(map_log_part(log_base, sc, lev0 + 1, sb_log_table));
+                    if (nlev > 1) L1 = finite_or_zero(map_log_part(log_base, sc, lev1 + 1, sb_log_table));
+                    if (nlev > 2) L2 = finite_or_zero(map_log_part(log_base, sc, lev2 + 1, sb_log_table));
+                }
+                mbar_wait(tfull0 + 8 * slot, use & 1u);
+                fence_after_sync();
+                const u32 tbase = tmem + ((warp * 32u) << 16) + slot * nlev * PL_NCOL;
+                for (u32 a = 0; a < nlev; a++) {
+                    double val[PL_COLS];
+                    read_acc(tbase + a * PL_NCOL, val);
+                    const double lk = a == 0 ? L0 : (a == 1 ? L1 : L2);
+#pragma unroll
+                    for (u32 j = 0; j < PL_COLS; j++) res[j] = fma(lk, val[j], res[j]);
+                }
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty0 + 8 * slot);  // this warp's quarter of the accumulators is free
+                if (cell < pl.n) {
+                    double *o = out + cell * (size_t)ldo + col0;
+#pragma unroll
+                    for (u32 j = 0; j < PL_COLS; j++)
+                        if (j < wt) atomicAdd(o + j, res[j] * sh->scale2[j]);  // other units (gene ranges, level triples) add into the same row
+                }
+                if (slot == 0) u0++;
+                else if (slot == 1) u1++;
+                else u2++;
+                if (nlev == 1) rr = rr == 2 ? 0 : rr + 1;
+            }
+        } else if (warp == PL_EPI_WARPS) {
+            // ===== MMA issue (one thread): a handful of instructions per stage -- the tensor pipe must never wait for this thread
+            if (lane == 0) {
+                const u32 a16 = sA_addr >> 4, b16 = sB_addr >> 4;
+                auto stage = [&](u32 kb, u32 acc) {
+                    const u32 s = q & (PT_NSTAGES - 1);
+                    mbar_wait(full0 + 8 * s, (q >> 3) & 1u);
+                    fence_after_sync();
+                    const u32 alo = a16 + s * (PT_STAGE_BYTES >> 4), blo = b16 + kb * (4 * PT_KCHUNK_BYTES >> 4);
+                    mma_i8(acc, da_hi | alo, db_hi | blo, idesc, kb);
+                    mma_i8(acc, da_hi | (alo + (2 * PL_TILE * 16 >> 4)), db_hi | (blo + (2 * PT_KCHUNK_BYTES >> 4)), idesc, 1u);
+                    commit(empty0 + 8 * s);  // the stage is reusable once these MMAs have read it
+                    q++;
+                };
+                for (u64 tile = t0; tile < t1; tile++) {
+                    const u32 slot = nlev == 1 ? rr : 0u;
+                    const u32 use = slot == 0 ? u0 : (slot == 1 ? u1 : u2);
+                    if (use > 0) {
+                        mbar_wait(tempty0 + 8 * slot, (use - 1) & 1u);
+                        fence_after_sync();
+                    }
+                    const u32 acc0 = tmem + slot * nlev * PL_NCOL;
+                    for (u32 kb = 0; kb < nkb0; kb++) {
+                        stage(kb, acc0);
+                        if (kb < nkb1) stage(kb, acc0 + PL_NCOL);
+                        if (kb < nkb2) stage(kb, acc0 + 2 * PL_NCOL);
+                    }
+                    commit(tfull0 + 8 * slot);  // accumulators of this tile complete
+                    if (slot == 0) u0++;
+                    else if (slot == 1) u1++;
+                    else u2++;
+                    if (nlev == 1) rr = rr == 2 ? 0 : rr + 1;
+                }
+            }
+        } else {
+            // ===== producers: plane words -> 0/1 int8 A tiles (K-major core matrices: [16-gene chunk][cell / 8][cell % 8][16 B])
+            // warp p fills stage slot p: the stages with global index = p (mod 8)
+            const u32 p = warp - (PL_EPI_WARPS + 1);
+            const u32 *stab = sh->stage_tab;
+            const u32 G0 = pl.G[lev0] >> 5, G1w = pl.G[lev1] >> 5, G2w = pl.G[lev2] >> 5;
+            const u32 *bits0 = pl.bits[lev0], *bits1 = pl.bits[lev1], *bits2 = pl.bits[lev2];
+            u64 tile = t0;
+            u32 i = (p + PT_NSTAGES - (q & (PT_NSTAGES - 1))) & (PT_NSTAGES - 1);  // my first stage inside this item
+            while (i >= S && tile < t1) {
+                i -= S;
+                tile++;
+            }
+            auto load_words = [&](u64 tl, u32 ii, u32 (&w)[8]) {
+                const u32 e = stab[ii];
+                const u32 kb = e >> 2, a = e & 3u;
+                const u32 Gw = a == 0 ? G0 : (a == 1 ? G1w : G2w);
+                const u32 *bp = a == 0 ? bits0 : (a == 1 ? bits1 : bits2);
+                const u32 *base = bp + ((size_t)tl * Gw + ((g0 + kb * 64) >> 5)) * PL_TILE + lane;
+#pragma unroll
+                for (u32 j = 0; j < 2; j++)
+#pragma unroll
+                    for (u32 c4 = 0; c4 < 4; c4++) w[j * 4 + c4] = __ldg(base + (size_t)j * PL_TILE + c4 * 32);
+            };
+            u32 cur[8], nxt[8];
+            bool live = tile < t1;
+            if (live) load_words(tile, i, cur);
+            const u32 st = sA_addr + p * PT_STAGE_BYTES + lane * 16;
+            while (live) {
+                // my next stage: prefetch its words before expanding the current ones
+                u64 ntile = tile;
+                u32 ni = i + PT_NSTAGES;
+                while (ni >= S && ntile < t1) {
+                    ni -= S;
+                    ntile++;
+                }
+                const bool more = ntile < t1;
+                if (more) load_words(ntile, ni, nxt);
+                if (fills > 0) mbar_wait(empty0 + 8 * p, (fills - 1) & 1u);
+#pragma unroll
+                for (u32 j = 0; j < 2; j++)
+#pragma unroll
+                    for (u32 c4 = 0; c4 < 4; c4++) {
+                        uint4 lo, hi;
+                        expand_bits32(cur[j * 4 + c4], lo, hi);
+                        st_shared_v4(st + (2 * j) * (PL_TILE * 16) + c4 * 512, lo);
+                        st_shared_v4(st + (2 * j + 1) * (PL_TILE * 16) + c4 * 512, hi);
+                    }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full0 + 8 * p);
+                fills++;
+                tile = ntile;
+                i = ni;
+                live = more;
+                if (more) {
+#pragma unroll
+                    for (u32 c = 0; c < 8; c++) cur[c] = nxt[c];
+                }
+            }
+            q += (u32)(t1 - t0) * S;  // stages of this item (the MMA thread advances its own q as it issues)
+            // slot bookkeeping is not needed here
+        }
+        // every role replicates the slot / use counters it needs; the epilogue and MMA roles advanced theirs above.  Roles that
+        // did not (producers; idle lanes of the MMA warp) must still agree on rr / u* for later items if they ever use them: they do not.
+        fence_before_sync();
+        __syncthreads();  // item boundary: accumulators drained, stages consumed, next item id visible
+        fence_after_sync();
     }
     fence_before_sync();
     __syncthreads();
@@ -698,6 +753,8 @@ k_planes_n(PlDev pl, const PlUnitN *__restrict__ units, u32 n_units, const signe
     const u64 t_begin = have ? pl.ntiles * sub / un.nctas : 0, t_end = have ? pl.ntiles * (sub + 1) / un.nctas : 0;
     have = have && t_end > t_begin;
     const u32 nlev = have ? un.nlev : 0;
+    u32 mt_pack = 0;  // four bits per level: M tiles of the level inside this group
+    for (u32 k = 0; k < nlev; k++) mt_pack |= un.mt[k] << (4 * k);
     const u32 full0 = smem_u32(sh->full), empty0 = smem_u32(sh->empty), tfull0 = smem_u32(&sh->tfull);
     if (tid == 0) {
         for (u32 i = 0; i < PN_NSTAGES; i++) {
@@ -720,7 +777,7 @@ k_planes_n(PlDev pl, const PlUnitN *__restrict__ units, u32 n_units, const signe
         mbar_wait(tfull0, 0);
         fence_after_sync();
         const u32 row = warp * 32 + lane;
-        for (u32 mtile = 0; mtile < un.mt[0]; mtile++) {
+        for (u32 mtile = 0; mtile < (mt_pack & 15u); mtile++) {
             double val[PL_COLS];
             read_acc(tmem + ((warp * 32u) << 16) + mtile * PL_NCOL, val);
             const u32 g = hot_idx[un.g0 + mtile * 128 + row];
@@ -730,68 +787,92 @@ k_planes_n(PlDev pl, const PlUnitN *__restrict__ units, u32 n_units, const signe
                 if (j < wt && val[j] != 0.0) atomicAdd(o + (size_t)(col0 + j) * col_stride, val[j] * sh->scale2[j]);
         }
     } else if (have && warp == PL_EPI_WARPS) {
-        // ===== MMA issue
+        // ===== MMA issue (one thread, a handful of instructions per stage)
         if (lane == 0) {
             const u32 idesc = instr_desc_i8(128, PL_NCOL, true, true);
+            const uint64_t da_hi = smem_desc(0, 128, 512);               // MN-major A: lbo = next 8 cells, sbo = next 16 genes
+            const uint64_t db_hi = smem_desc(0, PN_CELLGRP_BYTES, 128);  // MN-major B: lbo = next 8 cells, sbo = next 16 digit columns
+            const u32 s16 = sS_addr >> 4;
             u32 q = 0;
             u32 started = 0;  // bit mtile: the accumulator has been written
-            for (u64 tile = t_begin; tile < t_end; tile++)
-                for (u32 ks = 0; ks < 4; ks++)
-                    for (u32 k = 0; k < nlev; k++) {
-                        const u32 s = q % PN_NSTAGES;
-                        mbar_wait(full0 + 8 * s, (q / PN_NSTAGES) & 1u);
-                        fence_after_sync();
-                        const u32 st = sS_addr + s * PN_STAGE_BYTES;
-                        const uint64_t db = smem_desc(st + PN_A_BYTES, PN_CELLGRP_BYTES, 128);  // MN-major: lbo = next 8 cells, sbo = next 16 digit columns
-                        for (u32 mtile = 0; mtile < un.mt[k]; mtile++) {
-                            const uint64_t da = smem_desc(st + mtile * 4096, 128, 512);  // MN-major: lbo = next 8 cells, sbo = next 16 genes
-                            mma_i8(tmem + mtile * PL_NCOL, da, db, idesc, (started >> mtile) & 1u);
-                            started |= 1u << mtile;
-                        }
-                        commit(empty0 + 8 * s);
-                        q++;
-                    }
+            const u64 nsteps = (t_end - t_begin) * 4;
+            for (u64 step = 0; step < nsteps; step++) {
+                u32 mtp = mt_pack;
+                for (u32 k = 0; k < nlev; k++, mtp >>= 4) {
+                    const u32 s = q & (PN_NSTAGES - 1);
+                    mbar_wait(full0 + 8 * s, (q >> 3) & 1u);
+                    fence_after_sync();
+                    const u32 alo = s16 + s * (PN_STAGE_BYTES >> 4);
+                    const uint64_t db = db_hi | (alo + (PN_A_BYTES >> 4));
+                    const u32 nmt = mtp & 15u;
+                    mma_i8(tmem, da_hi | alo, db, idesc, started & 1u);
+                    if (nmt > 1) mma_i8(tmem + PL_NCOL, da_hi | (alo + 256), db, idesc, (started >> 1) & 1u);
+                    if (nmt > 2) mma_i8(tmem + 2 * PL_NCOL, da_hi | (alo + 512), db, idesc, (started >> 2) & 1u);
+                    started |= (1u << nmt) - 1u;
+                    commit(empty0 + 8 * s);
+                    q++;
+                }
+            }
             commit(tfull0);
         }
     } else if (have) {
         // ===== producers: stage = (32-cell K step, level): A tiles [M tile][16-gene chunk (8)][cell / 8 (4)][cell % 8][16 B] + B digit rows
+        // warp p fills stage slot p: stages q = p, p + 8, ...; q -> (tile, ks, k) kept incrementally (no divisions)
         const u32 p = warp - (PL_EPI_WARPS + 1);
-        const u64 per_tile = 4ull * nlev;
-        const u64 total = (t_end - t_begin) * per_tile;
+        const u32 per_tile = 4 * nlev;
         u32 fills = 0;
         u32 cur[12], nxt[12];
-        auto coords = [&](u64 q, u64 &tile, u32 &ks, u32 &k) {
-            tile = t_begin + q / per_tile;
-            const u32 r = (u32)(q % per_tile);
-            ks = r / nlev;
-            k = r - ks * nlev;
+        u64 tile = t_begin;
+        u32 r = p;  // position inside the tile: r = ks * nlev + k
+        while (r >= per_tile) {
+            r -= per_tile;
+            tile++;
+        }
+        const u32 g0w = un.g0 >> 5;
+        auto split = [&](u32 rr, u32 &ks, u32 &k) {
+            ks = 0;
+            k = rr;
+            while (k >= nlev) {
+                k -= nlev;
+                ks++;
+            }
         };
-        auto load_words = [&](u64 q, u32 (&w)[12]) {
-            u64 tile;
-            u32 ks, k;
-            coords(q, tile, ks, k);
-            const u32 *base = pl.bits[k] + ((size_t)tile * (pl.G[k] / 32) + un.g0 / 32) * PL_TILE + ks * 32 + lane;
+        auto load_words = [&](u64 tl, u32 ks, u32 k, u32 (&w)[12]) {
+            const u32 nw = ((mt_pack >> (4 * k)) & 15u) * 4;
+            const u32 *base = pl.bits[k] + ((size_t)tl * (pl.G[k] >> 5) + g0w) * PL_TILE + ks * 32 + lane;
 #pragma unroll
-            for (u32 j = 0; j < 12; j++) w[j] = (j < un.mt[k] * 4) ? __ldg(base + (size_t)j * PL_TILE) : 0u;
+            for (u32 j = 0; j < 12; j++) w[j] = (j < nw) ? __ldg(base + (size_t)j * PL_TILE) : 0u;
         };
-        u64 q = p;
-        if (q < total) load_words(q, cur);
-        for (; q < total; q += PN_NSTAGES) {
-            const bool more = q + PN_NSTAGES < total;
-            if (more) load_words(q + PN_NSTAGES, nxt);
-            u64 tile;
-            u32 ks, k;
-            coords(q, tile, ks, k);
+        bool live = tile < t_end;
+        u32 ks = 0, k = 0;
+        if (live) {
+            split(r, ks, k);
+            load_words(tile, ks, k, cur);
+        }
+        const u32 st = sS_addr + p * PN_STAGE_BYTES;
+        while (live) {
+            u64 ntile = tile;
+            u32 nr = r + PN_NSTAGES;
+            while (nr >= per_tile) {
+                nr -= per_tile;
+                ntile++;
+            }
+            const bool more = ntile < t_end;
+            u32 nks = 0, nk = 0;
+            if (more) {
+                split(nr, nks, nk);
+                load_words(ntile, nks, nk, nxt);
+            }
             // B rows of these 32 cells at level k (contiguous 4,608 bytes in Bn)
             const uint4 *bsrc = reinterpret_cast<const uint4 *>(Bn + ((size_t)k * (n_pad / 8) + (tile * PL_TILE + ks * 32) / 8) * PN_CELLGRP_BYTES);
             uint4 bv[PN_B_BYTES / 16 / 32];
 #pragma unroll
             for (u32 t = 0; t < PN_B_BYTES / 16 / 32; t++) bv[t] = __ldg(bsrc + lane + 32 * t);
+            const u32 nw = ((mt_pack >> (4 * k)) & 15u) * 4;
             if (fills > 0) mbar_wait(empty0 + 8 * p, (fills - 1) & 1u);
-            const u32 st = sS_addr + p * PN_STAGE_BYTES;
 #pragma unroll
             for (u32 j = 0; j < 12; j++) {
-                if (j < un.mt[k] * 4) {
+                if (j < nw) {
                     uint4 lo, hi;
                     expand_bits32(cur[j], lo, hi);
                     const u32 a0 = st + (j >> 2) * 4096 + (2 * (j & 3)) * 512 + lane * 16;
@@ -805,6 +886,11 @@ k_planes_n(PlDev pl, const PlUnitN *__restrict__ units, u32 n_units, const signe
             __syncwarp();
             if (lane == 0) mbar_arrive(full0 + 8 * p);
             fills++;
+            tile = ntile;
+            r = nr;
+            ks = nks;
+            k = nk;
+            live = more;
             if (more) {
 #pragma unroll
                 for (u32 j = 0; j < 12; j++) cur[j] = nxt[j];
@@ -851,8 +937,10 @@ int planes_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo) 
         k_pl_colmax_t<<<cdiv(items, 256), 256, 0, ctx->stream>>>(Y, ldy, mt->hot_idx.p, rs, G1, col0, wt, colmax.p);
         SB_TRY(scales_from_colmax(ctx, colmax, scale2, ex));
         k_pl_digits_t<<<cdiv(items, 256), 256, 0, ctx->stream>>>(Y, ldy, mt->hot_idx.p, rs, G1, col0, wt, ex.p, Bd.p);
-        k_planes_t<<<pl.t_grid, PL_THREADS, smem, ctx->stream>>>(make_pldev(mt), (const PlUnitT *)pl.units_t.p, pl.n_units_t, Bd.p, scale2.p,
-                                                                 a->col_scale.p, a->log_base, col0, wt, out, ldo);
+        SB_CUDA(cudaMemsetAsync(pl.counter.p, 0, sizeof(u32), ctx->stream));
+        k_planes_t<<<pl.t_grid, PL_THREADS, smem, ctx->stream>>>(make_pldev(mt), (const PlUnitT *)pl.units_t.p, (const PlItem *)pl.items_t.p,
+                                                                 pl.n_items_t, pl.counter.p, Bd.p, scale2.p, a->col_scale.p, a->log_base, col0, wt,
+                                                                 out, ldo);
         count_launch(ctx); count_launch(ctx); count_launch(ctx);
     }
     SB_CUDA(cudaGetLastError());
