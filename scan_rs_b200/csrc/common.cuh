@@ -129,6 +129,7 @@ struct sb_ctx {
     // dense half of the hybrid layout of matrices built afterwards: 0 none, 1 u8 panel on the FP64 mma.sync path (dense_panel.cu),
     // 2 bit planes on the int8 tensor cores (planes.cu)
     int panel_mode = 2;
+    int pl_debug = 0;                // timing experiments only (planes.cu): 1 no output reductions, 2 no epilogue arithmetic, 4 no tile expansion
     int plane_cap = 12288;           // most ranks a plane may cover
     int plane_levels = 6;            // most count levels kept as planes (<= PL_MAX_LEVELS)
     double plane_min_density = 0.01; // a 128-rank block joins level k only if this fraction of the cells has exactly that count
@@ -163,7 +164,7 @@ struct sb_ctx {
 #define PL_MAX_LEVELS 6
 struct PlUnitT {  // T side: a block of 1,024 ranks x up to three levels; CTAs [cta0, cta0 + nctas) stride over the cell tiles
     u32 g0, nlev;
-    u32 lev[3], nkb[3];  // level index; 64-gene K blocks of the level inside the block (non-increasing)
+    u32 lev[3], nkb[3];  // level index; 32-gene K blocks of the level inside the block (non-increasing, multiples of 4)
     u32 cta0, nctas;
 };
 struct PlUnitN {  // N side: a group of 384 ranks; levels 0..nlev-1; CTAs split the cell tiles into contiguous ranges
@@ -180,9 +181,9 @@ struct PlaneSet {
     u32 G[PL_MAX_LEVELS] = {0, 0, 0, 0, 0, 0};  // ranks covered by level k + 1: multiples of 128, non-increasing
     u64 ntiles = 0;                              // cell tiles of 128
     DevBuf<u32> bits[PL_MAX_LEVELS];             // [ntiles][G / 32][128] words
-    DevBuf<char> units_t, units_n, items_t;
+    DevBuf<char> units_t, units_n, items_t, items_n;
     DevBuf<u32> counter;  // work-queue head of the T-side kernel
-    u32 n_units_t = 0, n_units_n = 0, n_items_t = 0, t_grid = 0, n_grid = 0;
+    u32 n_units_t = 0, n_units_n = 0, n_items_t = 0, n_items_n = 0, t_grid = 0, n_grid = 0;
 };
 
 // One side of the panelled gather: the entry stream, its work units and (T side) the gene of every panel slot.

@@ -180,6 +180,10 @@ extern "C" int sb_set_option(sb_ctx *ctx, const char *name, double value) {
         ctx->panel_mode = (int)value;
         return SB_OK;
     }
+    if (!strcmp(name, "pl_debug")) {  // timing experiments: results are wrong on purpose
+        ctx->pl_debug = (int)value;
+        return SB_OK;
+    }
     if (!strcmp(name, "plane_cap")) {
         ctx->plane_cap = value < 0 ? 0 : (int)value;
         return SB_OK;

@@ -41,8 +41,12 @@ using namespace tc05;
 #define PT_RANGE 1024u                          // ranks per resident B block (T side)
 #define PT_B_BYTES (PT_RANGE * PL_NCOL)         // 147,456
 #define PT_KCHUNK_BYTES (PL_NCOL / 8 * 128)     // 2,304: one 16-gene K chunk of B (18 core matrices)
-#define PT_STAGE_BYTES (PL_TILE * 64u)          // 8,192: 128 cells x 64 genes of one level
-#define PT_NSTAGES 8u
+#define PT_WORDS 2u                             // 32-gene words per sub-stage (a sub-stage feeds PT_WORDS MMAs)
+#define PT_STAGE_BYTES (PL_TILE * 32u * PT_WORDS)  // 8,192: a sub-stage = 128 cells x 64 genes of one level
+#define PT_NSTAGES 8u                           // sub-stages in the ring, one per producer warp
+#define PT_SUB 2u                               // sub-stages per MMA stage: 128 genes, four MMAs per barrier round trip
+#define PT_NSTG (PT_NSTAGES / PT_SUB)
+#define PT_PROD_WARPS PT_NSTAGES
 #define PL_EPI_WARPS 4u
 #define PL_PROD_WARPS 8u
 #define PL_THREADS ((PL_EPI_WARPS + 1 + PL_PROD_WARPS) * 32)  // 416
@@ -51,7 +55,9 @@ using namespace tc05;
 #define PN_A_BYTES (3u * 4096u)
 #define PN_B_BYTES (32u * PL_NCOL)              // 4,608
 #define PN_STAGE_BYTES (PN_A_BYTES + PN_B_BYTES)  // 16,896
-#define PN_NSTAGES 8u
+#define PN_NSTAGES 12u                          // sub-stages (32 cells of one level) in the ring
+#define PN_SUB 4u                               // sub-stages per MMA stage: a whole 128-cell tile of one level, up to 12 MMAs
+#define PN_NSTG (PN_NSTAGES / PN_SUB)
 #define PN_CELLGRP_BYTES (PL_NCOL / 16 * 128)   // 1,152: digit rows of 8 cells (9 core matrices)
 
 struct PlDev {
@@ -207,7 +213,7 @@ int planes_select(sb_mat *mt, u64 c0, u64 c1) {
             for (size_t j = i; j < std::min(lv.size(), i + 3); j++) {
                 const u32 genes = std::min(pl.G[lv[j]], g0 + PT_RANGE) - g0;  // multiple of 128
                 u.lev[u.nlev] = lv[j];
-                u.nkb[u.nlev] = genes / 64;
+                u.nkb[u.nlev] = genes / 32;
                 u.nlev++;
                 c += genes;
             }
@@ -266,18 +272,33 @@ int planes_select(sb_mat *mt, u64 c0, u64 c1) {
         un.push_back(u);
         cost.push_back(c);
     }
-    units_round(nc, cost, (u32)ctx->sm_count);
-    at = 0;
-    for (size_t i = 0; i < un.size(); i++) {
-        // int32 accumulators: at most 2^24 cells per CTA range (|digit| <= 128)
-        const u32 need = (u32)((mt->n + (1u << 24) - 1) >> 24);
-        un[i].cta0 = at;
-        un[i].nctas = std::max(nc[i], std::max<u32>(1, need));
-        at += un[i].nctas;
+    {
+        double total = 0.0;
+        for (double c : cost) total += c * (double)pl.ntiles;
+        const double target = std::max(1.0, total / ((double)ctx->sm_count * 10.0));
+        std::vector<u32> uo(un.size());
+        std::iota(uo.begin(), uo.end(), 0u);
+        std::stable_sort(uo.begin(), uo.end(), [&](u32 x, u32 y) { return cost[x] > cost[y]; });
+        std::vector<PlItem> items;
+        for (u32 ui : uo) {
+            // int32 accumulators: at most 2^24 cells per item (|digit| <= 128)
+            const u64 per = std::min<u64>(std::max<u64>(1, (u64)(target / cost[ui] + 0.5)), (1u << 24) / PL_TILE);
+            for (u64 t0 = 0; t0 < pl.ntiles; t0 += per) {
+                PlItem it;
+                it.unit = ui;
+                it.t0 = (u32)t0;
+                it.t1 = (u32)std::min<u64>(pl.ntiles, t0 + per);
+                items.push_back(it);
+            }
+        }
+        pl.n_items_n = (u32)items.size();
+        pl.n_grid = (u32)std::min<size_t>((size_t)ctx->sm_count, std::max<size_t>(1, items.size()));
+        SB_TRY(pl.items_n.alloc(std::max<size_t>(1, items.size()) * sizeof(PlItem)));
+        if (!items.empty()) SB_CUDA(cudaMemcpyAsync(pl.items_n.p, items.data(), items.size() * sizeof(PlItem), cudaMemcpyHostToDevice, ctx->stream));
+        SB_CUDA(cudaStreamSynchronize(ctx->stream));  // `items` is a host temporary
     }
-    pl.n_grid = at;
     pl.n_units_n = (u32)un.size();
-    SB_TRY(pl.units_n.alloc(un.size() * sizeof(PlUnitN)));
+    SB_TRY(pl.units_n.alloc(std::max<size_t>(1, un.size()) * sizeof(PlUnitN)));
     SB_CUDA(cudaMemcpyAsync(pl.units_n.p, un.data(), un.size() * sizeof(PlUnitN), cudaMemcpyHostToDevice, ctx->stream));
     SB_CUDA(cudaStreamSynchronize(ctx->stream));  // host temporaries
     pl.active = true;
@@ -428,41 +449,78 @@ __device__ __forceinline__ void read_acc(u32 taddr, double (&val)[PL_COLS]) {
     }
 }
 
+// res[c] += lk * value_c, straight from the accumulator (keeps the epilogue's register footprint small)
+__device__ __forceinline__ void read_acc_fma(u32 taddr, double lk, double (&res)[PL_COLS]) {
+    double lo = 0.0, hi = 0.0;
+#pragma unroll
+    for (u32 cb = 0; cb < PL_NCOL; cb += 16) {
+        u32 r[16];
+        tmem_ld16(taddr + cb, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (u32 i = 0; i < 16; i++) {
+            const u32 n = cb + i;  // compile-time after unrolling
+            if (n < PL_COLS * PL_DIG) {
+                const u32 c = n / PL_DIG, s = n - c * PL_DIG;
+                const double d = i32_to_f64(r[i]);
+                if (s == 0) lo = d;
+                else if (s < 4) lo = fma(d, (double)(1u << (8 * s)), lo);
+                else if (s == 4) hi = d;
+                else hi = fma(d, (double)(1u << (8 * (s - 4))), hi);
+                if (s == PL_DIG - 1) res[c] = fma(lk, fma(hi, 4294967296.0, lo), res[c]);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------- k_planes_t
+// Roles: warps 0-3 epilogue, warp 4 MMA issue, warps 5-20 producers, warp 21 scheduler.  The producers' refill latency
+// (expand one sub-stage after its slot was freed) against the MMA work in flight in the ring decides the throughput: sixteen
+// warps each own a 4 KB sub-slot (one MMA's A operand), four sub-slots make a stage.
+#define PT_WARPS (PL_EPI_WARPS + 1 + PT_PROD_WARPS + 1)
+#define PT_THREADS (PT_WARPS * 32)
 struct PtShared {
-    unsigned long long full[PT_NSTAGES], empty[PT_NSTAGES], tfull[3], tempty[3];
+    unsigned long long full[PT_NSTG], empty[PT_NSTG], tfull[3], tempty[3], item_full[2], item_empty[2];
     u32 tmem;
-    u32 item[2];  // work item fetched for this round (double buffered)
+    u32 item[2];  // work-item ring filled by the scheduler warp
     u32 pad;
     double scale2[PL_COLS];
-    u32 stage_tab[48];  // stage i of a tile -> (kb << 2 | level slot); at most 3 x 16 stages per tile
 };
 
 // Persistent CTAs pull work items {unit, tile range} from a global queue (items are sized to ~equal cost and ordered by
-// unit, so the resident B block is reloaded only when the unit changes).  A CTA-wide barrier separates items; the
-// pipeline state (stage counter, barrier phases, accumulator slots) carries across them.
-__global__ void __launch_bounds__(PL_THREADS, 1)
+// unit, so the resident B block is reloaded only when the unit changes).  The scheduler warp keeps a two-deep ring of item
+// ids, so the roles run into the next item without draining the pipeline; only a change of unit (new B block) is a
+// CTA-wide barrier.  Pipeline state carried across items: the sub-stage counter q (A ring) and the job counter j -- one
+// job per (tile, level), accumulating into TMEM slot j % 3, so the epilogue of one level overlaps the MMAs of the next.
+// Output: the CTA's 20 values per (unit, cell) go to part[unit][cell][20] with plain stores -- every (unit, tile) is
+// produced exactly once -- and k_pl_reduce_t adds the units up (f64 reductions into T cost 1.3 cycles per lane on the
+// LSU and were the bottleneck of the first version: 0.43 of 1.5 ms).
+__global__ void __launch_bounds__(PT_THREADS, 1)
 k_planes_t(PlDev pl, const PlUnitT *__restrict__ units, const PlItem *__restrict__ items, u32 n_items, u32 *__restrict__ counter,
-           const signed char *__restrict__ Bd, const double *__restrict__ scale2_g, const double *__restrict__ cs, int log_base, u32 col0, u32 wt,
-           double *__restrict__ out, u32 ldo) {
+           const signed char *__restrict__ Bd, const double *__restrict__ scale2_g, const double *__restrict__ cs, int log_base, u32 wt,
+           double *__restrict__ part, u32 dbg) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *sB = smem;
     unsigned char *sA = sB + PT_B_BYTES;
     PtShared *sh = reinterpret_cast<PtShared *>(sA + PT_NSTAGES * PT_STAGE_BYTES);
     const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const u32 full0 = smem_u32(sh->full), empty0 = smem_u32(sh->empty), tfull0 = smem_u32(sh->tfull), tempty0 = smem_u32(sh->tempty);
+    const u32 ifull0 = smem_u32(sh->item_full), iempty0 = smem_u32(sh->item_empty);
 
     if (tid == 0) {
-        for (u32 i = 0; i < PT_NSTAGES; i++) {
-            mbar_init(full0 + 8 * i, 1);
+        for (u32 i = 0; i < PT_NSTG; i++) {
+            mbar_init(full0 + 8 * i, PT_SUB);  // one arrival per producer warp of the stage
             mbar_init(empty0 + 8 * i, 1);
         }
         for (u32 i = 0; i < 3; i++) {
             mbar_init(tfull0 + 8 * i, 1);
             mbar_init(tempty0 + 8 * i, PL_EPI_WARPS);
         }
+        for (u32 i = 0; i < 2; i++) {
+            mbar_init(ifull0 + 8 * i, 1);
+            mbar_init(iempty0 + 8 * i, PT_WARPS - 1);  // every consumer warp
+        }
         mbar_init_fence();
-        sh->item[0] = atomicAdd(counter, 1u);
     }
     if (warp == 0) tmem_alloc_512(smem_u32(&sh->tmem));
     if (tid < PL_COLS) sh->scale2[tid] = scale2_g[tid];
@@ -473,22 +531,41 @@ k_planes_t(PlDev pl, const PlUnitT *__restrict__ units, const PlItem *__restrict
     const u32 sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
     const u32 idesc = instr_desc_i8(PL_TILE, PL_NCOL, false, false);
     const uint64_t da_hi = smem_desc(0, PL_TILE * 16, 128), db_hi = smem_desc(0, PT_KCHUNK_BYTES, 128);
+    const u64 n_pad = pl.ntiles * PL_TILE;
+    const bool scheduler = warp == PT_WARPS - 1;
 
-    // pipeline state carried across items (each role uses its own part; all advance identically)
-    u32 q = 0;                    // stages issued / consumed so far (MMA thread), or before this item (producers)
-    u32 fills = 0;                // producer: fills of my stage slot
-    u32 rr = 0;                   // round-robin accumulator slot of single-level units
-    u32 u0 = 0, u1 = 0, u2 = 0;   // completed uses of accumulator slots 0..2
+    u32 q = 0;      // 64-gene sub-stages before this item (producers) / issued so far (MMA)
+    u32 job = 0;    // (tile, level) accumulation jobs so far
+    u32 fills = 0;  // producer: fills of my sub-slot
     u32 cur_unit = 0xFFFFFFFFu;
-    u32 g0 = 0, nlev = 0, nkb0 = 0, nkb1 = 0, nkb2 = 0, lev0 = 0, lev1 = 0, lev2 = 0, S = 1;
+    u32 g0 = 0, nlev = 0, nkb0 = 0, nkb1 = 0, nkb2 = 0, lev0 = 0, lev1 = 0, lev2 = 0, S = 2;
 
     for (u32 round = 0;; round++) {
-        const u32 it = sh->item[round & 1];
+        const u32 rs = round & 1u;
+        u32 it;
+        if (scheduler) {
+            if (round >= 2) mbar_wait(iempty0 + 8 * rs, ((round >> 1) - 1) & 1u);
+            it = 0;
+            if (lane == 0) {
+                it = atomicAdd(counter, 1u);
+                sh->item[rs] = it;
+            }
+            it = __shfl_sync(0xffffffffu, it, 0);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ifull0 + 8 * rs);
+        } else {
+            mbar_wait(ifull0 + 8 * rs, (round >> 1) & 1u);
+            it = sh->item[rs];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(iempty0 + 8 * rs);
+        }
         if (it >= n_items) break;
-        if (tid == 0) sh->item[(round + 1) & 1] = atomicAdd(counter, 1u);  // visible after the barrier that ends this round
         const PlItem item = items[it];
         if (item.unit != cur_unit) {
-            // every role is past the barrier of the previous round: all MMAs that read the old B block have completed
+            // new B block: drain (all MMAs that read the old block have completed once every role is here), reload, go on
+            fence_before_sync();
+            __syncthreads();
+            fence_after_sync();
             const PlUnitT un = units[item.unit];
             cur_unit = item.unit;
             g0 = un.g0;
@@ -499,30 +576,20 @@ k_planes_t(PlDev pl, const PlUnitT *__restrict__ units, const PlItem *__restrict
             lev0 = un.lev[0];
             lev1 = nlev > 1 ? un.lev[1] : 0;
             lev2 = nlev > 2 ? un.lev[2] : 0;
-            S = nkb0 + nkb1 + nkb2;
+            S = (nkb0 + nkb1 + nkb2) / PT_WORDS;  // sub-stages per tile, level-major: [level 0 | level 1 | level 2]
             const uint4 *src = reinterpret_cast<const uint4 *>(Bd + (size_t)(g0 / PT_RANGE) * PT_B_BYTES);
             uint4 *dst = reinterpret_cast<uint4 *>(sB);
-            for (u32 i = tid; i < PT_B_BYTES / 16; i += PL_THREADS) dst[i] = src[i];
-            for (u32 i = tid; i < S; i += PL_THREADS) {  // stage i of a tile -> (kb, level slot), in the MMA thread's order
-                u32 cnt = 0;
-                for (u32 kb = 0; kb < nkb0; kb++) {
-                    if (cnt == i) { sh->stage_tab[i] = kb << 2; break; }
-                    cnt++;
-                    if (kb < nkb1) { if (cnt == i) { sh->stage_tab[i] = (kb << 2) | 1u; break; } cnt++; }
-                    if (kb < nkb2) { if (cnt == i) { sh->stage_tab[i] = (kb << 2) | 2u; break; } cnt++; }
-                }
-            }
+            for (u32 i = tid; i < PT_B_BYTES / 16; i += PT_THREADS) dst[i] = src[i];
             fence_async_smem();
             __syncthreads();
         }
         const u64 t0 = item.t0, t1 = item.t1;
 
         if (warp < PL_EPI_WARPS) {
-            // ===== epilogue: TMEM -> registers -> f64 -> T (one thread per cell row)
+            // ===== epilogue: TMEM -> registers -> f64 -> partial output (one thread per cell row)
             const u32 row = warp * 32 + lane;
+            double *pu = part + (size_t)item.unit * n_pad * PL_COLS;
             for (u64 tile = t0; tile < t1; tile++) {
-                const u32 slot = nlev == 1 ? rr : 0u;
-                const u32 use = slot == 0 ? u0 : (slot == 1 ? u1 : u2);
                 const u64 cell = tile * PL_TILE + row;
                 double res[PL_COLS];
 #pragma unroll
@@ -534,94 +601,104 @@ k_planes_t(PlDev pl, const PlUnitT *__restrict__ units, const PlItem *__restrict
                     if (nlev > 1) L1 = finite_or_zero(map_log_part(log_base, sc, lev1 + 1, sb_log_table));
                     if (nlev > 2) L2 = finite_or_zero(map_log_part(log_base, sc, lev2 + 1, sb_log_table));
                 }
-                mbar_wait(tfull0 + 8 * slot, use & 1u);
-                fence_after_sync();
-                const u32 tbase = tmem + ((warp * 32u) << 16) + slot * nlev * PL_NCOL;
-                for (u32 a = 0; a < nlev; a++) {
-                    double val[PL_COLS];
-                    read_acc(tbase + a * PL_NCOL, val);
-                    const double lk = a == 0 ? L0 : (a == 1 ? L1 : L2);
-#pragma unroll
-                    for (u32 j = 0; j < PL_COLS; j++) res[j] = fma(lk, val[j], res[j]);
+                for (u32 a = 0; a < nlev; a++, job++) {
+                    const u32 slot = job % 3u;
+                    mbar_wait(tfull0 + 8 * slot, (job / 3u) & 1u);
+                    fence_after_sync();
+                    if (!(dbg & 2u)) read_acc_fma(tmem + ((warp * 32u) << 16) + slot * PL_NCOL, a == 0 ? L0 : (a == 1 ? L1 : L2), res);
+                    fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty0 + 8 * slot);  // this warp's quarter of the accumulator is free
                 }
-                fence_before_sync();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tempty0 + 8 * slot);  // this warp's quarter of the accumulators is free
-                if (cell < pl.n) {
-                    double *o = out + cell * (size_t)ldo + col0;
+                if (!(dbg & 1u)) {  // rows of a tile are adjacent: a warp writes 32 x 160 contiguous bytes
+                    double2 *o = reinterpret_cast<double2 *>(pu + cell * PL_COLS);
 #pragma unroll
-                    for (u32 j = 0; j < PL_COLS; j++)
-                        if (j < wt) atomicAdd(o + j, res[j] * sh->scale2[j]);  // other units (gene ranges, level triples) add into the same row
+                    for (u32 j = 0; j < PL_COLS; j += 2) o[j >> 1] = make_double2(res[j] * sh->scale2[j], res[j + 1] * sh->scale2[j + 1]);
                 }
-                if (slot == 0) u0++;
-                else if (slot == 1) u1++;
-                else u2++;
-                if (nlev == 1) rr = rr == 2 ? 0 : rr + 1;
             }
         } else if (warp == PL_EPI_WARPS) {
-            // ===== MMA issue (one thread): a handful of instructions per stage -- the tensor pipe must never wait for this thread
-            if (lane == 0) {
+            // ===== MMA issue.  The warp runs the loops converged, every value warp-uniform, and only the tensor-core instructions
+            // are predicated on an elected lane: that keeps descriptors and addresses in uniform registers (UIADD3 / ULOP3 +
+            // UTCIMMA).  Electing a lane around the whole loop instead makes the compiler wrap each UTCIMMA in an ELECT /
+            // 5 x R2UR.BROADCAST / branch loop -- ~90 instructions per 4-MMA stage, more than the 288 cycles the MMAs take.
+            {
                 const u32 a16 = sA_addr >> 4, b16 = sB_addr >> 4;
-                auto stage = [&](u32 kb, u32 acc) {
-                    const u32 s = q & (PT_NSTAGES - 1);
-                    mbar_wait(full0 + 8 * s, (q >> 3) & 1u);
-                    fence_after_sync();
-                    const u32 alo = a16 + s * (PT_STAGE_BYTES >> 4), blo = b16 + kb * (4 * PT_KCHUNK_BYTES >> 4);
-                    mma_i8(acc, da_hi | alo, db_hi | blo, idesc, kb);
-                    mma_i8(acc, da_hi | (alo + (2 * PL_TILE * 16 >> 4)), db_hi | (blo + (2 * PT_KCHUNK_BYTES >> 4)), idesc, 1u);
-                    commit(empty0 + 8 * s);  // the stage is reusable once these MMAs have read it
-                    q++;
-                };
-                for (u64 tile = t0; tile < t1; tile++) {
-                    const u32 slot = nlev == 1 ? rr : 0u;
-                    const u32 use = slot == 0 ? u0 : (slot == 1 ? u1 : u2);
-                    if (use > 0) {
-                        mbar_wait(tempty0 + 8 * slot, (use - 1) & 1u);
+                auto level = [&](u32 nkb) {
+                    const u32 slot = job % 3u;
+                    if (job >= 3u) {
+                        mbar_spin(tempty0 + 8 * slot, (job / 3u - 1u) & 1u);
                         fence_after_sync();
                     }
-                    const u32 acc0 = tmem + slot * nlev * PL_NCOL;
-                    for (u32 kb = 0; kb < nkb0; kb++) {
-                        stage(kb, acc0);
-                        if (kb < nkb1) stage(kb, acc0 + PL_NCOL);
-                        if (kb < nkb2) stage(kb, acc0 + 2 * PL_NCOL);
+                    const u32 acc = tmem + slot * PL_NCOL;
+                    for (u32 kb = 0; kb < nkb; kb += PT_SUB * PT_WORDS) {  // kb counts 32-gene blocks (one MMA each)
+                        const u32 sg = q / PT_SUB, ss = sg & (PT_NSTG - 1);
+                        mbar_spin(full0 + 8 * ss, (sg / PT_NSTG) & 1u);
+                        fence_after_sync();
+                        const u32 alo = a16 + ss * (PT_SUB * PT_STAGE_BYTES >> 4), blo = b16 + kb * (2 * PT_KCHUNK_BYTES >> 4);
+                        if (elect_one()) {
+#pragma unroll
+                            for (u32 t = 0; t < PT_SUB * PT_WORDS; t++)  // K = 32 per MMA = two 16-gene core-matrix columns (4 KB of A)
+                                mma_i8(acc, da_hi | (alo + t * (PL_TILE * 32 >> 4)), db_hi | (blo + t * (2 * PT_KCHUNK_BYTES >> 4)), idesc, kb | t);
+                            commit(empty0 + 8 * ss);  // the stage is reusable once these MMAs have read it
+                        }
+                        __syncwarp();
+                        q += PT_SUB;
                     }
-                    commit(tfull0 + 8 * slot);  // accumulators of this tile complete
-                    if (slot == 0) u0++;
-                    else if (slot == 1) u1++;
-                    else u2++;
-                    if (nlev == 1) rr = rr == 2 ? 0 : rr + 1;
+                    if (elect_one()) commit(tfull0 + 8 * slot);  // this level's accumulator is complete
+                    __syncwarp();
+                    job++;
+                };
+                for (u64 tile = t0; tile < t1; tile++) {
+                    level(nkb0);
+                    if (nlev > 1) level(nkb1);
+                    if (nlev > 2) level(nkb2);
                 }
             }
-        } else {
+        } else if (!scheduler) {
             // ===== producers: plane words -> 0/1 int8 A tiles (K-major core matrices: [16-gene chunk][cell / 8][cell % 8][16 B])
-            // warp p fills stage slot p: the stages with global index = p (mod 8)
+            // warp p fills sub-slot p: the sub-stages (PT_WORDS x 32 genes of one level) with global index = p (mod PT_NSTAGES)
             const u32 p = warp - (PL_EPI_WARPS + 1);
-            const u32 *stab = sh->stage_tab;
             const u32 G0 = pl.G[lev0] >> 5, G1w = pl.G[lev1] >> 5, G2w = pl.G[lev2] >> 5;
             const u32 *bits0 = pl.bits[lev0], *bits1 = pl.bits[lev1], *bits2 = pl.bits[lev2];
+            const u32 s0 = nkb0 / PT_WORDS, s1 = nkb1 / PT_WORDS;  // sub-stages of levels 0, 1 per tile
             u64 tile = t0;
-            u32 i = (p + PT_NSTAGES - (q & (PT_NSTAGES - 1))) & (PT_NSTAGES - 1);  // my first stage inside this item
+            u32 i = (p + PT_NSTAGES - (q & (PT_NSTAGES - 1))) & (PT_NSTAGES - 1);  // my first sub-stage inside this item
             while (i >= S && tile < t1) {
                 i -= S;
                 tile++;
             }
-            auto load_words = [&](u64 tl, u32 ii, u32 (&w)[8]) {
-                const u32 e = stab[ii];
-                const u32 kb = e >> 2, a = e & 3u;
-                const u32 Gw = a == 0 ? G0 : (a == 1 ? G1w : G2w);
-                const u32 *bp = a == 0 ? bits0 : (a == 1 ? bits1 : bits2);
-                const u32 *base = bp + ((size_t)tl * Gw + ((g0 + kb * 64) >> 5)) * PL_TILE + lane;
+            auto load_words = [&](u64 tl, u32 ii, u32 (&w)[4 * PT_WORDS]) {  // ii: sub-stage inside the tile, level-major
+                const bool in1 = ii >= s0, in2 = ii >= s0 + s1;
+                const u32 sb = ii - (in2 ? s0 + s1 : (in1 ? s0 : 0u));
+                const u32 Gw = in2 ? G2w : (in1 ? G1w : G0);
+                const u32 *bp = in2 ? bits2 : (in1 ? bits1 : bits0);
+                const u32 *base = bp + ((size_t)tl * Gw + (g0 >> 5) + sb * PT_WORDS) * PL_TILE + lane;
 #pragma unroll
-                for (u32 j = 0; j < 2; j++)
+                for (u32 j = 0; j < PT_WORDS; j++)
 #pragma unroll
                     for (u32 c4 = 0; c4 < 4; c4++) w[j * 4 + c4] = __ldg(base + (size_t)j * PL_TILE + c4 * 32);
             };
-            u32 cur[8], nxt[8];
+            // L2 prefetch: the plane words of a (tile, level) for this range are contiguous (nkb KB); when this warp first touches
+            // a tile it pulls its eighth of the tile two ahead towards L2
+            auto prefetch_tile = [&](u64 tl) {
+                if (tl >= t1) return;
+                const u32 line = p * (128 / PT_NSTAGES) + lane;  // 128-byte lines; a full range has 128 per level (4 per 32-gene block)
+                if (lane < 128 / PT_NSTAGES) {
+                    if (line < nkb0 * 4) prefetch_l2(bits0 + ((size_t)tl * G0 + (g0 >> 5)) * PL_TILE + line * 32);
+                    if (line < nkb1 * 4) prefetch_l2(bits1 + ((size_t)tl * G1w + (g0 >> 5)) * PL_TILE + line * 32);
+                    if (line < nkb2 * 4) prefetch_l2(bits2 + ((size_t)tl * G2w + (g0 >> 5)) * PL_TILE + line * 32);
+                }
+            };
+            u32 cur[4 * PT_WORDS], nxt[4 * PT_WORDS];
             bool live = tile < t1;
-            if (live) load_words(tile, i, cur);
+            if (live) {
+                prefetch_tile(tile + 1);
+                prefetch_tile(tile + 2);
+                load_words(tile, i, cur);
+            }
             const u32 st = sA_addr + p * PT_STAGE_BYTES + lane * 16;
             while (live) {
-                // my next stage: prefetch its words before expanding the current ones
+                // my next sub-stage: prefetch its words before expanding the current ones
                 u64 ntile = tile;
                 u32 ni = i + PT_NSTAGES;
                 while (ni >= S && ntile < t1) {
@@ -630,40 +707,55 @@ k_planes_t(PlDev pl, const PlUnitT *__restrict__ units, const PlItem *__restrict
                 }
                 const bool more = ntile < t1;
                 if (more) load_words(ntile, ni, nxt);
-                if (fills > 0) mbar_wait(empty0 + 8 * p, (fills - 1) & 1u);
+                if (ntile != tile) prefetch_tile(ntile + 2);
+                if (fills > 0) mbar_wait(empty0 + 8 * (p / PT_SUB), (fills - 1) & 1u);
+                if (!(dbg & 4u))
 #pragma unroll
-                for (u32 j = 0; j < 2; j++)
+                    for (u32 j = 0; j < PT_WORDS; j++)
 #pragma unroll
-                    for (u32 c4 = 0; c4 < 4; c4++) {
-                        uint4 lo, hi;
-                        expand_bits32(cur[j * 4 + c4], lo, hi);
-                        st_shared_v4(st + (2 * j) * (PL_TILE * 16) + c4 * 512, lo);
-                        st_shared_v4(st + (2 * j + 1) * (PL_TILE * 16) + c4 * 512, hi);
-                    }
+                        for (u32 c4 = 0; c4 < 4; c4++) {
+                            uint4 lo, hi;
+                            expand_bits32(cur[j * 4 + c4], lo, hi);
+                            st_shared_v4(st + (2 * j) * (PL_TILE * 16) + c4 * 512, lo);
+                            st_shared_v4(st + (2 * j + 1) * (PL_TILE * 16) + c4 * 512, hi);
+                        }
                 fence_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(full0 + 8 * p);
+                if (lane == 0) mbar_arrive(full0 + 8 * (p / PT_SUB));
                 fills++;
                 tile = ntile;
                 i = ni;
                 live = more;
                 if (more) {
 #pragma unroll
-                    for (u32 c = 0; c < 8; c++) cur[c] = nxt[c];
+                    for (u32 c = 0; c < 4 * PT_WORDS; c++) cur[c] = nxt[c];
                 }
             }
-            q += (u32)(t1 - t0) * S;  // stages of this item (the MMA thread advances its own q as it issues)
-            // slot bookkeeping is not needed here
+            q += (u32)(t1 - t0) * S;
         }
-        // every role replicates the slot / use counters it needs; the epilogue and MMA roles advanced theirs above.  Roles that
-        // did not (producers; idle lanes of the MMA warp) must still agree on rr / u* for later items if they ever use them: they do not.
-        fence_before_sync();
-        __syncthreads();  // item boundary: accumulators drained, stages consumed, next item id visible
-        fence_after_sync();
     }
     fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc_512(tmem);
+}
+
+// T[c, col0 + j] += sum over units of part[u][c][j]
+__global__ void k_pl_reduce_t(const double *__restrict__ part, u32 n_units, u64 n, u64 n_pad, u32 col0, u32 wt, double *__restrict__ out, u32 ldo) {
+    const u64 total = n * (PL_COLS / 2);
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (u64)gridDim.x * blockDim.x) {
+        const u64 c = i / (PL_COLS / 2);
+        const u32 j = (u32)(i - c * (PL_COLS / 2)) * 2;
+        if (j >= wt) continue;
+        double2 s = make_double2(0.0, 0.0);
+        for (u32 u = 0; u < n_units; u++) {
+            const double2 v = *reinterpret_cast<const double2 *>(part + ((size_t)u * n_pad + c) * PL_COLS + j);
+            s.x += v.x;
+            s.y += v.y;
+        }
+        double *o = out + c * (size_t)ldo + col0 + j;
+        o[0] += s.x;
+        if (j + 1 < wt) o[1] += s.y;
+    }
 }
 
 // ---------------------------------------------------------------- N side: digit rows of L_c(k) . X[c,:]
@@ -726,43 +818,33 @@ __global__ void k_pl_digits_n(const double *__restrict__ X, u32 ldx, u64 n, u64 
 
 // ---------------------------------------------------------------- k_planes_n
 struct PnShared {
-    unsigned long long full[PN_NSTAGES], empty[PN_NSTAGES], tfull;
+    unsigned long long full[PN_NSTG], empty[PN_NSTG], tfull;
     u32 tmem;
+    u32 item[2];
     u32 pad;
     double scale2[PL_COLS];
 };
 
 // out[gene * row_stride + (col0 + j) * col_stride] += value
+// Persistent CTAs pull work items {group of 384 ranks, range of cell tiles} from a global queue (about equal cost each); an item
+// ends with its epilogue (the accumulators are reused by the next item), so the CTA-wide barrier between items costs nothing extra.
 __global__ void __launch_bounds__(PL_THREADS, 1)
-k_planes_n(PlDev pl, const PlUnitN *__restrict__ units, u32 n_units, const signed char *__restrict__ Bn, u64 n_pad, const double *__restrict__ scale2_g,
-           const u32 *__restrict__ hot_idx, u32 col0, u32 wt, double *__restrict__ out, u64 row_stride, u64 col_stride) {
+k_planes_n(PlDev pl, const PlUnitN *__restrict__ units, const PlItem *__restrict__ items, u32 n_items, u32 *__restrict__ counter,
+           const signed char *__restrict__ Bn, u64 n_pad, const double *__restrict__ scale2_g, const u32 *__restrict__ hot_idx, u32 col0, u32 wt,
+           double *__restrict__ out, u64 row_stride, u64 col_stride) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char *sS = smem;  // PN_NSTAGES stages: [A: 3 M tiles x 4,096 | B: 4,608]
+    unsigned char *sS = smem;  // PN_NSTAGES sub-slots: [A: 3 M tiles x 4,096 | B: 4,608]
     PnShared *sh = reinterpret_cast<PnShared *>(sS + PN_NSTAGES * PN_STAGE_BYTES);
     const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    PlUnitN un;
-    bool have = false;
-    for (u32 i = 0; i < n_units; i++) {
-        const PlUnitN u = units[i];
-        if (blockIdx.x >= u.cta0 && blockIdx.x < u.cta0 + u.nctas) {
-            un = u;
-            have = true;
-        }
-    }
-    const u32 sub = have ? blockIdx.x - un.cta0 : 0;
-    const u64 t_begin = have ? pl.ntiles * sub / un.nctas : 0, t_end = have ? pl.ntiles * (sub + 1) / un.nctas : 0;
-    have = have && t_end > t_begin;
-    const u32 nlev = have ? un.nlev : 0;
-    u32 mt_pack = 0;  // four bits per level: M tiles of the level inside this group
-    for (u32 k = 0; k < nlev; k++) mt_pack |= un.mt[k] << (4 * k);
     const u32 full0 = smem_u32(sh->full), empty0 = smem_u32(sh->empty), tfull0 = smem_u32(&sh->tfull);
     if (tid == 0) {
-        for (u32 i = 0; i < PN_NSTAGES; i++) {
-            mbar_init(full0 + 8 * i, 1);
+        for (u32 i = 0; i < PN_NSTG; i++) {
+            mbar_init(full0 + 8 * i, PN_SUB);  // one arrival per producer warp of the stage
             mbar_init(empty0 + 8 * i, 1);
         }
         mbar_init(tfull0, 1);
         mbar_init_fence();
+        sh->item[0] = atomicAdd(counter, 1u);
     }
     if (warp == 0) tmem_alloc_512(smem_u32(&sh->tmem));
     if (tid < PL_COLS) sh->scale2[tid] = scale2_g[tid];
@@ -771,131 +853,154 @@ k_planes_n(PlDev pl, const PlUnitN *__restrict__ units, u32 n_units, const signe
     fence_after_sync();
     const u32 tmem = sh->tmem;
     const u32 sS_addr = smem_u32(sS);
+    const u32 idesc = instr_desc_i8(128, PL_NCOL, true, true);
+    const uint64_t da_hi = smem_desc(0, 128, 512);               // MN-major A: lbo = next 8 cells, sbo = next 16 genes
+    const uint64_t db_hi = smem_desc(0, PN_CELLGRP_BYTES, 128);  // MN-major B: lbo = next 8 cells, sbo = next 16 digit columns
 
-    if (have && warp < PL_EPI_WARPS) {
-        // ===== epilogue (once per CTA): TMEM lanes = gene rows of an M tile
-        mbar_wait(tfull0, 0);
-        fence_after_sync();
-        const u32 row = warp * 32 + lane;
-        for (u32 mtile = 0; mtile < (mt_pack & 15u); mtile++) {
-            double val[PL_COLS];
-            read_acc(tmem + ((warp * 32u) << 16) + mtile * PL_NCOL, val);
-            const u32 g = hot_idx[un.g0 + mtile * 128 + row];
-            double *o = out + (size_t)g * row_stride;
+    u32 sg = 0;  // stages issued (MMA) / sub-stages before this item (producers: Q0)
+    u32 Q0 = 0;
+    for (u32 round = 0;; round++) {
+        const u32 it = sh->item[round & 1];
+        if (it >= n_items) break;
+        if (tid == 0) sh->item[(round + 1) & 1] = atomicAdd(counter, 1u);  // visible after the barrier that ends this round
+        const PlItem item = items[it];
+        const PlUnitN un = units[item.unit];
+        const u32 nlev = un.nlev, g0w = un.g0 >> 5;
+        u32 mt_pack = 0;  // four bits per level: M tiles of the level inside this group
+        for (u32 k = 0; k < nlev; k++) mt_pack |= un.mt[k] << (4 * k);
+        const u64 t_begin = item.t0, t_end = item.t1;
+
+        if (warp < PL_EPI_WARPS) {
+            // ===== epilogue (once per item): TMEM lanes = gene rows of an M tile
+            mbar_wait_sleep(tfull0, round & 1u);
+            fence_after_sync();
+            const u32 row = warp * 32 + lane;
+            for (u32 mtile = 0; mtile < (mt_pack & 15u); mtile++) {
+                double val[PL_COLS];
+                read_acc(tmem + ((warp * 32u) << 16) + mtile * PL_NCOL, val);
+                const u32 g = hot_idx[un.g0 + mtile * 128 + row];
+                double *o = out + (size_t)g * row_stride;
 #pragma unroll
-            for (u32 j = 0; j < PL_COLS; j++)
-                if (j < wt && val[j] != 0.0) atomicAdd(o + (size_t)(col0 + j) * col_stride, val[j] * sh->scale2[j]);
-        }
-    } else if (have && warp == PL_EPI_WARPS) {
-        // ===== MMA issue (one thread, a handful of instructions per stage)
-        if (lane == 0) {
-            const u32 idesc = instr_desc_i8(128, PL_NCOL, true, true);
-            const uint64_t da_hi = smem_desc(0, 128, 512);               // MN-major A: lbo = next 8 cells, sbo = next 16 genes
-            const uint64_t db_hi = smem_desc(0, PN_CELLGRP_BYTES, 128);  // MN-major B: lbo = next 8 cells, sbo = next 16 digit columns
+                for (u32 j = 0; j < PL_COLS; j++)
+                    if (j < wt && val[j] != 0.0) atomicAdd(o + (size_t)(col0 + j) * col_stride, val[j] * sh->scale2[j]);
+            }
+        } else if (warp == PL_EPI_WARPS) {
+            // ===== MMA issue: converged warp, uniform values, an elected lane only around the tensor-core instructions (see k_planes_t);
+            // a stage = a whole 128-cell tile of one level = four K steps x up to three M tiles
             const u32 s16 = sS_addr >> 4;
-            u32 q = 0;
             u32 started = 0;  // bit mtile: the accumulator has been written
-            const u64 nsteps = (t_end - t_begin) * 4;
-            for (u64 step = 0; step < nsteps; step++) {
+            for (u64 tile = t_begin; tile < t_end; tile++) {
                 u32 mtp = mt_pack;
-                for (u32 k = 0; k < nlev; k++, mtp >>= 4) {
-                    const u32 s = q & (PN_NSTAGES - 1);
-                    mbar_wait(full0 + 8 * s, (q >> 3) & 1u);
+                for (u32 k = 0; k < nlev; k++, mtp >>= 4, sg++) {
+                    const u32 slot = sg % PN_NSTG;
+                    mbar_spin(full0 + 8 * slot, (sg / PN_NSTG) & 1u);
                     fence_after_sync();
-                    const u32 alo = s16 + s * (PN_STAGE_BYTES >> 4);
-                    const uint64_t db = db_hi | (alo + (PN_A_BYTES >> 4));
                     const u32 nmt = mtp & 15u;
-                    mma_i8(tmem, da_hi | alo, db, idesc, started & 1u);
-                    if (nmt > 1) mma_i8(tmem + PL_NCOL, da_hi | (alo + 256), db, idesc, (started >> 1) & 1u);
-                    if (nmt > 2) mma_i8(tmem + 2 * PL_NCOL, da_hi | (alo + 512), db, idesc, (started >> 2) & 1u);
+                    if (elect_one()) {
+#pragma unroll
+                        for (u32 ks = 0; ks < PN_SUB; ks++) {
+                            const u32 alo = s16 + (slot * PN_SUB + ks) * (PN_STAGE_BYTES >> 4);
+                            const uint64_t db = db_hi | (alo + (PN_A_BYTES >> 4));
+                            mma_i8(tmem, da_hi | alo, db, idesc, (started & 1u) | ks);
+                            if (nmt > 1) mma_i8(tmem + PL_NCOL, da_hi | (alo + 256), db, idesc, ((started >> 1) & 1u) | ks);
+                            if (nmt > 2) mma_i8(tmem + 2 * PL_NCOL, da_hi | (alo + 512), db, idesc, ((started >> 2) & 1u) | ks);
+                        }
+                        commit(empty0 + 8 * slot);
+                    }
+                    __syncwarp();
                     started |= (1u << nmt) - 1u;
-                    commit(empty0 + 8 * s);
-                    q++;
                 }
             }
-            commit(tfull0);
-        }
-    } else if (have) {
-        // ===== producers: stage = (32-cell K step, level): A tiles [M tile][16-gene chunk (8)][cell / 8 (4)][cell % 8][16 B] + B digit rows
-        // warp p fills stage slot p: stages q = p, p + 8, ...; q -> (tile, ks, k) kept incrementally (no divisions)
-        const u32 p = warp - (PL_EPI_WARPS + 1);
-        const u32 per_tile = 4 * nlev;
-        u32 fills = 0;
-        u32 cur[12], nxt[12];
-        u64 tile = t_begin;
-        u32 r = p;  // position inside the tile: r = ks * nlev + k
-        while (r >= per_tile) {
-            r -= per_tile;
-            tile++;
-        }
-        const u32 g0w = un.g0 >> 5;
-        auto split = [&](u32 rr, u32 &ks, u32 &k) {
-            ks = 0;
-            k = rr;
-            while (k >= nlev) {
-                k -= nlev;
-                ks++;
-            }
-        };
-        auto load_words = [&](u64 tl, u32 ks, u32 k, u32 (&w)[12]) {
-            const u32 nw = ((mt_pack >> (4 * k)) & 15u) * 4;
-            const u32 *base = pl.bits[k] + ((size_t)tl * (pl.G[k] >> 5) + g0w) * PL_TILE + ks * 32 + lane;
-#pragma unroll
-            for (u32 j = 0; j < 12; j++) w[j] = (j < nw) ? __ldg(base + (size_t)j * PL_TILE) : 0u;
-        };
-        bool live = tile < t_end;
-        u32 ks = 0, k = 0;
-        if (live) {
-            split(r, ks, k);
-            load_words(tile, ks, k, cur);
-        }
-        const u32 st = sS_addr + p * PN_STAGE_BYTES;
-        while (live) {
-            u64 ntile = tile;
-            u32 nr = r + PN_NSTAGES;
-            while (nr >= per_tile) {
-                nr -= per_tile;
-                ntile++;
-            }
-            const bool more = ntile < t_end;
-            u32 nks = 0, nk = 0;
-            if (more) {
-                split(nr, nks, nk);
-                load_words(ntile, nks, nk, nxt);
-            }
-            // B rows of these 32 cells at level k (contiguous 4,608 bytes in Bn)
-            const uint4 *bsrc = reinterpret_cast<const uint4 *>(Bn + ((size_t)k * (n_pad / 8) + (tile * PL_TILE + ks * 32) / 8) * PN_CELLGRP_BYTES);
-            uint4 bv[PN_B_BYTES / 16 / 32];
-#pragma unroll
-            for (u32 t = 0; t < PN_B_BYTES / 16 / 32; t++) bv[t] = __ldg(bsrc + lane + 32 * t);
-            const u32 nw = ((mt_pack >> (4 * k)) & 15u) * 4;
-            if (fills > 0) mbar_wait(empty0 + 8 * p, (fills - 1) & 1u);
-#pragma unroll
-            for (u32 j = 0; j < 12; j++) {
-                if (j < nw) {
-                    uint4 lo, hi;
-                    expand_bits32(cur[j], lo, hi);
-                    const u32 a0 = st + (j >> 2) * 4096 + (2 * (j & 3)) * 512 + lane * 16;
-                    st_shared_v4(a0, lo);
-                    st_shared_v4(a0 + 512, hi);
-                }
-            }
-#pragma unroll
-            for (u32 t = 0; t < PN_B_BYTES / 16 / 32; t++) st_shared_v4(st + PN_A_BYTES + (lane + 32 * t) * 16, bv[t]);
-            fence_async_smem();
+            if (elect_one()) commit(tfull0);
             __syncwarp();
-            if (lane == 0) mbar_arrive(full0 + 8 * p);
-            fills++;
-            tile = ntile;
-            r = nr;
-            ks = nks;
-            k = nk;
-            live = more;
-            if (more) {
+        } else {
+            // ===== producers: sub-stage = (32-cell K step, level): A tiles [M tile][16-gene chunk (8)][cell / 8 (4)][cell % 8][16 B] + B
+            // digit rows.  Sub-stage Q of the CTA (tile-major, then level, then K step) goes to ring slot Q % 12, filled by warp Q % 8.
+            const u32 p = warp - (PL_EPI_WARPS + 1);
+            const u32 per_tile = PN_SUB * nlev;
+            u32 cur[12], nxt[12];
+            u64 tile = t_begin;
+            u32 r = (p + PL_PROD_WARPS - (Q0 % PL_PROD_WARPS)) % PL_PROD_WARPS;  // my first sub-stage inside this item: r = k * 4 + ks
+            u32 Q = Q0 + r;                                                         // its global index
+            while (r >= per_tile && tile < t_end) {
+                r -= per_tile;
+                tile++;
+            }
+            auto load_words = [&](u64 tl, u32 ks, u32 k, u32 (&w)[12]) {
+                const u32 nw = ((mt_pack >> (4 * k)) & 15u) * 4;
+                const u32 *base = pl.bits[k] + ((size_t)tl * (pl.G[k] >> 5) + g0w) * PL_TILE + ks * 32 + lane;
 #pragma unroll
-                for (u32 j = 0; j < 12; j++) cur[j] = nxt[j];
+                for (u32 j = 0; j < 12; j++) w[j] = (j < nw) ? __ldg(base + (size_t)j * PL_TILE) : 0u;
+            };
+            // L2 prefetch two tiles ahead: per level the group's plane words (mt x 2 KB) and the digit rows of the tile's 128
+            // cells (18 KB) are contiguous; each producer warp pulls its share when it first touches a tile
+            auto prefetch_tile = [&](u64 tl) {
+                if (tl >= t_end) return;
+                for (u32 kk = 0; kk < nlev; kk++) {
+                    const u32 alines = ((mt_pack >> (4 * kk)) & 15u) * 16;  // 128-byte lines of A words
+                    const u32 line = p * 32 + lane;                          // 0..255: A lines first, then the 144 B lines
+                    if (line < alines) prefetch_l2(pl.bits[kk] + ((size_t)tl * (pl.G[kk] >> 5) + g0w) * PL_TILE + line * 32);
+                    else if (line - alines < 144) prefetch_l2(Bn + ((size_t)kk * (n_pad / 8) + tl * (PL_TILE / 8)) * PN_CELLGRP_BYTES + (size_t)(line - alines) * 128);
+                }
+            };
+            bool live = tile < t_end;
+            u32 ks = r & 3u, k = r >> 2;
+            if (live) {
+                prefetch_tile(tile + 1);
+                prefetch_tile(tile + 2);
+                load_words(tile, ks, k, cur);
+            }
+            while (live) {
+                u64 ntile = tile;
+                u32 nr = r + PL_PROD_WARPS;
+                while (nr >= per_tile) {
+                    nr -= per_tile;
+                    ntile++;
+                }
+                const bool more = ntile < t_end;
+                const u32 nks = nr & 3u, nk = nr >> 2;
+                if (more) load_words(ntile, nks, nk, nxt);
+                if (ntile != tile) prefetch_tile(ntile + 2);
+                // B rows of these 32 cells at level k (contiguous 4,608 bytes in Bn)
+                const uint4 *bsrc = reinterpret_cast<const uint4 *>(Bn + ((size_t)k * (n_pad / 8) + (tile * PL_TILE + ks * 32) / 8) * PN_CELLGRP_BYTES);
+                uint4 bv[PN_B_BYTES / 16 / 32];
+#pragma unroll
+                for (u32 t = 0; t < PN_B_BYTES / 16 / 32; t++) bv[t] = __ldg(bsrc + lane + 32 * t);
+                const u32 nw = ((mt_pack >> (4 * k)) & 15u) * 4;
+                const u32 sgq = Q / PN_SUB, slot = sgq % PN_NSTG, sub = Q % PN_NSTAGES;  // stage, its ring slot, my sub-slot (= slot * 4 + ks)
+                if (sgq >= PN_NSTG) mbar_wait(empty0 + 8 * slot, (sgq / PN_NSTG - 1) & 1u);
+                const u32 st = sS_addr + sub * PN_STAGE_BYTES;
+#pragma unroll
+                for (u32 j = 0; j < 12; j++) {
+                    if (j < nw) {
+                        uint4 lo, hi;
+                        expand_bits32(cur[j], lo, hi);
+                        const u32 a0 = st + (j >> 2) * 4096 + (2 * (j & 3)) * 512 + lane * 16;
+                        st_shared_v4(a0, lo);
+                        st_shared_v4(a0 + 512, hi);
+                    }
+                }
+#pragma unroll
+                for (u32 t = 0; t < PN_B_BYTES / 16 / 32; t++) st_shared_v4(st + PN_A_BYTES + (lane + 32 * t) * 16, bv[t]);
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full0 + 8 * slot);
+                Q += PL_PROD_WARPS;
+                tile = ntile;
+                r = nr;
+                ks = nks;
+                k = nk;
+                live = more;
+                if (more) {
+#pragma unroll
+                    for (u32 j = 0; j < 12; j++) cur[j] = nxt[j];
+                }
             }
         }
+        Q0 += (u32)(t_end - t_begin) * PN_SUB * nlev;
+        fence_before_sync();
+        __syncthreads();  // item boundary: the epilogue has read the accumulators, every stage was consumed, next item id visible
+        fence_after_sync();
     }
     fence_before_sync();
     __syncthreads();
@@ -919,17 +1024,20 @@ int planes_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo) 
     if (!pl.active || mt->n == 0 || w == 0) return SB_OK;
     const u32 G1 = pl.G[0];
     const u32 nranges = (G1 + PT_RANGE - 1) / PT_RANGE;
+    const u64 n_pad = pl.ntiles * PL_TILE;
     DevBuf<unsigned long long> colmax;
     DevBuf<signed char> Bd;
-    DevBuf<double> scale2;
+    DevBuf<double> scale2, part;
     DevBuf<int> ex;
     SB_TRY(colmax.alloc(PL_COLS));
     SB_TRY(Bd.alloc((size_t)nranges * PT_B_BYTES));
+    SB_TRY(part.alloc((size_t)pl.n_units_t * n_pad * PL_COLS));
     const double *rs = a->has_row_scale ? a->row_scale.p : nullptr;
     const size_t smem = (size_t)PT_B_BYTES + PT_NSTAGES * PT_STAGE_BYTES + sizeof(PtShared);
     cudaError_t e = cudaFuncSetAttribute(k_planes_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return sb_fail(SB_ERR_CUDA, "planes_t: %zu B of shared memory: %s", smem, cudaGetErrorString(e));
     const u32 items = G1 * PL_COLS;
+    const unsigned rblocks = (unsigned)std::max<u64>(1, std::min<u64>((mt->n * (PL_COLS / 2) + 255) / 256, (u64)ctx->sm_count * 16));
     for (u32 col0 = 0; col0 < w; col0 += PL_COLS) {
         const u32 wt = std::min(PL_COLS, w - col0);
         SB_CUDA(cudaMemsetAsync(colmax.p, 0, PL_COLS * sizeof(unsigned long long), ctx->stream));
@@ -938,10 +1046,11 @@ int planes_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo) 
         SB_TRY(scales_from_colmax(ctx, colmax, scale2, ex));
         k_pl_digits_t<<<cdiv(items, 256), 256, 0, ctx->stream>>>(Y, ldy, mt->hot_idx.p, rs, G1, col0, wt, ex.p, Bd.p);
         SB_CUDA(cudaMemsetAsync(pl.counter.p, 0, sizeof(u32), ctx->stream));
-        k_planes_t<<<pl.t_grid, PL_THREADS, smem, ctx->stream>>>(make_pldev(mt), (const PlUnitT *)pl.units_t.p, (const PlItem *)pl.items_t.p,
-                                                                 pl.n_items_t, pl.counter.p, Bd.p, scale2.p, a->col_scale.p, a->log_base, col0, wt,
-                                                                 out, ldo);
-        count_launch(ctx); count_launch(ctx); count_launch(ctx);
+        k_planes_t<<<pl.t_grid, PT_THREADS, smem, ctx->stream>>>(make_pldev(mt), (const PlUnitT *)pl.units_t.p, (const PlItem *)pl.items_t.p,
+                                                                 pl.n_items_t, pl.counter.p, Bd.p, scale2.p, a->col_scale.p, a->log_base, wt, part.p,
+                                                                 (u32)ctx->pl_debug);
+        k_pl_reduce_t<<<rblocks, 256, 0, ctx->stream>>>(part.p, pl.n_units_t, mt->n, n_pad, col0, wt, out, ldo);
+        count_launch(ctx); count_launch(ctx); count_launch(ctx); count_launch(ctx);
     }
     SB_CUDA(cudaGetLastError());
     return SB_OK;
@@ -969,8 +1078,10 @@ static int planes_n_impl(sb_nmat *a, const double *X, u32 ldx, u32 w, int mode, 
         k_pl_colmax_n<<<cm_blocks, 256, 0, ctx->stream>>>(X, ldx, mt->n, a->col_scale.p, a->log_base, pl.L, col0, wt, mode, colmax.p);
         SB_TRY(scales_from_colmax(ctx, colmax, scale2, ex));
         k_pl_digits_n<<<cdiv(n_pad * pl.L, 128), 128, 0, ctx->stream>>>(X, ldx, mt->n, n_pad, a->col_scale.p, a->log_base, pl.L, col0, wt, mode, ex.p, Bn.p);
-        k_planes_n<<<pl.n_grid, PL_THREADS, smem, ctx->stream>>>(make_pldev(mt), (const PlUnitN *)pl.units_n.p, pl.n_units_n, Bn.p, n_pad, scale2.p,
-                                                                 mt->hot_idx.p, col0, wt, out, row_stride, col_stride);
+        SB_CUDA(cudaMemsetAsync(pl.counter.p, 0, sizeof(u32), ctx->stream));
+        k_planes_n<<<pl.n_grid, PL_THREADS, smem, ctx->stream>>>(make_pldev(mt), (const PlUnitN *)pl.units_n.p, (const PlItem *)pl.items_n.p,
+                                                                 pl.n_items_n, pl.counter.p, Bn.p, n_pad, scale2.p, mt->hot_idx.p, col0, wt, out,
+                                                                 row_stride, col_stride);
         count_launch(ctx); count_launch(ctx); count_launch(ctx);
     }
     SB_CUDA(cudaGetLastError());

@@ -35,6 +35,23 @@ __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t da, uint64_t db
         : "memory");
 }
 
+// One lane of a converged warp (elect.sync).  The tcgen05 issue loops run warp-uniformly and predicate only the tensor-core
+// instructions with this: inside `if (lane == 0)` the compiler cannot keep the operands in uniform registers and wraps every
+// UTCIMMA in an ELECT / R2UR.BROADCAST loop (measured: 155-240 instructions per stage instead of ~25).
+__device__ __forceinline__ bool elect_one(uint32_t &leader) {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred px;\n\t"
+        "elect.sync %1|px, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t}\n"
+        : "=r"(pred), "=r"(leader));
+    return pred != 0;
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t leader;
+    return elect_one(leader);
+}
+
 // arrives (count 1) on the mbarrier once every tcgen05.mma issued so far by this thread has completed
 __device__ __forceinline__ void commit(uint32_t mbar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
@@ -57,6 +74,31 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
         "TC05_DONE_%=:\n\t}\n" ::"r"(mbar),
         "r"(parity)
         : "memory");
+}
+
+// tight poll (test_wait never suspends): for the one thread whose reaction time paces the tensor pipe
+__device__ __forceinline__ void mbar_spin(uint32_t mbar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done)
+                     : "r"(mbar), "r"(parity)
+                     : "memory");
+}
+
+// long waits (an epilogue waiting for a whole CTA's worth of MMAs): back off so the spinning warps leave the issue slots alone
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t mbar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(mbar), "r"(parity)
+            : "memory");
+        if (!done) __nanosleep(500);
+    }
 }
 
 // generic-proxy shared-memory writes -> visible to the tensor core (async proxy)
@@ -93,6 +135,8 @@ __device__ __forceinline__ void expand_bits32(uint32_t w, uint4 &lo, uint4 &hi) 
     hi.z = (((w >> 24) & 0xFu) * 0x00204081u) & 0x01010101u;
     hi.w = ((w >> 28) * 0x00204081u) & 0x01010101u;
 }
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ void st_shared_v4(uint32_t saddr, const uint4 &v) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
