@@ -177,6 +177,10 @@ SB_API int sb_nmat_to_dense(sb_nmat *a, double *out);
 SB_API int sb_nmat_dot(sb_nmat *a, const double *x, uint32_t w, double *out);
 /* Array2 . LowRankOffset (low_rank_offset.rs:83-96): out[w x n_local] = b[w x m] . A */
 SB_API int sb_nmat_rdot(sb_nmat *a, const double *b, uint32_t w, double *out);
+/* Squared Frobenius norm of the normalized matrix (offset included): the denominator of the DERIVED "variance explained"
+ * sigma_i^2 / ||A||_F^2.  Not part of the reference's result (PcaResult is (u, d, v), dim_red/mod.rs:47); north_star names it,
+ * so it is offered as a labelled convenience.  Log-chain normalizations only (SB_ERR_UNSUPPORTED otherwise). */
+SB_API int sb_nmat_frobenius_sq(sb_nmat *a, double *out);
 SB_API void sb_free_nmat(sb_nmat *a);
 
 /* ---------------------------------------------------------------- PCA
@@ -193,12 +197,25 @@ SB_API int sb_bksvd(sb_nmat *a, uint32_t k, uint32_t b, uint32_t n_iter, uint64_
 /* BkSvd::run_pca_cancellable (bk_svd.rs:48-52): b = ceil(k * k_multiplier), seed 0 */
 SB_API int sb_bksvd_run_pca(sb_nmat *a, uint32_t k, double k_multiplier, uint32_t n_iter, sb_progress_cb cb,
                      void *user, double *U, double *S, double *V);
+/* Diagnostics of the last sb_bksvd on this context: the condition estimate of the Krylov basis' triangular factor that gated the
+ * projection identity (0 when the direct pass ran unconditionally), the a-posteriori probe residual in units of sigma_1 (0 when
+ * no check ran) and how many fallbacks (Householder QR after a CholeskyQR breakdown, direct pass after a failed check) were taken. */
+SB_API int sb_pca_diagnostics(sb_ctx *ctx, double *cond_r, double *probe_resid, int *fallbacks);
 /* svd_rand (scan-rs/src/dim_red/rand_svd.rs:54-129); omega: (l x m) when n > m, (n_local x l) when m >= n */
 SB_API int sb_randsvd(sb_nmat *a, uint32_t k, uint32_t l, uint32_t n_iter, uint64_t seed, const double *omega,
                double *U, double *S, double *V);
 /* RandSvd::run_pca_cancellable (rand_svd.rs:44-49): l = max(k + 4, floor(k * l_multiplier)), seed 0 */
 SB_API int sb_randsvd_run_pca(sb_nmat *a, uint32_t k, double l_multiplier, uint32_t n_iter, double *U, double *S,
                        double *V);
+
+/* ---------------------------------------------------------------- kNN on the scores (next step of the pipeline)
+ * knn / find_nn (scan-rs/src/nn.rs:38-83): for every query row (n_queries x dim, row-major) the indices of its k nearest points
+ * (n_points x dim) in Euclidean distance, nearest first, into out[n_queries x k]; rows with fewer than k candidates are padded
+ * with 0xFFFFFFFF (the reference pads with T::max_value(), nn.rs:67).  include_self = 0 skips the point with index
+ * self_offset + row (knn() queries the tree with its own points; self_offset serves cell-sharded callers).  Among exactly
+ * equidistant points the lower index comes first. */
+SB_API int sb_knn(sb_ctx *ctx, const double *points, uint64_t n_points, uint32_t dim, const double *queries, uint64_t n_queries,
+           uint32_t k, int include_self, uint64_t self_offset, uint32_t *out);
 
 /* ---------------------------------------------------------------- measurement
  * Device-side timing on the context's own stream (CUDA events) and per-kernel accounting;

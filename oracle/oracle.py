@@ -60,6 +60,12 @@ def lib():
     return _LIB
 
 
+def set_num_threads(n: int) -> int:
+    """Pin the OpenMP thread count of the threaded products (independent of OMP_NUM_THREADS); returns the count in effect."""
+    lib().orc_set_num_threads(C.c_int(int(n)))
+    return int(lib().orc_num_threads())
+
+
 def _p(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -626,3 +632,28 @@ def principal_angle_sin(u0: np.ndarray, u1: np.ndarray) -> float:
     q1, _ = np.linalg.qr(u1)
     r = q1 - q0.dot(q0.T.dot(q1))
     return float(np.linalg.norm(r, 2))
+
+
+# --------------------------------------------------------------------------------------
+# kNN on the scores: scan-rs/src/nn.rs:38-83.  The reference answers queries through a ball tree (third-party crate
+# `ball-tree`, git dependency in Cargo.lock); its result is the exact k nearest neighbours, which is what the reference's own
+# tests check against an exhaustive search (nn.rs:104-152).  This restates that exhaustive search with Pt::distance (nn.rs:12-20).
+def find_nn(v: np.ndarray, k: int, points: np.ndarray, include_self: bool, self_offset: int = 0) -> np.ndarray:
+    v = np.asarray(v, dtype=np.float64)
+    points = np.asarray(points, dtype=np.float64)
+    out = np.full((v.shape[0], k), 0xFFFFFFFF, dtype=np.uint32)
+    for i in range(v.shape[0]):
+        d = np.zeros(points.shape[0])
+        for j in range(points.shape[1]):  # sum in coordinate order, like the iterator chain in Pt::distance
+            d = d + (points[:, j] - v[i, j]) ** 2
+        d = np.sqrt(d)
+        order = np.argsort(d, kind="stable")  # ties: lower index first
+        if not include_self:
+            order = order[order != self_offset + i]
+        order = order[:k]
+        out[i, : len(order)] = order
+    return out
+
+
+def knn(v: np.ndarray, k: int) -> np.ndarray:
+    return find_nn(v, k, v, include_self=False)

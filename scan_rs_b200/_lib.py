@@ -45,9 +45,9 @@ SYMBOLS = [
     "sb_upload", "sb_upload_compact", "sb_mat_shape", "sb_download", "sb_free_mat", "sb_cell_totals", "sb_gene_totals", "sb_gene_nnz",
     "sb_median_cell_total", "sb_partition", "sb_select_rows", "sb_select_cols", "sb_hvg_select",
     "sb_normalize", "sb_log_normalize", "sb_normalize_fixed_point", "sb_nmat_params", "sb_nmat_to_dense",
-    "sb_nmat_dot", "sb_nmat_rdot", "sb_free_nmat", "sb_omega", "sb_bksvd", "sb_bksvd_run_pca", "sb_randsvd",
+    "sb_nmat_dot", "sb_nmat_rdot", "sb_nmat_frobenius_sq", "sb_free_nmat", "sb_omega", "sb_bksvd", "sb_bksvd_run_pca", "sb_pca_diagnostics", "sb_randsvd",
     "sb_randsvd_run_pca", "sb_profile_enable", "sb_profile_reset", "sb_profile_get", "sb_timer_begin",
-    "sb_timer_end", "sb_flush_l2", "sb_synth_generate",
+    "sb_timer_end", "sb_flush_l2", "sb_synth_generate", "sb_knn",
 ]
 
 _lib = None

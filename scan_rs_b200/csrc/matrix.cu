@@ -685,9 +685,32 @@ static void trace_pool(sb_ctx *ctx, const char *label) {
     fprintf(stderr, "[scanb200] pool %-22s reserved %7.2f GB used %7.2f GB\n", label, reserved / 1e9, used / 1e9);
 }
 
+// Every rank of a sharded context must take the same turn before the collectives of an upload (global shape, hot-gene counts):
+// a rank that rejected its own input would otherwise leave the others waiting inside them.
+static int agree_status(sb_ctx *ctx, int rc, const char *what) {
+    if (ctx->nranks == 1) return rc;
+    int worst = rc;
+    const std::string mine = rc != SB_OK ? sb_last_error() : "";
+    int rc2 = comm_allreduce_max_i32(ctx, &worst);
+    if (rc2 != SB_OK) return rc2;
+    if (rc != SB_OK) return sb_fail(rc, "%s", mine.c_str());
+    if (worst != SB_OK) return sb_fail(worst, "%s: rejected on another rank", what);
+    return SB_OK;
+}
+
+// O(nvec) host pass over the caller's pointer array: starts at 0, never decreases, ends at nnz.  The pipelined upload takes its
+// copy extents from it, so it is checked before anything is copied or launched.
+static int validate_indptr_host(const u64 *indptr, u64 nvec) {
+    if (indptr[0] != 0) return sb_fail(SB_ERR_INVALID_ARG, "sb_upload: indptr is not monotone from 0");
+    for (u64 i = 0; i < nvec; i++)
+        if (indptr[i + 1] < indptr[i]) return sb_fail(SB_ERR_INVALID_ARG, "sb_upload: indptr is not monotone from 0 (at %llu)", (unsigned long long)i);
+    return SB_OK;
+}
+
 static int upload_impl(sb_ctx *ctx, int major, uint32_t m, uint64_t n_local, const uint64_t *indptr, const HostEntries &he, sb_mat **out) {
     *out = nullptr;
     SB_ENTER(ctx);
+    SB_TRY(agree_status(ctx, validate_indptr_host(indptr, major == SB_GENE_MAJOR ? (u64)m : n_local), "sb_upload"));
     trace_pool(ctx, "at upload start");
     SyncScope tr_total(ctx, "upload: whole call");
     u64 nvec = major == SB_GENE_MAJOR ? m : n_local;

@@ -127,6 +127,39 @@ static int moments(sb_nmat *a, double *S /* 2m */) {
     return SB_OK;
 }
 
+// sum_g ( rs_g^2 S2_g + 2 u_g rs_g S1_g + n u_g^2 ): the squared Frobenius norm of S + u 1^T from the gene moments
+__global__ void k_frob_from_moments(const double *__restrict__ S1, const double *__restrict__ S2, const double *__restrict__ rs,
+                                    const double *__restrict__ u, u32 m, double n, double *__restrict__ out) {
+    double acc = 0.0;
+    for (u32 g = blockIdx.x * blockDim.x + threadIdx.x; g < m; g += gridDim.x * blockDim.x) {
+        const double r = rs ? rs[g] : 1.0, ug = u ? u[g] : 0.0;
+        acc += r * r * S2[g] + 2.0 * ug * r * S1[g] + n * ug * ug;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
+extern "C" int sb_nmat_frobenius_sq(sb_nmat *a, double *out) {
+    if (!a || !out) return sb_fail(SB_ERR_INVALID_ARG, "sb_nmat_frobenius_sq: NULL argument");
+    sb_mat *mt = a->mat;
+    sb_ctx *ctx = mt->ctx;
+    SB_ENTER(ctx);
+    if (a->kind != 1 || !a->v_ones) return sb_fail(SB_ERR_UNSUPPORTED, "sb_nmat_frobenius_sq: log-chain normalizations only");
+    DevBuf<double> S, acc;
+    SB_TRY(S.alloc(2 * (size_t)mt->m + 1));
+    SB_TRY(acc.alloc(1));
+    SB_TRY(moments(a, S.p));  // all-reduced over ranks
+    SB_CUDA(cudaMemsetAsync(acc.p, 0, sizeof(double), ctx->stream));
+    if (mt->m) {
+        k_frob_from_moments<<<cdiv(mt->m, 256), 256, 0, ctx->stream>>>(S.p, S.p + mt->m, a->has_row_scale ? a->row_scale.p : nullptr,
+                                                                       a->has_offset ? a->u.p : nullptr, mt->m, (double)mt->n_global, acc.p);
+        count_launch(ctx);
+    }
+    SB_CUDA(cudaMemcpyAsync(out, acc.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+
 extern "C" int sb_log_normalize(sb_mat *mat, int has_target, double target, int log_base, const uint32_t *size_factors,
                                 int center_scale, const double *sd_override, sb_nmat **out) {
     if (!mat || !out) return sb_fail(SB_ERR_INVALID_ARG, "sb_log_normalize: NULL argument");

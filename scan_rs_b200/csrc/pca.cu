@@ -532,6 +532,14 @@ extern "C" int sb_bksvd(sb_nmat *a, uint32_t k, uint32_t b, uint32_t n_iter, uin
     return sb_fail(SB_ERR_LINALG, "sb_bksvd: no stable path");
 }
 
+extern "C" int sb_pca_diagnostics(sb_ctx *ctx, double *cond_r, double *probe_resid, int *fallbacks) {
+    if (!ctx) return sb_fail(SB_ERR_INVALID_ARG, "sb_pca_diagnostics: ctx is NULL");
+    if (cond_r) *cond_r = ctx->last_cond_r;
+    if (probe_resid) *probe_resid = ctx->last_probe_resid;
+    if (fallbacks) *fallbacks = ctx->last_fallbacks;
+    return SB_OK;
+}
+
 extern "C" int sb_bksvd_run_pca(sb_nmat *a, uint32_t k, double k_multiplier, uint32_t n_iter, sb_progress_cb cb, void *user, double *U, double *S,
                                 double *V) {
     u32 bsize = (u32)std::ceil((double)k * k_multiplier);  // bk_svd.rs:49

@@ -28,6 +28,12 @@ def _outputs(m, n, k, out=None):
     return U, S, V
 
 
+def variance_explained(array: LowRankOffset, s) -> np.ndarray:
+    """DERIVED output, not part of the reference's PcaResult (dim_red/mod.rs:47 returns (u, d, v) only): the fraction of the
+    normalized matrix's squared Frobenius norm carried by each singular value, sigma_i^2 / ||A||_F^2."""
+    return np.asarray(s, dtype=np.float64) ** 2 / array.frobenius_sq()
+
+
 def omega(seed: int, rows: int, cols: int) -> np.ndarray:
     """The start block: SmallRng::seed_from_u64(seed) + Uniform(-1, 1), row-major (bk_svd.rs:83-84)."""
     out = np.zeros((rows, cols))

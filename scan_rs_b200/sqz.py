@@ -59,6 +59,13 @@ class Context:
     def profile_reset(self):
         L.check(L.lib().sb_profile_reset(self._h))
 
+    def pca_diagnostics(self) -> dict:
+        """Of the last BkSvd on this context: condition estimate of the Krylov basis' R, probe residual of the projection
+        identity (units of sigma_1) and the number of fallbacks taken (include/scanb200.h: sb_pca_diagnostics)."""
+        cond, resid, fb = C.c_double(), C.c_double(), C.c_int()
+        L.check(L.lib().sb_pca_diagnostics(self._h, C.byref(cond), C.byref(resid), C.byref(fb)))
+        return {"cond_r": cond.value, "probe_resid": resid.value, "fallbacks": fb.value}
+
     def profile(self) -> dict:
         p = L.SbProfile()
         L.check(L.lib().sb_profile_get(self._h, C.byref(p)))
@@ -321,6 +328,12 @@ class LowRankOffset:
         out = np.zeros((m, rhs.shape[1]))
         L.check(L.lib().sb_nmat_dot(self._h, L.vp(rhs), C.c_uint32(rhs.shape[1]), L.vp(out)))
         return out
+
+    def frobenius_sq(self) -> float:
+        """||A||_F^2 of the normalized matrix, offset included (derived quantity, not in the reference)."""
+        out = C.c_double()
+        L.check(L.lib().sb_nmat_frobenius_sq(self._h, C.byref(out)))
+        return out.value
 
     def rdot(self, lhs: np.ndarray) -> np.ndarray:  # low_rank_offset.rs:83-96: lhs . A
         lhs = np.ascontiguousarray(lhs, dtype=np.float64)

@@ -359,19 +359,19 @@ def test_panelled_gather_matches_first_generation_kernels(ctx, n_cells, n_genes,
         assert np.abs(got[0][1] - got[1][1]).max() <= 1e-11 * np.abs(ref_t).max()
 
 
-@pytest.mark.skipif(__import__("os").environ.get("SCANB200_TEST_EXPERIMENTAL") != "1",
-                    reason="experimental tcgen05 int8 panel kernel (csrc/panel_i8.cu): default off, not yet validated on hardware; "
-                           "set SCANB200_TEST_EXPERIMENTAL=1 to run")
-def test_experimental_int8_panel_matches_fp64_panel(ctx):
-    """T-side dense panel on the integer tensor cores (option panel_i8) against the FP64 mma.sync panel and the oracle,
-    on a panel restricted to counts 1..3 (option dense_max_count)."""
+def test_int8_draft_panel_matches_fp64_panel(ctx):
+    """Round 1's draft of the T-side panel on the integer tensor cores (csrc/panel_i8.cu, option panel_i8 over the u8 panel of
+    panel_mode 1 restricted to counts 1..3): first run on hardware in round 2, agrees with the FP64 mma.sync panel and the
+    oracle.  Superseded by the bit-plane kernels (csrc/planes.cu, panel_mode 2, the default); kept as the validated reference point."""
     n_cells, n_genes = 6000, 33538
-    cfg, cm, _, (ip, g, c) = synth_pair(ctx, n_cells, n_genes, seed=44)
     try:
+        ctx.set_option("panel_mode", 1)
         ctx.set_option("dense_max_count", 3)
+        cfg, cm, _, (ip, g, c) = synth_pair(ctx, n_cells, n_genes, seed=44)
         dm = sb.AdaptiveMat.from_csc(ctx, n_genes, n_cells, ip, g, c)
     finally:
         ctx.set_option("dense_max_count", 15)
+        ctx.set_option("panel_mode", 2)
     a_o, a_g = orc.normalize(cm, orc.CELLRANGER), sb.normalize(dm, sb.Normalization.CellRanger)
     rng = np.random.default_rng(8)
     for w in (20, 7):
@@ -387,6 +387,157 @@ def test_experimental_int8_panel_matches_fp64_panel(ctx):
             assert np.abs(got[on] - ref).max() <= 1e-10 * np.abs(ref).max(), (on, w)
         assert np.abs(got[0] - got[1]).max() <= 1e-11 * np.abs(ref).max()
         assert np.abs(got[0] - got[1]).max() > 0.0  # the two paths really are different kernels
+
+
+@pytest.mark.parametrize("n_cells,n_genes,kw", [(3000, 2500, dict(n_dense=40, dense_mean=40.0)), (6000, 33538, {}), (1000, 200, {}),
+                                                 (130, 400, {}), (20000, 9000, dict(depth=6000.0))])
+def test_plane_kernels_match_oracle_and_other_layouts(ctx, n_cells, n_genes, kw):
+    """The three layouts of the dense half -- none (pure sparse gather), u8 panel on the FP64 mma.sync path, bit planes on the
+    tcgen05 int8 path (default) -- give the same normalization parameters and products, and all match the oracle: widths with
+    one, partial and several column passes; a ragged last cell tile; matrices with one to six count levels."""
+    cfg, cm, _, (ip, g, c) = synth_pair(ctx, n_cells, n_genes, seed=37, **kw)
+    a_o = orc.normalize(cm, orc.CELLRANGER)
+    ref_p = (a_o.mat.spec.col_scale, a_o.mat.spec.row_scale, a_o.u.ravel(), a_o.v.ravel())
+    rng = np.random.default_rng(5)
+    xs = {w: rng.standard_normal((n_cells, w)) for w in (20, 7, 45)}
+    ys = {w: rng.standard_normal((w, n_genes)) for w in (20, 7, 45)}
+    ref_n = {w: a_o.dot(xs[w]) for w in xs}
+    ref_t = {w: a_o.rdot(ys[w]) for w in ys}
+    got = {}
+    for mode in (0, 1, 2):
+        try:
+            ctx.set_option("panel_mode", mode)
+            dm = sb.AdaptiveMat.from_csc(ctx, n_genes, n_cells, ip, g, c)
+        finally:
+            ctx.set_option("panel_mode", 2)
+        a = sb.normalize(dm, sb.Normalization.CellRanger)
+        for p_g, p_o in zip(a.params(), ref_p):
+            np.testing.assert_allclose(p_g, p_o, rtol=1e-9, atol=1e-12)
+        got[mode] = a.params()
+        for w in xs:
+            assert np.abs(a.dot(xs[w]) - ref_n[w]).max() <= 1e-10 * np.abs(ref_n[w]).max(), (mode, w)
+            assert np.abs(a.rdot(ys[w]) - ref_t[w]).max() <= 1e-10 * np.abs(ref_t[w]).max(), (mode, w)
+        a.free()
+        dm.free()
+    for p2, p0 in zip(got[2], got[0]):
+        np.testing.assert_allclose(p2, p0, rtol=1e-11, atol=1e-13)
+
+
+@pytest.mark.parametrize("norm", [sb.Normalization.SeuratLog, sb.Normalization.CellRanger8, sb.Normalization.LogTransform])
+def test_plane_kernels_other_log_chains(ctx, norm):
+    """ln / no row scale / unit size factors through the plane kernels (the level values L_c(k) change, the planes do not)."""
+    cfg, cm, dm, _ = synth_pair(ctx, 5000, 6000, seed=51)
+    a_o, a_g = orc.normalize_with_size_factor(cm, NORMS[norm], None), sb.normalize_with_size_factor(dm, norm, None)
+    rng = np.random.default_rng(6)
+    x, y = rng.standard_normal((5000, 20)), rng.standard_normal((20, 6000))
+    rn, rt = a_o.dot(x), a_o.rdot(y)
+    assert np.abs(a_g.dot(x) - rn).max() <= 1e-10 * np.abs(rn).max()
+    assert np.abs(a_g.rdot(y) - rt).max() <= 1e-10 * np.abs(rt).max()
+
+
+@pytest.mark.parametrize("n_cells,n_genes,k,kw", [(20000, 3000, 30, {}), (12000, 3000, 50, {}), (8000, 2400, 100, {}),
+                                                   (9000, 2600, 30, dict(n_dense=200, dense_mean=300.0, sigma_g=3.0))])
+def test_bksvd_larger_k_matches_oracle(ctx, n_cells, n_genes, k, kw):
+    """BASELINE configs 2, 4, 5 in shape: k = 30 / 50 / 100 (b = 200, b.q = 1000 <= m: the R^-T identity and cond(K) at their
+    hardest) and a matrix with 200 dense antibody-like features whose counts are far above 255 -- against the oracle, with the
+    projection identity (default), with the direct wide pass, and with the identity forced through its a-posteriori check."""
+    cfg, cm, dm, _ = synth_pair(ctx, n_cells, n_genes, seed=61, **kw)
+    a_o, a_g = orc.normalize(cm, orc.CELLRANGER), sb.normalize(dm, sb.Normalization.CellRanger)
+    res_o = orc.BkSvd().run_pca(a_o, k, threads=True)
+    check_pca_parity(sb.BkSvd().run_pca(a_g, k), res_o)
+    try:
+        ctx.set_option("direct_projection", 1)
+        check_pca_parity(sb.BkSvd().run_pca(a_g, k), res_o)
+    finally:
+        ctx.set_option("direct_projection", 0)
+    try:
+        ctx.set_option("verify_projection", 1)
+        check_pca_parity(sb.BkSvd().run_pca(a_g, k), res_o)
+        d = ctx.pca_diagnostics()
+        assert d["cond_r"] > 1.0 and d["probe_resid"] <= 1e-8
+    finally:
+        ctx.set_option("verify_projection", 0)
+    try:  # the cuSOLVER Householder / cuBLAS path (own_dense = 0) stays a valid alternative
+        ctx.set_option("own_dense", 0)
+        check_pca_parity(sb.BkSvd().run_pca(a_g, k), res_o)
+    finally:
+        ctx.set_option("own_dense", 1)
+
+
+def test_projection_guard_falls_back_on_ill_conditioned_krylov_basis(ctx):
+    """A matrix of numerical rank far below b.q makes the Krylov basis K (numerically) rank deficient: CholeskyQR breaks down
+    (device flag -> the Householder path reruns) and cond(R) is past every threshold, so the projection runs as the reference's
+    direct wide pass.  The result still matches the oracle on the well-determined triplets."""
+    rng = np.random.default_rng(3)
+    n_cells, n_genes, rank = 4000, 600, 6
+    base = rng.poisson(0.4, size=(n_genes, rank)).astype(np.uint32)
+    mix = rng.integers(0, 3, size=(rank, n_cells)).astype(np.uint32)
+    dense = (base @ mix).astype(np.uint32)
+    dense[0, :] += 1  # no empty cells
+    cm = orc.CountMatrix.from_dense(dense)
+    dm = sb.AdaptiveMat.from_dense(ctx, dense)
+    a_o = orc.normalize_with_size_factor(cm, orc.LOG_TRANSFORM, None)
+    a_g = sb.normalize_with_size_factor(dm, sb.Normalization.LogTransform, None)
+    k = 4
+    u, s, v = sb.BkSvd().run_pca(a_g, k)
+    uo, so, vo = orc.BkSvd().run_pca(a_o, k)
+    d = ctx.pca_diagnostics()
+    assert d["fallbacks"] >= 1 or d["cond_r"] > 1e9, d
+    assert np.abs(s - so).max() / so.max() < 1e-6
+    assert np.isfinite(u).all() and np.isfinite(v).all()
+    for i in range(k):  # triplet identities hold whatever path ran
+        assert np.abs(a_g.rdot(u[:, i][None, :]).ravel() - s[i] * v[:, i]).max() <= 1e-8 * s[0]
+
+
+def test_pca_run_to_run_drift_is_bounded(ctx):
+    """f64 reductions (RED.ADD.F64 in the gather, atomics in the plane epilogues) are order-nondeterministic: two runs on the same
+    input may differ in the last bits.  The amplified drift must stay far inside the parity bars (sigma 1e-6, angle 1e-5)."""
+    cfg, cm, dm, _ = synth_pair(ctx, 30000, 5000, seed=71)
+    a = sb.normalize(dm, sb.Normalization.CellRanger)
+    u1, s1, v1 = (np.array(x) for x in sb.BkSvd().run_pca(a, 10))
+    u2, s2, v2 = (np.array(x) for x in sb.BkSvd().run_pca(a, 10))
+    assert np.abs(s1 - s2).max() / s1.max() < 1e-9
+    assert orc.principal_angle_sin(u1, u2) < 1e-7 and orc.principal_angle_sin(v1, v2) < 1e-7
+
+
+def test_select_rows_clones_duplicates_in_any_order(ctx):  # sqz/src/mat.rs:1040-1046
+    cfg, cm, dm, _ = synth_pair(ctx, 700, 900, seed=9, depth=60.0)
+    for rows in ([5, 5, 3, 899, 3, 0], [10, 9, 8], [2, 2, 2]):
+        s_o, s_g = cm.select_rows(rows), dm.select_rows(rows)
+        assert s_g.rows() == len(rows)
+        for a, b in zip(s_g.to_csr(), (s_o.indptr, s_o.idx, s_o.val)):
+            np.testing.assert_array_equal(a, b)
+        np.testing.assert_array_equal(s_g.sum_axis_u32(0), s_o.sum_axis_u32(0))
+
+
+def test_pipelined_upload_rejects_malformed_indptr(ctx):
+    """The pipelined upload takes its copy extents from the caller's indptr: a non-monotone or overshooting pointer array must be
+    refused on the host before any copy or kernel uses it."""
+    cfg, cm, dm, (ip, g, c) = synth_pair(ctx, 20000, 3000, seed=38)
+    assert len(g) >= (1 << 22)  # large enough for the pipelined path
+    for bad_at, bad_val in ((7000, int(ip[-1]) + 10), (12000, 0)):
+        ip2 = ip.copy()
+        ip2[bad_at] = bad_val
+        with pytest.raises(sb.ScanError) as e:
+            sb.AdaptiveMat.from_csc(ctx, 3000, 20000, ip2, g, c)
+        assert "indptr" in str(e.value)
+    ip3 = ip.copy()
+    ip3[0] = 1
+    with pytest.raises(sb.ScanError):
+        sb.AdaptiveMat.from_csc(ctx, 3000, 20000, ip3, g, c)
+    sb.AdaptiveMat.from_csc(ctx, 3000, 20000, ip, g, c).free()  # the context stays usable
+
+
+def test_variance_explained_is_a_labelled_derived_output(ctx):
+    """north_star mentions 'variance explained'; the reference returns (u, d, v) only.  The derived field: sigma_i^2 over
+    the squared Frobenius norm of the normalized matrix (computed on the device from the same map)."""
+    cfg, cm, dm, _ = synth_pair(ctx, 2500, 800, seed=12)
+    a_o, a_g = orc.normalize(cm, orc.CELLRANGER), sb.normalize(dm, sb.Normalization.CellRanger)
+    u, s, v = sb.BkSvd().run_pca(a_g, 10)
+    ve = sb.variance_explained(a_g, s)
+    dense = a_o.to_dense()
+    np.testing.assert_allclose(ve, np.array(s) ** 2 / (dense ** 2).sum(), rtol=1e-9)
+    assert 0.0 < ve.sum() < 1.0 and np.all(np.diff(ve) <= 0)
 
 
 @pytest.mark.skipif(__import__("os").environ.get("SCANB200_TEST_EXPERIMENTAL") != "1",
@@ -597,3 +748,45 @@ def test_load_mtx(ctx, tmp_path):
     lm = load_mtx(ctx, str(path))
     for a, b in zip(lm.to_csr(), dm.to_csr()):
         np.testing.assert_array_equal(a, b)
+
+
+# ------------------------------------------------------------------ kNN on the scores (scan-rs/src/nn.rs)
+def test_find_nn_reference_case(ctx):  # nn.rs:170-196
+    all_pts = np.array([[float(i), float(i)] for i in range(10)])
+    ball = all_pts[[1, 3, 4, 7]]
+    out = sb.find_nn(ctx, all_pts, 1, ball, include_self=True)
+    np.testing.assert_array_equal(out.ravel(), [0, 0, 0, 1, 2, 2, 3, 3, 3, 3])
+    np.testing.assert_array_equal(out, orc.find_nn(all_pts, 1, ball, True))
+
+
+@pytest.mark.parametrize("ncells", [3, 5, 50, 100, 1000])
+@pytest.mark.parametrize("d", [1, 2, 3, 5, 10, 20, 50])
+def test_knn_matches_exhaustive_search(ctx, ncells, d):  # nn.rs:154-167 (validate_knn: k = cells - 1 up to 5 neighbours)
+    v = np.random.default_rng(ncells * 100 + d).standard_normal((ncells, d))
+    k = min(ncells - 1, 5)
+    np.testing.assert_array_equal(sb.knn(ctx, v, k), orc.knn(v, k))
+
+
+def test_knn_symmetry_case_as_sets(ctx):  # nn.rs:198-211: equidistant points -- the reference's order there is the ball tree's
+    v = np.eye(5)
+    v[0, 4] = 3.0
+    got = sb.knn(ctx, v, 4)
+    correct = np.array([[4, 2, 1, 3], [4, 2, 3, 0], [4, 1, 3, 0], [4, 1, 2, 0], [2, 1, 3, 0]])
+    for r in range(5):
+        assert set(got[r]) == set(correct[r])
+    # where distances differ the order is the reference's: the outlier (row 0) is everyone's farthest, row 4's nearest are 1..3
+    assert all(got[r][-1] == 0 for r in range(1, 5))
+    np.testing.assert_array_equal(got, orc.knn(v, 4))
+
+
+def test_knn_on_pca_scores_with_padding_and_offset(ctx):
+    cfg, cm, dm, _ = synth_pair(ctx, 3000, 900, seed=21)
+    u, s, v = sb.BkSvd().run_pca(sb.normalize(dm, sb.Normalization.CellRanger), 10)
+    scores = np.array(v) * np.array(s)
+    np.testing.assert_array_equal(sb.knn(ctx, scores, 15), orc.knn(scores, 15))
+    # a cell shard queries the full point set: its own rows are excluded through the offset
+    np.testing.assert_array_equal(sb.find_nn(ctx, scores[1000:1200], 7, scores, False, self_offset=1000),
+                                  orc.find_nn(scores[1000:1200], 7, scores, False, self_offset=1000))
+    tiny = scores[:3]
+    out = sb.knn(ctx, tiny, 5)  # fewer candidates than k: padded like the reference's T::max_value()
+    assert (out[:, 2:] == 0xFFFFFFFF).all() and (out[:, :2] != 0xFFFFFFFF).all()
