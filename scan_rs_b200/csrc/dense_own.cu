@@ -223,85 +223,227 @@ int gemm_tall(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 lda, const doub
     return SB_OK;
 }
 
-// ---------------------------------------------------------------- small SPD: Cholesky + inverse of the factor (one CTA)
-// G: column-major w x w symmetric (upper triangle read).  On return the upper triangle of G holds R (G + shift I = R^T R) and
-// Rinv (column-major, upper, zero below) its inverse.  shift = shift_coef * trace(G).  flag |= 1 on a non-positive pivot.
+// ---------------------------------------------------------------- small SPD: blocked Cholesky + inverse of the factor
+// G: column-major w x w symmetric (upper triangle read and overwritten by R, G + shift I = R^T R); Rinv (column-major, upper, zero
+// below) = R^-1.  shift = shift_coef * trace(G).  flag |= 1 on a non-positive pivot.  Blocks of 64: per block step one CTA
+// factors the diagonal block in shared memory (and inverts it), a row of CTAs solves the block row, a triangle of CTAs updates
+// the trailing matrix; the inverse is assembled block column by block column (one CTA each, back substitution over block rows).
+// A first version did all of it in one CTA straight from global memory: 100 ms for w = 1000 (b = 200 Krylov blocks, k = 100).
+#define CB 64
+#define CB_LD 65
 #define CH_THREADS 1024
-__global__ void __launch_bounds__(CH_THREADS, 1) k_chol_inv(double *__restrict__ G, u32 w, double shift_coef, double *__restrict__ Rinv, int *__restrict__ flag) {
-    extern __shared__ __align__(16) double ch_smem[];
+
+__device__ __forceinline__ double *ch_elem(double *G, u32 w, u32 r, u32 c) { return G + (size_t)c * w + r; }
+
+__global__ void k_chol_shift(double *__restrict__ G, u32 w, double shift_coef) {
     __shared__ double s_red[32];
-    __shared__ double s_piv;
-    __shared__ double s_row[1024];  // row j of R (w <= 1024)
     const u32 t = threadIdx.x;
-    const bool in_smem = (size_t)w * w * sizeof(double) <= 160 * 1024;
-    double *M = in_smem ? ch_smem : G;
-    if (in_smem)
-        for (u32 i = t; i < w * w; i += CH_THREADS) M[i] = G[i];
-    // trace
     double tr = 0.0;
-    for (u32 i = t; i < w; i += CH_THREADS) tr += G[(size_t)i * w + i];
+    for (u32 i = t; i < w; i += blockDim.x) tr += G[(size_t)i * w + i];
     for (int o = 16; o > 0; o >>= 1) tr += __shfl_xor_sync(0xffffffffu, tr, o);
     if ((t & 31) == 0) s_red[t >> 5] = tr;
     __syncthreads();
     if (t < 32) {
-        double v = s_red[t];
+        double v = t < (blockDim.x >> 5) ? s_red[t] : 0.0;
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (t == 0) s_red[0] = v;
     }
     __syncthreads();
     const double shift = shift_coef * s_red[0];
+    for (u32 i = t; i < w; i += blockDim.x) G[(size_t)i * w + i] += shift;
+}
+
+// factors the diagonal block at j0 (nb <= 64 rows) in shared memory, writes R_jj back and its inverse into Dinv (64 x 64, col-major)
+__global__ void __launch_bounds__(CH_THREADS, 1) k_chol_diag(double *__restrict__ G, u32 w, u32 j0, u32 nb, double *__restrict__ Dinv, int *__restrict__ flag) {
+    extern __shared__ __align__(16) double ch_dsm[];
+    double(*A)[CB_LD] = reinterpret_cast<double(*)[CB_LD]>(ch_dsm);
+    double(*X)[CB_LD] = reinterpret_cast<double(*)[CB_LD]>(ch_dsm + CB * CB_LD);
+    __shared__ double s_piv;
+    const u32 t = threadIdx.x;
+    for (u32 i = t; i < CB * CB; i += CH_THREADS) {
+        const u32 r = i % CB, c = i / CB;
+        A[r][c] = (r <= c && c < nb) ? *ch_elem(G, w, j0 + r, j0 + c) : 0.0;
+        X[r][c] = 0.0;
+    }
     __syncthreads();
-    for (u32 i = t; i < w; i += CH_THREADS) M[(size_t)i * w + i] += shift;
-    __syncthreads();
-    // right-looking Cholesky on the upper triangle: element (r, c), r <= c, at M[c * w + r]
-    for (u32 j = 0; j < w; j++) {
+    for (u32 k = 0; k < nb; k++) {
         if (t == 0) {
-            double d = M[(size_t)j * w + j];
+            double d = A[k][k];
             if (!(d > 0.0)) {
                 atomicOr(flag, 1);
                 d = 1.0;
             }
             s_piv = sqrt(d);
-            M[(size_t)j * w + j] = s_piv;
+            A[k][k] = s_piv;
         }
         __syncthreads();
         const double inv = 1.0 / s_piv;
-        for (u32 c = j + 1 + t; c < w; c += CH_THREADS) {
-            const double v = M[(size_t)c * w + j] * inv;
-            M[(size_t)c * w + j] = v;
-            s_row[c] = v;
-        }
+        if (t > k && t < nb) A[k][t] *= inv;
         __syncthreads();
-        // trailing update: M(r, c) -= R(j, r) R(j, c) for j < r <= c: a warp per column c, lanes along r (contiguous)
-        for (u32 c = j + 1 + (t >> 5); c < w; c += CH_THREADS / 32) {
-            const double rc = s_row[c];
-            for (u32 r = j + 1 + (t & 31); r <= c; r += 32) M[(size_t)c * w + r] -= s_row[r] * rc;
+        for (u32 e = t; e < CB * CB; e += CH_THREADS) {
+            const u32 r = e % CB, c = e / CB;
+            if (r > k && r <= c && c < nb) A[r][c] -= A[k][r] * A[k][c];
         }
         __syncthreads();
     }
-    // inverse of the upper factor, one column per thread: R x = e_c
-    for (u32 c = t; c < w; c += CH_THREADS) {
-        double *x = Rinv + (size_t)c * w;
-        for (u32 i = c + 1; i < w; i++) x[i] = 0.0;
-        x[c] = 1.0 / M[(size_t)c * w + c];
+    if (t < nb) {  // inverse of the upper factor, one column per thread
+        const u32 c = t;
+        X[c][c] = 1.0 / A[c][c];
         for (u32 ii = c; ii-- > 0;) {
-            double s = 0.0;
-            for (u32 kk = ii + 1; kk <= c; kk++) s += M[(size_t)kk * w + ii] * x[kk];
-            x[ii] = -s / M[(size_t)ii * w + ii];
+            double sum = 0.0;
+            for (u32 kk = ii + 1; kk <= c; kk++) sum += A[ii][kk] * X[kk][c];
+            X[ii][c] = -sum / A[ii][ii];
         }
     }
     __syncthreads();
-    if (in_smem)
-        for (u32 i = t; i < w * w; i += CH_THREADS) G[i] = M[i];
+    for (u32 i = t; i < CB * CB; i += CH_THREADS) {
+        const u32 r = i % CB, c = i / CB;
+        if (r <= c && c < nb) *ch_elem(G, w, j0 + r, j0 + c) = A[r][c];
+        Dinv[(size_t)c * CB + r] = X[r][c];
+    }
+}
+
+// block row j: R[j, c] = R_jj^-T G[j, c] for the block columns c right of j (one CTA each)
+__global__ void __launch_bounds__(CH_THREADS, 1) k_chol_panel(double *__restrict__ G, u32 w, u32 j0, u32 nb, const double *__restrict__ Dinv) {
+    extern __shared__ __align__(16) double ch_dsm[];
+    double(*D)[CB_LD] = reinterpret_cast<double(*)[CB_LD]>(ch_dsm);
+    double(*B)[CB_LD] = reinterpret_cast<double(*)[CB_LD]>(ch_dsm + CB * CB_LD);
+    const u32 t = threadIdx.x;
+    const u32 c0 = j0 + nb + blockIdx.x * CB;
+    const u32 nc = min((u32)CB, w - c0);
+    for (u32 i = t; i < CB * CB; i += CH_THREADS) {
+        const u32 r = i % CB, c = i / CB;
+        D[r][c] = Dinv[(size_t)c * CB + r];
+        B[r][c] = (r < nb && c < nc) ? *ch_elem(G, w, j0 + r, c0 + c) : 0.0;
+    }
+    __syncthreads();
+    for (u32 e = t; e < CB * CB; e += CH_THREADS) {
+        const u32 r = e % CB, c = e / CB;
+        if (r < nb && c < nc) {
+            double sum = 0.0;
+            for (u32 k = 0; k <= r; k++) sum += D[k][r] * B[k][c];  // (D^T B)[r][c], D upper
+            *ch_elem(G, w, j0 + r, c0 + c) = sum;
+        }
+    }
+}
+
+// trailing update: G[r, c] -= R[j, r]^T R[j, c] for block pairs j < r <= c (blockIdx.x enumerates the pairs)
+__global__ void __launch_bounds__(CH_THREADS, 1) k_chol_update(double *__restrict__ G, u32 w, u32 j0, u32 nb, u32 nrem) {
+    extern __shared__ __align__(16) double ch_dsm[];
+    double(*Rr)[CB_LD] = reinterpret_cast<double(*)[CB_LD]>(ch_dsm);
+    double(*Rc)[CB_LD] = reinterpret_cast<double(*)[CB_LD]>(ch_dsm + CB * CB_LD);
+    u32 br = 0, bc = 0;
+    {
+        u32 p = blockIdx.x;
+        for (br = 0; br < nrem; br++) {
+            const u32 cnt = nrem - br;
+            if (p < cnt) {
+                bc = br + p;
+                break;
+            }
+            p -= cnt;
+        }
+    }
+    const u32 t = threadIdx.x;
+    const u32 r0 = j0 + nb + br * CB, c0 = j0 + nb + bc * CB;
+    const u32 nr = min((u32)CB, w - r0), nc = min((u32)CB, w - c0);
+    for (u32 i = t; i < CB * CB; i += CH_THREADS) {
+        const u32 k = i % CB, c = i / CB;
+        Rr[k][c] = (k < nb && c < nr) ? *ch_elem(G, w, j0 + k, r0 + c) : 0.0;
+        Rc[k][c] = (k < nb && c < nc) ? *ch_elem(G, w, j0 + k, c0 + c) : 0.0;
+    }
+    __syncthreads();
+    for (u32 e = t; e < CB * CB; e += CH_THREADS) {
+        const u32 r = e % CB, c = e / CB;
+        if (r < nr && c < nc && r0 + r <= c0 + c) {
+            double sum = 0.0;
+            for (u32 k = 0; k < nb; k++) sum += Rr[k][r] * Rc[k][c];
+            *ch_elem(G, w, r0 + r, c0 + c) -= sum;
+        }
+    }
+}
+
+// Rinv block column bj (one CTA): X_jj = D_j; X_ij = -D_i (sum_{i < k <= j} R_ik X_kj), block rows i descending.  Dall: the
+// inverted diagonal blocks, 64 x 64 each.
+__global__ void __launch_bounds__(CH_THREADS, 1) k_tri_inv_blocks(const double *__restrict__ G, u32 w, const double *__restrict__ Dall, double *__restrict__ Rinv) {
+    extern __shared__ __align__(16) double ch_dsm[];
+    double(*Ablk)[CB_LD] = reinterpret_cast<double(*)[CB_LD]>(ch_dsm);
+    double(*Xblk)[CB_LD] = reinterpret_cast<double(*)[CB_LD]>(ch_dsm + CB * CB_LD);
+    double(*Acc)[CB_LD] = reinterpret_cast<double(*)[CB_LD]>(ch_dsm + 2 * CB * CB_LD);
+    const u32 t = threadIdx.x;
+    const u32 bj = blockIdx.x, c0 = bj * CB, nc = min((u32)CB, w - c0);
+    // zero the block column (also below the diagonal), then the diagonal block
+    for (u32 i = t; i < w * nc; i += CH_THREADS) Rinv[(size_t)(c0 + i / w) * w + i % w] = 0.0;
+    __syncthreads();
+    for (u32 i = t; i < CB * CB; i += CH_THREADS) {
+        const u32 r = i % CB, c = i / CB;
+        if (r < nc && c < nc) Rinv[(size_t)(c0 + c) * w + c0 + r] = Dall[(size_t)bj * CB * CB + (size_t)c * CB + r];
+    }
+    __syncthreads();
+    for (u32 bi = bj; bi-- > 0;) {
+        const u32 r0 = bi * CB;  // full block of 64 rows (only the last block can be short, and bi < bj)
+        for (u32 i = t; i < CB * CB; i += CH_THREADS) Acc[i % CB][i / CB] = 0.0;
+        __syncthreads();
+        for (u32 bk = bi + 1; bk <= bj; bk++) {
+            const u32 k0 = bk * CB, nk = min((u32)CB, w - k0);
+            for (u32 i = t; i < CB * CB; i += CH_THREADS) {
+                const u32 r = i % CB, c = i / CB;
+                Ablk[r][c] = c < nk ? G[(size_t)(k0 + c) * w + r0 + r] : 0.0;                      // R[bi, bk] (row r, col c)
+                Xblk[r][c] = (r < nk && c < nc) ? Rinv[(size_t)(c0 + c) * w + k0 + r] : 0.0;       // X[bk, bj]
+            }
+            __syncthreads();
+            for (u32 e = t; e < CB * CB; e += CH_THREADS) {
+                const u32 r = e % CB, c = e / CB;
+                double sum = 0.0;
+                for (u32 k = 0; k < CB; k++) sum += Ablk[r][k] * Xblk[k][c];
+                Acc[r][c] += sum;
+            }
+            __syncthreads();
+        }
+        // X[bi, bj] = -D_bi . Acc
+        for (u32 i = t; i < CB * CB; i += CH_THREADS) {
+            const u32 r = i % CB, c = i / CB;
+            Ablk[r][c] = Dall[(size_t)bi * CB * CB + (size_t)c * CB + r];
+        }
+        __syncthreads();
+        for (u32 e = t; e < CB * CB; e += CH_THREADS) {
+            const u32 r = e % CB, c = e / CB;
+            if (c < nc) {
+                double sum = 0.0;
+                for (u32 k = r; k < CB; k++) sum += Ablk[r][k] * Acc[k][c];  // D upper
+                Rinv[(size_t)(c0 + c) * w + r0 + r] = -sum;
+            }
+        }
+        __syncthreads();
+    }
 }
 
 int chol_inv(sb_ctx *ctx, double *G, u32 w, double shift_coef, double *Rinv, int *flag) {
     if (w == 0) return SB_OK;
-    if (w > 1024) return sb_fail(SB_ERR_UNSUPPORTED, "chol_inv: more than 1024 columns");
-    const size_t bytes = (size_t)w * w * sizeof(double);
-    const size_t smem = bytes <= 160 * 1024 ? bytes : 0;
-    SB_CUDA(cudaFuncSetAttribute(k_chol_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    k_chol_inv<<<1, CH_THREADS, smem, ctx->stream>>>(G, w, shift_coef, Rinv, flag);
+    const u32 nblk = (w + CB - 1) / CB;
+    DevBuf<double> Dall;
+    SB_TRY(Dall.alloc((size_t)nblk * CB * CB));
+    const size_t sm2 = (size_t)2 * CB * CB_LD * sizeof(double), sm3 = (size_t)3 * CB * CB_LD * sizeof(double);
+    SB_CUDA(cudaFuncSetAttribute(k_chol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));  // per device: cheap, so every call
+    SB_CUDA(cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+    SB_CUDA(cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+    SB_CUDA(cudaFuncSetAttribute(k_tri_inv_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
+    if (shift_coef != 0.0) {
+        k_chol_shift<<<1, 1024, 0, ctx->stream>>>(G, w, shift_coef);
+        count_launch(ctx);
+    }
+    for (u32 b = 0; b < nblk; b++) {
+        const u32 j0 = b * CB, nb = std::min<u32>(CB, w - j0);
+        k_chol_diag<<<1, CH_THREADS, sm2, ctx->stream>>>(G, w, j0, nb, Dall.p + (size_t)b * CB * CB, flag);
+        count_launch(ctx);
+        const u32 nrem = nblk - b - 1;
+        if (nrem) {
+            k_chol_panel<<<nrem, CH_THREADS, sm2, ctx->stream>>>(G, w, j0, nb, Dall.p + (size_t)b * CB * CB);
+            k_chol_update<<<nrem * (nrem + 1) / 2, CH_THREADS, sm2, ctx->stream>>>(G, w, j0, nb, nrem);
+            count_launch(ctx); count_launch(ctx);
+        }
+    }
+    k_tri_inv_blocks<<<nblk, CH_THREADS, sm3, ctx->stream>>>(G, w, Dall.p, Rinv);
     count_launch(ctx);
     SB_CUDA(cudaGetLastError());
     return SB_OK;
