@@ -120,6 +120,34 @@ SB_API void sb_host_free(void *p);
  * counts non-zero (what AdaptiveVec guarantees); zeros are dropped. */
 SB_API int sb_upload(sb_ctx *ctx, int major, uint32_t m, uint64_t n_local, const uint64_t *indptr,
               const uint32_t *idx, const uint32_t *cnt, sb_mat **out);
+/* The reference's own storage as upload input: one AdaptiveVec (sqz/src/vec.rs:1029-1053) described by the raw parts of its Rust
+ * struct.  variant follows the enum order: 0 D3, 1 D4, 2 D8, 3 D16, 4 V, 5 S3, 6 S4, 7 S8.
+ *   D3/D4/D8/D16 : dense = Dense3.data (u64 words, 21 x 3 bits) / Dense4.data (bytes, 2 x 4 bits) / DenseW.data (u8 / u16), one code
+ *                  per position; fb_* = the SimpleSparse fallback holding the values the narrow code cannot (vec.rs:660-1023)
+ *   V            : fb_* = SimpleSparse.indexes / values (vec.rs:123-127); dense unused
+ *   S3/S4/S8     : CompressedIndexSparse (vec.rs:222-227): index_bytes[n_index] (position inside a block of 256), block_starts
+ *                  [n_block_starts]; dense / fb_* describe its dense_data (a D3 / D4 / D8 vector of length n_index)
+ * len = the vector's logical length.  All arrays stay owned by the caller. */
+typedef struct sb_adaptive_vec {
+    uint32_t variant;
+    uint32_t reserved;
+    uint64_t len;
+    const void *dense;
+    const uint32_t *fb_idx;
+    const uint32_t *fb_val;
+    uint64_t fb_len;
+    const uint8_t *index_bytes;
+    uint64_t n_index;
+    const uint32_t *block_starts;
+    uint64_t n_block_starts;
+} sb_adaptive_vec;
+/* AdaptiveVec::foreach (vec.rs:1230-1273) for one vector: (index, value) ascending, stored zeros skipped.  idx / val may be NULL
+ * to count only. */
+SB_API int sb_adaptive_decode_vec(const sb_adaptive_vec *vec, uint32_t *idx, uint32_t *val, uint64_t capacity, uint64_t *nnz);
+/* AdaptiveMat (sqz/src/mat.rs:34-42) -> device matrix: decodes the m (SB_GENE_MAJOR, the reference's CSR storage) or n_local
+ * (SB_CELL_MAJOR) vectors on `threads` host threads (0 = all) and uploads. */
+SB_API int sb_upload_adaptive(sb_ctx *ctx, int major, uint32_t m, uint64_t n_local, const sb_adaptive_vec *vecs, int threads,
+                       sb_mat **out);
 /* The same constructor for a cell-major matrix in a narrow host form, for m <= 65536: u16 gene index + u8 count per entry
  * (3 bytes over PCIe instead of 8 -- the host-to-device copy is the largest part of an end-to-end call).  Counts >= 255
  * are written as 255 in cnt8 and listed in the side arrays: entry big_pos[i] (ascending stream positions) has count

@@ -152,6 +152,8 @@ struct sb_ctx {
     void *pinned = nullptr;  // small pinned staging (4 KB)
     std::vector<double> omega_cache;  // last generated start block (host)
     u64 omega_seed = ~0ull, omega_rows = 0, omega_cols = 0;
+    DevBuf<double> omega_dev;         // the same block already in the device layout the n > m branch starts from (m x b, even ld)
+    u64 omega_dev_seed = ~0ull, omega_dev_rows = 0, omega_dev_cols = 0;
 };
 
 // The packed gene-major entry: x = gene | (cell_local << SB_GENE_BITS), y = count.

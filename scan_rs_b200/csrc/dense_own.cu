@@ -254,7 +254,10 @@ __global__ void k_chol_shift(double *__restrict__ G, u32 w, double shift_coef) {
 }
 
 // factors the diagonal block at j0 (nb <= 64 rows) in shared memory, writes R_jj back and its inverse into Dinv (64 x 64, col-major)
-__global__ void __launch_bounds__(CH_THREADS, 1) k_chol_diag(double *__restrict__ G, u32 w, u32 j0, u32 nb, double *__restrict__ Dinv, int *__restrict__ flag) {
+// (shift_coef != 0 only when the block is the whole matrix: the trace of the block is then the trace of G; Rinv_small != NULL
+// writes the inverse as the w x w result directly -- one launch does the whole factorisation of a matrix of at most 64 columns)
+__global__ void __launch_bounds__(CH_THREADS, 1) k_chol_diag(double *__restrict__ G, u32 w, u32 j0, u32 nb, double *__restrict__ Dinv, int *__restrict__ flag,
+                                                             double shift_coef, double *__restrict__ Rinv_small) {
     extern __shared__ __align__(16) double ch_dsm[];
     double(*A)[CB_LD] = reinterpret_cast<double(*)[CB_LD]>(ch_dsm);
     double(*X)[CB_LD] = reinterpret_cast<double(*)[CB_LD]>(ch_dsm + CB * CB_LD);
@@ -266,6 +269,16 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_diag(double *__restrict_
         X[r][c] = 0.0;
     }
     __syncthreads();
+    if (shift_coef != 0.0) {
+        if (t == 0) {
+            double tr = 0.0;
+            for (u32 i = 0; i < nb; i++) tr += A[i][i];
+            s_piv = shift_coef * tr;
+        }
+        __syncthreads();
+        if (t < nb) A[t][t] += s_piv;
+        __syncthreads();
+    }
     for (u32 k = 0; k < nb; k++) {
         if (t == 0) {
             double d = A[k][k];
@@ -299,7 +312,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_diag(double *__restrict_
     for (u32 i = t; i < CB * CB; i += CH_THREADS) {
         const u32 r = i % CB, c = i / CB;
         if (r <= c && c < nb) *ch_elem(G, w, j0 + r, j0 + c) = A[r][c];
-        Dinv[(size_t)c * CB + r] = X[r][c];
+        if (Dinv) Dinv[(size_t)c * CB + r] = X[r][c];
+        if (Rinv_small && r < nb && c < nb) Rinv_small[(size_t)c * w + r] = X[r][c];
     }
 }
 
@@ -428,13 +442,19 @@ int chol_inv(sb_ctx *ctx, double *G, u32 w, double shift_coef, double *Rinv, int
     SB_CUDA(cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
     SB_CUDA(cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
     SB_CUDA(cudaFuncSetAttribute(k_tri_inv_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
+    if (nblk == 1) {  // the whole matrix is one block: shift, factor and invert in one launch
+        k_chol_diag<<<1, CH_THREADS, sm2, ctx->stream>>>(G, w, 0, w, nullptr, flag, shift_coef, Rinv);
+        count_launch(ctx);
+        SB_CUDA(cudaGetLastError());
+        return SB_OK;
+    }
     if (shift_coef != 0.0) {
         k_chol_shift<<<1, 1024, 0, ctx->stream>>>(G, w, shift_coef);
         count_launch(ctx);
     }
     for (u32 b = 0; b < nblk; b++) {
         const u32 j0 = b * CB, nb = std::min<u32>(CB, w - j0);
-        k_chol_diag<<<1, CH_THREADS, sm2, ctx->stream>>>(G, w, j0, nb, Dall.p + (size_t)b * CB * CB, flag);
+        k_chol_diag<<<1, CH_THREADS, sm2, ctx->stream>>>(G, w, j0, nb, Dall.p + (size_t)b * CB * CB, flag, 0.0, nullptr);
         count_launch(ctx);
         const u32 nrem = nblk - b - 1;
         if (nrem) {

@@ -413,8 +413,22 @@ static int bksvd_impl(sb_nmat *a, uint32_t k, uint32_t b, uint32_t n_iter, uint6
     {
         TraceScope t0(ctx, "bksvd: omega + buffers");
         SB_TRY(Y.init(ctx, m, b));
-        if (!omega) omega = omega_cached(ctx, seed, b, m);  // :118 (b x m, row-major fill)
-        SB_TRY(upload_tall(ctx, Y, omega, true));  // Y[g, j] = B[j, g]
+        if (!omega) {
+            // :118 (b x m, row-major fill).  BkSvd::run_pca always asks for seed 0: the block is generated, transposed and uploaded
+            // once per (seed, shape) and then copied on the device (the host transpose + pageable copy were ~2 ms of every call)
+            if (ctx->omega_dev_seed != seed || ctx->omega_dev_rows != b || ctx->omega_dev_cols != m || !ctx->omega_dev.p) {
+                SB_TRY(upload_tall(ctx, Y, omega_cached(ctx, seed, b, m), true));  // Y[g, j] = B[j, g]
+                SB_TRY(ctx->omega_dev.alloc((size_t)m * Y.ld));
+                SB_CUDA(cudaMemcpyAsync(ctx->omega_dev.p, Y.buf.p, (size_t)m * Y.ld * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+                ctx->omega_dev_seed = seed;
+                ctx->omega_dev_rows = b;
+                ctx->omega_dev_cols = m;
+            } else {
+                SB_CUDA(cudaMemcpyAsync(Y.buf.p, ctx->omega_dev.p, (size_t)m * Y.ld * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+        } else {
+            SB_TRY(upload_tall(ctx, Y, omega, true));  // Y[g, j] = B[j, g]
+        }
         SB_TRY(Kt.init(ctx, m, bq));
         SB_TRY(T.init(ctx, n, b));
         SB_TRY(P.init(ctx, m, b, 1));

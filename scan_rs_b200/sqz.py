@@ -16,6 +16,39 @@ import numpy as np
 from . import _lib as L
 
 
+_VARIANT_ID = {"D3": 0, "D4": 1, "D8": 2, "D16": 3, "V": 4, "S3": 5, "S4": 6, "S8": 7}
+
+
+class SbAdaptiveVec(C.Structure):  # include/scanb200.h: sb_adaptive_vec
+    _fields_ = [("variant", C.c_uint32), ("reserved", C.c_uint32), ("len", C.c_uint64), ("dense", C.c_void_p), ("fb_idx", C.c_void_p),
+                ("fb_val", C.c_void_p), ("fb_len", C.c_uint64), ("index_bytes", C.c_void_p), ("n_index", C.c_uint64),
+                ("block_starts", C.c_void_p), ("n_block_starts", C.c_uint64)]
+
+
+def adaptive_views(vecs):
+    """ctypes array of sb_adaptive_vec over the numpy buffers of `vecs` (+ the list that keeps those buffers alive)"""
+    arr = (SbAdaptiveVec * max(1, len(vecs)))()
+    keep = []
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
+    for i, v in enumerate(vecs):
+        bufs = [None if b is None else np.ascontiguousarray(b) for b in (v.dense, v.fb_idx, v.fb_val, v.index_bytes, v.block_starts)]
+        keep.append(bufs)
+        d, fi, fv, ib, bs = bufs
+        arr[i] = SbAdaptiveVec(_VARIANT_ID[v.variant], 0, int(v.len), ptr(d), ptr(fi), ptr(fv), 0 if fi is None else int(fi.size), ptr(ib),
+                               0 if ib is None else int(ib.size), ptr(bs), 0 if bs is None else int(bs.size))
+    return arr, keep
+
+
+def adaptive_decode(vec):
+    """AdaptiveVec::foreach through the C ABI (sb_adaptive_decode_vec): (indexes, values) of one vector"""
+    arr, keep = adaptive_views([vec])
+    nnz = C.c_uint64()
+    L.check(L.lib().sb_adaptive_decode_vec(arr, None, None, C.c_uint64(0), C.byref(nnz)))
+    idx, val = np.zeros(nnz.value, dtype=np.uint32), np.zeros(nnz.value, dtype=np.uint32)
+    L.check(L.lib().sb_adaptive_decode_vec(arr, L.vp(idx), L.vp(val), C.c_uint64(nnz.value), C.byref(nnz)))
+    return idx, val
+
+
 class Context:
     """One GPU + stream (+ optional NCCL communicator)."""
 
@@ -230,6 +263,17 @@ class AdaptiveMat:
                                      C.byref(kept), C.byref(resid), L.vp(rows), C.byref(nr), L.vp(cols), C.byref(nc)))
         return (AdaptiveMat(self.ctx, kept), AdaptiveMat(self.ctx, resid), rows[: nr.value].astype(np.int64),
                 cols[: nc.value].astype(np.int64))
+
+    @classmethod
+    def from_adaptive(cls, ctx, m: int, n: int, vecs, major: str = "gene", threads: int = 0) -> "AdaptiveMat":
+        """Upload from the reference's own storage: a list of AdaptiveVec raw parts (objects with .variant/.len/.dense/.fb_idx/
+        .fb_val/.index_bytes/.block_starts, e.g. oracle.adaptive_vec.Parts), one per gene (`major="gene"`, the reference's CSR
+        storage, mtx.rs:49-50) or per cell.  Decoded on the host by the library (csrc/adaptive.cu)."""
+        arr, keep = adaptive_views(vecs)
+        h = C.c_void_p()
+        L.check(L.lib().sb_upload_adaptive(ctx._h, C.c_int(L.SB_GENE_MAJOR if major == "gene" else L.SB_CELL_MAJOR), C.c_uint32(m), C.c_uint64(n),
+                                           arr, C.c_int(threads), C.byref(h)))
+        return cls(ctx, h)
 
     def select_rows(self, rows: Sequence[int]) -> "AdaptiveMat":  # mat.rs:1040-1071
         r = np.ascontiguousarray(rows, dtype=np.uint32)
