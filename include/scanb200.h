@@ -171,12 +171,14 @@ SB_API int sb_gene_nnz(sb_mat *mat, uint64_t *out_m);
  * *nonempty = 0 when there are no cells (the caller then uses 1.0, normalization.rs:166) */
 SB_API int sb_median_cell_total(sb_mat *mat, uint32_t *median, int *nonempty);
 
-/* partition_on_thresholds (mat.rs:772-889).  Single-rank only.  `rows_out`/`cols_out` need room
- * for m / n_local entries and receive the selected indices; kept/residual may be NULL. */
+/* partition_on_thresholds (mat.rs:772-889).  `rows_out`/`cols_out` need room for m / n_local entries and receive the
+ * selected indices; kept/residual may be NULL.  Sharded contexts: gene sums are all-reduced every round, cell verdicts stay
+ * local; cols_out are LOCAL cell indices and the returned matrices hold this rank's shard. */
 SB_API int sb_partition(sb_mat *mat, int has_row_thr, double row_thr, int has_col_thr, double col_thr,
                  sb_mat **kept, sb_mat **residual, uint64_t *rows_out, uint64_t *n_rows_out,
                  uint64_t *cols_out, uint64_t *n_cols_out);
-/* select_rows / select_cols (mat.rs:1004-1071): new matrix with the given rows/cols in the given order */
+/* select_rows / select_cols (mat.rs:1004-1071): new matrix with the given rows/cols in the given order (sharded contexts:
+ * every rank passes the same rows; cols are LOCAL cell indices of its own shard) */
 SB_API int sb_select_rows(sb_mat *mat, const uint32_t *rows, uint32_t count, sb_mat **out);
 SB_API int sb_select_cols(sb_mat *mat, const uint64_t *cols, uint64_t count, sb_mat **out);
 /* Highly-variable-gene selection (NOT in the reference; builder-defined): exact u64
@@ -235,6 +237,37 @@ SB_API int sb_randsvd(sb_nmat *a, uint32_t k, uint32_t l, uint32_t n_iter, uint6
 /* RandSvd::run_pca_cancellable (rand_svd.rs:44-49): l = max(k + 4, floor(k * l_multiplier)), seed 0 */
 SB_API int sb_randsvd_run_pca(sb_nmat *a, uint32_t k, double l_multiplier, uint32_t n_iter, double *U, double *S,
                        double *V);
+
+/* irlba (scan-rs/src/dim_red/irlba.rs:71-215): implicitly restarted Lanczos bidiagonalisation, nu triplets, tolerance tol
+ * (Irlba::new: 1e-4), at most maxit restarts (50); working dimension m_b = min(nu + 20, 3 nu, n) (:87).  v0[n_local] = this rank's
+ * slice of the start vector (normalised inside), or NULL for sb_irlba_start(0, n_global).  The reference draws it from rand_distr's
+ * Normal on SmallRng seed 0, a third-party stream that cannot be restated offline (parity unpinned, like Omega).  The
+ * `resid[i] < tol * smax` test carries no absolute value in the reference (:176-181); it is kept, with sign-canonical singular
+ * vectors of the small matrix (largest-magnitude entry of each right vector positive).  Progress milestones it / maxit (:206).
+ * Outputs U[m x nu], S[nu], V[n_local x nu] row-major; mprod_out / iters_out (optional): matrix products, restarts taken. */
+SB_API int sb_irlba(sb_nmat *a, uint32_t nu, double tol, uint32_t maxit, const double *v0, sb_progress_cb cb, void *user,
+             double *U, double *S, double *V, uint32_t *mprod_out, uint32_t *iters_out);
+/* The builder-defined default start vector of sb_irlba: Box-Muller on the Xoshiro256++ stream of sb_omega, entry i for global cell i. */
+SB_API int sb_irlba_start(uint64_t seed, uint64_t n, double *out);
+
+/* ---------------------------------------------------------------- moment consumers (diff-exp's reads of the count matrix)
+ * mean_var_axis (sqz/src/mat.rs:285-329): V[X] = E[X^2] - E[X]^2 along an axis.  axis 1: per gene over all cells (m values,
+ * summed over ranks); axis 0: per local cell over the m genes.  cell_div (n_local values or NULL): the SizeNormalized view
+ * `v as f64 / size_factor[c]` (diff-exp/src/diff_exp.rs:340-358; NaN factors become 0).  Without cell_div the sums are exact. */
+SB_API int sb_mean_var_axis(sb_mat *mat, int axis, const double *cell_div, double *mean, double *var);
+/* mean_var_rows (mat.rs:332-374): per gene over the listed cells (LOCAL indices of this rank's shard; a cell listed twice counts
+ * twice, as the reference's CSC branch); the divisor is the number of listed cells over all ranks. */
+SB_API int sb_mean_var_rows(sb_mat *mat, const uint64_t *cols, uint64_t n_cols, const double *cell_div, double *mean, double *var);
+/* sum_rows / sum_cols / sum_rows_dual (mat.rs:414-476, 484-583) as exact u64 sums: per gene over the listed cells, per listed cell
+ * over the genes, per gene over two lists at once (a cell in both lists adds to both). */
+SB_API int sb_sum_rows(sb_mat *mat, const uint64_t *cols, uint64_t n_cols, uint64_t *out_m);
+SB_API int sb_sum_cols(sb_mat *mat, const uint64_t *cols, uint64_t n_cols, uint64_t *out);
+SB_API int sb_sum_rows_dual(sb_mat *mat, const uint64_t *cols1, uint64_t n1, const uint64_t *cols2, uint64_t n2, uint64_t *sum1,
+                     uint64_t *sum2);
+/* size_factors (diff_exp.rs:314-334): counts per cell / their median (50th percentile with linear interpolation,
+ * diff-exp/src/stat.rs:107-163), over the listed local cells (NULL: all) of all ranks; umi_counts (optional) replaces the totals,
+ * one value per listed cell.  out[n_local]: 0 at unlisted cells. */
+SB_API int sb_size_factors(sb_mat *mat, const uint64_t *cells, uint64_t n_cells, const double *umi_counts, double *out);
 
 /* ---------------------------------------------------------------- kNN on the scores (next step of the pipeline)
  * knn / find_nn (scan-rs/src/nn.rs:38-83): for every query row (n_queries x dim, row-major) the indices of its k nearest points

@@ -622,6 +622,207 @@ class RandSvd:  # rand_svd.rs:13-50
         return u, s, vt.T
 
 
+# --------------------------------------------------------------------------------------
+# IRLBA: scan-rs/src/dim_red/irlba.rs:71-215 (b = 1 Lanczos bidiagonalisation with implicit restarts).
+# Two things the reference takes from third-party crates cannot be restated bit for bit offline and are therefore
+# PARAMETERS here (parity unpinned for them, as for the Omega stream): the start vector (rand_distr 0.6 `Normal` on
+# SmallRng seed 0, a ziggurat sampler whose tables are not on disk) and the signs LAPACK's dgesvd gives the singular vectors
+# of the small matrix B.  The signs matter because the reference tests `resid[i] < tol * smax` WITHOUT an absolute value
+# (irlba.rs:176-181): a Ritz pair whose last u component is negative counts as converged.  Both sides of the parity tests
+# therefore use the same rule: the start vector of irlba_start() and sign-canonical singular vectors (_svd_canonical).
+# --------------------------------------------------------------------------------------
+def irlba_start(seed: int, n: int) -> np.ndarray:
+    """Builder-defined stand-in for `Normal::new(0, 1)` on SmallRng::seed_from_u64(seed) (irlba.rs:106-113): Box-Muller on
+    the Xoshiro256++ stream, two uniforms per pair of normals; NOT the reference's ziggurat stream (unpinned)."""
+    rng = Xoshiro256PlusPlus.seed_from_u64(seed)
+    u = rng.fill_u64(2 * ((n + 1) // 2))
+    f = ((u >> np.uint64(11)).astype(np.float64) + 0.5) * (1.0 / 9007199254740992.0)  # (0, 1)
+    r = np.sqrt(-2.0 * np.log(f[0::2]))
+    t = 2.0 * np.pi * f[1::2]
+    out = np.empty(2 * r.shape[0])
+    out[0::2] = r * np.cos(t)
+    out[1::2] = r * np.sin(t)
+    return out[:n].copy()
+
+
+def _svd_canonical(B: np.ndarray):
+    """SVD::svd(&B, true, true) (dgesvd) with a fixed sign rule: the largest-magnitude entry of every right vector is positive
+    (first such entry on ties)."""
+    u, s, vt = sla.svd(B, full_matrices=True, lapack_driver="gesvd", check_finite=False)
+    for i in range(vt.shape[0]):
+        j = int(np.argmax(np.abs(vt[i])))
+        if vt[i, j] < 0.0:
+            vt[i] = -vt[i]
+            u[:, i] = -u[:, i]
+    return u, s, vt
+
+
+def _norm(x):  # irlba.rs:12-14
+    return float(np.sqrt(np.sum(x * x)))
+
+
+def _orthog(y, X):  # irlba.rs:19-22
+    return y - X.dot(X.T.dot(y))
+
+
+def _invcheck(x):  # irlba.rs:25-33
+    return 1.0 / x if x > 2.0 * np.finfo(np.float64).eps else 0.0
+
+
+def irlba(A, nu: int, tol: float = 1e-4, maxit: int = 50, v0: Optional[np.ndarray] = None,
+          snoop: Optional[Callable[[float], bool]] = None, threads: bool = False):
+    """irlba.rs:71-215.  Returns (U m x nu, sigma nu, V n x nu, mprod, iterations)."""
+    m, n = A.shape
+    if m < 2 or n < 2:
+        raise ValueError("The input matrix must be at least 2x2.")    # :84
+    if nu > min(m, n):
+        raise ValueError("invalid k")                                 # :85
+    m_b = min(nu + 20, min(3 * nu, n))                                # :87
+    mprod, it, j, k = 0, 0, 0, nu
+    smax = -np.finfo(np.float64).max                                  # f64::MIN
+    V = np.zeros((n, m_b)); W = np.zeros((m, m_b)); F = np.zeros(n); B = np.zeros((m_b, m_b))
+    u = np.zeros((1, 1)); sigma = np.zeros(nu); vt = np.zeros((1, 1))
+    r = irlba_start(0, n) if v0 is None else np.array(v0, dtype=np.float64)
+    V[:, 0] = r * (1.0 / _norm(r))                                    # :111-113
+    dot1 = lambda x: A.dot(x.reshape(-1, 1), threads)[:, 0]
+    rdot1 = lambda y: A.rdot(y.reshape(1, -1), threads)[0, :]
+    fnorm = 0.0
+    while it < maxit:
+        if it > 0:
+            j = k
+        W[:, j] = dot1(V[:, j]); mprod += 1                           # :121
+        if it > 0:
+            W[:, k] = _orthog(W[:, j], W[:, :j])                      # :125-126
+        s = _norm(W[:, j]); sinv = _invcheck(s)
+        W[:, j] *= sinv
+        fnorm = 0.0
+        while j < m_b:                                                # Lanczos process :136-167
+            F = rdot1(W[:, j]); mprod += 1
+            F = F - V[:, j] * s
+            F = _orthog(F, V[:, :j + 1])
+            fnorm = _norm(F)
+            F = F * _invcheck(fnorm)
+            if j == m_b - 1:
+                B[j, j] = s
+            else:
+                V[:, j + 1] = F
+                B[j, j] = s
+                B[j, j + 1] = fnorm
+                mprod += 1                                            # :152-153 (the reference forms A.V[:, j+1] twice: same values)
+                nw = dot1(V[:, j + 1])
+                nw = nw - W[:, j] * fnorm
+                nw = _orthog(nw, W[:, :j + 1])
+                s = _norm(nw); sinv = _invcheck(s)
+                W[:, j + 1] = nw * sinv
+            j += 1
+        u, sigma, vt = _svd_canonical(B)                              # :169-172
+        resid = fnorm * u[m_b - 1, :]
+        smax = sigma[0] if sigma[0] > smax else smax
+        num_converged = int(sum(1 for i in range(nu) if resid[i] < tol * smax))   # no abs: as the reference
+        if num_converged < nu:
+            k = max(num_converged + nu, k)
+            k = min(k, m_b - 3)
+        else:
+            break
+        V[:, :k] = V[:, :m_b].dot(vt.T[:, :k])                        # :191-193
+        V[:, k] = F
+        B = np.zeros((m_b, m_b))
+        for l in range(k):
+            B[l, l] = sigma[l]
+        B[:k, k] = resid[:k]
+        W[:, :k] = W[:, :m_b].dot(u[:, :k])                           # :202-203
+        it += 1
+        if snoop is not None and snoop(it / maxit):
+            raise CancellationError()
+    U = W[:, :m_b].dot(u[:, :nu])
+    Vo = V[:, :m_b].dot(vt.T[:, :nu])
+    return U, sigma[:nu].copy(), Vo, mprod, it
+
+
+class Irlba:  # irlba.rs:36-69
+    def __init__(self, tol: float = 0.0001, max_iter: int = 50):
+        self.tol, self.max_iter = tol, max_iter
+
+    def run_pca(self, array, k: int, v0=None, threads=False):
+        u, s, v, _, _ = irlba(array, k, self.tol, self.max_iter, v0, None, threads)
+        return u, s, v
+
+
+# --------------------------------------------------------------------------------------
+# The per-gene moment consumers of diff-exp on size-normalized counts: sqz/src/mat.rs:285-374 (mean_var_axis, mean_var_rows),
+# :414-476 (sum_cols, sum_rows), :484-583 (sum_rows_dual); diff-exp/src/diff_exp.rs:314-334 (size_factors), :340-358
+# (SizeNormalized: v / size_factor[c]), diff-exp/src/stat.rs:107-163 (median = 50th percentile, linear interpolation).
+# Plain numpy over the cell-major arrays (summation in storage order like the reference's CSC branch).
+# --------------------------------------------------------------------------------------
+def percentile_median(x: np.ndarray) -> float:  # stat.rs:116-118, :140-163
+    s = np.sort(np.asarray(x, dtype=np.float64))
+    if s.shape[0] == 1:
+        return float(s[0])
+    rank = 0.5 * (s.shape[0] - 1)
+    lo = int(np.floor(rank))
+    d = rank - lo
+    return float(s[lo] + (s[lo + 1] - s[lo]) * d)
+
+
+def size_factors(mat: CountMatrix, cell_indices=None, umi_counts=None) -> np.ndarray:  # diff_exp.rs:314-334
+    if umi_counts is not None:
+        cpc = np.asarray(umi_counts, dtype=np.float64)
+    else:
+        tot = mat.sum_axis_u64(0).astype(np.float64)
+        cpc = tot if cell_indices is None else tot[np.asarray(cell_indices, dtype=np.int64)]
+    med = percentile_median(cpc)
+    if cell_indices is None:
+        return cpc / med
+    out = np.zeros(mat.cols)
+    out[np.asarray(cell_indices, dtype=np.int64)] = cpc / med
+    return out
+
+
+def _mapped_entries(mat: CountMatrix, sf: Optional[np.ndarray]):
+    ip, g, c = mat.cell_major()
+    cell = np.repeat(np.arange(mat.cols, dtype=np.int64), np.diff(ip).astype(np.int64))
+    val = c.astype(np.float64)
+    if sf is not None:
+        d = np.where(np.isnan(sf), 0.0, np.asarray(sf, dtype=np.float64))  # SizeNormalized::new, diff_exp.rs:341-344
+        with np.errstate(divide="ignore", invalid="ignore"):
+            val = val / d[cell]
+    return g.astype(np.int64), cell, val
+
+
+def mean_var_axis(mat: CountMatrix, axis: int, sf: Optional[np.ndarray] = None):  # mat.rs:285-329
+    g, cell, val = _mapped_entries(mat, sf)
+    key, sz = (cell, mat.cols) if axis == 0 else (g, mat.rows)
+    means = np.bincount(key, weights=val, minlength=sz)
+    sq = np.bincount(key, weights=val * val, minlength=sz)
+    mm = float(mat.shape[axis])
+    means = means / mm
+    return means, sq / mm - means * means
+
+
+def mean_var_rows(mat: CountMatrix, cols, sf: Optional[np.ndarray] = None):  # mat.rs:332-374
+    g, cell, val = _mapped_entries(mat, sf)
+    cols = np.asarray(cols, dtype=np.int64)
+    mult = np.bincount(cols, minlength=mat.cols)  # CSC branch: a column listed twice is walked twice
+    w = mult[cell].astype(np.float64)
+    means = np.bincount(g, weights=val * w, minlength=mat.rows)
+    sq = np.bincount(g, weights=val * val * w, minlength=mat.rows)
+    mm = float(cols.shape[0])
+    means = means / mm
+    return means, sq / mm - means * means
+
+
+def sum_rows_dual(mat: CountMatrix, cols1, cols2):  # mat.rs:484-583 (u64 sums: exact)
+    ip, g, c = mat.cell_major()
+    cell = np.repeat(np.arange(mat.cols, dtype=np.int64), np.diff(ip).astype(np.int64))
+    out = []
+    for cols in (cols1, cols2):
+        sel = np.zeros(mat.cols, dtype=bool)
+        sel[np.asarray(cols, dtype=np.int64)] = True  # merge_join_by over sorted unique lists: membership
+        k = sel[cell]
+        out.append(np.bincount(g[k].astype(np.int64), weights=c[k].astype(np.float64), minlength=mat.rows).astype(np.uint64))
+    return out[0], out[1]
+
+
 def frobenius(a: np.ndarray) -> float:  # dim_red/mod.rs:114-122
     return float(np.sqrt(np.sum(a * a)) / (a.shape[0] * a.shape[1]))
 

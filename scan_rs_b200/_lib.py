@@ -48,6 +48,7 @@ SYMBOLS = [
     "sb_nmat_dot", "sb_nmat_rdot", "sb_nmat_frobenius_sq", "sb_free_nmat", "sb_omega", "sb_bksvd", "sb_bksvd_run_pca", "sb_pca_diagnostics", "sb_randsvd",
     "sb_randsvd_run_pca", "sb_profile_enable", "sb_profile_reset", "sb_profile_get", "sb_timer_begin",
     "sb_timer_end", "sb_flush_l2", "sb_synth_generate", "sb_knn",
+    "sb_irlba", "sb_irlba_start", "sb_mean_var_axis", "sb_mean_var_rows", "sb_sum_rows", "sb_sum_cols", "sb_sum_rows_dual", "sb_size_factors",
 ]
 
 _lib = None

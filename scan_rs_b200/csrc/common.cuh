@@ -130,10 +130,12 @@ struct sb_ctx {
     // 2 bit planes on the int8 tensor cores (planes.cu)
     int panel_mode = 2;
     int pl_debug = 0;                // timing experiments only (planes.cu): 1 no output reductions, 2 no epilogue arithmetic, 4 no tile expansion
+    int pl_variant = 3;              // kernel generations of planes.cu (A/B): bit 0 T side (warp layout, paired stages), bit 1 N side (bulk-copied digit rows, 12 producers)
     int plane_cap = 12288;           // most ranks a plane may cover
     int plane_levels = 6;            // most count levels kept as planes (<= PL_MAX_LEVELS)
     double plane_min_density = 0.01; // a 128-rank block joins level k only if this fraction of the cells has exactly that count
     bool upload_sync = true;         // pipelined upload: synchronise the build stream after every chunk (matrix.cu)
+    int gather_items_per_cta = 6;    // T-side gather: work items per CTA on the ticket queue (1 = one static share per CTA)
     bool use_gather = true;          // panelled gather kernels (gather.cu); false: the first-generation K7 / K8 of spmm.cu
     bool direct_projection = false;  // true: always run the wide Q^T A pass (bk_svd.rs:102,131) instead of the R^-T identity
     bool verify_projection = false;  // true: always check the R^-T identity a posteriori (default: only when cond(R) > 1e9)
@@ -199,7 +201,12 @@ struct GatherLayout {
     DevBuf<GUnit> units;
     u32 n_units = 0;
     u32 grid = 0;
-    DevBuf<u32> cta_first;  // N side: [grid + 1] first unit of every CTA (contiguous, nnz-balanced)
+    DevBuf<u32> cta_first;  // [n_items + 1] first unit of every work item (an item = the units one CTA processes back to back)
+    u32 n_items = 0;        // 0: one item per CTA (grid items)
+    // Items are handed to the persistent CTAs through a ticket counter: launch i serves tickets [base_i, base_i + n_items) and every
+    // CTA draws one failing ticket on its way out, so base advances by n_items + grid per launch and the counter is never reset.
+    mutable DevBuf<u32> tickets;
+    mutable u32 ticket_base = 0;
     DevBuf<u32> slot_gene;  // T side: [npanels * rows] gene of a slot or 0xFFFFFFFF
 };
 

@@ -180,6 +180,15 @@ extern "C" int sb_set_option(sb_ctx *ctx, const char *name, double value) {
         ctx->panel_mode = (int)value;
         return SB_OK;
     }
+    if (!strcmp(name, "gather_items_per_cta")) {  // applies to matrices built afterwards
+        if (value < 1 || value > 64) return sb_fail(SB_ERR_INVALID_ARG, "sb_set_option: gather_items_per_cta must be 1..64");
+        ctx->gather_items_per_cta = (int)value;
+        return SB_OK;
+    }
+    if (!strcmp(name, "pl_variant")) {
+        ctx->pl_variant = (int)value;
+        return SB_OK;
+    }
     if (!strcmp(name, "pl_debug")) {  // timing experiments: results are wrong on purpose
         ctx->pl_debug = (int)value;
         return SB_OK;

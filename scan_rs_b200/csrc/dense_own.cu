@@ -483,7 +483,9 @@ __global__ void k_tri_mul(const double *__restrict__ A, const double *__restrict
 // ---------------------------------------------------------------- thin QR by shifted CholeskyQR3
 // A (row-major rows x w, ld) is replaced by Q; Rinv_out (device, column-major w x w, may be NULL) receives R^-1 with A_in = Q R.
 // tmp: a scratch block of the same shape as A.  Needs rows >= w.  *flag is raised on breakdown (the caller falls back).
-int qr_chol(sb_ctx *ctx, double *A, double *tmp, u64 rows, u32 w, u32 ld, double *Rinv_out, int *flag) {
+// rows_global != 0: A is row-sharded over the ranks (a cell-side block) -- the w x w Gram matrices are all-reduced, everything
+// else is local, and every rank ends with its rows of the same Q and the same R^-1 (distributed CholeskyQR).
+int qr_chol(sb_ctx *ctx, double *A, double *tmp, u64 rows, u32 w, u32 ld, double *Rinv_out, int *flag, u64 rows_global) {
     ProfScope ps(ctx, PH_DENSE);
     DevBuf<double> G, Ri, Racc, Rtmp;
     SB_TRY(G.alloc((size_t)w * w));
@@ -491,10 +493,11 @@ int qr_chol(sb_ctx *ctx, double *A, double *tmp, u64 rows, u32 w, u32 ld, double
     if (Rinv_out) SB_TRY(Rtmp.alloc((size_t)w * w));
     // shift of the first round: 11 (m n + n (n + 1)) u ||A||_2^2, with the trace as the bound on ||A||_2^2
     const double u = 1.1102230246251565e-16;
-    const double coef0 = 11.0 * ((double)rows * w + (double)w * (w + 1)) * u;
+    const double coef0 = 11.0 * ((double)(rows_global ? rows_global : rows) * w + (double)w * (w + 1)) * u;
     double *src = A, *dst = tmp;
     for (int pass = 0; pass < 3; pass++) {
         SB_TRY(syrk_tall(ctx, src, rows, w, ld, G.p));
+        if (rows_global) SB_TRY(comm_allreduce_f64(ctx, G.p, (size_t)w * w));
         SB_TRY(chol_inv(ctx, G.p, w, pass == 0 ? coef0 : 0.0, Ri.p, flag));
         SB_TRY(gemm_tall(ctx, src, rows, w, ld, Ri.p, w, w, dst, ld));
         if (Rinv_out) {

@@ -43,9 +43,10 @@
 
 template <int MODE, int TAIL>  // MODE 0: N side, 1: T side.  TAIL: the pass has columns 16..19
 __global__ void __launch_bounds__(GA_THREADS, 1)
-k_gather(const uint2 *__restrict__ ent, const GUnit *__restrict__ units, const u32 *__restrict__ cta_first, u32 n_units, u32 rows,
-         u64 n_cells, MapDev mp, const double *__restrict__ B, u32 ldb, u32 col0, u32 wt, u32 w, const u32 *__restrict__ slot_gene,
-         double *__restrict__ out, u32 ldo) {
+k_gather(const uint2 *__restrict__ ent, const GUnit *__restrict__ units, const u32 *__restrict__ item_first, u32 n_units, u32 n_items,
+         u32 *__restrict__ tickets, u32 ticket_base, u32 rows, u64 n_cells, MapDev mp, const double *__restrict__ B, u32 ldb, u32 col0, u32 wt, u32 w,
+         const u32 *__restrict__ slot_gene, double *__restrict__ out, u32 ldo) {
+    __shared__ u32 s_item;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *XA = reinterpret_cast<double *>(smem_raw);                   // (rows + 1) x 16; row `rows` is all zero
     double *XB = XA + (size_t)(rows + 1) * 16;                            // (rows + 1) x 4 (TAIL only)
@@ -72,9 +73,19 @@ k_gather(const uint2 *__restrict__ ent, const GUnit *__restrict__ units, const u
 
     for (int i = threadIdx.x; i < 128; i += blockDim.x) ltab[i] = sb_log_table[i];
 
-    const u32 u_begin = cta_first[blockIdx.x], u_end = min(n_units, cta_first[blockIdx.x + 1]);
     u32 staged = GA_NONE;
 
+    // Persistent CTAs draw work items (runs of units, panel-major) from a ticket counter: the cost model that cuts the T-side line
+    // into items is only approximate (ncu: sm__cycles_active 1.19 / 1.49 / 1.79 M min / avg / max with one static share per CTA),
+    // so the line is cut several times finer than the grid and whoever finishes early takes the next piece -- usually of the
+    // panel it has already staged.
+    for (;;) {
+    __syncthreads();  // every warp is done with the previous item (and has read s_item)
+    if (threadIdx.x == 0) s_item = atomicAdd(tickets, 1u) - ticket_base;
+    __syncthreads();
+    const u32 item = s_item;
+    if (item >= n_items) break;
+    const u32 u_begin = item_first[item], u_end = min(n_units, item_first[item + 1]);
     for (u32 ui = u_begin; ui < u_end; ui++) {
         const GUnit un = units[ui];
         if (un.panel != staged) {
@@ -168,8 +179,6 @@ k_gather(const uint2 *__restrict__ ent, const GUnit *__restrict__ units, const u
             // general entries carry an explicit factor; a count of 1 under the log chain is the staged row itself (N side)
             // or is scaled once per run at the flush (T side)
             const bool general = valid && (!logchain || z.y != 1u);
-            double l1v = 0.0;
-            if (MODE == 1 && valid) l1v = logchain ? mp.l1[key] : 1.0;
             double x = 0.0;
             if (general) {
                 if (MODE == 0) {
@@ -184,6 +193,9 @@ k_gather(const uint2 *__restrict__ ent, const GUnit *__restrict__ units, const u
             u32 prev = __shfl_up_sync(FULLMASK, key, 1, 8);
             if (lig == 0) prev = carry;
             const bool head = valid && key != prev;
+            // T side: L_c(1) is consumed once per run (at its flush): only the entry that opens a run fetches it
+            double l1v = 0.0;
+            if (MODE == 1 && head) l1v = logchain ? mp.l1[key] : 1.0;
             carry = __shfl_sync(FULLMASK, key, 7, 8);
             const u32 myh = (__ballot_sync(FULLMASK, head) >> (8 * grp)) & 0xFFu;
             const u32 myg = (__ballot_sync(FULLMASK, general) >> (8 * grp)) & 0xFFu;
@@ -191,7 +203,7 @@ k_gather(const uint2 *__restrict__ ent, const GUnit *__restrict__ units, const u
             asm volatile("st.shared.u16 [%0], %1;" ::"r"(stage_grp + (u32)lig * 2u), "h"((unsigned short)(valid ? local * 8u : zero_off16)) : "memory");
             asm volatile("st.shared.u32 [%0], %1;" ::"r"(stage_grp + GA_ST_KEYS + (u32)lig * 4u), "r"(key) : "memory");
             if (general) asm volatile("st.shared.f64 [%0], %1;" ::"r"(stage_grp + GA_ST_XS + (u32)lig * 8u), "d"(x) : "memory");
-            if (MODE == 1) asm volatile("st.shared.f64 [%0], %1;" ::"r"(stage_grp + GA_ST_L1 + (u32)lig * 8u), "d"(l1v) : "memory");
+            if (MODE == 1 && head) asm volatile("st.shared.f64 [%0], %1;" ::"r"(stage_grp + GA_ST_L1 + (u32)lig * 8u), "d"(l1v) : "memory");
             __syncwarp();
             u32 ov[4];
             asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(ov[0]), "=r"(ov[1]), "=r"(ov[2]), "=r"(ov[3]) : "r"(stage_grp));
@@ -230,6 +242,7 @@ k_gather(const uint2 *__restrict__ ent, const GUnit *__restrict__ units, const u
         }
         flush();
     }
+    }
 }
 
 // out[c, j] = v_c * uy[j] (or 0): the rank-1 offset of A^T.Y; the dense panel kernel and the gather add on top
@@ -258,7 +271,17 @@ static size_t gather_smem(u32 rows, bool tail) {
 int gather_run(sb_ctx *ctx, const GatherLayout &L, int mode, const MapDev &mp, u64 n_cells, const double *B, u32 ldb, u32 w, double *out, u32 ldo) {
     if (!L.ready) return sb_fail(SB_ERR_UNSUPPORTED, "gather_run: layout not built");
     if (L.nnz == 0 || L.n_units == 0 || w == 0) return SB_OK;
+    const u32 n_items = L.n_items ? L.n_items : L.grid;
+    if (!L.tickets.p) {
+        SB_TRY(L.tickets.alloc(1));
+        SB_CUDA(cudaMemsetAsync(L.tickets.p, 0, sizeof(u32), ctx->stream));
+        L.ticket_base = 0;
+    }
     for (u32 col0 = 0; col0 < w; col0 += GA_TILE) {
+        if (L.ticket_base > 0x7F000000u) {  // long before the u32 ticket counter could wrap
+            SB_CUDA(cudaMemsetAsync(L.tickets.p, 0, sizeof(u32), ctx->stream));
+            L.ticket_base = 0;
+        }
         const u32 wt = std::min(GA_TILE, w - col0);
         const bool tail = wt > 16;
         const size_t smem = gather_smem(L.rows, tail);
@@ -266,8 +289,8 @@ int gather_run(sb_ctx *ctx, const GatherLayout &L, int mode, const MapDev &mp, u
 #define GA_LAUNCH(M, T)                                                                                                                        \
     e = cudaFuncSetAttribute(k_gather<M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                          \
     if (e == cudaSuccess)                                                                                                                      \
-        k_gather<M, T><<<L.grid, GA_THREADS, smem, ctx->stream>>>(L.ent, L.units.p, L.cta_first.p, L.n_units, L.rows, n_cells,                    \
-                                                                  mp, B, ldb, col0, wt, w, L.slot_gene.p, out, ldo);
+        k_gather<M, T><<<L.grid, GA_THREADS, smem, ctx->stream>>>(L.ent, L.units.p, L.cta_first.p, L.n_units, n_items, L.tickets.p, L.ticket_base, \
+                                                                  L.rows, n_cells, mp, B, ldb, col0, wt, w, L.slot_gene.p, out, ldo);
         if (mode == 0) {
             if (tail) { GA_LAUNCH(0, 1) } else { GA_LAUNCH(0, 0) }
         } else {
@@ -275,6 +298,7 @@ int gather_run(sb_ctx *ctx, const GatherLayout &L, int mode, const MapDev &mp, u
         }
 #undef GA_LAUNCH
         if (e != cudaSuccess) return sb_fail(SB_ERR_CUDA, "gather_run: %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+        L.ticket_base += n_items + L.grid;
         count_launch(ctx);
     }
     SB_CUDA(cudaGetLastError());
@@ -473,8 +497,10 @@ int gather_finish_t(sb_mat *mt, const std::vector<u64> &seg_len, const std::vect
     mt->t_seg_runs = seg_runs;
     std::vector<GUnit> units;
     std::vector<u32> first;
-    gather_units_t(seg_len, seg_runs, L.npanels, (u32)ctx->sm_count, GA_FLUSH_COST, units, first);
-    L.grid = (u32)first.size() - 1;
+    const u32 per_cta = (u32)std::max(1, ctx->gather_items_per_cta);
+    gather_units_t(seg_len, seg_runs, L.npanels, (u32)ctx->sm_count * per_cta, GA_FLUSH_COST, units, first);
+    L.n_items = (u32)first.size() - 1;
+    L.grid = std::min<u32>(L.n_items, (u32)ctx->sm_count);
     L.n_units = (u32)units.size();
     SB_TRY(L.units.alloc(units.size()));
     SB_TRY(L.cta_first.alloc(first.size()));

@@ -1201,7 +1201,6 @@ extern "C" int sb_select_rows(sb_mat *mat, const uint32_t *rows, uint32_t count,
 
 extern "C" int sb_select_cols(sb_mat *mat, const uint64_t *cols, uint64_t count, sb_mat **out) {
     if (!mat || !out || (count && !cols)) return sb_fail(SB_ERR_INVALID_ARG, "sb_select_cols: NULL argument");
-    if (mat->ctx->nranks > 1) return sb_fail(SB_ERR_UNSUPPORTED, "sb_select_cols: single-rank only");
     SB_ENTER(mat->ctx);
     *out = nullptr;
     return select_cols_dev(mat, cols, count, out);
@@ -1212,7 +1211,9 @@ extern "C" int sb_partition(sb_mat *mat, int has_row_thr, double row_thr, int ha
                             sb_mat **residual, uint64_t *rows_out, uint64_t *n_rows_out, uint64_t *cols_out, uint64_t *n_cols_out) {
     if (!mat) return sb_fail(SB_ERR_INVALID_ARG, "sb_partition: mat is NULL");
     sb_ctx *ctx = mat->ctx;
-    if (ctx->nranks > 1) return sb_fail(SB_ERR_UNSUPPORTED, "sb_partition: single-rank only");
+    // Sharded contexts: a cell belongs to one rank, so the column sums and the column verdicts stay local; the row
+    // (gene) sums are all-reduced every round (exact u64) and so is the "something changed" flag -- every rank runs the same
+    // number of rounds and ends with the same row set.  cols_out are LOCAL cell indices.
     SB_ENTER(ctx);
     if (kept) *kept = nullptr;
     if (residual) *residual = nullptr;
@@ -1223,9 +1224,9 @@ extern "C" int sb_partition(sb_mat *mat, int has_row_thr, double row_thr, int ha
     SB_TRY(sums.alloc(std::max<u64>(mat->m, mat->n)));
     SB_CUDA(cudaMemsetAsync(ex_rows.p, 0, mat->m ? mat->m : 1, ctx->stream));
     SB_CUDA(cudaMemsetAsync(ex_cols.p, 0, mat->n ? mat->n : 1, ctx->stream));
-    void *scr;
-    SB_TRY(ctx_scratch(ctx, 256, &scr));
-    int *d_upd = (int *)scr;
+    DevBuf<int> upd_flag;  // private: the context scratch is the staging buffer of the collectives below
+    SB_TRY(upd_flag.alloc(1));
+    int *d_upd = upd_flag.p;
     for (;;) {
         SB_CUDA(cudaMemsetAsync(d_upd, 0, sizeof(int), ctx->stream));
         if (has_col_thr && mat->n) {  // mat.rs:783-790
@@ -1235,13 +1236,14 @@ extern "C" int sb_partition(sb_mat *mat, int has_row_thr, double row_thr, int ha
             count_launch(ctx); count_launch(ctx);
         }
         if (has_row_thr && mat->m) {  // mat.rs:791-798
-            SB_TRY(mat_gene_sums_dev(mat, 0, ex_cols.p, ex_rows.p, sums.p, false));
+            SB_TRY(mat_gene_sums_dev(mat, 0, ex_cols.p, ex_rows.p, sums.p, ctx->nranks > 1));
             k_apply_threshold<<<cdiv(mat->m, 256), 256, 0, ctx->stream>>>((unsigned long long *)sums.p, mat->m, row_thr, ex_rows.p, d_upd);
             count_launch(ctx);
         }
         int upd = 0;
         SB_CUDA(cudaMemcpyAsync(&upd, d_upd, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         SB_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->nranks > 1) SB_TRY(comm_allreduce_max_i32(ctx, &upd));
         if (!upd) break;
     }
     std::vector<unsigned char> hr(mat->m), hc(mat->n);

@@ -17,7 +17,7 @@ int gemm_tall_small(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 lda, cons
 // dense_own.cu: the repo's own tall-skinny kernels (FP64 mma.sync) and the CholeskyQR3 factorisation
 int syrk_tall(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 ld, double *G);
 int gemm_tall(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 lda, const double *S, u32 k, u32 lds, double *Out, u32 ldo);
-int qr_chol(sb_ctx *ctx, double *A, double *tmp, u64 rows, u32 w, u32 ld, double *Rinv_out, int *flag);
+int qr_chol(sb_ctx *ctx, double *A, double *tmp, u64 rows, u32 w, u32 ld, double *Rinv_out, int *flag, u64 rows_global = 0);
 int topk_select(sb_ctx *ctx, const double *W, const double *ev, u32 wq, u32 k, double *Wsel, double *Wsc, double *S);
 int comm_allreduce_f64(sb_ctx *ctx, double *buf, size_t count);
 
@@ -300,11 +300,14 @@ static int check_shape(const sb_nmat *a, u32 k) {
 // ---------------------------------------------------------------- block Krylov SVD
 // Thin QR of a tall block in place.  own: shifted CholeskyQR3 on the repo's kernels (dense_own.cu), no host synchronisation,
 // Rinv_out (optional) = R^-1; otherwise LAPACK-style Householder through cuSOLVER (dense.cu), R_out (optional) = R.
-static int qr_block(sb_ctx *ctx, bool own, Tall &A, Tall &tmp, u32 *wq, double *tri_out, int *flag_dev) {
+// rows_global != 0: A is a cell-side block row-sharded over the ranks; only the CholeskyQR path can factor it (one all-reduce of
+// the Gram matrix per round), so `own` must hold.
+static int qr_block(sb_ctx *ctx, bool own, Tall &A, Tall &tmp, u32 *wq, double *tri_out, int *flag_dev, u64 rows_global = 0) {
     if (own) {
         *wq = A.w;
-        return qr_chol(ctx, A.buf.p, tmp.buf.p, A.rows, A.w, A.ld, tri_out, flag_dev);
+        return qr_chol(ctx, A.buf.p, tmp.buf.p, A.rows, A.w, A.ld, tri_out, flag_dev, rows_global);
     }
+    if (rows_global) return sb_fail(SB_ERR_UNSUPPORTED, "the Householder QR of a cell-side block is single-rank (sharded runs need own_dense = 1 and a block with 4 w <= n)");
     return qr_tall(ctx, A.buf.p, A.rows, A.w, A.ld, wq, tri_out);
 }
 
@@ -345,13 +348,14 @@ static int bksvd_impl(sb_nmat *a, uint32_t k, uint32_t b, uint32_t n_iter, uint6
     double cond = 0.0;
 
     if ((u64)m >= ng) {
-        // ---- m >= n (bk_svd.rs:89-115): block on the cell side; single rank only
-        if (ctx->nranks > 1) return sb_fail(SB_ERR_UNSUPPORTED, "sb_bksvd: the m >= n branch is single-rank");
+        // ---- m >= n (bk_svd.rs:89-115): block on the cell side.  Sharded: B and K are row-sharded like the cells, their QRs are
+        // distributed CholeskyQR (Gram matrices all-reduced), A.B is all-reduced by spmm_n, T = A.Q and its SVD are replicated.
+        const u64 sh = ctx->nranks > 1 ? ng : 0;  // rows_global of the cell-side blocks
         Tall B, Kc, W, WK, tmpB, tmpK;
-        const bool fast = !ctx->direct_projection && !force_direct && (b % 2 == 0) && (u64)bq <= n;
-        const bool own_b = own_qr && n >= 4ull * b, own_k = own_qr && n >= 4ull * bq;
+        const bool fast = !ctx->direct_projection && !force_direct && (b % 2 == 0) && (u64)bq <= ng;
+        const bool own_b = own_qr && ng >= 4ull * b, own_k = own_qr && ng >= 4ull * bq;
         SB_TRY(B.init(ctx, n, b));
-        if (!omega) omega = omega_cached(ctx, seed, n, b);  // :90 (n x b, row-major fill)
+        if (!omega) omega = omega_cached(ctx, seed, ng, b) + (size_t)mt->cell_offset * b;  // :90 (n x b, row-major fill): this rank's rows
         SB_TRY(upload_tall(ctx, B, omega, false));
         SB_TRY(Kc.init(ctx, n, bq));
         SB_TRY(W.init(ctx, m, b, 1));
@@ -363,7 +367,7 @@ static int bksvd_impl(sb_nmat *a, uint32_t k, uint32_t b, uint32_t n_iter, uint6
             SB_TRY(spmm_n(a, B.buf.p, B.ld, b, Wp, Wld));                   // A.dot(&B)
             SB_TRY(spmm_t(a, Wp, Wld, b, B.buf.p, B.ld, uy.p));              // (.)^T.dot(A) ^T
             u32 wq = 0;
-            SB_TRY(qr_block(ctx, own_b, B, tmpB, &wq, nullptr, chol_flag));  // .qr()?.0   :94
+            SB_TRY(qr_block(ctx, own_b, B, tmpB, &wq, nullptr, chol_flag, sh));  // .qr()?.0   :94
             SB_TRY(copy_block(ctx, Kc.buf.p, Kc.ld, i * b, B.buf.p, B.ld, n, b));  // :95
             SB_TRY(progress(ctx, cb, user, (double)i / (double)n_iter * 0.8));     // :96
         }
@@ -372,7 +376,7 @@ static int bksvd_impl(sb_nmat *a, uint32_t k, uint32_t b, uint32_t n_iter, uint6
         SB_TRY(tri.alloc((size_t)bq * bq));
         if (fast) SB_TRY(spmm_n(a, B.buf.p, B.ld, b, WK.buf.p + (size_t)(n_iter - 1) * b, WK.ld));  // A . B_q
         if (own_k) SB_TRY(tmpK.init(ctx, n, bq));
-        SB_TRY(qr_block(ctx, own_k, Kc, tmpK, &wq, tri.p, chol_flag));       // :98
+        SB_TRY(qr_block(ctx, own_k, Kc, tmpK, &wq, tri.p, chol_flag, sh));   // :98
         tmpK.buf.release();
         SB_TRY(progress(ctx, cb, user, 0.82));
         int mode = 0;
@@ -399,6 +403,7 @@ static int bksvd_impl(sb_nmat *a, uint32_t k, uint32_t b, uint32_t n_iter, uint6
         SB_CUDA(cudaMemcpyAsync(&hst, status.p, sizeof(hst), cudaMemcpyDeviceToHost, ctx->stream));
         SB_TRY(download_tall(ctx, Uo, U));
         SB_TRY(download_tall(ctx, Vo, V));
+        if (hst.chol_flag && sh) return sb_fail(SB_ERR_LINALG, "sb_bksvd: CholeskyQR broke down on a sharded cell-side block (rank-deficient Krylov block)");
         if (hst.chol_flag) { *retry_householder = true; return SB_OK; }
         if (hst.eig_info != 0) return sb_fail(SB_ERR_LINALG, "eigendecomposition failed: info = %d", hst.eig_info);
         SB_TRY(progress(ctx, cb, user, 1.0));
@@ -567,10 +572,12 @@ extern "C" int sb_randsvd(sb_nmat *a, uint32_t k, uint32_t l, uint32_t n_iter, u
     sb_ctx *ctx = mt->ctx;
     SB_ENTER(ctx);
     SB_TRY(check_shape(a, k));
-    if (ctx->nranks > 1) return sb_fail(SB_ERR_UNSUPPORTED, "sb_randsvd: single-rank only (its QR runs on the cell side)");
     const u32 m = mt->m;
-    const u64 n = mt->n;
-    if ((u64)l > std::min<u64>(m, n)) return sb_fail(SB_ERR_UNSUPPORTED, "sb_randsvd: l = %u exceeds min(m, n)", l);
+    const u64 n = mt->n, ng = mt->n_global;
+    // Sharded: the gene-side blocks are replicated (any QR), the cell-side blocks are row-sharded (distributed CholeskyQR).
+    const u64 sh = ctx->nranks > 1 ? ng : 0;
+    if ((u64)l > std::min<u64>(m, ng)) return sb_fail(SB_ERR_UNSUPPORTED, "sb_randsvd: l = %u exceeds min(m, n)", l);
+    if (sh && !(ctx->own_dense && ng >= 4ull * l)) return sb_fail(SB_ERR_UNSUPPORTED, "sb_randsvd: sharded runs need own_dense = 1 and 4 l <= n");
     if (l < k) return sb_fail(SB_ERR_INVALID_K, "invalid k");
     DevBuf<double> uy;
     SB_TRY(uy.alloc(even_up(l) + 2));
@@ -581,28 +588,38 @@ extern "C" int sb_randsvd(sb_nmat *a, uint32_t k, uint32_t l, uint32_t n_iter, u
     SB_TRY(S_dev.alloc(k));
     SB_TRY(einfo.alloc(1));
     SB_CUDA(cudaMemsetAsync(einfo.p, 0, sizeof(int), ctx->stream));
-    Tall Qm, Qn;  // gene-side (m x l, +1 row for spmm_n) and cell-side (n x l) blocks
+    Tall Qm, Qn, tmpN;  // gene-side (m x l, +1 row for spmm_n) and cell-side (n x l) blocks
     SB_TRY(Qm.init(ctx, m, l, 1));
     SB_TRY(Qn.init(ctx, n, l));
+    DevBuf<int> cflag;
+    SB_TRY(cflag.alloc(1));
+    SB_CUDA(cudaMemsetAsync(cflag.p, 0, sizeof(int), ctx->stream));
+    if (sh) SB_TRY(tmpN.init(ctx, n, l));
     u32 wq = 0;
-    if ((u64)m >= n) {  // rand_svd.rs:85-105
+    // the cell-side QR: Householder on one rank (as the reference), distributed CholeskyQR3 on a sharded context
+    auto qr_cells = [&]() -> int {
+        if (!sh) return qr_tall(ctx, Qn.buf.p, n, l, Qn.ld, &wq);
+        wq = l;
+        return qr_chol(ctx, Qn.buf.p, tmpN.buf.p, n, l, Qn.ld, nullptr, cflag.p, sh);
+    };
+    if ((u64)m >= ng) {  // rand_svd.rs:85-105
         if (!omega) {
-            h_om.resize((size_t)n * l);
-            SB_TRY(sb_omega(seed, n, l, h_om.data()));
-            omega = h_om.data();
+            h_om.resize((size_t)ng * l);
+            SB_TRY(sb_omega(seed, ng, l, h_om.data()));
+            omega = h_om.data() + (size_t)mt->cell_offset * l;  // this rank's rows of the n x l start block
         }
         SB_TRY(upload_tall(ctx, Qn, omega, false));
         SB_TRY(spmm_n(a, Qn.buf.p, Qn.ld, l, Qm.buf.p, Qm.ld));              // Q = A.dot(&omega).qr()  :87
         SB_TRY(qr_tall(ctx, Qm.buf.p, m, l, Qm.ld, &wq));
         for (u32 i = 0; i < n_iter; i++) {
             SB_TRY(spmm_t(a, Qm.buf.p, Qm.ld, l, Qn.buf.p, Qn.ld, uy.p));     // Q.t().dot(A)^T .qr()    :90
-            SB_TRY(qr_tall(ctx, Qn.buf.p, n, l, Qn.ld, &wq));
+            SB_TRY(qr_cells());
             SB_TRY(spmm_n(a, Qn.buf.p, Qn.ld, l, Qm.buf.p, Qm.ld));          // A.dot(&Q).qr()          :91
             SB_TRY(qr_tall(ctx, Qm.buf.p, m, l, Qm.ld, &wq));
         }
         SB_TRY(spmm_t(a, Qm.buf.p, Qm.ld, l, Qn.buf.p, Qn.ld, uy.p));         // B = Q.t().dot(A)        :96  (stored as B^T)
         Tall Vo, Uo;
-        SB_TRY(finish_svd(ctx, Qn, Qm, l, k, false, S_dev.p, einfo.p, Vo, Uo)); // U = Q.U_B               :104
+        SB_TRY(finish_svd(ctx, Qn, Qm, l, k, sh != 0, S_dev.p, einfo.p, Vo, Uo)); // U = Q.U_B             :104 (Gram of the sharded B^T: all-reduced)
         SB_CUDA(cudaMemcpyAsync(S, S_dev.p, k * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         SB_CUDA(cudaMemcpyAsync(&h_info, einfo.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         SB_TRY(download_tall(ctx, Uo, U));
@@ -615,12 +632,12 @@ extern "C" int sb_randsvd(sb_nmat *a, uint32_t k, uint32_t l, uint32_t n_iter, u
         }
         SB_TRY(upload_tall(ctx, Qm, omega, true));
         SB_TRY(spmm_t(a, Qm.buf.p, Qm.ld, l, Qn.buf.p, Qn.ld, uy.p));         // omega.dot(A)^T .qr()    :109
-        SB_TRY(qr_tall(ctx, Qn.buf.p, n, l, Qn.ld, &wq));
+        SB_TRY(qr_cells());
         for (u32 i = 0; i < n_iter; i++) {
             SB_TRY(spmm_n(a, Qn.buf.p, Qn.ld, l, Qm.buf.p, Qm.ld));          // A.dot(&Q).qr()          :112
             SB_TRY(qr_tall(ctx, Qm.buf.p, m, l, Qm.ld, &wq));
             SB_TRY(spmm_t(a, Qm.buf.p, Qm.ld, l, Qn.buf.p, Qn.ld, uy.p));     // Q.t().dot(A)^T .qr()    :113
-            SB_TRY(qr_tall(ctx, Qn.buf.p, n, l, Qn.ld, &wq));
+            SB_TRY(qr_cells());
         }
         SB_TRY(spmm_n(a, Qn.buf.p, Qn.ld, l, Qm.buf.p, Qm.ld));              // B = A.dot(&Q)           :118
         Tall Uo, Vo;
@@ -631,6 +648,12 @@ extern "C" int sb_randsvd(sb_nmat *a, uint32_t k, uint32_t l, uint32_t n_iter, u
         SB_TRY(download_tall(ctx, Vo, V));
     }
     if (h_info != 0) return sb_fail(SB_ERR_LINALG, "eigendecomposition failed: info = %d", h_info);
+    if (sh) {
+        int h_flag = 0;
+        SB_CUDA(cudaMemcpyAsync(&h_flag, cflag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        SB_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (h_flag) return sb_fail(SB_ERR_LINALG, "sb_randsvd: CholeskyQR broke down on a sharded cell-side block");
+    }
     return SB_OK;
 }
 

@@ -477,8 +477,25 @@ __device__ __forceinline__ void read_acc_fma(u32 taddr, double lk, double (&res)
 // Roles: warps 0-3 epilogue, warp 4 MMA issue, warps 5-20 producers, warp 21 scheduler.  The producers' refill latency
 // (expand one sub-stage after its slot was freed) against the MMA work in flight in the ring decides the throughput: sixteen
 // warps each own a 4 KB sub-slot (one MMA's A operand), four sub-slots make a stage.
-#define PT_WARPS (PL_EPI_WARPS + 1 + PT_PROD_WARPS + 1)
-#define PT_THREADS (PT_WARPS * 32)
+// Two warp layouts.  V = 0 (first version): warps 0-3 epilogue, 4 MMA, 5-12 producers, 13 item scheduler.  V = 1: a warp's
+// scheduler is warp % 4, and the MMA-issuing warp is the critical path of the kernel (ncu, profiles/planes_r02_ncu.md: the tensor
+// pipe idles while warp 4 works through ~60 instructions per 4-MMA stage), so it shares its scheduler only with epilogue warp 0
+// and two warps that are almost always asleep (the item scheduler and a spare): epilogue 0-3, MMA 4, item scheduler 8, spare 12,
+// producers 5-7, 9-11, 13-14.
+template <int V> struct PtLayout;
+template <> struct PtLayout<0> {
+    static constexpr u32 WARPS = PL_EPI_WARPS + 1 + PT_PROD_WARPS + 1;
+    __device__ static __forceinline__ bool is_sched(u32 w) { return w == WARPS - 1; }
+    __device__ static __forceinline__ bool is_spare(u32) { return false; }
+    __device__ static __forceinline__ u32 prod_index(u32 w) { return w - (PL_EPI_WARPS + 1); }
+};
+template <> struct PtLayout<1> {
+    static constexpr u32 WARPS = 15;
+    __device__ static __forceinline__ bool is_sched(u32 w) { return w == 8; }
+    __device__ static __forceinline__ bool is_spare(u32 w) { return w == 12; }
+    __device__ static __forceinline__ u32 prod_index(u32 w) { return w < 8 ? w - 5 : (w < 12 ? w - 6 : w - 7); }  // 5,6,7,9,10,11,13,14 -> 0..7
+};
+#define PT_MAX_THREADS (15 * 32)
 struct PtShared {
     unsigned long long full[PT_NSTG], empty[PT_NSTG], tfull[3], tempty[3], item_full[2], item_empty[2];
     u32 tmem;
@@ -495,7 +512,8 @@ struct PtShared {
 // Output: the CTA's 20 values per (unit, cell) go to part[unit][cell][20] with plain stores -- every (unit, tile) is
 // produced exactly once -- and k_pl_reduce_t adds the units up (f64 reductions into T cost 1.3 cycles per lane on the
 // LSU and were the bottleneck of the first version: 0.43 of 1.5 ms).
-__global__ void __launch_bounds__(PT_THREADS, 1)
+template <int V>
+__global__ void __launch_bounds__(PtLayout<V>::WARPS * 32, 1)
 k_planes_t(PlDev pl, const PlUnitT *__restrict__ units, const PlItem *__restrict__ items, u32 n_items, u32 *__restrict__ counter,
            const signed char *__restrict__ Bd, const double *__restrict__ scale2_g, const double *__restrict__ cs, int log_base, u32 wt,
            double *__restrict__ part, u32 dbg) {
@@ -503,6 +521,8 @@ k_planes_t(PlDev pl, const PlUnitT *__restrict__ units, const PlItem *__restrict
     unsigned char *sB = smem;
     unsigned char *sA = sB + PT_B_BYTES;
     PtShared *sh = reinterpret_cast<PtShared *>(sA + PT_NSTAGES * PT_STAGE_BYTES);
+    using LY = PtLayout<V>;
+    constexpr u32 PT_WARPS = LY::WARPS, PT_THREADS = LY::WARPS * 32;
     const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const u32 full0 = smem_u32(sh->full), empty0 = smem_u32(sh->empty), tfull0 = smem_u32(sh->tfull), tempty0 = smem_u32(sh->tempty);
     const u32 ifull0 = smem_u32(sh->item_full), iempty0 = smem_u32(sh->item_empty);
@@ -532,7 +552,7 @@ k_planes_t(PlDev pl, const PlUnitT *__restrict__ units, const PlItem *__restrict
     const u32 idesc = instr_desc_i8(PL_TILE, PL_NCOL, false, false);
     const uint64_t da_hi = smem_desc(0, PL_TILE * 16, 128), db_hi = smem_desc(0, PT_KCHUNK_BYTES, 128);
     const u64 n_pad = pl.ntiles * PL_TILE;
-    const bool scheduler = warp == PT_WARPS - 1;
+    const bool scheduler = LY::is_sched(warp);
 
     u32 q = 0;      // 64-gene sub-stages before this item (producers) / issued so far (MMA)
     u32 job = 0;    // (tile, level) accumulation jobs so far
@@ -623,6 +643,9 @@ k_planes_t(PlDev pl, const PlUnitT *__restrict__ units, const PlItem *__restrict
             // 5 x R2UR.BROADCAST / branch loop -- ~90 instructions per 4-MMA stage, more than the 288 cycles the MMAs take.
             {
                 const u32 a16 = sA_addr >> 4, b16 = sB_addr >> 4;
+                // V = 1: the low descriptor words carry the leading-byte-offset field (bits 16-29; the 14-bit address field below
+                // it never carries into it), so a descriptor is one add away from the previous one and the high word is an immediate
+                const u32 a16x = a16 + ((PL_TILE * 16u >> 4) << 16), b16x = b16 + ((PT_KCHUNK_BYTES >> 4) << 16);
                 auto level = [&](u32 nkb) {
                     const u32 slot = job % 3u;
                     if (job >= 3u) {
@@ -630,7 +653,47 @@ k_planes_t(PlDev pl, const PlUnitT *__restrict__ units, const PlItem *__restrict
                         fence_after_sync();
                     }
                     const u32 acc = tmem + slot * PL_NCOL;
-                    for (u32 kb = 0; kb < nkb; kb += PT_SUB * PT_WORDS) {  // kb counts 32-gene blocks (one MMA each)
+                    u32 kb = 0;
+                    if (V == 1) {
+                        // two stages (eight MMAs) per election when the second stage is already full: the loop / election /
+                        // reconvergence overhead of the issuing warp is paid once per 576 tensor-pipe cycles instead of per 288
+                        while (kb < nkb) {
+                            const u32 sg = q / PT_SUB, ss = sg & (PT_NSTG - 1);
+                            mbar_spin(full0 + 8 * ss, (sg / PT_NSTG) & 1u);
+                            const u32 sg2 = sg + 1, ss2 = sg2 & (PT_NSTG - 1);
+                            bool two = kb + 2 * PT_SUB * PT_WORDS <= nkb;
+                            if (two) two = __all_sync(0xffffffffu, mbar_test(full0 + 8 * ss2, (sg2 / PT_NSTG) & 1u));
+                            fence_after_sync();
+                            const u32 alo = a16x + ss * (PT_SUB * PT_STAGE_BYTES >> 4), blo = b16x + kb * (2 * PT_KCHUNK_BYTES >> 4);
+                            if (two) {
+                                const u32 alo2 = a16x + ss2 * (PT_SUB * PT_STAGE_BYTES >> 4);
+                                if (elect_one()) {
+#pragma unroll
+                                    for (u32 t = 0; t < PT_SUB * PT_WORDS; t++)
+                                        mma_i8_lo<0x4008u, 0x4008u>(acc, alo + t * (PL_TILE * 32 >> 4), blo + t * (2 * PT_KCHUNK_BYTES >> 4), idesc, kb | t);
+                                    commit(empty0 + 8 * ss);
+#pragma unroll
+                                    for (u32 t = 0; t < PT_SUB * PT_WORDS; t++)
+                                        mma_i8_lo<0x4008u, 0x4008u>(acc, alo2 + t * (PL_TILE * 32 >> 4), blo + (PT_SUB * PT_WORDS + t) * (2 * PT_KCHUNK_BYTES >> 4), idesc, 1u);
+                                    commit(empty0 + 8 * ss2);
+                                }
+                                __syncwarp();
+                                q += 2 * PT_SUB;
+                                kb += 2 * PT_SUB * PT_WORDS;
+                            } else {
+                                if (elect_one()) {
+#pragma unroll
+                                    for (u32 t = 0; t < PT_SUB * PT_WORDS; t++)
+                                        mma_i8_lo<0x4008u, 0x4008u>(acc, alo + t * (PL_TILE * 32 >> 4), blo + t * (2 * PT_KCHUNK_BYTES >> 4), idesc, kb | t);
+                                    commit(empty0 + 8 * ss);
+                                }
+                                __syncwarp();
+                                q += PT_SUB;
+                                kb += PT_SUB * PT_WORDS;
+                            }
+                        }
+                    }
+                    for (; kb < nkb; kb += PT_SUB * PT_WORDS) {  // kb counts 32-gene blocks (one MMA each)
                         const u32 sg = q / PT_SUB, ss = sg & (PT_NSTG - 1);
                         mbar_spin(full0 + 8 * ss, (sg / PT_NSTG) & 1u);
                         fence_after_sync();
@@ -654,10 +717,10 @@ k_planes_t(PlDev pl, const PlUnitT *__restrict__ units, const PlItem *__restrict
                     if (nlev > 2) level(nkb2);
                 }
             }
-        } else if (!scheduler) {
+        } else if (!scheduler && !LY::is_spare(warp)) {
             // ===== producers: plane words -> 0/1 int8 A tiles (K-major core matrices: [16-gene chunk][cell / 8][cell % 8][16 B])
             // warp p fills sub-slot p: the sub-stages (PT_WORDS x 32 genes of one level) with global index = p (mod PT_NSTAGES)
-            const u32 p = warp - (PL_EPI_WARPS + 1);
+            const u32 p = LY::prod_index(warp);
             const u32 G0 = pl.G[lev0] >> 5, G1w = pl.G[lev1] >> 5, G2w = pl.G[lev2] >> 5;
             const u32 *bits0 = pl.bits[lev0], *bits1 = pl.bits[lev1], *bits2 = pl.bits[lev2];
             const u32 s0 = nkb0 / PT_WORDS, s1 = nkb1 / PT_WORDS;  // sub-stages of levels 0, 1 per tile
@@ -828,7 +891,11 @@ struct PnShared {
 // out[gene * row_stride + (col0 + j) * col_stride] += value
 // Persistent CTAs pull work items {group of 384 ranks, range of cell tiles} from a global queue (about equal cost each); an item
 // ends with its epilogue (the accumulators are reused by the next item), so the CTA-wide barrier between items costs nothing extra.
-__global__ void __launch_bounds__(PL_THREADS, 1)
+// V = 1: twelve producer warps (ncu: the N side waits on its producers -- 114 polls of the `full` barrier per stage by the MMA
+// warp, producers busy 80 % of the time) and the digit rows of a sub-stage (4,608 contiguous bytes) arrive by one bulk
+// asynchronous copy (cp.async.bulk, completion counted on the stage's `full` barrier) instead of 9 LDG.128 + 9 STS.128 per lane.
+template <int V>
+__global__ void __launch_bounds__((PL_EPI_WARPS + 1 + (V ? 12 : 8)) * 32, 1)
 k_planes_n(PlDev pl, const PlUnitN *__restrict__ units, const PlItem *__restrict__ items, u32 n_items, u32 *__restrict__ counter,
            const signed char *__restrict__ Bn, u64 n_pad, const double *__restrict__ scale2_g, const u32 *__restrict__ hot_idx, u32 col0, u32 wt,
            double *__restrict__ out, u64 row_stride, u64 col_stride) {
@@ -837,6 +904,7 @@ k_planes_n(PlDev pl, const PlUnitN *__restrict__ units, const PlItem *__restrict
     PnShared *sh = reinterpret_cast<PnShared *>(sS + PN_NSTAGES * PN_STAGE_BYTES);
     const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const u32 full0 = smem_u32(sh->full), empty0 = smem_u32(sh->empty), tfull0 = smem_u32(&sh->tfull);
+    constexpr u32 PW = V ? 12u : 8u;  // producer warps
     if (tid == 0) {
         for (u32 i = 0; i < PN_NSTG; i++) {
             mbar_init(full0 + 8 * i, PN_SUB);  // one arrival per producer warp of the stage
@@ -896,7 +964,19 @@ k_planes_n(PlDev pl, const PlUnitN *__restrict__ units, const PlItem *__restrict
                     mbar_spin(full0 + 8 * slot, (sg / PN_NSTG) & 1u);
                     fence_after_sync();
                     const u32 nmt = mtp & 15u;
-                    if (elect_one()) {
+                    if (V == 1) {
+                        if (elect_one()) {
+#pragma unroll
+                            for (u32 ks = 0; ks < PN_SUB; ks++) {
+                                const u32 alo = s16 + (slot * PN_SUB + ks) * (PN_STAGE_BYTES >> 4) + ((128u >> 4) << 16);
+                                const u32 blo = s16 + (slot * PN_SUB + ks) * (PN_STAGE_BYTES >> 4) + (PN_A_BYTES >> 4) + ((PN_CELLGRP_BYTES >> 4) << 16);
+                                mma_i8_lo<0x4020u, 0x4008u>(tmem, alo, blo, idesc, (started & 1u) | ks);
+                                if (nmt > 1) mma_i8_lo<0x4020u, 0x4008u>(tmem + PL_NCOL, alo + 256, blo, idesc, ((started >> 1) & 1u) | ks);
+                                if (nmt > 2) mma_i8_lo<0x4020u, 0x4008u>(tmem + 2 * PL_NCOL, alo + 512, blo, idesc, ((started >> 2) & 1u) | ks);
+                            }
+                            commit(empty0 + 8 * slot);
+                        }
+                    } else if (elect_one()) {
 #pragma unroll
                         for (u32 ks = 0; ks < PN_SUB; ks++) {
                             const u32 alo = s16 + (slot * PN_SUB + ks) * (PN_STAGE_BYTES >> 4);
@@ -920,7 +1000,7 @@ k_planes_n(PlDev pl, const PlUnitN *__restrict__ units, const PlItem *__restrict
             const u32 per_tile = PN_SUB * nlev;
             u32 cur[12], nxt[12];
             u64 tile = t_begin;
-            u32 r = (p + PL_PROD_WARPS - (Q0 % PL_PROD_WARPS)) % PL_PROD_WARPS;  // my first sub-stage inside this item: r = k * 4 + ks
+            u32 r = (p + PW - (Q0 % PW)) % PW;  // my first sub-stage inside this item: r = k * 4 + ks
             u32 Q = Q0 + r;                                                         // its global index
             while (r >= per_tile && tile < t_end) {
                 r -= per_tile;
@@ -952,7 +1032,7 @@ k_planes_n(PlDev pl, const PlUnitN *__restrict__ units, const PlItem *__restrict
             }
             while (live) {
                 u64 ntile = tile;
-                u32 nr = r + PL_PROD_WARPS;
+                u32 nr = r + PW;
                 while (nr >= per_tile) {
                     nr -= per_tile;
                     ntile++;
@@ -963,13 +1043,19 @@ k_planes_n(PlDev pl, const PlUnitN *__restrict__ units, const PlItem *__restrict
                 if (ntile != tile) prefetch_tile(ntile + 2);
                 // B rows of these 32 cells at level k (contiguous 4,608 bytes in Bn)
                 const uint4 *bsrc = reinterpret_cast<const uint4 *>(Bn + ((size_t)k * (n_pad / 8) + (tile * PL_TILE + ks * 32) / 8) * PN_CELLGRP_BYTES);
-                uint4 bv[PN_B_BYTES / 16 / 32];
+                uint4 bv[V ? 1 : PN_B_BYTES / 16 / 32];
+                if (V == 0) {
 #pragma unroll
-                for (u32 t = 0; t < PN_B_BYTES / 16 / 32; t++) bv[t] = __ldg(bsrc + lane + 32 * t);
+                    for (u32 t = 0; t < PN_B_BYTES / 16 / 32; t++) bv[V ? 0 : t] = __ldg(bsrc + lane + 32 * t);
+                }
                 const u32 nw = ((mt_pack >> (4 * k)) & 15u) * 4;
                 const u32 sgq = Q / PN_SUB, slot = sgq % PN_NSTG, sub = Q % PN_NSTAGES;  // stage, its ring slot, my sub-slot (= slot * 4 + ks)
                 if (sgq >= PN_NSTG) mbar_wait(empty0 + 8 * slot, (sgq / PN_NSTG - 1) & 1u);
                 const u32 st = sS_addr + sub * PN_STAGE_BYTES;
+                if (V == 1 && lane == 0) {  // the slot is free: start the bulk copy of the digit rows, its bytes complete on the stage's barrier
+                    mbar_expect_tx(full0 + 8 * slot, PN_B_BYTES);
+                    bulk_g2s(st + PN_A_BYTES, bsrc, PN_B_BYTES, full0 + 8 * slot);
+                }
 #pragma unroll
                 for (u32 j = 0; j < 12; j++) {
                     if (j < nw) {
@@ -980,12 +1066,14 @@ k_planes_n(PlDev pl, const PlUnitN *__restrict__ units, const PlItem *__restrict
                         st_shared_v4(a0 + 512, hi);
                     }
                 }
+                if (V == 0) {
 #pragma unroll
-                for (u32 t = 0; t < PN_B_BYTES / 16 / 32; t++) st_shared_v4(st + PN_A_BYTES + (lane + 32 * t) * 16, bv[t]);
+                    for (u32 t = 0; t < PN_B_BYTES / 16 / 32; t++) st_shared_v4(st + PN_A_BYTES + (lane + 32 * t) * 16, bv[V ? 0 : t]);
+                }
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(full0 + 8 * slot);
-                Q += PL_PROD_WARPS;
+                Q += PW;
                 tile = ntile;
                 r = nr;
                 ks = nks;
@@ -1034,7 +1122,9 @@ int planes_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo) 
     SB_TRY(part.alloc((size_t)pl.n_units_t * n_pad * PL_COLS));
     const double *rs = a->has_row_scale ? a->row_scale.p : nullptr;
     const size_t smem = (size_t)PT_B_BYTES + PT_NSTAGES * PT_STAGE_BYTES + sizeof(PtShared);
-    cudaError_t e = cudaFuncSetAttribute(k_planes_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const bool v1 = ctx->pl_variant & 1;
+    cudaError_t e = v1 ? cudaFuncSetAttribute(k_planes_t<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                       : cudaFuncSetAttribute(k_planes_t<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return sb_fail(SB_ERR_CUDA, "planes_t: %zu B of shared memory: %s", smem, cudaGetErrorString(e));
     const u32 items = G1 * PL_COLS;
     const unsigned rblocks = (unsigned)std::max<u64>(1, std::min<u64>((mt->n * (PL_COLS / 2) + 255) / 256, (u64)ctx->sm_count * 16));
@@ -1046,9 +1136,14 @@ int planes_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo) 
         SB_TRY(scales_from_colmax(ctx, colmax, scale2, ex));
         k_pl_digits_t<<<cdiv(items, 256), 256, 0, ctx->stream>>>(Y, ldy, mt->hot_idx.p, rs, G1, col0, wt, ex.p, Bd.p);
         SB_CUDA(cudaMemsetAsync(pl.counter.p, 0, sizeof(u32), ctx->stream));
-        k_planes_t<<<pl.t_grid, PT_THREADS, smem, ctx->stream>>>(make_pldev(mt), (const PlUnitT *)pl.units_t.p, (const PlItem *)pl.items_t.p,
-                                                                 pl.n_items_t, pl.counter.p, Bd.p, scale2.p, a->col_scale.p, a->log_base, wt, part.p,
-                                                                 (u32)ctx->pl_debug);
+        if (v1)
+            k_planes_t<1><<<pl.t_grid, PtLayout<1>::WARPS * 32, smem, ctx->stream>>>(make_pldev(mt), (const PlUnitT *)pl.units_t.p,
+                                                                                     (const PlItem *)pl.items_t.p, pl.n_items_t, pl.counter.p, Bd.p, scale2.p,
+                                                                                     a->col_scale.p, a->log_base, wt, part.p, (u32)ctx->pl_debug);
+        else
+            k_planes_t<0><<<pl.t_grid, PtLayout<0>::WARPS * 32, smem, ctx->stream>>>(make_pldev(mt), (const PlUnitT *)pl.units_t.p,
+                                                                                     (const PlItem *)pl.items_t.p, pl.n_items_t, pl.counter.p, Bd.p, scale2.p,
+                                                                                     a->col_scale.p, a->log_base, wt, part.p, (u32)ctx->pl_debug);
         k_pl_reduce_t<<<rblocks, 256, 0, ctx->stream>>>(part.p, pl.n_units_t, mt->n, n_pad, col0, wt, out, ldo);
         count_launch(ctx); count_launch(ctx); count_launch(ctx); count_launch(ctx);
     }
@@ -1069,7 +1164,9 @@ static int planes_n_impl(sb_nmat *a, const double *X, u32 ldx, u32 w, int mode, 
     SB_TRY(colmax.alloc(PL_COLS));
     SB_TRY(Bn.alloc((size_t)pl.L * (n_pad / 8) * PN_CELLGRP_BYTES));
     const size_t smem = (size_t)PN_NSTAGES * PN_STAGE_BYTES + sizeof(PnShared);
-    cudaError_t e = cudaFuncSetAttribute(k_planes_n, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const bool v1 = ctx->pl_variant & 2;
+    cudaError_t e = v1 ? cudaFuncSetAttribute(k_planes_n<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                       : cudaFuncSetAttribute(k_planes_n<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return sb_fail(SB_ERR_CUDA, "planes_n: %zu B of shared memory: %s", smem, cudaGetErrorString(e));
     const int cm_blocks = (int)std::max<u64>(1, std::min<u64>((mt->n + 255) / 256, (u64)ctx->sm_count * 4));
     for (u32 col0 = 0; col0 < w; col0 += PL_COLS) {
@@ -1079,9 +1176,14 @@ static int planes_n_impl(sb_nmat *a, const double *X, u32 ldx, u32 w, int mode, 
         SB_TRY(scales_from_colmax(ctx, colmax, scale2, ex));
         k_pl_digits_n<<<cdiv(n_pad * pl.L, 128), 128, 0, ctx->stream>>>(X, ldx, mt->n, n_pad, a->col_scale.p, a->log_base, pl.L, col0, wt, mode, ex.p, Bn.p);
         SB_CUDA(cudaMemsetAsync(pl.counter.p, 0, sizeof(u32), ctx->stream));
-        k_planes_n<<<pl.n_grid, PL_THREADS, smem, ctx->stream>>>(make_pldev(mt), (const PlUnitN *)pl.units_n.p, (const PlItem *)pl.items_n.p,
-                                                                 pl.n_items_n, pl.counter.p, Bn.p, n_pad, scale2.p, mt->hot_idx.p, col0, wt, out,
-                                                                 row_stride, col_stride);
+        if (v1)
+            k_planes_n<1><<<pl.n_grid, (PL_EPI_WARPS + 1 + 12) * 32, smem, ctx->stream>>>(make_pldev(mt), (const PlUnitN *)pl.units_n.p,
+                                                                                          (const PlItem *)pl.items_n.p, pl.n_items_n, pl.counter.p, Bn.p, n_pad,
+                                                                                          scale2.p, mt->hot_idx.p, col0, wt, out, row_stride, col_stride);
+        else
+            k_planes_n<0><<<pl.n_grid, PL_THREADS, smem, ctx->stream>>>(make_pldev(mt), (const PlUnitN *)pl.units_n.p, (const PlItem *)pl.items_n.p,
+                                                                        pl.n_items_n, pl.counter.p, Bn.p, n_pad, scale2.p, mt->hot_idx.p, col0, wt, out,
+                                                                        row_stride, col_stride);
         count_launch(ctx); count_launch(ctx); count_launch(ctx);
     }
     SB_CUDA(cudaGetLastError());

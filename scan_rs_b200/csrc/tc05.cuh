@@ -35,6 +35,18 @@ __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t da, uint64_t db
         : "memory");
 }
 
+// The same MMA from the LOW descriptor words (address | leading byte offset); the high words (stride byte offset, descriptor
+// version) are compile-time immediates, so consecutive descriptors differ by one 32-bit add.
+template <uint32_t HI_A, uint32_t HI_B>
+__device__ __forceinline__ void mma_i8_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %6};\n\tmov.b64 db, {%2, %7};\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(0u), "n"(HI_A), "n"(HI_B)
+        : "memory");
+}
+
 // One lane of a converged warp (elect.sync).  The tcgen05 issue loops run warp-uniformly and predicate only the tensor-core
 // instructions with this: inside `if (lane == 0)` the compiler cannot keep the operands in uniform registers and wraps every
 // UTCIMMA in an ELECT / R2UR.BROADCAST loop (measured: 155-240 instructions per stage instead of ~25).
@@ -84,6 +96,27 @@ __device__ __forceinline__ void mbar_spin(uint32_t mbar, uint32_t parity) {
                      : "=r"(done)
                      : "r"(mbar), "r"(parity)
                      : "memory");
+}
+
+// Bulk asynchronous copy global -> shared (the TMA engine's 1-D form): `bytes` (multiple of 16, both addresses 16-byte aligned)
+// land in shared memory and are counted as completed transaction bytes on `mbar`, which must expect them (mbar_expect_tx).
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_saddr, const void *src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_saddr), "l"(src), "r"(bytes),
+                 "r"(mbar)
+                 : "memory");
+}
+
+// one non-blocking look at a barrier phase
+__device__ __forceinline__ bool mbar_test(uint32_t mbar, uint32_t parity) {
+    uint32_t done = 0;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done)
+                 : "r"(mbar), "r"(parity)
+                 : "memory");
+    return done != 0;
 }
 
 // long waits (an epilogue waiting for a whole CTA's worth of MMAs): back off so the spinning warps leave the issue slots alone

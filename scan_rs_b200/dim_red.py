@@ -1,4 +1,4 @@
-"""Mirror of scan_rs::dim_red (scan-rs/src/dim_red/{mod,bk_svd,rand_svd}.rs) on the device path."""
+"""Mirror of scan_rs::dim_red (scan-rs/src/dim_red/{mod,bk_svd,rand_svd,irlba}.rs) on the device path."""
 from __future__ import annotations
 
 import ctypes as C
@@ -106,3 +106,37 @@ class RandSvd:
 
     def run_pca(self, array: LowRankOffset, k: int, out=None):
         return self.run_pca_cancellable(array, k, None, out)
+
+
+def irlba_start(seed: int, n: int) -> np.ndarray:
+    """The builder-defined default start vector of `irlba` (the reference's rand_distr Normal stream cannot be restated offline)."""
+    out = np.zeros(n)
+    L.check(L.lib().sb_irlba_start(C.c_uint64(seed), C.c_uint64(n), L.vp(out)))
+    return out
+
+
+def irlba(A: LowRankOffset, nu: int, tol: float = 1e-4, maxit: int = 50, v0: Optional[np.ndarray] = None, snoop=None, info: Optional[dict] = None):
+    """irlba.rs:71-215 -> (U m x nu, sigma nu, V n_local x nu); `info` receives mprod (matrix products) and iterations."""
+    m, n = A.shape()
+    U, S, V = np.zeros((m, nu)), np.zeros(nu), np.zeros((n, nu))
+    cb = _make_cb(snoop or NoOpSnoop())
+    v = None if v0 is None else np.ascontiguousarray(v0, dtype=np.float64)
+    mprod, iters = C.c_uint32(), C.c_uint32()
+    L.check(L.lib().sb_irlba(A._h, C.c_uint32(nu), C.c_double(tol), C.c_uint32(maxit), L.vp(v), cb, None, L.vp(U), L.vp(S), L.vp(V),
+                             C.byref(mprod), C.byref(iters)))
+    if info is not None:
+        info["mprod"], info["iterations"] = mprod.value, iters.value
+    return U, S, V
+
+
+class Irlba:
+    """irlba.rs:36-69: defaults tol = 0.0001, max_iter = 50."""
+
+    def __init__(self, tol: float = 0.0001, max_iter: int = 50):
+        self.tol, self.max_iter = tol, max_iter
+
+    def run_pca_cancellable(self, array: LowRankOffset, k: int, snoop, v0=None):
+        return irlba(array, k, self.tol, self.max_iter, v0, snoop)
+
+    def run_pca(self, array: LowRankOffset, k: int, v0=None):
+        return self.run_pca_cancellable(array, k, NoOpSnoop(), v0)

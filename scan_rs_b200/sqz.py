@@ -287,6 +287,50 @@ class AdaptiveMat:
         L.check(L.lib().sb_select_cols(self._h, L.vp(c), C.c_uint64(c.shape[0]), C.byref(h)))
         return AdaptiveMat(self.ctx, h)
 
+    # ---- moment consumers (diff-exp's reads of the matrix); `size_factors`, when given, is the SizeNormalized view v / sf[c]
+    @staticmethod
+    def _cells(cols):
+        return np.ascontiguousarray(cols, dtype=np.uint64)
+
+    def mean_var_axis(self, axis: int, size_factors=None):  # mat.rs:285-329
+        n_out = self.cols() if axis == 0 else self.rows()
+        mean, var = np.zeros(n_out), np.zeros(n_out)
+        sf = None if size_factors is None else np.ascontiguousarray(size_factors, dtype=np.float64)
+        L.check(L.lib().sb_mean_var_axis(self._h, C.c_int(axis), L.vp(sf), L.vp(mean), L.vp(var)))
+        return mean, var
+
+    def mean_var_rows(self, cols, size_factors=None):  # mat.rs:332-374
+        c = self._cells(cols)
+        mean, var = np.zeros(self.rows()), np.zeros(self.rows())
+        sf = None if size_factors is None else np.ascontiguousarray(size_factors, dtype=np.float64)
+        L.check(L.lib().sb_mean_var_rows(self._h, L.vp(c), C.c_uint64(c.shape[0]), L.vp(sf), L.vp(mean), L.vp(var)))
+        return mean, var
+
+    def sum_rows(self, cols) -> np.ndarray:  # mat.rs:449-476
+        c = self._cells(cols)
+        out = np.zeros(self.rows(), dtype=np.uint64)
+        L.check(L.lib().sb_sum_rows(self._h, L.vp(c), C.c_uint64(c.shape[0]), L.vp(out)))
+        return out
+
+    def sum_cols(self, cols) -> np.ndarray:  # mat.rs:414-446
+        c = self._cells(cols)
+        out = np.zeros(c.shape[0], dtype=np.uint64)
+        L.check(L.lib().sb_sum_cols(self._h, L.vp(c), C.c_uint64(c.shape[0]), L.vp(out)))
+        return out
+
+    def sum_rows_dual(self, cols1, cols2):  # mat.rs:484-583
+        c1, c2 = self._cells(cols1), self._cells(cols2)
+        o1, o2 = np.zeros(self.rows(), dtype=np.uint64), np.zeros(self.rows(), dtype=np.uint64)
+        L.check(L.lib().sb_sum_rows_dual(self._h, L.vp(c1), C.c_uint64(c1.shape[0]), L.vp(c2), C.c_uint64(c2.shape[0]), L.vp(o1), L.vp(o2)))
+        return o1, o2
+
+    def size_factors(self, cell_indices=None, umi_counts=None) -> np.ndarray:  # diff-exp/src/diff_exp.rs:314-334
+        c = None if cell_indices is None else self._cells(cell_indices)
+        u = None if umi_counts is None else np.ascontiguousarray(umi_counts, dtype=np.float64)
+        out = np.zeros(self.cols())
+        L.check(L.lib().sb_size_factors(self._h, L.vp(c), C.c_uint64(0 if c is None else c.shape[0]), L.vp(u), L.vp(out)))
+        return out
+
     def hvg_select(self, n_top: int) -> np.ndarray:
         """Builder-defined highly-variable-gene selection (not in the reference)."""
         out = np.zeros(self.rows(), dtype=np.uint32)

@@ -790,3 +790,94 @@ def test_knn_on_pca_scores_with_padding_and_offset(ctx):
     tiny = scores[:3]
     out = sb.knn(ctx, tiny, 5)  # fewer candidates than k: padded like the reference's T::max_value()
     assert (out[:, 2:] == 0xFFFFFFFF).all() and (out[:, :2] != 0xFFFFFFFF).all()
+
+
+# ------------------------------------------------------------------ IRLBA and the diff-exp moment consumers
+@pytest.mark.parametrize("n_cells,n_genes,nu", [(3000, 1200, 5), (900, 2500, 10)])
+def test_irlba_matches_oracle(ctx, n_cells, n_genes, nu):
+    """irlba.rs:71-215 on both shapes (n > m and m >= n) with a shared start vector and the shared sign rule; the restart
+    decisions (`resid < tol * smax`, no absolute value) must agree, so the product counts are compared too."""
+    cfg, cm, dm, _ = synth_pair(ctx, n_cells, n_genes, seed=71)
+    a_o, a_g = orc.normalize(cm, orc.CELLRANGER), sb.normalize(dm, sb.Normalization.CellRanger)
+    v0 = orc.irlba_start(0, n_cells)
+    np.testing.assert_allclose(sb.irlba_start(0, n_cells), v0, rtol=0, atol=1e-15)
+    uo, so, vo, mprod_o, it_o = orc.irlba(a_o, nu, tol=1e-5, maxit=50, v0=v0)
+    info = {}
+    ug, sg, vg = sb.irlba(a_g, nu, tol=1e-5, maxit=50, v0=v0, info=info)
+    check_pca_parity((ug, sg, vg), (uo, so, vo))
+    assert info["mprod"] == mprod_o and info["iterations"] == it_o, (info, mprod_o, it_o)
+    # the default start vector and the Pca front end
+    u2, s2, v2 = sb.Irlba().run_pca(a_g, nu)
+    u3, s3, v3 = orc.Irlba().run_pca(a_o, nu)
+    assert np.abs(s2 - s3).max() / s3.max() < 1e-6
+    # against the truth: A^T u = sigma v
+    at_u = a_o.rdot(np.ascontiguousarray(ug.T)).T
+    assert np.abs(at_u - vg * sg).max() < 1e-3 * sg[0]
+    with pytest.raises(sb.ScanError, match="invalid k"):
+        sb.irlba(a_g, min(n_cells, n_genes) + 1)
+
+
+def test_irlba_cancel(ctx):
+    cfg, cm, dm, _ = synth_pair(ctx, 600, 400, seed=72)
+    a_g = sb.normalize(dm, sb.Normalization.CellRanger)
+    snoop = sb.AtomicSnoop()
+    snoop.cancel()
+    with pytest.raises(sb.CancellationError):
+        sb.irlba(a_g, 4, tol=1e-12, maxit=50, snoop=snoop)
+
+
+def test_moment_consumers_golden(ctx):  # sqz/src/mat.rs:1302-1370 on input_a
+    dense = np.array([[136, 936, 0, 0, 264], [134, 682, 417, 8, 391], [0, 133, 780, 885, 0], [396, 76, 96, 198, 0]], dtype=np.uint32)
+    mtx = sb.AdaptiveMat.from_dense(ctx, dense)
+    mean0, var0 = mtx.mean_var_axis(0)
+    np.testing.assert_allclose(mean0, [166.5, 456.75, 323.25, 272.75, 163.75], atol=1e-7)
+    np.testing.assert_allclose(var0, [20594.75, 132550.6875, 93385.6875, 131230.6875, 28830.1875], atol=1e-7)
+    mean1, var1 = mtx.mean_var_axis(1)
+    np.testing.assert_allclose(mean1, [267.2, 326.4, 359.6, 153.2], atol=1e-7)
+    np.testing.assert_allclose(var1, [121461.76, 55445.84, 152550.64, 18732.16], atol=1e-7)
+    meanc, varc = mtx.mean_var_rows([1, 2, 3])
+    densef = dense[:, 1:4].astype(np.float64)
+    np.testing.assert_allclose(meanc, densef.mean(axis=1), atol=1e-7)
+    np.testing.assert_allclose(varc, densef.var(axis=1), atol=1e-7)
+    np.testing.assert_array_equal(mtx.sum_cols([1, 2, 3]), dense[:, 1:4].sum(axis=0))
+    np.testing.assert_array_equal(mtx.sum_rows([1, 2, 3]), dense[:, 1:4].sum(axis=1))
+    s1, s2 = mtx.sum_rows_dual([1, 2, 3], [2, 3, 4])
+    np.testing.assert_array_equal(s1, dense[:, 1:4].sum(axis=1))
+    np.testing.assert_array_equal(s2, dense[:, 2:5].sum(axis=1))
+    np.testing.assert_allclose(mtx.size_factors(), dense.sum(axis=0) / 1091.0, rtol=1e-15)
+
+
+def test_moment_consumers_match_oracle(ctx):
+    """The sSeq moment path of diff-exp (diff_exp.rs:458-472): size factors -> SizeNormalized view -> per-gene mean / variance,
+    on all cells and on a cell subset; integer sums bit-exact, f64 moments to 1e-12 relative (reduction order)."""
+    cfg, cm, dm, _ = synth_pair(ctx, 5000, 1500, seed=73)
+    rng = np.random.default_rng(3)
+    sf_o, sf_g = orc.size_factors(cm), dm.size_factors()
+    np.testing.assert_array_equal(sf_g, sf_o)
+    for axis in (0, 1):
+        mo, vo = orc.mean_var_axis(cm, axis, sf_o)
+        mg, vg = dm.mean_var_axis(axis, sf_g)
+        np.testing.assert_allclose(mg, mo, rtol=1e-12, atol=1e-300)
+        np.testing.assert_allclose(vg, vo, rtol=1e-10, atol=1e-12 * np.abs(vo).max())
+        mo, vo = orc.mean_var_axis(cm, axis)
+        mg, vg = dm.mean_var_axis(axis)
+        np.testing.assert_allclose(mg, mo, rtol=1e-15)
+        np.testing.assert_allclose(vg, vo, rtol=1e-12, atol=1e-12 * np.abs(vo).max())
+    cells = np.sort(rng.choice(5000, size=1200, replace=False))
+    sfs_o, sfs_g = orc.size_factors(cm, cells), dm.size_factors(cells)
+    np.testing.assert_array_equal(sfs_g, sfs_o)
+    mo, vo = orc.mean_var_rows(cm, cells, sfs_o)
+    mg, vg = dm.mean_var_rows(cells, sfs_g)
+    np.testing.assert_allclose(mg, mo, rtol=1e-12, atol=1e-300)
+    np.testing.assert_allclose(vg, vo, rtol=1e-10, atol=1e-12 * np.abs(vo).max())
+    other = np.sort(rng.choice(5000, size=900, replace=False))
+    s1o, s2o = orc.sum_rows_dual(cm, cells, other)
+    s1g, s2g = dm.sum_rows_dual(cells, other)
+    np.testing.assert_array_equal(s1g, s1o)
+    np.testing.assert_array_equal(s2g, s2o)
+    np.testing.assert_array_equal(dm.sum_rows(other), s2o)
+    np.testing.assert_array_equal(dm.sum_cols(other), cm.sum_axis_u64(0)[other])
+    umi = rng.uniform(500, 5000, size=cells.shape[0])
+    np.testing.assert_array_equal(dm.size_factors(cells, umi), orc.size_factors(cm, cells, umi))
+    with pytest.raises(sb.ScanError, match="out of range"):
+        dm.mean_var_rows([5000])

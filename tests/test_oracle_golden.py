@@ -190,6 +190,45 @@ def test_svd_vs_full(shape, algo):  # scan-rs/src/dim_red/test.rs:58-110, three 
     assert np.abs((np.abs(av) - av_gt) / av_gt).max() < 1e-3
 
 
+@pytest.mark.parametrize("shape", [(100, 1000), (1000, 100)])
+def test_irlba_vs_full(shape):  # scan-rs/src/dim_red/test.rs:133-139 (Irlba { tol: 1e-5, .. }, nu = 10), metrics of :58-110
+    a = simple_deterministic_ex(*shape)
+    u, s, v, mprod, it = orc.irlba(orc.DenseOp(a), 10, tol=1e-5, maxit=50)
+    assert u.shape == (shape[0], 10) and v.shape == (shape[1], 10) and mprod > 0
+    ut, st, vt = np.linalg.svd(a, full_matrices=False)
+    av = a.dot(v)
+    assert orc.frobenius(av - u * s) < 1e-3
+    assert np.abs((s - st[:10]) / st[:10]).max() < 1e-3
+    av_gt = np.abs(a.dot(vt[:10].T))
+    assert np.abs((np.abs(av) - av_gt) / av_gt).max() < 1e-3
+    with pytest.raises(ValueError, match="at least 2x2"):
+        orc.irlba(orc.DenseOp(np.ones((1, 5))), 1)
+    with pytest.raises(ValueError, match="invalid k"):
+        orc.irlba(orc.DenseOp(np.ones((3, 5))), 4)
+
+
+def test_moment_consumers():  # sqz/src/mat.rs:1302-1370 (input_a), diff-exp/src/stat.rs:172-178 (median 3.5)
+    m = orc.CountMatrix.from_dense(INPUT_A)
+    mean0, var0 = orc.mean_var_axis(m, 0)
+    np.testing.assert_allclose(mean0, [166.5, 456.75, 323.25, 272.75, 163.75], atol=1e-7)
+    np.testing.assert_allclose(var0, [20594.75, 132550.6875, 93385.6875, 131230.6875, 28830.1875], atol=1e-7)
+    mean1, var1 = orc.mean_var_axis(m, 1)
+    np.testing.assert_allclose(mean1, [267.2, 326.4, 359.6, 153.2], atol=1e-7)
+    np.testing.assert_allclose(var1, [121461.76, 55445.84, 152550.64, 18732.16], atol=1e-7)
+    densef = INPUT_A[:, 1:4].astype(np.float64)
+    meanc, varc = orc.mean_var_rows(m, [1, 2, 3])
+    np.testing.assert_allclose(meanc, densef.mean(axis=1), atol=1e-7)
+    np.testing.assert_allclose(varc, densef.var(axis=1), atol=1e-7)
+    s1, s2 = orc.sum_rows_dual(m, [1, 2, 3], [2, 3, 4])
+    np.testing.assert_array_equal(s1, INPUT_A[:, 1:4].sum(axis=1))
+    np.testing.assert_array_equal(s2, INPUT_A[:, 2:5].sum(axis=1))
+    assert orc.percentile_median(np.array([1, 2, 4, 3, 5, 6])) == 3.5
+    sf = orc.size_factors(m)
+    np.testing.assert_allclose(sf, INPUT_A.sum(axis=0) / 1091.0, rtol=1e-15)
+    sf_sub = orc.size_factors(m, cell_indices=[0, 3])
+    np.testing.assert_allclose(sf_sub, [666 / 878.5, 0, 0, 1091 / 878.5, 0], rtol=1e-15)
+
+
 def test_svd_bk_errors_and_cancel():  # bk_svd.rs:73-79, :96
     with pytest.raises(ValueError, match="at least 2x2"):
         orc.svd_bk(orc.DenseOp(np.ones((1, 5))), 1, 2, 5)
