@@ -93,6 +93,19 @@ SB_API void sb_shutdown(sb_ctx *ctx);
 SB_API int sb_comm_unique_id(char id[128]);
 SB_API int sb_comm_init(sb_ctx *ctx, int nranks, int rank, const char id[128]);
 SB_API int sb_sync(sb_ctx *ctx);
+/* One host thread, every GPU of the box (the reference's caller is a single process, tools/src/bin/cmd.rs:67-81).
+ * sb_multi_init creates one context per device (devices == NULL: 0..n-1), joins them to one communicator and starts one worker
+ * thread per device.  sb_multi_run executes fn(rank, ctx, user) on every worker concurrently and returns when all are done (the
+ * first non-zero status, with "rank r: message" as the error): inside fn each rank makes the ordinary single-context calls on
+ * its own cell shard, exactly the sequence one-process-per-GPU callers make.  Handles created inside fn stay valid across
+ * sb_multi_run calls and must be freed before sb_multi_shutdown. */
+typedef struct sb_multi sb_multi;
+typedef int (*sb_rank_fn)(int rank, sb_ctx *ctx, void *user);
+SB_API int sb_multi_init(int n, const int *devices, sb_multi **out);
+SB_API int sb_multi_size(const sb_multi *mm);
+SB_API int sb_multi_ctx(sb_multi *mm, int rank, sb_ctx **out);
+SB_API int sb_multi_run(sb_multi *mm, sb_rank_fn fn, void *user);
+SB_API void sb_multi_shutdown(sb_multi *mm);
 /* Options: "direct_projection" (0/1, default 0): 1 forces the wide projection pass T = Q^T A of
  * bk_svd.rs:102,131 to run as a sparse product; 0 lets the library use Q^T A = R^-T (K^T A) when R is usable.
  * "gather" (default 1): 1 = panelled gather kernels for the sparse halves of both products, 0 = the first-generation
@@ -154,6 +167,15 @@ SB_API int sb_upload_adaptive(sb_ctx *ctx, int major, uint32_t m, uint64_t n_loc
  * big_cnt[i].  The Rust side fills these from the same AdaptiveVec `foreach` walk (vec.rs:1230-1273) as sb_upload's. */
 SB_API int sb_upload_compact(sb_ctx *ctx, uint32_t m, uint64_t n_local, const uint64_t *indptr, const uint16_t *idx16,
                       const uint8_t *cnt8, uint64_t n_big, const uint64_t *big_pos, const uint32_t *big_cnt, sb_mat **out);
+/* The loaders' device half.  sb_upload_unsorted: cell-major arrays whose gene indices are in ANY order inside
+ * a cell -- the Cell Ranger 3 defect that hdf5-io/src/matrix.rs:63-78 repairs with `new_from_unsorted_csc`; every cell's entries
+ * are sorted on the device, a duplicate index inside a cell is SB_ERR_INVALID_ARG.  sb_filter_genes: compute_genes_filter + the
+ * row selection of read_adaptive_csr_matrix (matrix.rs:93-192): type_keep[m] (NULL = all) marks the features whose type matches
+ * `retain_feature_like`, min_total is `shrink_row`; kept_rows (room for m) receives the survivors in file order. */
+SB_API int sb_upload_unsorted(sb_ctx *ctx, uint32_t m, uint64_t n_local, const uint64_t *indptr, const uint32_t *idx,
+                       const uint32_t *cnt, sb_mat **out);
+SB_API int sb_filter_genes(sb_mat *mat, const uint8_t *type_keep, uint64_t min_total, uint32_t *kept_rows, uint32_t *n_kept,
+                    sb_mat **out);
 /* rows(), cols(), shape() (mat.rs:160-176) + nnz() (:155-157); n_global == n_local without a communicator */
 SB_API int sb_mat_shape(const sb_mat *mat, uint32_t *m, uint64_t *n_local, uint64_t *n_global, uint64_t *nnz_local);
 /* to_csmat (mat.rs:207-239): sizes from sb_mat_shape; indptr has m+1 or n_local+1 entries */

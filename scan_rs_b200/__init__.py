@@ -20,3 +20,4 @@ ScanError = ScanB200Error
 from .snoop import AtomicSnoop, NoOpSnoop  # noqa: F401
 from .mtx import load_mtx  # noqa: F401
 from .nn import find_nn, knn  # noqa: F401
+from .multi import MultiContext  # noqa: F401

@@ -48,7 +48,7 @@ SYMBOLS = [
     "sb_nmat_dot", "sb_nmat_rdot", "sb_nmat_frobenius_sq", "sb_free_nmat", "sb_omega", "sb_bksvd", "sb_bksvd_run_pca", "sb_pca_diagnostics", "sb_randsvd",
     "sb_randsvd_run_pca", "sb_profile_enable", "sb_profile_reset", "sb_profile_get", "sb_timer_begin",
     "sb_timer_end", "sb_flush_l2", "sb_synth_generate", "sb_knn",
-    "sb_irlba", "sb_irlba_start", "sb_mean_var_axis", "sb_mean_var_rows", "sb_sum_rows", "sb_sum_cols", "sb_sum_rows_dual", "sb_size_factors",
+    "sb_irlba", "sb_irlba_start", "sb_mean_var_axis", "sb_mean_var_rows", "sb_sum_rows", "sb_sum_cols", "sb_sum_rows_dual", "sb_size_factors", "sb_upload_unsorted", "sb_filter_genes", "sb_multi_init", "sb_multi_size", "sb_multi_ctx", "sb_multi_run", "sb_multi_shutdown",
 ]
 
 _lib = None
@@ -65,12 +65,14 @@ def lib():
         _lib.sb_last_error.restype = C.c_char_p
         for name in SYMBOLS:
             fn = getattr(_lib, name)
-            if name not in ("sb_last_error", "sb_shutdown", "sb_free_mat", "sb_free_nmat", "sb_host_free"):
+            if name not in ("sb_last_error", "sb_shutdown", "sb_free_mat", "sb_free_nmat", "sb_host_free", "sb_multi_shutdown"):
                 fn.restype = C.c_int
         _lib.sb_shutdown.restype = None
         _lib.sb_free_mat.restype = None
         _lib.sb_free_nmat.restype = None
         _lib.sb_host_free.restype = None
+        _lib.sb_multi_shutdown.restype = None
+        _lib.sb_multi_shutdown.argtypes = [C.c_void_p]
         _lib.sb_host_free.argtypes = [C.c_void_p]
     return _lib
 

@@ -104,13 +104,28 @@ class Context:
         L.check(L.lib().sb_profile_get(self._h, C.byref(p)))
         return p.as_dict()
 
+    @classmethod
+    def _adopt(cls, handle, device: int, nranks: int, rank: int) -> "Context":
+        """A context owned by a MultiContext (multi.py): same interface, shut down by its owner."""
+        self = cls.__new__(cls)
+        self._h = handle
+        self.device = device
+        self.nranks, self.rank = nranks, rank
+        self._mats, self._nmats = weakref.WeakSet(), weakref.WeakSet()
+        self._owned = False
+        return self
+
+    def _release_handles(self):
+        for a in list(self._nmats):  # handles borrow the context: free them first
+            a.free()
+        for m in list(self._mats):
+            m.free()
+
     def close(self):
         if self._h:
-            for a in list(self._nmats):  # handles borrow the context: free them first
-                a.free()
-            for m in list(self._mats):
-                m.free()
-            L.lib().sb_shutdown(self._h)
+            self._release_handles()
+            if getattr(self, "_owned", True):
+                L.lib().sb_shutdown(self._h)
             self._h = C.c_void_p()
 
     def __enter__(self):
@@ -163,6 +178,27 @@ class AdaptiveMat:
         L.check(L.lib().sb_upload(ctx._h, C.c_int(major), C.c_uint32(rows), C.c_uint64(cols), L.vp(indptr), L.vp(idx),
                                   L.vp(val), C.byref(h)))
         return cls(ctx, h)
+
+    @classmethod
+    def from_csc_unsorted(cls, ctx: Context, rows: int, cols: int, indptr, idx, val) -> "AdaptiveMat":
+        """Cell-major arrays with the gene indices of a cell in any order (hdf5-io/src/matrix.rs:63-78: the Cell Ranger 3 repair
+        `new_from_unsorted_csc`): sorted per cell on the device; duplicates inside a cell are an error."""
+        ip = np.ascontiguousarray(indptr, dtype=np.uint64)
+        ix = np.ascontiguousarray(idx, dtype=np.uint32)
+        vv = np.ascontiguousarray(val, dtype=np.uint32)
+        h = C.c_void_p()
+        L.check(L.lib().sb_upload_unsorted(ctx._h, C.c_uint32(rows), C.c_uint64(cols), L.vp(ip), L.vp(ix), L.vp(vv), C.byref(h)))
+        return cls(ctx, h)
+
+    def filter_genes(self, type_keep=None, min_total: int = 0):
+        """compute_genes_filter + the row selection of read_adaptive_csr_matrix (hdf5-io/src/matrix.rs:93-192) -> (matrix of the
+        surviving features, their indices in file order).  type_keep: boolean mask of the features whose type is retained."""
+        tk = None if type_keep is None else np.ascontiguousarray(type_keep, dtype=np.uint8)
+        kept = np.zeros(self.rows(), dtype=np.uint32)
+        nk = C.c_uint32()
+        h = C.c_void_p()
+        L.check(L.lib().sb_filter_genes(self._h, L.vp(tk), C.c_uint64(min_total), L.vp(kept), C.byref(nk), C.byref(h)))
+        return AdaptiveMat(self.ctx, h), kept[: nk.value].copy()
 
     @staticmethod
     def compact_csc(idx, val):

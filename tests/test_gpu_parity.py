@@ -881,3 +881,84 @@ def test_moment_consumers_match_oracle(ctx):
     np.testing.assert_array_equal(dm.size_factors(cells, umi), orc.size_factors(cm, cells, umi))
     with pytest.raises(sb.ScanError, match="out of range"):
         dm.mean_var_rows([5000])
+
+
+# ------------------------------------------------------------------ the 10x HDF5 loader with the Cell Ranger 3 repair
+def test_load_h5_repairs_unsorted_indices_and_filters_features(ctx, tmp_path):
+    """hdf5-io/src/matrix.rs:56-192: a `matrix` group whose gene indices are shuffled inside every cell (the CR3 defect) loads to
+    the same matrix as the sorted arrays; compute_genes_filter drops the unlike feature types and the low-count features."""
+    from scan_rs_b200 import h5
+    cfg, cm, dm, (ip, g, c) = synth_pair(ctx, 700, 500, seed=81)
+    rng = np.random.default_rng(5)
+    g_shuf, c_shuf = g.copy(), c.copy()
+    for j in range(700):
+        s, e = int(ip[j]), int(ip[j + 1])
+        p = rng.permutation(e - s)
+        g_shuf[s:e], c_shuf[s:e] = g[s:e][p], c[s:e][p]
+    ftype = np.array([b"Gene Expression" if i % 7 else b"Antibody Capture" for i in range(500)], dtype="S20")
+    tree = {"matrix": {"shape": np.array([500, 700], dtype=np.int32), "indptr": ip.astype(np.int64), "indices": g_shuf.astype(np.int64),
+                       "data": c_shuf.astype(np.int32), "barcodes": np.array([f"BC{i:06d}-1".encode() for i in range(700)], dtype="S18"),
+                       "features": {"id": np.array([f"ENSG{i:08d}".encode() for i in range(500)], dtype="S16"),
+                                    "name": np.array([f"g{i}".encode() for i in range(500)], dtype="S8"), "feature_type": ftype}}}
+    path = str(tmp_path / "filtered_feature_bc_matrix.h5")
+    h5.write_h5(path, tree, chunk=2048)
+    # no filter: the repaired matrix equals the sorted one, bit for bit
+    full, meta = h5.load_h5(ctx, path)
+    assert meta["repaired_unsorted_indices"] and meta["removed"] == []
+    for got, want in zip(full.to_csc(), dm.to_csc()):
+        np.testing.assert_array_equal(got, want)
+    # feature-type + minimum-count filter against the reference's rule on the dense counts
+    tot = cm.sum_axis_u64(1)
+    want_keep = np.array([i for i in range(500) if b"Gene" in ftype[i] and tot[i] >= 30])
+    sub, meta = h5.load_h5(ctx, path, retain_feature_like="Gene", shrink_row=30)
+    np.testing.assert_array_equal(sorted(set(range(500)) - set(meta["removed"])), want_keep)
+    np.testing.assert_array_equal(sub.to_dense(), cm.to_dense()[want_keep])
+    assert list(meta["feature_id"]) == [f"ENSG{i:08d}".encode() for i in want_keep]
+    # a duplicate gene inside a cell is rejected (sprs' StructureError)
+    bad = g_shuf.copy()
+    s = int(ip[3])
+    if ip[4] - ip[3] >= 2:
+        bad[s + 1] = bad[s]
+        with pytest.raises(sb.ScanError, match="duplicate"):
+            sb.AdaptiveMat.from_csc_unsorted(ctx, 500, 700, ip, bad, c_shuf)
+    for h in (full, sub, dm):
+        h.free()
+
+
+# ------------------------------------------------------------------ one host thread, every GPU (sb_multi, SURVEY 8b)
+def test_single_process_multi_gpu_matches_oracle():
+    """sb_multi: one process, one caller thread, a worker per GPU.  With two or more GPUs the cells are sharded over two ranks
+    and the collectives meet across the worker threads; on a one-GPU box the same code runs with a single rank."""
+    from scan_rs_b200.dist import shard_bounds
+    from scan_rs_b200.synth import SynthConfig, generate_host
+    n_gpu = C.c_int(0)
+    cuda = C.CDLL("libcuda.so.1")
+    cuda.cuDeviceGetCount(C.byref(n_gpu))
+    world = 2 if n_gpu.value >= 2 else 1
+    cfg = SynthConfig(n_cells=4000, n_genes=1100, seed=91)
+    ip, g, c = generate_host(cfg)
+    cm = orc.CountMatrix.from_cell_major(cfg.n_genes, cfg.n_cells, ip, g, c)
+    res_o = orc.BkSvd().run_pca(orc.normalize(cm, orc.CELLRANGER), 6)
+    with sb.MultiContext(n=world) as mc:
+        def rank_fn(rank, rctx):
+            lo, hi = shard_bounds(cfg.n_cells, world, rank)
+            s0, s1 = int(ip[lo]), int(ip[hi])
+            dm = sb.AdaptiveMat.from_csc(rctx, cfg.n_genes, hi - lo, ip[lo:hi + 1] - ip[lo], g[s0:s1], c[s0:s1])
+            a = sb.normalize(dm, sb.Normalization.CellRanger)
+            u, s, v = sb.BkSvd().run_pca(a, 6)
+            tot = dm.sum_axis_u32(0)
+            gene_tot = dm.gene_totals()
+            a.free()
+            dm.free()
+            return np.array(u), np.array(s), np.array(v), tot, gene_tot
+        out = mc.run(rank_fn)
+        # a failing rank surfaces as an exception in the caller
+        with pytest.raises(sb.ScanError, match="invalid k"):
+            mc.run(lambda rank, rctx: sb.BkSvd().run_pca(sb.normalize(sb.AdaptiveMat.from_dense(rctx, DENSE_A), sb.Normalization.CellRanger), 99))
+    u, s = out[0][0], out[0][1]
+    v = np.concatenate([o[2] for o in out], axis=0)
+    np.testing.assert_array_equal(np.concatenate([o[3] for o in out]), cm.sum_axis_u32(0))
+    for o in out:
+        np.testing.assert_array_equal(o[4], cm.sum_axis_u64(1))
+        np.testing.assert_array_equal(o[0], u)  # gene-sized results are replicated
+    check_pca_parity((u, s, v), res_o)

@@ -111,3 +111,23 @@ def test_gather_work_units_cover_every_entry_once():
         subprocess.check_call(["g++", "-std=c++17", "-O1", src, "-o", exe])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "ALL PASSED" in out.stdout, out.stdout + out.stderr
+
+
+def test_rust_ffi_matches_header():
+    """rust/scan-b200/src/ffi.rs is generated from include/scanb200.h (scripts/gen_rust_ffi.py): every SB_API symbol is declared
+    there, the committed file is current, and every declared symbol is exported by the library and listed for ctypes."""
+    import importlib.util
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_rust_ffi", os.path.join(root, "scripts", "gen_rust_ffi.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    decls = gen.declarations(open(os.path.join(root, "include", "scanb200.h")).read())
+    committed = open(os.path.join(root, "rust", "scan-b200", "src", "ffi.rs")).read()
+    assert committed == gen.render(decls), "run python scripts/gen_rust_ffi.py"
+    names = [d[0] for d in decls]
+    assert sorted(names) == sorted(set(names)) and sorted(names) == sorted(L.SYMBOLS)
+    assert sorted(re.findall(r"pub fn (sb_\w+)\(", committed)) == sorted(names)
+    for crate_file in ("Cargo.toml", "build.rs", os.path.join("src", "lib.rs")):
+        assert os.path.exists(os.path.join(root, "rust", "scan-b200", crate_file))
