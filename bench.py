@@ -123,6 +123,22 @@ def bind_to_gpu_numa(local_rank):
         if use and node not in ("-1", ""):
             os.sched_setaffinity(0, use)
             return f"numa node {node}, {len(use)} local cpus"
+        # sysfs has no NUMA node for the device (virtualised PCI topology): ask the driver (nvidia-smi topo -m: "CPU Affinity" column)
+        topo = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        for line in topo.splitlines():
+            f = line.replace("\x1b[4m", "").replace("\x1b[0m", "").split("\t")
+            if f and f[0].strip() == f"GPU{local_rank}":
+                aff = [x.strip() for x in f if "-" in x and x.strip().replace("-", "").replace(",", "").isdigit()]
+                if aff:
+                    ids = set()
+                    for part in aff[0].split(","):
+                        a, _, b = part.partition("-")
+                        ids.update(range(int(a), int(b or a) + 1))
+                    use = ids & allowed
+                    if use and use != allowed:
+                        os.sched_setaffinity(0, use)
+                        return f"nvidia-smi topo: cpus {aff[0]} ({len(use)} bound)"
+                    return f"nvidia-smi topo: cpus {aff[0]} = every visible cpu (one NUMA domain: nothing to bind)"
         return f"numa node {node} (no binding)"
     except Exception as e:  # sysfs layout differs in some containers: binding is an optimisation only
         return f"unbound ({type(e).__name__})"

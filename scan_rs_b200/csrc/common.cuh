@@ -64,6 +64,9 @@ int sb_fail(int code, const char *fmt, ...);
 // published by every API entry through sb_set_alloc_stream().
 cudaStream_t sb_alloc_stream();
 void sb_set_alloc_stream(cudaStream_t s);
+// streams of live contexts: a buffer that outlives its context (a handle freed after sb_shutdown) is returned with a plain cudaFree
+bool sb_stream_alive(cudaStream_t s);
+void sb_stream_register(cudaStream_t s, bool alive);
 
 template <typename T>
 struct DevBuf {
@@ -75,7 +78,10 @@ struct DevBuf {
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFreeAsync(p, st);
+        if (p) {
+            if (sb_stream_alive(st)) cudaFreeAsync(p, st);
+            else cudaFree(p);
+        }
         p = nullptr;
         n = 0;
     }
@@ -123,7 +129,6 @@ struct sb_ctx {
     int nranks = 1, rank = 0;
     int dense_cap = 2048;            // max genes in the dense hot panel (0 disables the hybrid layout)
     double dense_min_density = 0.12; // a gene joins the panel only if nnz/n_global is at least this
-    bool gather_split = false;       // EXPERIMENTAL (gather_split.cu): separate 4-byte stream for the entries with a count of 1
     bool panel_i8 = false;           // EXPERIMENTAL (panel_i8.cu): T-side dense panel on tcgen05 int8 instead of FP64 mma.sync
     int dense_max_count = 15;        // largest count kept in the dense panel of matrices uploaded afterwards (<= 15)
     // dense half of the hybrid layout of matrices built afterwards: 0 none, 1 u8 panel on the FP64 mma.sync path (dense_panel.cu),
@@ -135,7 +140,7 @@ struct sb_ctx {
     int plane_levels = 6;            // most count levels kept as planes (<= PL_MAX_LEVELS)
     double plane_min_density = 0.01; // a 128-rank block joins level k only if this fraction of the cells has exactly that count
     bool upload_sync = true;         // pipelined upload: synchronise the build stream after every chunk (matrix.cu)
-    int gather_items_per_cta = 6;    // T-side gather: work items per CTA on the ticket queue (1 = one static share per CTA)
+    int gather_items_per_cta = 1;    // T-side gather: work items per CTA on the ticket queue (1 = one static share per CTA; 6 measured slower: 7.28 vs 6.85 ms per C3 pass -- finer pieces re-stage panels and lose the L2 locality of sweeping the cell blocks together)
     bool use_gather = true;          // panelled gather kernels (gather.cu); false: the first-generation K7 / K8 of spmm.cu
     bool direct_projection = false;  // true: always run the wide Q^T A pass (bk_svd.rs:102,131) instead of the R^-T identity
     bool verify_projection = false;  // true: always check the R^-T identity a posteriori (default: only when cond(R) > 1e9)
@@ -210,14 +215,6 @@ struct GatherLayout {
     DevBuf<u32> slot_gene;  // T side: [npanels * rows] gene of a slot or 0xFFFFFFFF
 };
 
-// EXPERIMENTAL (gather_split.cu, default off): each side's stream split into a 4-byte "count == 1" stream and a general one
-struct GatherSplit {
-    bool tried = false, ready = false;
-    DevBuf<u32> n_ones, t_ones;
-    DevBuf<uint2> n_gen, t_gen;
-    GatherLayout n1, ng, t1, tg;  // units of the four streams (n1 / t1: ones, walked by k_gather_ones)
-};
-
 struct sb_mat {
     sb_ctx *ctx = nullptr;
     u32 m = 0;            // genes
@@ -253,8 +250,6 @@ struct sb_mat {
     // panelled gather layouts over the sparse set the products use (the cold entries when gd > 0, else all entries)
     GatherLayout gn, gt;
     DevBuf<u32> slot_of_gene;  // [m] T-side slot (rank by expression) of a gene
-    std::vector<u64> t_seg_len, t_seg_runs;  // T side: entries / runs of every (block, panel) segment, in stream order
-    GatherSplit split;
     // cached integer reductions
     DevBuf<u32> cell_tot;
     bool have_cell_tot = false;

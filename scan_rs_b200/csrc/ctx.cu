@@ -3,6 +3,8 @@
 
 #include <chrono>
 #include <cstdlib>
+#include <mutex>
+#include <set>
 
 #include "common.cuh"
 
@@ -10,6 +12,18 @@ static thread_local char g_err[1024] = "";
 static thread_local cudaStream_t g_alloc_stream = nullptr;
 cudaStream_t sb_alloc_stream() { return g_alloc_stream; }
 void sb_set_alloc_stream(cudaStream_t s) { g_alloc_stream = s; }
+
+static std::mutex g_streams_mu;
+static std::set<cudaStream_t> g_streams;
+bool sb_stream_alive(cudaStream_t s) {
+    std::lock_guard<std::mutex> lk(g_streams_mu);
+    return g_streams.count(s) != 0;
+}
+void sb_stream_register(cudaStream_t s, bool alive) {
+    std::lock_guard<std::mutex> lk(g_streams_mu);
+    if (alive) g_streams.insert(s);
+    else g_streams.erase(s);
+}
 
 void sb_set_error(const char *fmt, ...) {
     va_list ap;
@@ -60,6 +74,7 @@ extern "C" int sb_init(int device, sb_ctx **out) {
     ctx->sm_count = prop.multiProcessorCount;
     ctx->l2_bytes = (size_t)prop.l2CacheSize;
     SB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    sb_stream_register(ctx->stream, true);
     {
         cudaMemPool_t pool;
         SB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -95,8 +110,11 @@ extern "C" void sb_shutdown(sb_ctx *ctx) {
     if (ctx->t0) cudaEventDestroy(ctx->t0);
     if (ctx->t1) cudaEventDestroy(ctx->t1);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    // every device buffer the context owns goes back to the pool while its stream still exists (a DevBuf released by `delete ctx`
+    // below would hand cudaFreeAsync a destroyed stream: a crash at shutdown, seen with the cached start block)
     ctx->flush_buf.release();
     ctx->scratch.release();
+    ctx->omega_dev.release();
     cudaStreamSynchronize(ctx->stream);
     {
         cudaMemPool_t pool;
@@ -109,7 +127,10 @@ extern "C" void sb_shutdown(sb_ctx *ctx) {
     }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream) {
+        sb_stream_register(ctx->stream, false);
+        cudaStreamDestroy(ctx->stream);
+    }
     delete ctx;
 }
 
@@ -143,10 +164,6 @@ extern "C" int sb_set_option(sb_ctx *ctx, const char *name, double value) {
     }
     if (!strcmp(name, "overlap_t")) {  // same for A^T.Y
         ctx->overlap_t = value != 0.0;
-        return SB_OK;
-    }
-    if (!strcmp(name, "gather_split")) {  // experimental, see gather_split.cu
-        ctx->gather_split = value != 0.0;
         return SB_OK;
     }
     if (!strcmp(name, "panel_i8")) {  // experimental, see panel_i8.cu

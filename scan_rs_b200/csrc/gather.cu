@@ -493,8 +493,6 @@ int gather_finish_t(sb_mat *mt, const std::vector<u64> &seg_len, const std::vect
     u64 total_nnz = 0;
     for (u64 x : seg_len) total_nnz += x;
     L.nnz = total_nnz;
-    mt->t_seg_len = seg_len;  // kept for gather_split.cu
-    mt->t_seg_runs = seg_runs;
     std::vector<GUnit> units;
     std::vector<u32> first;
     const u32 per_cta = (u32)std::max(1, ctx->gather_items_per_cta);

@@ -396,9 +396,10 @@ __global__ void k_pl_colmax_t(const double *__restrict__ Y, u32 ldy, const u32 *
     atomic_max_abs(&colmax_bits[c], finite_or_zero(v));
 }
 
-// Bd[range][k / 16][n / 8][n % 8][k % 16], k = rank % 1024, n = 7 c + s (digit s of column c)
+// Bd[range][k / 16][n / 8][n % 8][k % 16], k = rank % 1024, n = 7 c + s (digit s of column c); with `split` the second ten columns
+// start at accumulator column 72 (a multiple of 8) so that each half of the epilogue warps reads its own aligned 72-column range
 __global__ void k_pl_digits_t(const double *__restrict__ Y, u32 ldy, const u32 *__restrict__ hot_idx, const double *__restrict__ rs, u32 G1, u32 col0,
-                              u32 wt, const int *__restrict__ ex, signed char *__restrict__ Bd) {
+                              u32 wt, const int *__restrict__ ex, signed char *__restrict__ Bd, u32 split) {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= G1 * PL_COLS) return;
     const u32 r = i / PL_COLS, c = i - r * PL_COLS;
@@ -412,7 +413,7 @@ __global__ void k_pl_digits_t(const double *__restrict__ Y, u32 ldy, const u32 *
     signed char *base = Bd + (size_t)range * PT_B_BYTES + (size_t)(k >> 4) * PT_KCHUNK_BYTES + (k & 15);
 #pragma unroll
     for (u32 s = 0; s < PL_DIG; s++) {
-        const u32 n = c * PL_DIG + s;
+        const u32 n = c * PL_DIG + s + ((split && c >= PL_COLS / 2) ? 2u : 0u);
         base[(size_t)(n >> 3) * 128 + (n & 7) * 16] = d[s];
     }
 }
@@ -473,31 +474,67 @@ __device__ __forceinline__ void read_acc_fma(u32 taddr, double lk, double (&res)
     }
 }
 
+// Ten columns (70 digit columns, read as 4 x 16 + 8 accumulator columns from `taddr`): res[c] += lk * value_c.  The loads of the
+// next chunk pair are in flight while the current pair is recombined (tcgen05.wait::ld waits for every outstanding load, so the
+// chunks are issued two at a time).
+__device__ __forceinline__ void read_acc_fma_half(u32 taddr, double lk, double (&res)[PL_COLS / 2]) {
+    u32 ra[16], rb[16], rc[16], rd[16], re[8];
+    double lo = 0.0, hi = 0.0;
+    auto eat = [&](const u32 *r, u32 n0, u32 cnt) {
+#pragma unroll
+        for (u32 i = 0; i < cnt; i++) {
+            const u32 n = n0 + i;  // compile-time after unrolling
+            if (n < (PL_COLS / 2) * PL_DIG) {
+                const u32 c = n / PL_DIG, sdig = n - c * PL_DIG;
+                const double d = i32_to_f64(r[i]);
+                if (sdig == 0) lo = d;
+                else if (sdig < 4) lo = fma(d, (double)(1u << (8 * sdig)), lo);
+                else if (sdig == 4) hi = d;
+                else hi = fma(d, (double)(1u << (8 * (sdig - 4))), hi);
+                if (sdig == PL_DIG - 1) res[c] = fma(lk, fma(hi, 4294967296.0, lo), res[c]);
+            }
+        }
+    };
+    tmem_ld16(taddr, ra);
+    tmem_ld16(taddr + 16, rb);
+    tmem_ld_wait();
+    tmem_ld16(taddr + 32, rc);
+    tmem_ld16(taddr + 48, rd);
+    eat(ra, 0, 16);
+    eat(rb, 16, 16);
+    tmem_ld_wait();
+    tmem_ld8(taddr + 64, re);
+    eat(rc, 32, 16);
+    eat(rd, 48, 16);
+    tmem_ld_wait();
+    eat(re, 64, 8);
+}
+
 // ---------------------------------------------------------------- k_planes_t
 // Roles: warps 0-3 epilogue, warp 4 MMA issue, warps 5-20 producers, warp 21 scheduler.  The producers' refill latency
 // (expand one sub-stage after its slot was freed) against the MMA work in flight in the ring decides the throughput: sixteen
 // warps each own a 4 KB sub-slot (one MMA's A operand), four sub-slots make a stage.
-// Two warp layouts.  V = 0 (first version): warps 0-3 epilogue, 4 MMA, 5-12 producers, 13 item scheduler.  V = 1: a warp's
-// scheduler is warp % 4, and the MMA-issuing warp is the critical path of the kernel (ncu, profiles/planes_r02_ncu.md: the tensor
-// pipe idles while warp 4 works through ~60 instructions per 4-MMA stage), so it shares its scheduler only with epilogue warp 0
-// and two warps that are almost always asleep (the item scheduler and a spare): epilogue 0-3, MMA 4, item scheduler 8, spare 12,
-// producers 5-7, 9-11, 13-14.
+// Two generations of the kernel (A/B through the option pl_variant bit 0; profiles/planes_r02_findings.md).
+//   V = 0: warps 0-3 epilogue, 4 MMA issue, 5-12 producers, 13 item scheduler.
+//   V = 1: what ncu showed of V = 0 at 400k cells -- (1) 17 % of all warp samples sit in the reload of the resident B block at a
+//          unit change (a 21-iteration LDG -> STS loop per thread, one exposed L2 round trip each: ~16 us per change); (2) the four
+//          epilogue warps are busy 70 % of the time: 3,600 cycles per (tile, level) job, a single warp per scheduler working
+//          through nine dependent tcgen05.ld -> convert -> FMA chains, against 576-2,304 cycles of MMAs per job -- the epilogue,
+//          not the tensor pipe (32 % busy), paces the kernel.  So: the B block arrives by bulk asynchronous copies (cp.async.bulk,
+//          one thread, completion on an mbarrier); EIGHT epilogue warps, two per TMEM lane quarter (a warp may only touch lanes
+//          32 (warp % 4) ..), each owning ten of the twenty columns, with the TMEM loads of the next chunk in flight while the
+//          current one is recombined; descriptor low words carry the leading-byte-offset field so an MMA costs 7 issue slots
+//          instead of 11.  Warps: 0-7 epilogue, 8 MMA, 9 item scheduler, 10-17 producers.
+//          (Measured without effect and dropped: isolating the MMA warp on its scheduler, issuing two stages per election.)
 template <int V> struct PtLayout;
 template <> struct PtLayout<0> {
-    static constexpr u32 WARPS = PL_EPI_WARPS + 1 + PT_PROD_WARPS + 1;
-    __device__ static __forceinline__ bool is_sched(u32 w) { return w == WARPS - 1; }
-    __device__ static __forceinline__ bool is_spare(u32) { return false; }
-    __device__ static __forceinline__ u32 prod_index(u32 w) { return w - (PL_EPI_WARPS + 1); }
+    static constexpr u32 WARPS = PL_EPI_WARPS + 1 + PT_PROD_WARPS + 1, EPI = PL_EPI_WARPS;
 };
 template <> struct PtLayout<1> {
-    static constexpr u32 WARPS = 15;
-    __device__ static __forceinline__ bool is_sched(u32 w) { return w == 8; }
-    __device__ static __forceinline__ bool is_spare(u32 w) { return w == 12; }
-    __device__ static __forceinline__ u32 prod_index(u32 w) { return w < 8 ? w - 5 : (w < 12 ? w - 6 : w - 7); }  // 5,6,7,9,10,11,13,14 -> 0..7
+    static constexpr u32 WARPS = 8 + 1 + 1 + PT_PROD_WARPS, EPI = 8;
 };
-#define PT_MAX_THREADS (15 * 32)
 struct PtShared {
-    unsigned long long full[PT_NSTG], empty[PT_NSTG], tfull[3], tempty[3], item_full[2], item_empty[2];
+    unsigned long long full[PT_NSTG], empty[PT_NSTG], tfull[3], tempty[3], item_full[2], item_empty[2], bload;
     u32 tmem;
     u32 item[2];  // work-item ring filled by the scheduler warp
     u32 pad;
@@ -522,10 +559,12 @@ k_planes_t(PlDev pl, const PlUnitT *__restrict__ units, const PlItem *__restrict
     unsigned char *sA = sB + PT_B_BYTES;
     PtShared *sh = reinterpret_cast<PtShared *>(sA + PT_NSTAGES * PT_STAGE_BYTES);
     using LY = PtLayout<V>;
-    constexpr u32 PT_WARPS = LY::WARPS, PT_THREADS = LY::WARPS * 32;
+    constexpr u32 PT_WARPS = LY::WARPS, PT_THREADS = LY::WARPS * 32, EPI = LY::EPI;  // roles: [0, EPI) epilogue, EPI MMA, EPI + 1 .. producers, last (V0) / EPI + 1 (V1) item scheduler
+    constexpr u32 W_MMA = EPI, W_SCHED = V ? EPI + 1 : PT_WARPS - 1, W_PROD0 = V ? EPI + 2 : EPI + 1;
     const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const u32 full0 = smem_u32(sh->full), empty0 = smem_u32(sh->empty), tfull0 = smem_u32(sh->tfull), tempty0 = smem_u32(sh->tempty);
-    const u32 ifull0 = smem_u32(sh->item_full), iempty0 = smem_u32(sh->item_empty);
+    const u32 ifull0 = smem_u32(sh->item_full), iempty0 = smem_u32(sh->item_empty), bload0 = smem_u32(&sh->bload);
+    u32 breloads = 0;  // V1: bulk reloads of the B block so far (phase of `bload`)
 
     if (tid == 0) {
         for (u32 i = 0; i < PT_NSTG; i++) {
@@ -534,8 +573,9 @@ k_planes_t(PlDev pl, const PlUnitT *__restrict__ units, const PlItem *__restrict
         }
         for (u32 i = 0; i < 3; i++) {
             mbar_init(tfull0 + 8 * i, 1);
-            mbar_init(tempty0 + 8 * i, PL_EPI_WARPS);
+            mbar_init(tempty0 + 8 * i, EPI);
         }
+        mbar_init(bload0, 1);
         for (u32 i = 0; i < 2; i++) {
             mbar_init(ifull0 + 8 * i, 1);
             mbar_init(iempty0 + 8 * i, PT_WARPS - 1);  // every consumer warp
@@ -552,7 +592,7 @@ k_planes_t(PlDev pl, const PlUnitT *__restrict__ units, const PlItem *__restrict
     const u32 idesc = instr_desc_i8(PL_TILE, PL_NCOL, false, false);
     const uint64_t da_hi = smem_desc(0, PL_TILE * 16, 128), db_hi = smem_desc(0, PT_KCHUNK_BYTES, 128);
     const u64 n_pad = pl.ntiles * PL_TILE;
-    const bool scheduler = LY::is_sched(warp);
+    const bool scheduler = warp == W_SCHED;
 
     u32 q = 0;      // 64-gene sub-stages before this item (producers) / issued so far (MMA)
     u32 job = 0;    // (tile, level) accumulation jobs so far
@@ -597,15 +637,61 @@ k_planes_t(PlDev pl, const PlUnitT *__restrict__ units, const PlItem *__restrict
             lev1 = nlev > 1 ? un.lev[1] : 0;
             lev2 = nlev > 2 ? un.lev[2] : 0;
             S = (nkb0 + nkb1 + nkb2) / PT_WORDS;  // sub-stages per tile, level-major: [level 0 | level 1 | level 2]
-            const uint4 *src = reinterpret_cast<const uint4 *>(Bd + (size_t)(g0 / PT_RANGE) * PT_B_BYTES);
-            uint4 *dst = reinterpret_cast<uint4 *>(sB);
-            for (u32 i = tid; i < PT_B_BYTES / 16; i += PT_THREADS) dst[i] = src[i];
-            fence_async_smem();
-            __syncthreads();
+            if (V == 1) {
+                // one thread starts nine 16 KB bulk copies (the TMA engine's 1-D form); everybody waits on their byte count
+                if (tid == 0) {
+                    mbar_expect_tx(bload0, PT_B_BYTES);
+                    const signed char *src = Bd + (size_t)(g0 / PT_RANGE) * PT_B_BYTES;
+#pragma unroll 1
+                    for (u32 o = 0; o < PT_B_BYTES; o += 16384u) bulk_g2s(sB_addr + o, src + o, 16384u, bload0);
+                    mbar_arrive(bload0);
+                }
+                mbar_wait(bload0, breloads & 1u);
+                breloads++;
+            } else {
+                const uint4 *src = reinterpret_cast<const uint4 *>(Bd + (size_t)(g0 / PT_RANGE) * PT_B_BYTES);
+                uint4 *dst = reinterpret_cast<uint4 *>(sB);
+                for (u32 i = tid; i < PT_B_BYTES / 16; i += PT_THREADS) dst[i] = src[i];
+                fence_async_smem();
+                __syncthreads();
+            }
         }
         const u64 t0 = item.t0, t1 = item.t1;
 
-        if (warp < PL_EPI_WARPS) {
+        if (V == 1 && warp < EPI) {
+            // ===== epilogue, V1: warp w reads TMEM lanes 32 (w % 4) .. of columns [72 (w / 4), 72 (w / 4) + 72): ten columns of 32 cells
+            const u32 quarter = warp & 3u, half = warp >> 2;
+            const u32 row = quarter * 32 + lane;
+            double *pu = part + (size_t)item.unit * n_pad * PL_COLS + half * (PL_COLS / 2);
+            for (u64 tile = t0; tile < t1; tile++) {
+                const u64 cell = tile * PL_TILE + row;
+                double res[PL_COLS / 2];
+#pragma unroll
+                for (u32 j = 0; j < PL_COLS / 2; j++) res[j] = 0.0;
+                double L0 = 0.0, L1 = 0.0, L2 = 0.0;
+                if (cell < pl.n) {
+                    const double sc = cs[cell];
+                    L0 = finite_or_zero(map_log_part(log_base, sc, lev0 + 1, sb_log_table));
+                    if (nlev > 1) L1 = finite_or_zero(map_log_part(log_base, sc, lev1 + 1, sb_log_table));
+                    if (nlev > 2) L2 = finite_or_zero(map_log_part(log_base, sc, lev2 + 1, sb_log_table));
+                }
+                for (u32 a = 0; a < nlev; a++, job++) {
+                    const u32 slot = job % 3u;
+                    mbar_wait(tfull0 + 8 * slot, (job / 3u) & 1u);
+                    fence_after_sync();
+                    if (!(dbg & 2u)) read_acc_fma_half(tmem + ((quarter * 32u) << 16) + slot * PL_NCOL + half * 72u, a == 0 ? L0 : (a == 1 ? L1 : L2), res);
+                    fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty0 + 8 * slot);
+                }
+                if (!(dbg & 1u)) {
+                    double2 *o = reinterpret_cast<double2 *>(pu + cell * PL_COLS);
+#pragma unroll
+                    for (u32 j = 0; j < PL_COLS / 2; j += 2)
+                        o[j >> 1] = make_double2(res[j] * sh->scale2[half * (PL_COLS / 2) + j], res[j + 1] * sh->scale2[half * (PL_COLS / 2) + j + 1]);
+                }
+            }
+        } else if (warp < EPI) {
             // ===== epilogue: TMEM -> registers -> f64 -> partial output (one thread per cell row)
             const u32 row = warp * 32 + lane;
             double *pu = part + (size_t)item.unit * n_pad * PL_COLS;
@@ -636,7 +722,7 @@ k_planes_t(PlDev pl, const PlUnitT *__restrict__ units, const PlItem *__restrict
                     for (u32 j = 0; j < PL_COLS; j += 2) o[j >> 1] = make_double2(res[j] * sh->scale2[j], res[j + 1] * sh->scale2[j + 1]);
                 }
             }
-        } else if (warp == PL_EPI_WARPS) {
+        } else if (warp == W_MMA) {
             // ===== MMA issue.  The warp runs the loops converged, every value warp-uniform, and only the tensor-core instructions
             // are predicated on an elected lane: that keeps descriptors and addresses in uniform registers (UIADD3 / ULOP3 +
             // UTCIMMA).  Electing a lane around the whole loop instead makes the compiler wrap each UTCIMMA in an ELECT /
@@ -655,42 +741,19 @@ k_planes_t(PlDev pl, const PlUnitT *__restrict__ units, const PlItem *__restrict
                     const u32 acc = tmem + slot * PL_NCOL;
                     u32 kb = 0;
                     if (V == 1) {
-                        // two stages (eight MMAs) per election when the second stage is already full: the loop / election /
-                        // reconvergence overhead of the issuing warp is paid once per 576 tensor-pipe cycles instead of per 288
-                        while (kb < nkb) {
+                        for (; kb < nkb; kb += PT_SUB * PT_WORDS) {
                             const u32 sg = q / PT_SUB, ss = sg & (PT_NSTG - 1);
                             mbar_spin(full0 + 8 * ss, (sg / PT_NSTG) & 1u);
-                            const u32 sg2 = sg + 1, ss2 = sg2 & (PT_NSTG - 1);
-                            bool two = kb + 2 * PT_SUB * PT_WORDS <= nkb;
-                            if (two) two = __all_sync(0xffffffffu, mbar_test(full0 + 8 * ss2, (sg2 / PT_NSTG) & 1u));
                             fence_after_sync();
                             const u32 alo = a16x + ss * (PT_SUB * PT_STAGE_BYTES >> 4), blo = b16x + kb * (2 * PT_KCHUNK_BYTES >> 4);
-                            if (two) {
-                                const u32 alo2 = a16x + ss2 * (PT_SUB * PT_STAGE_BYTES >> 4);
-                                if (elect_one()) {
+                            if (elect_one()) {
 #pragma unroll
-                                    for (u32 t = 0; t < PT_SUB * PT_WORDS; t++)
-                                        mma_i8_lo<0x4008u, 0x4008u>(acc, alo + t * (PL_TILE * 32 >> 4), blo + t * (2 * PT_KCHUNK_BYTES >> 4), idesc, kb | t);
-                                    commit(empty0 + 8 * ss);
-#pragma unroll
-                                    for (u32 t = 0; t < PT_SUB * PT_WORDS; t++)
-                                        mma_i8_lo<0x4008u, 0x4008u>(acc, alo2 + t * (PL_TILE * 32 >> 4), blo + (PT_SUB * PT_WORDS + t) * (2 * PT_KCHUNK_BYTES >> 4), idesc, 1u);
-                                    commit(empty0 + 8 * ss2);
-                                }
-                                __syncwarp();
-                                q += 2 * PT_SUB;
-                                kb += 2 * PT_SUB * PT_WORDS;
-                            } else {
-                                if (elect_one()) {
-#pragma unroll
-                                    for (u32 t = 0; t < PT_SUB * PT_WORDS; t++)
-                                        mma_i8_lo<0x4008u, 0x4008u>(acc, alo + t * (PL_TILE * 32 >> 4), blo + t * (2 * PT_KCHUNK_BYTES >> 4), idesc, kb | t);
-                                    commit(empty0 + 8 * ss);
-                                }
-                                __syncwarp();
-                                q += PT_SUB;
-                                kb += PT_SUB * PT_WORDS;
+                                for (u32 t = 0; t < PT_SUB * PT_WORDS; t++)
+                                    mma_i8_lo<0x4008u, 0x4008u>(acc, alo + t * (PL_TILE * 32 >> 4), blo + t * (2 * PT_KCHUNK_BYTES >> 4), idesc, kb | t);
+                                commit(empty0 + 8 * ss);
                             }
+                            __syncwarp();
+                            q += PT_SUB;
                         }
                     }
                     for (; kb < nkb; kb += PT_SUB * PT_WORDS) {  // kb counts 32-gene blocks (one MMA each)
@@ -717,10 +780,10 @@ k_planes_t(PlDev pl, const PlUnitT *__restrict__ units, const PlItem *__restrict
                     if (nlev > 2) level(nkb2);
                 }
             }
-        } else if (!scheduler && !LY::is_spare(warp)) {
+        } else if (!scheduler) {
             // ===== producers: plane words -> 0/1 int8 A tiles (K-major core matrices: [16-gene chunk][cell / 8][cell % 8][16 B])
             // warp p fills sub-slot p: the sub-stages (PT_WORDS x 32 genes of one level) with global index = p (mod PT_NSTAGES)
-            const u32 p = LY::prod_index(warp);
+            const u32 p = warp - W_PROD0;
             const u32 G0 = pl.G[lev0] >> 5, G1w = pl.G[lev1] >> 5, G2w = pl.G[lev2] >> 5;
             const u32 *bits0 = pl.bits[lev0], *bits1 = pl.bits[lev1], *bits2 = pl.bits[lev2];
             const u32 s0 = nkb0 / PT_WORDS, s1 = nkb1 / PT_WORDS;  // sub-stages of levels 0, 1 per tile
@@ -1134,7 +1197,7 @@ int planes_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo) 
         if (col0 == 0) SB_CUDA(cudaMemsetAsync(Bd.p, 0, (size_t)nranges * PT_B_BYTES, ctx->stream));  // padding columns / ranks stay zero
         k_pl_colmax_t<<<cdiv(items, 256), 256, 0, ctx->stream>>>(Y, ldy, mt->hot_idx.p, rs, G1, col0, wt, colmax.p);
         SB_TRY(scales_from_colmax(ctx, colmax, scale2, ex));
-        k_pl_digits_t<<<cdiv(items, 256), 256, 0, ctx->stream>>>(Y, ldy, mt->hot_idx.p, rs, G1, col0, wt, ex.p, Bd.p);
+        k_pl_digits_t<<<cdiv(items, 256), 256, 0, ctx->stream>>>(Y, ldy, mt->hot_idx.p, rs, G1, col0, wt, ex.p, Bd.p, v1 ? 1u : 0u);
         SB_CUDA(cudaMemsetAsync(pl.counter.p, 0, sizeof(u32), ctx->stream));
         if (v1)
             k_planes_t<1><<<pl.t_grid, PtLayout<1>::WARPS * 32, smem, ctx->stream>>>(make_pldev(mt), (const PlUnitT *)pl.units_t.p,

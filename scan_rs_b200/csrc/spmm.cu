@@ -392,20 +392,6 @@ int mat_ensure_full_gm(sb_mat *mt);
 // gather.cu
 int gather_run(sb_ctx *ctx, const GatherLayout &L, int mode, const MapDev &mp, u64 n_cells, const double *B, u32 ldb, u32 w, double *out, u32 ldo);
 int gather_t_init(sb_ctx *ctx, double *out, u64 n, u32 w, u32 ldo, const double *uy, const double *v);
-// gather_split.cu (experimental, default off)
-int gather_split_build(sb_mat *mt);
-int gather_split_run(sb_mat *mt, int mode, const MapDev &mp, const double *B, u32 ldb, u32 w, double *out, u32 ldo);
-
-// the split streams serve the log chain only; built lazily at the first product that wants them
-static int want_split(sb_nmat *a, bool *use) {
-    sb_mat *mt = a->mat;
-    *use = false;
-    if (!mt->ctx->gather_split || a->kind != 1) return SB_OK;
-    if (!mt->split.tried) SB_TRY(gather_split_build(mt));
-    *use = mt->split.ready;
-    return SB_OK;
-}
-
 // the panelled gather layouts cover the cold entries of a hybrid matrix, or every entry of a matrix without a dense panel
 static bool gather_usable(const sb_nmat *a, const GatherLayout &L) {
     const sb_mat *mt = a->mat;
@@ -430,10 +416,7 @@ int spmm_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo, do
         // T = v (u^T Y)  ->  += dense panel (DMMA)  ->  += panelled gather of the sparse set (f64 reductions)
         SB_TRY(gather_t_init(ctx, out, mt->n, w, ldo, uy, a->v_ones ? nullptr : a->v.p));
         if (hybrid) SB_TRY(dense_t(a, Y, ldy, w, out, ldo, ctx->stream, false));
-        bool split = false;
-        SB_TRY(want_split(a, &split));
-        if (split) SB_TRY(gather_split_run(mt, 1, mp, Y, ldy, w, out, ldo));
-        else SB_TRY(gather_run(ctx, mt->gt, 1, mp, mt->n, Y, ldy, w, out, ldo));
+        SB_TRY(gather_run(ctx, mt->gt, 1, mp, mt->n, Y, ldy, w, out, ldo));
         account(ctx, mt, w, true);
         return SB_OK;
     }
@@ -499,10 +482,7 @@ int spmm_n(sb_nmat *a, const double *X, u32 ldx, u32 w, double *P, u32 ldp) {
         // Overlap: this kernel is bound by the shared-memory pipe, the panel kernel by the FP64 tensor pipe and it needs
         // little shared memory; with 512-thread CTAs here and 256-thread CTAs there both are resident on every SM.
         if (gather_usable(a, mt->gn)) {
-            bool split = false;
-            SB_TRY(want_split(a, &split));
-            if (split) SB_TRY(gather_split_run(mt, 0, mp, X, ldx, w, P, ldp));
-            else SB_TRY(gather_run(ctx, mt->gn, 0, mp, mt->n, X, ldx, w, P, ldp));
+            SB_TRY(gather_run(ctx, mt->gn, 0, mp, mt->n, X, ldx, w, P, ldp));
             if (hybrid) SB_TRY(dense_n(a, X, ldx, w, P, ldp, ctx->stream, false));
             account(ctx, mt, w, false);
             SB_CUDA(cudaGetLastError());

@@ -12,11 +12,11 @@ ctx = sb.Context(0)
 x = np.random.default_rng(0).standard_normal((n, 20))
 y = np.random.default_rng(1).standard_normal((20, 33538))
 ref = None
-for items in (1, 6):
+for items in (1,):
     ctx.set_option("gather_items_per_cta", items)
     dm = generate_device(ctx, SynthConfig(n_cells=n, n_genes=33538, seed=3))
     a = sb.normalize(dm, sb.Normalization.CellRanger)
-    for variant in (0, 1, 2, 3):
+    for variant in (0, 3, 0, 3):
         ctx.set_option("pl_variant", variant)
         pn, pt = a.dot(x), a.rdot(y)
         ctx.profile_enable(True); ctx.profile_reset()

@@ -540,33 +540,6 @@ def test_variance_explained_is_a_labelled_derived_output(ctx):
     assert 0.0 < ve.sum() < 1.0 and np.all(np.diff(ve) <= 0)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("SCANB200_TEST_EXPERIMENTAL") != "1",
-                    reason="experimental split gather streams (csrc/gather_split.cu): default off, not yet validated on hardware; "
-                           "set SCANB200_TEST_EXPERIMENTAL=1 to run")
-@pytest.mark.parametrize("n_cells,n_genes", [(3000, 2500), (40000, 1500)])
-def test_experimental_split_streams_match_combined_stream(ctx, n_cells, n_genes):
-    """Option gather_split (a 4-byte stream of the count-1 entries + a general stream per side) against the combined
-    stream and the oracle, both products, widths with and without the tail."""
-    cfg, cm, dm, _ = synth_pair(ctx, n_cells, n_genes, seed=45, depth=600.0)
-    a_o, a_g = orc.normalize(cm, orc.CELLRANGER), sb.normalize(dm, sb.Normalization.CellRanger)
-    rng = np.random.default_rng(9)
-    for w in (20, 16, 45):
-        x = rng.standard_normal((n_cells, w))
-        y = rng.standard_normal((w, n_genes))
-        ref_n, ref_t = a_o.dot(x), a_o.rdot(y)
-        got = {}
-        for on in (0, 1):
-            try:
-                ctx.set_option("gather_split", on)
-                got[on] = (a_g.dot(x), a_g.rdot(y))
-            finally:
-                ctx.set_option("gather_split", 0)
-            assert np.abs(got[on][0] - ref_n).max() <= 1e-10 * np.abs(ref_n).max(), (on, w)
-            assert np.abs(got[on][1] - ref_t).max() <= 1e-10 * np.abs(ref_t).max(), (on, w)
-        assert np.abs(got[0][0] - got[1][0]).max() <= 1e-11 * np.abs(ref_n).max()
-        assert np.abs(got[0][1] - got[1][1]).max() <= 1e-11 * np.abs(ref_t).max()
-
-
 def test_pipelined_upload_matches_plain_upload(ctx):
     """Large cell-major uploads are chunked and overlapped with the layout build (hot genes picked from the first
     chunk); the result must be the same matrix as the unpipelined gene-major upload and match the oracle."""
