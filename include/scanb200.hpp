@@ -185,6 +185,30 @@ class AdaptiveMat {
         check(sb_gene_totals(h_, 0, out.data()));
         return out;
     }
+    // mean_var_axis (mat.rs:285-329); size_factors (optional, one per cell): the SizeNormalized view of diff-exp (diff_exp.rs:340-358)
+    std::pair<std::vector<double>, std::vector<double>> mean_var_axis(int axis, const std::vector<double> *size_factors = nullptr) const {
+        std::vector<double> mean(axis == 0 ? cols() : rows()), var(mean.size());
+        check(sb_mean_var_axis(h_, axis, size_factors ? size_factors->data() : nullptr, mean.data(), var.data()));
+        return {std::move(mean), std::move(var)};
+    }
+    // mean_var_rows (mat.rs:332-374)
+    std::pair<std::vector<double>, std::vector<double>> mean_var_rows(const std::vector<uint64_t> &cells, const std::vector<double> *size_factors = nullptr) const {
+        std::vector<double> mean(rows()), var(rows());
+        check(sb_mean_var_rows(h_, cells.data(), cells.size(), size_factors ? size_factors->data() : nullptr, mean.data(), var.data()));
+        return {std::move(mean), std::move(var)};
+    }
+    // sum_rows_dual (mat.rs:484-583), exact u64
+    std::pair<std::vector<uint64_t>, std::vector<uint64_t>> sum_rows_dual(const std::vector<uint64_t> &cols1, const std::vector<uint64_t> &cols2) const {
+        std::vector<uint64_t> a(rows()), b(rows());
+        check(sb_sum_rows_dual(h_, cols1.data(), cols1.size(), cols2.data(), cols2.size(), a.data(), b.data()));
+        return {std::move(a), std::move(b)};
+    }
+    // size_factors (diff-exp/src/diff_exp.rs:314-334) over all cells
+    std::vector<double> size_factors() const {
+        std::vector<double> out(cols());
+        check(sb_size_factors(h_, nullptr, 0, nullptr, out.data()));
+        return out;
+    }
     Partition partition_on_threshold(double threshold) const { return partition_on_thresholds(true, threshold, true, threshold); }  // mat.rs:766
     // partition_on_thresholds(Option<f64>, Option<f64>) (mat.rs:772-889)
     Partition partition_on_thresholds(bool has_row, double row_thr, bool has_col, double col_thr) const {
@@ -367,6 +391,17 @@ struct RandSvd : Pca {  // rand_svd.rs:13-50 (ignores the snoop, :44-45)
     PcaResult run_pca_cancellable(const sqz::LowRankOffset &array, size_t k, snoop::CancelProgress &) const override {
         PcaResult r{Array2(array.rows(), k), std::vector<double>(k), Array2(array.cols(), k)};
         check(sb_randsvd_run_pca(array.raw(), (uint32_t)k, l_multiplier, (uint32_t)n_iter, r.u.data.data(), r.s.data(), r.v.data.data()));
+        return r;
+    }
+};
+
+struct Irlba : Pca {  // irlba.rs:36-69 (the reference cannot run it on a LowRankOffset: no 1-D Dot; the device type can)
+    double tol = 0.0001;
+    size_t max_iter = 50;
+    PcaResult run_pca_cancellable(const sqz::LowRankOffset &array, size_t k, snoop::CancelProgress &c) const override {
+        PcaResult r{Array2(array.rows(), k), std::vector<double>(k), Array2(array.cols(), k)};
+        check(sb_irlba(array.raw(), (uint32_t)k, tol, (uint32_t)max_iter, nullptr, snoop::trampoline, &c, r.u.data.data(), r.s.data(), r.v.data.data(),
+                       nullptr, nullptr));
         return r;
     }
 };

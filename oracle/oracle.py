@@ -803,6 +803,8 @@ def mean_var_rows(mat: CountMatrix, cols, sf: Optional[np.ndarray] = None):  # m
     g, cell, val = _mapped_entries(mat, sf)
     cols = np.asarray(cols, dtype=np.int64)
     mult = np.bincount(cols, minlength=mat.cols)  # CSC branch: a column listed twice is walked twice
+    keep = mult[cell] > 0                          # only the listed columns are walked (their size factors may be the only non-zero ones)
+    g, cell, val = g[keep], cell[keep], val[keep]
     w = mult[cell].astype(np.float64)
     means = np.bincount(g, weights=val * w, minlength=mat.rows)
     sq = np.bincount(g, weights=val * val * w, minlength=mat.rows)

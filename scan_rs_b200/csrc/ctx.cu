@@ -202,6 +202,16 @@ extern "C" int sb_set_option(sb_ctx *ctx, const char *name, double value) {
         ctx->gather_items_per_cta = (int)value;
         return SB_OK;
     }
+    if (!strcmp(name, "gather_flush_cost")) {  // applies to matrices built afterwards
+        if (!(value >= 0.0 && value <= 1000.0)) return sb_fail(SB_ERR_INVALID_ARG, "sb_set_option: gather_flush_cost must be in [0, 1000]");
+        ctx->gather_flush_cost = value;
+        return SB_OK;
+    }
+    if (!strcmp(name, "plane_items_per_cta")) {  // applies to matrices built afterwards
+        if (value < 1 || value > 256) return sb_fail(SB_ERR_INVALID_ARG, "sb_set_option: plane_items_per_cta must be 1..256");
+        ctx->plane_items_per_cta = (int)value;
+        return SB_OK;
+    }
     if (!strcmp(name, "pl_variant")) {
         ctx->pl_variant = (int)value;
         return SB_OK;

@@ -229,7 +229,7 @@ int planes_select(sb_mat *mt, u64 c0, u64 c1) {
     {
         double total = 0.0;
         for (double c : cost) total += c * (double)pl.ntiles;
-        const double target = std::max(1.0, total / ((double)ctx->sm_count * 16.0));
+        const double target = std::max(1.0, total / ((double)ctx->sm_count * (double)std::max(1, ctx->plane_items_per_cta)));
         std::vector<u32> uo(ut.size());
         std::iota(uo.begin(), uo.end(), 0u);
         std::stable_sort(uo.begin(), uo.end(), [&](u32 x, u32 y) { return cost[x] > cost[y]; });
@@ -834,6 +834,33 @@ k_planes_t(PlDev pl, const PlUnitT *__restrict__ units, const PlItem *__restrict
                 const bool more = ntile < t1;
                 if (more) load_words(ntile, ni, nxt);
                 if (ntile != tile) prefetch_tile(ntile + 2);
+                if (V == 1) {
+                    // the refill of a freed slot is on the critical path of the ring (microbenchmarks: 190 cycles from the last MMA to
+                    // the `empty` phase, 125-215 per barrier hop, against 1,152 cycles of MMAs in the whole ring): the expansion
+                    // arithmetic happens BEFORE the wait, into registers, and only the sixteen stores follow it
+                    // (the first 32-gene word group only: all sixteen vectors would need 64 registers and spill under the 96 this CTA
+                    // size allows; the second group is expanded after the wait, while the first group's stores drain)
+                    uint4 ex[8];
+#pragma unroll
+                    for (u32 c4 = 0; c4 < 4; c4++) expand_bits32(cur[c4], ex[2 * c4], ex[2 * c4 + 1]);
+                    if (fills > 0) mbar_wait(empty0 + 8 * (p / PT_SUB), (fills - 1) & 1u);
+                    if (!(dbg & 4u)) {
+#pragma unroll
+                        for (u32 c4 = 0; c4 < 4; c4++) {
+                            st_shared_v4(st + c4 * 512, ex[2 * c4]);
+                            st_shared_v4(st + (PL_TILE * 16) + c4 * 512, ex[2 * c4 + 1]);
+                        }
+#pragma unroll
+                        for (u32 j = 1; j < PT_WORDS; j++)
+#pragma unroll
+                            for (u32 c4 = 0; c4 < 4; c4++) {
+                                uint4 lo, hi;
+                                expand_bits32(cur[j * 4 + c4], lo, hi);
+                                st_shared_v4(st + (2 * j) * (PL_TILE * 16) + c4 * 512, lo);
+                                st_shared_v4(st + (2 * j + 1) * (PL_TILE * 16) + c4 * 512, hi);
+                            }
+                    }
+                } else {
                 if (fills > 0) mbar_wait(empty0 + 8 * (p / PT_SUB), (fills - 1) & 1u);
                 if (!(dbg & 4u))
 #pragma unroll
@@ -845,6 +872,7 @@ k_planes_t(PlDev pl, const PlUnitT *__restrict__ units, const PlItem *__restrict
                             st_shared_v4(st + (2 * j) * (PL_TILE * 16) + c4 * 512, lo);
                             st_shared_v4(st + (2 * j + 1) * (PL_TILE * 16) + c4 * 512, hi);
                         }
+                }
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(full0 + 8 * (p / PT_SUB));

@@ -94,11 +94,56 @@ static void test_bksvd(Context &ctx) {  // dim_red/test.rs:58-110 on a sparse co
     EXPECT(normalization::from_str("seuratlog") == Normalization::SeuratLog);
 }
 
+static void test_mean_var_and_sum_fns(Context &ctx) {  // sqz/src/mat.rs:1302-1370 on input_a
+    std::vector<uint32_t> dense = {136, 936, 0, 0, 264, 134, 682, 417, 8, 391, 0, 133, 780, 885, 0, 396, 76, 96, 198, 0};
+    auto mtx = sqz::AdaptiveMat::from_dense(ctx, 4, 5, dense);
+    auto mv0 = mtx.mean_var_axis(0);
+    const double e_mean0[] = {166.5, 456.75, 323.25, 272.75, 163.75}, e_var0[] = {20594.75, 132550.6875, 93385.6875, 131230.6875, 28830.1875};
+    for (int i = 0; i < 5; i++) EXPECT(std::fabs(mv0.first[i] - e_mean0[i]) < 1e-7 && std::fabs(mv0.second[i] - e_var0[i]) < 1e-7);
+    auto mv1 = mtx.mean_var_axis(1);
+    const double e_mean1[] = {267.2, 326.4, 359.6, 153.2}, e_var1[] = {121461.76, 55445.84, 152550.64, 18732.16};
+    for (int i = 0; i < 4; i++) EXPECT(std::fabs(mv1.first[i] - e_mean1[i]) < 1e-7 && std::fabs(mv1.second[i] - e_var1[i]) < 1e-7);
+    auto dual = mtx.sum_rows_dual({1, 2, 3}, {2, 3, 4});
+    const uint64_t e1[] = {936, 1107, 1798, 370}, e2[] = {264, 816, 1665, 294};
+    for (int i = 0; i < 4; i++) EXPECT(dual.first[i] == e1[i] && dual.second[i] == e2[i]);
+    auto sf = mtx.size_factors();  // counts / median (diff_exp.rs:314-334): totals 666 1827 1293 1091 655 -> median 1091
+    EXPECT(std::fabs(sf[0] - 666.0 / 1091.0) < 1e-15 && std::fabs(sf[3] - 1.0) < 1e-15);
+}
+
+static void test_irlba(Context &ctx) {  // dim_red/test.rs:133-139: Irlba { tol: 1e-5 }, A^T u = s v to the tolerance
+    const uint32_t m = 200;
+    const uint64_t n = 700;
+    std::vector<uint32_t> dense(m * n, 0);
+    uint64_t s = 777;
+    for (size_t i = 0; i < dense.size(); i++) {
+        s = s * 6364136223846793005ULL + 1442695040888963407ULL;
+        uint32_t r = (uint32_t)(s >> 40);
+        dense[i] = (r % 4 == 0) ? 1 + (r >> 8) % 5 + ((i / n) % 3 == 0 ? 3 : 0) : 0;
+    }
+    auto mtx = sqz::AdaptiveMat::from_dense(ctx, m, n, dense);
+    auto a = normalization::normalize(mtx, Normalization::CellRanger);
+    dim_red::Irlba irl;
+    irl.tol = 1e-5;
+    auto res = irl.run_pca(a, 5);
+    EXPECT(res.u.rows == m && res.v.rows == n && res.s.size() == 5);
+    for (size_t i = 1; i < 5; i++) EXPECT(res.s[i] <= res.s[i - 1]);
+    Array2 ut(5, m);
+    for (size_t r = 0; r < m; r++)
+        for (size_t j = 0; j < 5; j++) ut(j, r) = res.u(r, j);
+    Array2 uta = a.dot_left(ut);
+    double worst = 0.0;
+    for (size_t j = 0; j < 5; j++)
+        for (size_t c = 0; c < n; c++) worst = std::fmax(worst, std::fabs(uta(j, c) - res.s[j] * res.v(c, j)));
+    EXPECT(worst < 1e-3 * res.s[0]);
+}
+
 int main() {
     try {
         Context ctx(0);
         test_cellranger_normalisation(ctx);
         test_bksvd(ctx);
+        test_mean_var_and_sum_fns(ctx);
+        test_irlba(ctx);
     } catch (const Error &e) {
         std::printf("FAIL: exception %d: %s\n", e.code, e.what());
         return 2;
