@@ -104,9 +104,23 @@ k_syrk_tall(const double *__restrict__ A, u64 rows, u32 w, u32 ld, double *__res
         for (int nt = 0; nt < 4; nt++) {
             const u32 i = I0 + (wr * 4 + mt) * 8 + fr;
             const u32 j = J0 + (wc * 4 + nt) * 8 + 2 * fk;
-            if (i < w && j < w) atomicAdd(G + (size_t)j * w + i, acc[mt][nt][0]);
-            if (i < w && j + 1 < w) atomicAdd(G + (size_t)(j + 1) * w + i, acc[mt][nt][1]);
+            // plain stores into this row chunk's own copy of G: k_syrk_reduce adds the chunks up in a fixed order, so the result is
+            // bit-reproducible -- the gene-side blocks are factored redundantly on every rank and must come out identical there
+            double *Gc = G + (size_t)blockIdx.x * w * w;
+            if (i < w && j < w) Gc[(size_t)j * w + i] = acc[mt][nt][0];
+            if (i < w && j + 1 < w) Gc[(size_t)(j + 1) * w + i] = acc[mt][nt][1];
         }
+}
+
+// G[e] = sum over the row chunks, in chunk order, of the blocks on or above the block diagonal
+__global__ void k_syrk_reduce(const double *__restrict__ parts, u32 chunks, u32 w, double *__restrict__ G) {
+    const u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (u64)w * w) return;
+    const u32 j = (u32)(idx / w), i = (u32)(idx - (u64)j * w);
+    double s = 0.0;
+    if (i / SY_BLK <= j / SY_BLK)
+        for (u32 c = 0; c < chunks; c++) s += parts[(size_t)c * w * w + idx];
+    G[idx] = s;
 }
 
 // fills the blocks below the block diagonal from their transposes
@@ -122,11 +136,20 @@ int syrk_tall(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 ld, double *G) 
     if (rows == 0 || w == 0) return SB_OK;
     const u32 nb = (w + SY_BLK - 1) / SY_BLK;
     const u32 pairs = nb * (nb + 1) / 2;
-    u32 chunks = std::max<u32>(1, (u32)std::min<u64>((rows + 4 * SY_RC - 1) / (4 * SY_RC), std::max<u32>(1, (u32)ctx->sm_count * 2 / pairs)));
+    // row chunks: enough CTAs to fill the machine on a tall block, but at least 2,048 rows each -- every chunk costs a w x w partial
+    // that k_syrk_reduce reads back (the five 33,538 x 20 Krylov blocks took 53 + 41 us per call with 296 chunks of 113 rows)
+    u32 chunks = std::max<u32>(1, (u32)std::min<u64>((rows + 2047) / 2048, std::max<u32>(1, (u32)ctx->sm_count * 2 / pairs)));
     const size_t smem = (size_t)4 * SY_RC * SY_STRIDE * sizeof(double);
     SB_CUDA(cudaFuncSetAttribute(k_syrk_tall, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_syrk_tall<<<dim3(chunks, pairs), SY_THREADS, smem, ctx->stream>>>(A, rows, w, ld, G, nb);
-    count_launch(ctx);
+    // row chunks that get no rows return early: only the first `valid` copies are written (the kernel's own split, restated)
+    u64 per = (rows + chunks - 1) / chunks;
+    per = (per + SY_RC - 1) / SY_RC * SY_RC;
+    const u32 valid = (u32)((rows + per - 1) / per);
+    DevBuf<double> parts;
+    SB_TRY(parts.alloc((size_t)valid * w * w));
+    k_syrk_tall<<<dim3(chunks, pairs), SY_THREADS, smem, ctx->stream>>>(A, rows, w, ld, parts.p, nb);
+    k_syrk_reduce<<<cdiv((u64)w * w, 64), 64, 0, ctx->stream>>>(parts.p, valid, w, G);  // small blocks: the sums spread over many SMs
+    count_launch(ctx); count_launch(ctx);
     if (nb > 1) {
         k_symmetrize_blocks<<<cdiv((u64)w * w, 256), 256, 0, ctx->stream>>>(G, w);
         count_launch(ctx);
@@ -293,9 +316,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_diag(double *__restrict_
         const double inv = 1.0 / s_piv;
         if (t > k && t < nb) A[k][t] *= inv;
         __syncthreads();
-        for (u32 e = t; e < CB * CB; e += CH_THREADS) {
-            const u32 r = e % CB, c = e / CB;
-            if (r > k && r <= c && c < nb) A[r][c] -= A[k][r] * A[k][c];
+        for (u32 e = t; e < nb * nb; e += CH_THREADS) {  // the live nb x nb corner only (nb = 20 for the Krylov blocks: 400 of 4,096 entries)
+            const u32 r = e % nb, c = e / nb;
+            if (r > k && r <= c) A[r][c] -= A[k][r] * A[k][c];
         }
         __syncthreads();
     }
@@ -513,6 +536,136 @@ int qr_chol(sb_ctx *ctx, double *A, double *tmp, u64 rows, u32 w, u32 ld, double
     }
     // three swaps: the result is in `tmp`
     SB_CUDA(cudaMemcpyAsync(A, tmp, rows * (size_t)ld * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    return SB_OK;
+}
+
+// ---------------------------------------------------------------- symmetric eigendecomposition of the small Gram matrix
+// Parallel cyclic Jacobi in one CTA, the whole problem in shared memory: A (w x w, the Gram matrix of the projected block) and the
+// accumulated rotations V.  A sweep is w - 1 rounds of a round-robin tournament; the w / 2 disjoint rotations of a round are
+// computed by one thread each, then every thread applies them to columns (A J, V J) and to rows (J^T A).  Replaces cuSOLVER's
+// syevd at bk_svd.rs:105,134 / rand_svd.rs:98,120 (after the Gram reformulation) for w <= EJ_MAX: 1.77 ms of library
+// kernels for the 100 x 100 case, identical on every rank, were the largest fixed cost of a sharded step.  Deterministic (fixed
+// pairing and order), so replicated ranks get identical bits.  Output like syevd: eigenvalues ascending, eigenvectors in the
+// columns of G (column-major).
+#define EJ_MAX 112
+#define EJ_THREADS 1024
+__global__ void __launch_bounds__(EJ_THREADS, 1) k_eigh_jacobi(double *__restrict__ G, u32 w, double *__restrict__ evals, int *__restrict__ info) {
+    extern __shared__ double ej_smem[];
+    const u32 ld = w + 1;  // odd stride when w is even: the row and column walks hit different banks
+    double *A = ej_smem, *V = A + (size_t)w * ld, *cs = V + (size_t)w * ld;  // cs: c[np] | s[np]
+    __shared__ double red[2];
+    __shared__ u32 pp[EJ_MAX / 2 + 1], qq[EJ_MAX / 2 + 1];
+    const u32 t = threadIdx.x;
+    for (u32 i = t; i < w * w; i += EJ_THREADS) {
+        const u32 r = i % w, c = i / w;
+        A[r * ld + c] = G[i];  // symmetric input: orientation does not matter
+        V[r * ld + c] = r == c ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    const u32 ne = (w + 1) & ~1u, np = ne / 2;
+    int converged = 0;
+    double prev_off = 1.0e300;
+    for (int sweep = 0; sweep < 30 && !converged; sweep++) {
+        for (u32 round = 0; round + 1 < ne; round++) {
+            if (t < np) {
+                u32 p = t == 0 ? round : (round + t) % (ne - 1);
+                u32 q = t == 0 ? ne - 1 : (round + ne - 1 - t) % (ne - 1);
+                if (p > q) { const u32 x = p; p = q; q = x; }
+                double c = 1.0, sn = 0.0;
+                if (q < w) {
+                    const double apq = A[p * ld + q], app = A[p * ld + p], aqq = A[q * ld + q];
+                    if (apq != 0.0 && fabs(apq) > 1.0e-300) {
+                        const double tau = (aqq - app) / (2.0 * apq);
+                        if (fabs(tau) < 1.0e150) {  // beyond that the rotation is the identity to every digit
+                            const double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                            c = 1.0 / sqrt(1.0 + tt * tt);
+                            sn = tt * c;
+                        }
+                    }
+                }
+                pp[t] = p;
+                qq[t] = q;
+                cs[t] = c;
+                cs[np + t] = sn;
+            }
+            __syncthreads();
+            // columns p, q of A and V:  x_p' = c x_p - s x_q,  x_q' = s x_p + c x_q
+            for (u32 i = t; i < 2 * w * np; i += EJ_THREADS) {
+                const u32 which = i / (w * np), rem = i - which * (w * np);
+                const u32 pr = rem / w, row = rem - pr * w;
+                const u32 p = pp[pr], q = qq[pr];
+                if (q >= w) continue;
+                const double c = cs[pr], sn = cs[np + pr];
+                double *M = which ? V : A;
+                const double xp = M[row * ld + p], xq = M[row * ld + q];
+                M[row * ld + p] = c * xp - sn * xq;
+                M[row * ld + q] = sn * xp + c * xq;
+            }
+            __syncthreads();
+            // rows p, q of A
+            for (u32 i = t; i < w * np; i += EJ_THREADS) {
+                const u32 pr = i / w, col = i - pr * w;
+                const u32 p = pp[pr], q = qq[pr];
+                if (q >= w) continue;
+                const double c = cs[pr], sn = cs[np + pr];
+                const double xp = A[p * ld + col], xq = A[q * ld + col];
+                A[p * ld + col] = c * xp - sn * xq;
+                A[q * ld + col] = sn * xp + c * xq;
+            }
+            __syncthreads();
+        }
+        // off-diagonal mass against the diagonal
+        double off = 0.0, dg = 0.0;
+        for (u32 i = t; i < w * w; i += EJ_THREADS) {
+            const u32 r = i / w, c = i - r * w;
+            const double x = A[r * ld + c];
+            if (r == c) dg += x * x;
+            else off += x * x;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            off += __shfl_xor_sync(0xffffffffu, off, o);
+            dg += __shfl_xor_sync(0xffffffffu, dg, o);
+        }
+        if (t == 0) red[0] = red[1] = 0.0;
+        __syncthreads();
+        if ((t & 31) == 0) {
+            atomicAdd(&red[0], off);
+            atomicAdd(&red[1], dg);
+        }
+        __syncthreads();
+        // done when the off-diagonal mass is at rounding level, or has stopped shrinking (it stalls at ~eps^2 of the largest eigenvalues)
+        converged = red[0] <= 1.0e-30 * red[1] || red[0] == 0.0 || (sweep >= 5 && red[0] > 0.1 * prev_off);
+        prev_off = red[0];
+        __syncthreads();
+    }
+    // ascending order (ties by index), eigenvector j -> column rank(j) of G
+    if (t < w) {
+        const double lam = A[t * ld + t];
+        u32 rank = 0;
+        for (u32 j = 0; j < w; j++) {
+            const double lj = A[j * ld + j];
+            rank += (lj < lam || (lj == lam && j < t)) ? 1u : 0u;
+        }
+        evals[rank] = lam;
+        cs[t] = (double)rank;
+    }
+    __syncthreads();
+    for (u32 i = t; i < w * w; i += EJ_THREADS) {
+        const u32 r = i % w, j = i / w;
+        G[(size_t)((u32)cs[j]) * w + r] = V[r * ld + j];
+    }
+    if (t == 0) *info = converged ? 0 : 1;
+}
+
+int eigh_jacobi(sb_ctx *ctx, double *G, u32 w, double *evals_dev, int *info_dev) {
+    if (w == 0) return SB_OK;
+    if (w > EJ_MAX) return sb_fail(SB_ERR_UNSUPPORTED, "eigh_jacobi: order %u exceeds %d", w, EJ_MAX);
+    ProfScope ps(ctx, PH_DENSE);
+    const size_t smem = ((size_t)2 * w * (w + 1) + 2 * (EJ_MAX / 2 + 1) + 2) * sizeof(double);
+    SB_CUDA(cudaFuncSetAttribute(k_eigh_jacobi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_eigh_jacobi<<<1, EJ_THREADS, smem, ctx->stream>>>(G, w, evals_dev, info_dev);
+    count_launch(ctx);
+    SB_CUDA(cudaGetLastError());
     return SB_OK;
 }
 

@@ -18,6 +18,7 @@ int gemm_tall_small(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 lda, cons
 int syrk_tall(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 ld, double *G);
 int gemm_tall(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 lda, const double *S, u32 k, u32 lds, double *Out, u32 ldo);
 int qr_chol(sb_ctx *ctx, double *A, double *tmp, u64 rows, u32 w, u32 ld, double *Rinv_out, int *flag, u64 rows_global = 0);
+int eigh_jacobi(sb_ctx *ctx, double *G, u32 w, double *evals_dev, int *info_dev);
 int topk_select(sb_ctx *ctx, const double *W, const double *ev, u32 wq, u32 k, double *Wsel, double *Wsc, double *S);
 int comm_allreduce_f64(sb_ctx *ctx, double *buf, size_t count);
 
@@ -127,7 +128,8 @@ static int finish_svd(sb_ctx *ctx, const Tall &Tt, const Tall &Q, u32 wq, u32 k,
     } else {
         SB_TRY(gram(ctx, Tt.buf.p, Tt.rows, wq, Tt.ld, G.p, reduce_gram));
     }
-    SB_TRY(eigh(ctx, G.p, wq, ev.p, info_dev));
+    if (ctx->own_dense && wq <= 112) SB_TRY(eigh_jacobi(ctx, G.p, wq, ev.p, info_dev));  // own one-CTA Jacobi (dense_own.cu)
+    else SB_TRY(eigh(ctx, G.p, wq, ev.p, info_dev));                                       // larger Gram matrices: cuSOLVER syevd
     double *dWsel = Wk.p, *dWsc = Wk.p + (size_t)wq * k;
     SB_TRY(topk_select(ctx, G.p, ev.p, wq, k, dWsel, dWsc, S_dev));
     SB_TRY(from_t.init(ctx, Tt.rows, k));
@@ -361,10 +363,14 @@ static int bksvd_impl(sb_nmat *a, uint32_t k, uint32_t b, uint32_t n_iter, uint6
         SB_TRY(W.init(ctx, m, b, 1));
         if (own_b) SB_TRY(tmpB.init(ctx, n, b));
         if (fast) SB_TRY(WK.init(ctx, m, bq, 1));  // column block i-1 keeps A . B_i (B_i = block i of K)
+        // sharded: spmm_n all-reduces its output in place and needs a contiguous block, so the product lands in W and the column
+        // block of WK is a copy of it
+        const bool via_w = sh != 0;
         for (u32 i = 0; i < n_iter; i++) {
-            double *Wp = (fast && i > 0) ? WK.buf.p + (size_t)(i - 1) * b : W.buf.p;
-            u32 Wld = (fast && i > 0) ? WK.ld : W.ld;
+            double *Wp = (fast && i > 0 && !via_w) ? WK.buf.p + (size_t)(i - 1) * b : W.buf.p;
+            u32 Wld = (fast && i > 0 && !via_w) ? WK.ld : W.ld;
             SB_TRY(spmm_n(a, B.buf.p, B.ld, b, Wp, Wld));                   // A.dot(&B)
+            if (fast && i > 0 && via_w) SB_TRY(copy_block(ctx, WK.buf.p, WK.ld, (i - 1) * b, W.buf.p, W.ld, m, b));
             SB_TRY(spmm_t(a, Wp, Wld, b, B.buf.p, B.ld, uy.p));              // (.)^T.dot(A) ^T
             u32 wq = 0;
             SB_TRY(qr_block(ctx, own_b, B, tmpB, &wq, nullptr, chol_flag, sh));  // .qr()?.0   :94
@@ -374,7 +380,11 @@ static int bksvd_impl(sb_nmat *a, uint32_t k, uint32_t b, uint32_t n_iter, uint6
         u32 wq = 0;
         DevBuf<double> tri;
         SB_TRY(tri.alloc((size_t)bq * bq));
-        if (fast) SB_TRY(spmm_n(a, B.buf.p, B.ld, b, WK.buf.p + (size_t)(n_iter - 1) * b, WK.ld));  // A . B_q
+        if (fast && !via_w) SB_TRY(spmm_n(a, B.buf.p, B.ld, b, WK.buf.p + (size_t)(n_iter - 1) * b, WK.ld));  // A . B_q
+        if (fast && via_w) {
+            SB_TRY(spmm_n(a, B.buf.p, B.ld, b, W.buf.p, W.ld));
+            SB_TRY(copy_block(ctx, WK.buf.p, WK.ld, (n_iter - 1) * b, W.buf.p, W.ld, m, b));
+        }
         if (own_k) SB_TRY(tmpK.init(ctx, n, bq));
         SB_TRY(qr_block(ctx, own_k, Kc, tmpK, &wq, tri.p, chol_flag, sh));   // :98
         tmpK.buf.release();

@@ -933,5 +933,5 @@ def test_single_process_multi_gpu_matches_oracle():
     np.testing.assert_array_equal(np.concatenate([o[3] for o in out]), cm.sum_axis_u32(0))
     for o in out:
         np.testing.assert_array_equal(o[4], cm.sum_axis_u64(1))
-        np.testing.assert_array_equal(o[0], u)  # gene-sized results are replicated
+        assert np.abs(o[0] - u).max() < 1e-12 and np.abs(o[1] - s).max() < 1e-12 * s[0]  # gene-sized results are replicated
     check_pca_parity((u, s, v), res_o)
