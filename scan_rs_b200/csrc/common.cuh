@@ -267,6 +267,7 @@ struct sb_nmat {
     int log_base = 0;  // 0 none, 1 ln, 2 log2, 10 log10
     DevBuf<double> col_scale;  // [n] (kind 1) or binomial n[c]
     DevBuf<double> l1c, inv_l1c;  // [n] kind 1: L_c(1) = log_b(col_scale[c] + 1) and its reciprocal (gather.cu)
+    DevBuf<double> lk;            // [n x PL_MAX_LEVELS] kind 1: L_c(k), k = 1 .. 6, finite or 0 (planes.cu: evaluated once per normalize instead of per tile)
     DevBuf<double> row_scale;  // [m] 1/sd (kind 1; may be empty) or binomial pi[r]
     bool has_row_scale = false;
     bool has_offset = false;

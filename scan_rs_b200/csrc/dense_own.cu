@@ -539,136 +539,6 @@ int qr_chol(sb_ctx *ctx, double *A, double *tmp, u64 rows, u32 w, u32 ld, double
     return SB_OK;
 }
 
-// ---------------------------------------------------------------- symmetric eigendecomposition of the small Gram matrix
-// Parallel cyclic Jacobi in one CTA, the whole problem in shared memory: A (w x w, the Gram matrix of the projected block) and the
-// accumulated rotations V.  A sweep is w - 1 rounds of a round-robin tournament; the w / 2 disjoint rotations of a round are
-// computed by one thread each, then every thread applies them to columns (A J, V J) and to rows (J^T A).  Replaces cuSOLVER's
-// syevd at bk_svd.rs:105,134 / rand_svd.rs:98,120 (after the Gram reformulation) for w <= EJ_MAX: 1.77 ms of library
-// kernels for the 100 x 100 case, identical on every rank, were the largest fixed cost of a sharded step.  Deterministic (fixed
-// pairing and order), so replicated ranks get identical bits.  Output like syevd: eigenvalues ascending, eigenvectors in the
-// columns of G (column-major).
-#define EJ_MAX 112
-#define EJ_THREADS 1024
-__global__ void __launch_bounds__(EJ_THREADS, 1) k_eigh_jacobi(double *__restrict__ G, u32 w, double *__restrict__ evals, int *__restrict__ info) {
-    extern __shared__ double ej_smem[];
-    const u32 ld = w + 1;  // odd stride when w is even: the row and column walks hit different banks
-    double *A = ej_smem, *V = A + (size_t)w * ld, *cs = V + (size_t)w * ld;  // cs: c[np] | s[np]
-    __shared__ double red[2];
-    __shared__ u32 pp[EJ_MAX / 2 + 1], qq[EJ_MAX / 2 + 1];
-    const u32 t = threadIdx.x;
-    for (u32 i = t; i < w * w; i += EJ_THREADS) {
-        const u32 r = i % w, c = i / w;
-        A[r * ld + c] = G[i];  // symmetric input: orientation does not matter
-        V[r * ld + c] = r == c ? 1.0 : 0.0;
-    }
-    __syncthreads();
-    const u32 ne = (w + 1) & ~1u, np = ne / 2;
-    int converged = 0;
-    double prev_off = 1.0e300;
-    for (int sweep = 0; sweep < 30 && !converged; sweep++) {
-        for (u32 round = 0; round + 1 < ne; round++) {
-            if (t < np) {
-                u32 p = t == 0 ? round : (round + t) % (ne - 1);
-                u32 q = t == 0 ? ne - 1 : (round + ne - 1 - t) % (ne - 1);
-                if (p > q) { const u32 x = p; p = q; q = x; }
-                double c = 1.0, sn = 0.0;
-                if (q < w) {
-                    const double apq = A[p * ld + q], app = A[p * ld + p], aqq = A[q * ld + q];
-                    if (apq != 0.0 && fabs(apq) > 1.0e-300) {
-                        const double tau = (aqq - app) / (2.0 * apq);
-                        if (fabs(tau) < 1.0e150) {  // beyond that the rotation is the identity to every digit
-                            const double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                            c = 1.0 / sqrt(1.0 + tt * tt);
-                            sn = tt * c;
-                        }
-                    }
-                }
-                pp[t] = p;
-                qq[t] = q;
-                cs[t] = c;
-                cs[np + t] = sn;
-            }
-            __syncthreads();
-            // columns p, q of A and V:  x_p' = c x_p - s x_q,  x_q' = s x_p + c x_q
-            for (u32 i = t; i < 2 * w * np; i += EJ_THREADS) {
-                const u32 which = i / (w * np), rem = i - which * (w * np);
-                const u32 pr = rem / w, row = rem - pr * w;
-                const u32 p = pp[pr], q = qq[pr];
-                if (q >= w) continue;
-                const double c = cs[pr], sn = cs[np + pr];
-                double *M = which ? V : A;
-                const double xp = M[row * ld + p], xq = M[row * ld + q];
-                M[row * ld + p] = c * xp - sn * xq;
-                M[row * ld + q] = sn * xp + c * xq;
-            }
-            __syncthreads();
-            // rows p, q of A
-            for (u32 i = t; i < w * np; i += EJ_THREADS) {
-                const u32 pr = i / w, col = i - pr * w;
-                const u32 p = pp[pr], q = qq[pr];
-                if (q >= w) continue;
-                const double c = cs[pr], sn = cs[np + pr];
-                const double xp = A[p * ld + col], xq = A[q * ld + col];
-                A[p * ld + col] = c * xp - sn * xq;
-                A[q * ld + col] = sn * xp + c * xq;
-            }
-            __syncthreads();
-        }
-        // off-diagonal mass against the diagonal
-        double off = 0.0, dg = 0.0;
-        for (u32 i = t; i < w * w; i += EJ_THREADS) {
-            const u32 r = i / w, c = i - r * w;
-            const double x = A[r * ld + c];
-            if (r == c) dg += x * x;
-            else off += x * x;
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-            off += __shfl_xor_sync(0xffffffffu, off, o);
-            dg += __shfl_xor_sync(0xffffffffu, dg, o);
-        }
-        if (t == 0) red[0] = red[1] = 0.0;
-        __syncthreads();
-        if ((t & 31) == 0) {
-            atomicAdd(&red[0], off);
-            atomicAdd(&red[1], dg);
-        }
-        __syncthreads();
-        // done when the off-diagonal mass is at rounding level, or has stopped shrinking (it stalls at ~eps^2 of the largest eigenvalues)
-        converged = red[0] <= 1.0e-30 * red[1] || red[0] == 0.0 || (sweep >= 5 && red[0] > 0.1 * prev_off);
-        prev_off = red[0];
-        __syncthreads();
-    }
-    // ascending order (ties by index), eigenvector j -> column rank(j) of G
-    if (t < w) {
-        const double lam = A[t * ld + t];
-        u32 rank = 0;
-        for (u32 j = 0; j < w; j++) {
-            const double lj = A[j * ld + j];
-            rank += (lj < lam || (lj == lam && j < t)) ? 1u : 0u;
-        }
-        evals[rank] = lam;
-        cs[t] = (double)rank;
-    }
-    __syncthreads();
-    for (u32 i = t; i < w * w; i += EJ_THREADS) {
-        const u32 r = i % w, j = i / w;
-        G[(size_t)((u32)cs[j]) * w + r] = V[r * ld + j];
-    }
-    if (t == 0) *info = converged ? 0 : 1;
-}
-
-int eigh_jacobi(sb_ctx *ctx, double *G, u32 w, double *evals_dev, int *info_dev) {
-    if (w == 0) return SB_OK;
-    if (w > EJ_MAX) return sb_fail(SB_ERR_UNSUPPORTED, "eigh_jacobi: order %u exceeds %d", w, EJ_MAX);
-    ProfScope ps(ctx, PH_DENSE);
-    const size_t smem = ((size_t)2 * w * (w + 1) + 2 * (EJ_MAX / 2 + 1) + 2) * sizeof(double);
-    SB_CUDA(cudaFuncSetAttribute(k_eigh_jacobi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_eigh_jacobi<<<1, EJ_THREADS, smem, ctx->stream>>>(G, w, evals_dev, info_dev);
-    count_launch(ctx);
-    SB_CUDA(cudaGetLastError());
-    return SB_OK;
-}
-
 // ---------------------------------------------------------------- top-k eigenpairs -> projection matrices (device resident)
 // W: eigenvectors, column-major wq x wq, eigenvalues ascending.  Wsel[i] = eigenvector of the i-th largest eigenvalue,
 // Wsc[i] = Wsel[i] / sigma_i, S[i] = sigma_i = sqrt(max(lambda, 0)).

@@ -34,6 +34,17 @@ __global__ void k_l1_tables(const double *__restrict__ cs, u64 n, int log_base, 
     }
 }
 
+// lk[c * PL_MAX_LEVELS + k - 1] = L_c(k) for the count levels the bit planes can hold; non-finite values (a zero total gives an
+// infinite, never-used column scale, normalization.rs:169) are stored as 0, as the plane kernels want them
+__global__ void k_level_table(const double *__restrict__ cs, u64 n, int log_base, double *__restrict__ lk) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * PL_MAX_LEVELS) return;
+    const u64 c = i / PL_MAX_LEVELS;
+    const u32 k = (u32)(i - c * PL_MAX_LEVELS) + 1u;
+    const double v = map_log_part(log_base, cs[c], k, sb_log_table);
+    lk[i] = (v == v && fabs(v) < 1.0e300) ? v : 0.0;
+}
+
 __global__ void k_fill(double *p, u64 n, double v) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -196,6 +207,9 @@ extern "C" int sb_log_normalize(sb_mat *mat, int has_target, double target, int 
         SB_TRY(a->l1c.alloc(mat->n));
         SB_TRY(a->inv_l1c.alloc(mat->n));
         k_l1_tables<<<cdiv(mat->n, 256), 256, 0, ctx->stream>>>(a->col_scale.p, mat->n, log_base, a->l1c.p, a->inv_l1c.p);
+        SB_TRY(a->lk.alloc(mat->n * PL_MAX_LEVELS));
+        k_level_table<<<cdiv(mat->n * PL_MAX_LEVELS, 256), 256, 0, ctx->stream>>>(a->col_scale.p, mat->n, log_base, a->lk.p);
+        count_launch(ctx);
         count_launch(ctx); count_launch(ctx);
         SB_CUDA(cudaStreamSynchronize(ctx->stream));
     }

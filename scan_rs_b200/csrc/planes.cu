@@ -552,7 +552,7 @@ struct PtShared {
 template <int V>
 __global__ void __launch_bounds__(PtLayout<V>::WARPS * 32, 1)
 k_planes_t(PlDev pl, const PlUnitT *__restrict__ units, const PlItem *__restrict__ items, u32 n_items, u32 *__restrict__ counter,
-           const signed char *__restrict__ Bd, const double *__restrict__ scale2_g, const double *__restrict__ cs, int log_base, u32 wt,
+           const signed char *__restrict__ Bd, const double *__restrict__ scale2_g, const double *__restrict__ lk, u32 wt,
            double *__restrict__ part, u32 dbg) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *sB = smem;
@@ -669,11 +669,11 @@ k_planes_t(PlDev pl, const PlUnitT *__restrict__ units, const PlItem *__restrict
 #pragma unroll
                 for (u32 j = 0; j < PL_COLS / 2; j++) res[j] = 0.0;
                 double L0 = 0.0, L1 = 0.0, L2 = 0.0;
-                if (cell < pl.n) {
-                    const double sc = cs[cell];
-                    L0 = finite_or_zero(map_log_part(log_base, sc, lev0 + 1, sb_log_table));
-                    if (nlev > 1) L1 = finite_or_zero(map_log_part(log_base, sc, lev1 + 1, sb_log_table));
-                    if (nlev > 2) L2 = finite_or_zero(map_log_part(log_base, sc, lev2 + 1, sb_log_table));
+                if (cell < pl.n) {  // L_c(level) from the per-cell table written by sb_normalize
+                    const double *lc = lk + cell * PL_MAX_LEVELS;
+                    L0 = lc[lev0];
+                    if (nlev > 1) L1 = lc[lev1];
+                    if (nlev > 2) L2 = lc[lev2];
                 }
                 for (u32 a = 0; a < nlev; a++, job++) {
                     const u32 slot = job % 3u;
@@ -701,11 +701,11 @@ k_planes_t(PlDev pl, const PlUnitT *__restrict__ units, const PlItem *__restrict
 #pragma unroll
                 for (u32 j = 0; j < PL_COLS; j++) res[j] = 0.0;
                 double L0 = 0.0, L1 = 0.0, L2 = 0.0;
-                if (cell < pl.n) {
-                    const double sc = cs[cell];
-                    L0 = finite_or_zero(map_log_part(log_base, sc, lev0 + 1, sb_log_table));
-                    if (nlev > 1) L1 = finite_or_zero(map_log_part(log_base, sc, lev1 + 1, sb_log_table));
-                    if (nlev > 2) L2 = finite_or_zero(map_log_part(log_base, sc, lev2 + 1, sb_log_table));
+                if (cell < pl.n) {  // L_c(level) from the per-cell table written by sb_normalize
+                    const double *lc = lk + cell * PL_MAX_LEVELS;
+                    L0 = lc[lev0];
+                    if (nlev > 1) L1 = lc[lev1];
+                    if (nlev > 2) L2 = lc[lev2];
                 }
                 for (u32 a = 0; a < nlev; a++, job++) {
                     const u32 slot = job % 3u;
@@ -914,13 +914,13 @@ __global__ void k_pl_reduce_t(const double *__restrict__ part, u32 n_units, u64 
 
 // ---------------------------------------------------------------- N side: digit rows of L_c(k) . X[c,:]
 // mode 0: value_j = L_c(k) * X[c, col0 + j]; mode 1 (moments): value_0 = L_c(k), value_1 = L_c(k)^2
-__global__ void k_pl_colmax_n(const double *__restrict__ X, u32 ldx, u64 n, const double *__restrict__ cs, int log_base, u32 Ltop, u32 col0, u32 wt,
+__global__ void k_pl_colmax_n(const double *__restrict__ X, u32 ldx, u64 n, const double *__restrict__ lk, u32 Ltop, u32 col0, u32 wt,
                               int mode, unsigned long long *__restrict__ colmax_bits) {
     double mx[PL_COLS];
 #pragma unroll
     for (u32 j = 0; j < PL_COLS; j++) mx[j] = 0.0;
     for (u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (u64)gridDim.x * blockDim.x) {
-        const double l = finite_or_zero(map_log_part(log_base, cs[c], Ltop, sb_log_table));  // L_c(k) grows with k: the top level bounds all
+        const double l = lk[c * PL_MAX_LEVELS + Ltop - 1];  // L_c(k) grows with k: the top level bounds all
         if (mode == 1) {
             mx[0] = fmax(mx[0], fabs(l));
             mx[1] = fmax(mx[1], l * l);
@@ -939,7 +939,7 @@ __global__ void k_pl_colmax_n(const double *__restrict__ X, u32 ldx, u64 n, cons
 }
 
 // Bn[level][cell / 8][n / 16][cell % 8][n % 16] over the padded cells (zero rows beyond n): one thread per (cell, level)
-__global__ void k_pl_digits_n(const double *__restrict__ X, u32 ldx, u64 n, u64 n_pad, const double *__restrict__ cs, int log_base, u32 L, u32 col0,
+__global__ void k_pl_digits_n(const double *__restrict__ X, u32 ldx, u64 n, u64 n_pad, const double *__restrict__ lk, u32 L, u32 col0,
                               u32 wt, int mode, const int *__restrict__ ex, signed char *__restrict__ Bn) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pad * L) return;
@@ -949,7 +949,7 @@ __global__ void k_pl_digits_n(const double *__restrict__ X, u32 ldx, u64 n, u64 
 #pragma unroll
     for (u32 t = 0; t < PL_NCOL / 4; t++) pk[t] = 0u;
     if (c < n) {
-        const double l = finite_or_zero(map_log_part(log_base, cs[c], lv + 1, sb_log_table));
+        const double l = lk[c * PL_MAX_LEVELS + lv];
 #pragma unroll
         for (u32 j = 0; j < PL_COLS; j++) {
             double v = 0.0;
@@ -1230,11 +1230,11 @@ int planes_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo) 
         if (v1)
             k_planes_t<1><<<pl.t_grid, PtLayout<1>::WARPS * 32, smem, ctx->stream>>>(make_pldev(mt), (const PlUnitT *)pl.units_t.p,
                                                                                      (const PlItem *)pl.items_t.p, pl.n_items_t, pl.counter.p, Bd.p, scale2.p,
-                                                                                     a->col_scale.p, a->log_base, wt, part.p, (u32)ctx->pl_debug);
+                                                                                     a->lk.p, wt, part.p, (u32)ctx->pl_debug);
         else
             k_planes_t<0><<<pl.t_grid, PtLayout<0>::WARPS * 32, smem, ctx->stream>>>(make_pldev(mt), (const PlUnitT *)pl.units_t.p,
                                                                                      (const PlItem *)pl.items_t.p, pl.n_items_t, pl.counter.p, Bd.p, scale2.p,
-                                                                                     a->col_scale.p, a->log_base, wt, part.p, (u32)ctx->pl_debug);
+                                                                                     a->lk.p, wt, part.p, (u32)ctx->pl_debug);
         k_pl_reduce_t<<<rblocks, 256, 0, ctx->stream>>>(part.p, pl.n_units_t, mt->n, n_pad, col0, wt, out, ldo);
         count_launch(ctx); count_launch(ctx); count_launch(ctx); count_launch(ctx);
     }
@@ -1263,9 +1263,9 @@ static int planes_n_impl(sb_nmat *a, const double *X, u32 ldx, u32 w, int mode, 
     for (u32 col0 = 0; col0 < w; col0 += PL_COLS) {
         const u32 wt = std::min(PL_COLS, w - col0);
         SB_CUDA(cudaMemsetAsync(colmax.p, 0, PL_COLS * sizeof(unsigned long long), ctx->stream));
-        k_pl_colmax_n<<<cm_blocks, 256, 0, ctx->stream>>>(X, ldx, mt->n, a->col_scale.p, a->log_base, pl.L, col0, wt, mode, colmax.p);
+        k_pl_colmax_n<<<cm_blocks, 256, 0, ctx->stream>>>(X, ldx, mt->n, a->lk.p, pl.L, col0, wt, mode, colmax.p);
         SB_TRY(scales_from_colmax(ctx, colmax, scale2, ex));
-        k_pl_digits_n<<<cdiv(n_pad * pl.L, 128), 128, 0, ctx->stream>>>(X, ldx, mt->n, n_pad, a->col_scale.p, a->log_base, pl.L, col0, wt, mode, ex.p, Bn.p);
+        k_pl_digits_n<<<cdiv(n_pad * pl.L, 128), 128, 0, ctx->stream>>>(X, ldx, mt->n, n_pad, a->lk.p, pl.L, col0, wt, mode, ex.p, Bn.p);
         SB_CUDA(cudaMemsetAsync(pl.counter.p, 0, sizeof(u32), ctx->stream));
         if (v1)
             k_planes_n<1><<<pl.n_grid, (PL_EPI_WARPS + 1 + 12) * 32, smem, ctx->stream>>>(make_pldev(mt), (const PlUnitN *)pl.units_n.p,
