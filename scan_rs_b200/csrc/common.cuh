@@ -141,6 +141,7 @@ struct sb_ctx {
     int plane_levels = 6;            // most count levels kept as planes (<= PL_MAX_LEVELS)
     double plane_min_density = 0.01; // a 128-rank block joins level k only if this fraction of the cells has exactly that count
     bool upload_sync = true;         // pipelined upload: synchronise the build stream after every chunk (matrix.cu)
+    double gather_seg_cost = 0.0;    // T-side gather cost model: fixed cost of a non-empty (cell block, gene panel) segment, in entries
     double gather_flush_cost = 5.0;  // T-side gather cost model: cost of a run end (flush: ~25 instructions + 20 reductions) in entries
     int gather_items_per_cta = 1;    // T-side gather: work items per CTA on the ticket queue (1 = one static share per CTA; 6 measured slower: 7.28 vs 6.85 ms per C3 pass -- finer pieces re-stage panels and lose the L2 locality of sweeping the cell blocks together)
     bool use_gather = true;          // panelled gather kernels (gather.cu); false: the first-generation K7 / K8 of spmm.cu
@@ -158,6 +159,7 @@ struct sb_ctx {
     DevBuf<char> flush_buf;
     // scratch reused by reductions / collectives
     DevBuf<char> scratch;
+    DevBuf<double> syrk_parts;  // grow-only: per-chunk partial Gram matrices of syrk_tall (dense_own.cu)
     void *pinned = nullptr;  // small pinned staging (4 KB)
     std::vector<double> omega_cache;  // last generated start block (host)
     u64 omega_seed = ~0ull, omega_rows = 0, omega_cols = 0;
@@ -194,6 +196,13 @@ struct PlaneSet {
     DevBuf<u32> bits[PL_MAX_LEVELS];             // [ntiles][G / 32][128] words
     DevBuf<char> units_t, units_n, items_t, items_n;
     DevBuf<u32> counter;  // work-queue head of the T-side kernel
+    // per-pass workspaces, grow-only and kept with the matrix: the digit planes of both sides, the per-unit partial rows of the T side
+    // (2.5 GB at C3) and the small scale tables.  Allocating them per pass from the stream-ordered pool works until some other
+    // allocation pattern fragments the pool; then these, the largest requests, pay for the remapping.
+    mutable DevBuf<signed char> ws_bd, ws_bn;
+    mutable DevBuf<double> ws_part, ws_scale2;
+    mutable DevBuf<unsigned long long> ws_colmax;
+    mutable DevBuf<int> ws_ex;
     u32 n_units_t = 0, n_units_n = 0, n_items_t = 0, n_items_n = 0, t_grid = 0, n_grid = 0;
 };
 

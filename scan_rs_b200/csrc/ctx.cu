@@ -115,6 +115,7 @@ extern "C" void sb_shutdown(sb_ctx *ctx) {
     ctx->flush_buf.release();
     ctx->scratch.release();
     ctx->omega_dev.release();
+    ctx->syrk_parts.release();
     cudaStreamSynchronize(ctx->stream);
     {
         cudaMemPool_t pool;
@@ -200,6 +201,11 @@ extern "C" int sb_set_option(sb_ctx *ctx, const char *name, double value) {
     if (!strcmp(name, "gather_items_per_cta")) {  // applies to matrices built afterwards
         if (value < 1 || value > 64) return sb_fail(SB_ERR_INVALID_ARG, "sb_set_option: gather_items_per_cta must be 1..64");
         ctx->gather_items_per_cta = (int)value;
+        return SB_OK;
+    }
+    if (!strcmp(name, "gather_seg_cost")) {  // applies to matrices built afterwards
+        if (!(value >= 0.0 && value <= 1.0e7)) return sb_fail(SB_ERR_INVALID_ARG, "sb_set_option: gather_seg_cost must be in [0, 1e7]");
+        ctx->gather_seg_cost = value;
         return SB_OK;
     }
     if (!strcmp(name, "gather_flush_cost")) {  // applies to matrices built afterwards

@@ -112,15 +112,19 @@ k_syrk_tall(const double *__restrict__ A, u64 rows, u32 w, u32 ld, double *__res
         }
 }
 
-// G[e] = sum over the row chunks, in chunk order, of the blocks on or above the block diagonal
+// G[e] = sum over the row chunks of the blocks on or above the block diagonal.  One warp per element: lane l adds chunks l, l + 32,
+// ... in order, then a fixed shuffle tree -- the same association on every rank and every run.
 __global__ void k_syrk_reduce(const double *__restrict__ parts, u32 chunks, u32 w, double *__restrict__ G) {
-    const u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 idx = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const u32 lane = threadIdx.x & 31;
     if (idx >= (u64)w * w) return;
     const u32 j = (u32)(idx / w), i = (u32)(idx - (u64)j * w);
     double s = 0.0;
-    if (i / SY_BLK <= j / SY_BLK)
-        for (u32 c = 0; c < chunks; c++) s += parts[(size_t)c * w * w + idx];
-    G[idx] = s;
+    if (i / SY_BLK <= j / SY_BLK) {
+        for (u32 c = lane; c < chunks; c += 32) s += parts[(size_t)c * w * w + idx];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    }
+    if (lane == 0) G[idx] = s;
 }
 
 // fills the blocks below the block diagonal from their transposes
@@ -136,19 +140,20 @@ int syrk_tall(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 ld, double *G) 
     if (rows == 0 || w == 0) return SB_OK;
     const u32 nb = (w + SY_BLK - 1) / SY_BLK;
     const u32 pairs = nb * (nb + 1) / 2;
-    // row chunks: enough CTAs to fill the machine on a tall block, but at least 2,048 rows each -- every chunk costs a w x w partial
-    // that k_syrk_reduce reads back (the five 33,538 x 20 Krylov blocks took 53 + 41 us per call with 296 chunks of 113 rows)
-    u32 chunks = std::max<u32>(1, (u32)std::min<u64>((rows + 2047) / 2048, std::max<u32>(1, (u32)ctx->sm_count * 2 / pairs)));
+    u32 chunks = std::max<u32>(1, (u32)std::min<u64>((rows + 4 * SY_RC - 1) / (4 * SY_RC), std::max<u32>(1, (u32)ctx->sm_count * 2 / pairs)));
     const size_t smem = (size_t)4 * SY_RC * SY_STRIDE * sizeof(double);
     SB_CUDA(cudaFuncSetAttribute(k_syrk_tall, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // row chunks that get no rows return early: only the first `valid` copies are written (the kernel's own split, restated)
     u64 per = (rows + chunks - 1) / chunks;
     per = (per + SY_RC - 1) / SY_RC * SY_RC;
     const u32 valid = (u32)((rows + per - 1) / per);
-    DevBuf<double> parts;
-    SB_TRY(parts.alloc((size_t)valid * w * w));
-    k_syrk_tall<<<dim3(chunks, pairs), SY_THREADS, smem, ctx->stream>>>(A, rows, w, ld, parts.p, nb);
-    k_syrk_reduce<<<cdiv((u64)w * w, 64), 64, 0, ctx->stream>>>(parts.p, valid, w, G);  // small blocks: the sums spread over many SMs
+    // the per-chunk copies live in a grow-only buffer of the context: a fresh stream-ordered allocation per call (a few hundred KB to
+    // 24 MB, a dozen times per PCA) fragmented the pool and the large per-pass buffers of the products paid for its remapping
+    // (measured: 18.7 -> 55 ms per step at 162k cells)
+    SB_TRY(ctx->syrk_parts.ensure((size_t)valid * w * w));
+    double *parts = ctx->syrk_parts.p;
+    k_syrk_tall<<<dim3(chunks, pairs), SY_THREADS, smem, ctx->stream>>>(A, rows, w, ld, parts, nb);
+    k_syrk_reduce<<<cdiv((u64)w * w * 32, 256), 256, 0, ctx->stream>>>(parts, valid, w, G);
     count_launch(ctx); count_launch(ctx);
     if (nb > 1) {
         k_symmetrize_blocks<<<cdiv((u64)w * w, 256), 256, 0, ctx->stream>>>(G, w);

@@ -496,7 +496,7 @@ int gather_finish_t(sb_mat *mt, const std::vector<u64> &seg_len, const std::vect
     std::vector<GUnit> units;
     std::vector<u32> first;
     const u32 per_cta = (u32)std::max(1, ctx->gather_items_per_cta);
-    gather_units_t(seg_len, seg_runs, L.npanels, (u32)ctx->sm_count * per_cta, ctx->gather_flush_cost, units, first);
+    gather_units_t(seg_len, seg_runs, L.npanels, (u32)ctx->sm_count * per_cta, ctx->gather_flush_cost, units, first, ctx->gather_seg_cost);
     L.n_items = (u32)first.size() - 1;
     L.grid = std::min<u32>(L.n_items, (u32)ctx->sm_count);
     L.n_units = (u32)units.size();

@@ -48,8 +48,10 @@ inline void gather_units_n(const std::vector<uint64_t> &base, uint64_t nnz, uint
 // all CTAs move through the cell blocks together the output rows they reduce into stay in L2.  CTAs are handed out along
 // the panel-major line of cost = entries + flush_cost * runs, cut into G equal intervals: a CTA gets the fraction
 // [f0, f1) of every segment of a panel (and, where an interval crosses a panel boundary, a fraction of the next panel).
+// seg_cost: fixed cost of a non-empty (block, panel) segment, in entries (the warps of a CTA split every segment's span, so a short
+// segment keeps most of them idle: panels of rarely expressed genes are sequences of short segments).
 inline void gather_units_t(const std::vector<uint64_t> &seg_len, const std::vector<uint64_t> &seg_runs, uint32_t np, uint32_t G, double flush_cost,
-                           std::vector<GUnit> &units, std::vector<uint32_t> &first) {
+                           std::vector<GUnit> &units, std::vector<uint32_t> &first, double seg_cost = 0.0) {
     units.clear();
     first.clear();
     const size_t nblk = np ? seg_len.size() / np : 0;
@@ -58,7 +60,7 @@ inline void gather_units_t(const std::vector<uint64_t> &seg_len, const std::vect
     double total = 0.0;
     for (size_t k = 0; k < seg_len.size(); k++) {
         seg_pos[k + 1] = seg_pos[k] + seg_len[k];
-        const double cost = (double)seg_len[k] + flush_cost * (double)seg_runs[k];
+        const double cost = (double)seg_len[k] + flush_cost * (double)seg_runs[k] + (seg_len[k] ? seg_cost : 0.0);
         pn[k % np] += cost;
         total += cost;
     }

@@ -1188,8 +1188,8 @@ k_planes_n(PlDev pl, const PlUnitN *__restrict__ units, const PlItem *__restrict
 
 // ---------------------------------------------------------------- launchers
 static int scales_from_colmax(sb_ctx *ctx, DevBuf<unsigned long long> &colmax, DevBuf<double> &scale2, DevBuf<int> &ex) {
-    SB_TRY(scale2.alloc(PL_COLS));
-    SB_TRY(ex.alloc(PL_COLS));
+    SB_TRY(scale2.ensure(PL_COLS));
+    SB_TRY(ex.ensure(PL_COLS));
     k_pl_scales<<<1, 32, 0, ctx->stream>>>(colmax.p, scale2.p, ex.p);
     count_launch(ctx);
     return SB_OK;
@@ -1204,13 +1204,13 @@ int planes_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo) 
     const u32 G1 = pl.G[0];
     const u32 nranges = (G1 + PT_RANGE - 1) / PT_RANGE;
     const u64 n_pad = pl.ntiles * PL_TILE;
-    DevBuf<unsigned long long> colmax;
-    DevBuf<signed char> Bd;
-    DevBuf<double> scale2, part;
-    DevBuf<int> ex;
-    SB_TRY(colmax.alloc(PL_COLS));
-    SB_TRY(Bd.alloc((size_t)nranges * PT_B_BYTES));
-    SB_TRY(part.alloc((size_t)pl.n_units_t * n_pad * PL_COLS));
+    DevBuf<unsigned long long> &colmax = pl.ws_colmax;
+    DevBuf<signed char> &Bd = pl.ws_bd;
+    DevBuf<double> &scale2 = pl.ws_scale2, &part = pl.ws_part;
+    DevBuf<int> &ex = pl.ws_ex;
+    SB_TRY(colmax.ensure(PL_COLS));
+    SB_TRY(Bd.ensure((size_t)nranges * PT_B_BYTES));
+    SB_TRY(part.ensure((size_t)pl.n_units_t * n_pad * PL_COLS));
     const double *rs = a->has_row_scale ? a->row_scale.p : nullptr;
     const size_t smem = (size_t)PT_B_BYTES + PT_NSTAGES * PT_STAGE_BYTES + sizeof(PtShared);
     const bool v1 = ctx->pl_variant & 1;
@@ -1248,12 +1248,12 @@ static int planes_n_impl(sb_nmat *a, const double *X, u32 ldx, u32 w, int mode, 
     const PlaneSet &pl = mt->pl;
     if (!pl.active || mt->n == 0 || w == 0) return SB_OK;
     const u64 n_pad = pl.ntiles * PL_TILE;
-    DevBuf<unsigned long long> colmax;
-    DevBuf<signed char> Bn;
-    DevBuf<double> scale2;
-    DevBuf<int> ex;
-    SB_TRY(colmax.alloc(PL_COLS));
-    SB_TRY(Bn.alloc((size_t)pl.L * (n_pad / 8) * PN_CELLGRP_BYTES));
+    DevBuf<unsigned long long> &colmax = pl.ws_colmax;
+    DevBuf<signed char> &Bn = pl.ws_bn;
+    DevBuf<double> &scale2 = pl.ws_scale2;
+    DevBuf<int> &ex = pl.ws_ex;
+    SB_TRY(colmax.ensure(PL_COLS));
+    SB_TRY(Bn.ensure((size_t)pl.L * (n_pad / 8) * PN_CELLGRP_BYTES));
     const size_t smem = (size_t)PN_NSTAGES * PN_STAGE_BYTES + sizeof(PnShared);
     const bool v1 = ctx->pl_variant & 2;
     cudaError_t e = v1 ? cudaFuncSetAttribute(k_planes_n<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
