@@ -147,6 +147,7 @@ struct sb_ctx {
     bool use_gather = true;          // panelled gather kernels (gather.cu); false: the first-generation K7 / K8 of spmm.cu
     bool direct_projection = false;  // true: always run the wide Q^T A pass (bk_svd.rs:102,131) instead of the R^-T identity
     bool verify_projection = false;  // true: always check the R^-T identity a posteriori (default: only when cond(R) > 1e9)
+    bool eig_jacobi = false;         // 1: cusolverDnDsyevj for Gram matrices of order <= 192 (measured 2.7 ms vs syevd 1.8 + its ~230 launches at w = 100: no gain)
     bool own_dense = true;           // QR / Gram / projections on the repo's kernels (dense_own.cu); false: cuSOLVER / cuBLAS (dense.cu)
     double last_cond_r = 0.0, last_probe_resid = 0.0;  // diagnostics of the last sb_bksvd
     int last_fallbacks = 0;

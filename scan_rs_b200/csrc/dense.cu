@@ -112,6 +112,27 @@ int gram(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 ld, double *G, bool 
 int eigh(sb_ctx *ctx, double *G, u32 w, double *evals_dev, int *info_dev) {
     TraceScope trc(ctx, "dense: eigh");
     ProfScope ps(ctx, PH_DENSE);
+    if (w <= 192 && ctx->eig_jacobi) {
+        // small Gram matrices (w = 100 at k = 10): cuSOLVER's Jacobi solver -- a handful of launches instead of the ~230 tiny kernels
+        // of syevd's tridiagonalisation + divide and conquer (1.8 ms at w = 100, the largest fixed cost of a sharded step)
+        syevjInfo_t par = nullptr;
+        SB_CUSOLVER(cusolverDnCreateSyevjInfo(&par));
+        cusolverDnXsyevjSetTolerance(par, 1.0e-15);
+        cusolverDnXsyevjSetMaxSweeps(par, 100);
+        cusolverDnXsyevjSetSortEig(par, 1);
+        int lw = 0;
+        cusolverStatus_t st = cusolverDnDsyevj_bufferSize(ctx->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)w, G, (int)w, evals_dev, &lw, par);
+        DevBuf<double> wk;
+        int rc = SB_OK;
+        if (st == CUSOLVER_STATUS_SUCCESS) rc = wk.alloc(lw);
+        if (st == CUSOLVER_STATUS_SUCCESS && rc == SB_OK)
+            st = cusolverDnDsyevj(ctx->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)w, G, (int)w, evals_dev, wk.p, lw, info_dev, par);
+        cusolverDnDestroySyevjInfo(par);
+        SB_TRY(rc);
+        if (st != CUSOLVER_STATUS_SUCCESS) return sb_fail(SB_ERR_LINALG, "cuSOLVER syevj error %d", (int)st);
+        count_launch(ctx, false);
+        return SB_OK;
+    }
     int lwork = 0;
     SB_CUSOLVER(cusolverDnDsyevd_bufferSize(ctx->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)w, G, (int)w, evals_dev, &lwork));
     DevBuf<double> work;

@@ -127,8 +127,9 @@ static int finish_svd(sb_ctx *ctx, const Tall &Tt, const Tall &Q, u32 wq, u32 k,
     } else {
         SB_TRY(gram(ctx, Tt.buf.p, Tt.rows, wq, Tt.ld, G.p, reduce_gram));
     }
-    // the w x w Gram matrix (w = 100 at k = 10) goes to cuSOLVER's syevd: a one-CTA parallel Jacobi solver written for this step
-    // was measured at 8 ms against syevd's 1.8 (three barriers and 30,000 element updates per tournament round, ~800 rounds)
+    // the w x w Gram matrix (w = 100 at k = 10) goes to cuSOLVER (dense.cu: syevj for small orders, syevd above): a one-CTA parallel
+    // Jacobi solver written for this step was measured at 8 ms against syevd's 1.8 (three barriers and 30,000 element updates per
+    // tournament round, ~800 rounds)
     SB_TRY(eigh(ctx, G.p, wq, ev.p, info_dev));
     double *dWsel = Wk.p, *dWsc = Wk.p + (size_t)wq * k;
     SB_TRY(topk_select(ctx, G.p, ev.p, wq, k, dWsel, dWsc, S_dev));
