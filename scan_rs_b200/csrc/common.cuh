@@ -63,7 +63,8 @@ int sb_fail(int code, const char *fmt, ...);
 // cudaMalloc/cudaFree device synchronisation each.  The stream is the calling context's stream,
 // published by every API entry through sb_set_alloc_stream().
 cudaStream_t sb_alloc_stream();
-void sb_set_alloc_stream(cudaStream_t s);
+cudaMemPool_t sb_alloc_pool();
+void sb_set_alloc_stream(cudaStream_t s, cudaMemPool_t pool = nullptr);
 // streams of live contexts: a buffer that outlives its context (a handle freed after sb_shutdown) is returned with a plain cudaFree
 bool sb_stream_alive(cudaStream_t s);
 void sb_stream_register(cudaStream_t s, bool alive);
@@ -78,10 +79,8 @@ struct DevBuf {
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { release(); }
     void release() {
-        if (p) {
-            if (sb_stream_alive(st)) cudaFreeAsync(p, st);
-            else cudaFree(p);
-        }
+        // a buffer that outlives its context (a handle freed after sb_shutdown) needs no free: its memory went with the context's pool
+        if (p && sb_stream_alive(st)) cudaFreeAsync(p, st);
         p = nullptr;
         n = 0;
     }
@@ -90,7 +89,8 @@ struct DevBuf {
         n = count;
         if (count == 0) count = 1;
         st = sb_alloc_stream();
-        cudaError_t e = cudaMallocAsync((void **)&p, count * sizeof(T), st);
+        cudaMemPool_t pool = sb_alloc_pool();
+        cudaError_t e = pool ? cudaMallocFromPoolAsync((void **)&p, count * sizeof(T), pool, st) : cudaMallocAsync((void **)&p, count * sizeof(T), st);
         if (e != cudaSuccess) {
             p = nullptr;
             n = 0;
@@ -116,6 +116,7 @@ struct sb_ctx {
     int sm_count = 148;
     size_t l2_bytes = 0;
     cudaStream_t stream = nullptr;
+    cudaMemPool_t pool = nullptr;        // the context's own stream-ordered memory pool (nothing is changed on the device's default pool)
     cudaStream_t copy_stream = nullptr;  // host -> device copies of the pipelined upload
     cudaStream_t aux_stream = nullptr;   // the dense panel kernels when overlapped with the sparse kernels
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -311,7 +312,7 @@ int comm_allgather_u64_host(sb_ctx *ctx, u64 mine, std::vector<u64> &all);
 #define SB_ENTER(ctx_ptr)                         \
     do {                                          \
         SB_CUDA(cudaSetDevice((ctx_ptr)->device)); \
-        sb_set_alloc_stream((ctx_ptr)->stream);    \
+        sb_set_alloc_stream((ctx_ptr)->stream, (ctx_ptr)->pool); \
     } while (0)
 
 // SCANB200_TRACE=1: host wall-clock trace of the upload / build stages (synchronising; diagnostics only)

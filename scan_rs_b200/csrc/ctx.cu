@@ -10,8 +10,13 @@
 
 static thread_local char g_err[1024] = "";
 static thread_local cudaStream_t g_alloc_stream = nullptr;
+static thread_local cudaMemPool_t g_alloc_pool = nullptr;
 cudaStream_t sb_alloc_stream() { return g_alloc_stream; }
-void sb_set_alloc_stream(cudaStream_t s) { g_alloc_stream = s; }
+cudaMemPool_t sb_alloc_pool() { return g_alloc_pool; }
+void sb_set_alloc_stream(cudaStream_t s, cudaMemPool_t pool) {
+    g_alloc_stream = s;
+    g_alloc_pool = pool;
+}
 
 static std::mutex g_streams_mu;
 static std::set<cudaStream_t> g_streams;
@@ -76,12 +81,19 @@ extern "C" int sb_init(int device, sb_ctx **out) {
     SB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     sb_stream_register(ctx->stream, true);
     {
-        cudaMemPool_t pool;
-        SB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        // a private pool: the release threshold ("never give memory back between calls") and the trim at shutdown are this context's
+        // business and must not touch the default pool other CUDA users of the process (PyTorch, another library) allocate from
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof(props));
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        SB_CUDA(cudaMemPoolCreate(&ctx->pool, &props));
         uint64_t never = UINT64_MAX;
-        SB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &never));
+        SB_CUDA(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &never));
     }
-    sb_set_alloc_stream(ctx->stream);
+    sb_set_alloc_stream(ctx->stream, ctx->pool);
     SB_CUBLAS(cublasCreate(&ctx->cublas));
     SB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
     SB_CUSOLVER(cusolverDnCreate(&ctx->cusolver));
@@ -100,7 +112,7 @@ extern "C" int sb_init(int device, sb_ctx **out) {
 extern "C" void sb_shutdown(sb_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    sb_set_alloc_stream(ctx->stream);
+    sb_set_alloc_stream(ctx->stream, ctx->pool);
     cudaStreamSynchronize(ctx->stream);
     prof_collect(ctx);
     for (auto ev : ctx->event_pool) cudaEventDestroy(ev);
@@ -117,10 +129,7 @@ extern "C" void sb_shutdown(sb_ctx *ctx) {
     ctx->omega_dev.release();
     ctx->syrk_parts.release();
     cudaStreamSynchronize(ctx->stream);
-    {
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
-    }
+
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->aux_stream) {
         cudaStreamSynchronize(ctx->aux_stream);
@@ -132,6 +141,8 @@ extern "C" void sb_shutdown(sb_ctx *ctx) {
         sb_stream_register(ctx->stream, false);
         cudaStreamDestroy(ctx->stream);
     }
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);  // returns whatever handles created on this context still hold
+    sb_set_alloc_stream(nullptr, nullptr);
     delete ctx;
 }
 

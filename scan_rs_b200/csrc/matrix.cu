@@ -677,8 +677,8 @@ static int upload_pipelined(sb_mat *mt, const u64 *h_indptr, const HostEntries &
 // SCANB200_TRACE: state of the stream-ordered pool (reserved = held from the driver, used = handed out)
 static void trace_pool(sb_ctx *ctx, const char *label) {
     if (!TraceScope::on()) return;
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) != cudaSuccess) return;
+    cudaMemPool_t pool = ctx->pool;
+    if (!pool) return;
     unsigned long long reserved = 0, used = 0;
     cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
     cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
