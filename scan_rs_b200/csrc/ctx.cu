@@ -83,6 +83,13 @@ extern "C" int sb_init(int device, sb_ctx **out) {
     {
         // a private pool: the release threshold ("never give memory back between calls") and the trim at shutdown are this context's
         // business and must not touch the default pool other CUDA users of the process (PyTorch, another library) allocate from
+        const char *dp = getenv("SCANB200_DEFAULT_POOL");  // diagnostics: 1 = allocate from the device's default pool instead
+        if (dp && *dp == '1') {
+            cudaMemPool_t pool;
+            SB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+            uint64_t never0 = UINT64_MAX;
+            SB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &never0));
+        } else {
         cudaMemPoolProps props;
         memset(&props, 0, sizeof(props));
         props.allocType = cudaMemAllocationTypePinned;
@@ -92,6 +99,7 @@ extern "C" int sb_init(int device, sb_ctx **out) {
         SB_CUDA(cudaMemPoolCreate(&ctx->pool, &props));
         uint64_t never = UINT64_MAX;
         SB_CUDA(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &never));
+        }
     }
     sb_set_alloc_stream(ctx->stream, ctx->pool);
     SB_CUBLAS(cublasCreate(&ctx->cublas));
