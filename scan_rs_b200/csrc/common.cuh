@@ -142,6 +142,7 @@ struct sb_ctx {
     int plane_levels = 6;            // most count levels kept as planes (<= PL_MAX_LEVELS)
     double plane_min_density = 0.01; // a 128-rank block joins level k only if this fraction of the cells has exactly that count
     bool upload_sync = true;         // pipelined upload: synchronise the build stream after every chunk (matrix.cu)
+    int gather_calibrate = 1;        // T-side gather: number of timed passes (per matrix) after which the static shares are re-cut by the measured panel rates (0 = off)
     double gather_seg_cost = 0.0;    // T-side gather cost model: fixed cost of a non-empty (cell block, gene panel) segment, in entries
     double gather_flush_cost = 5.0;  // T-side gather cost model: cost of a run end (flush: ~25 instructions + 20 reductions) in entries
     int gather_items_per_cta = 1;    // T-side gather: work items per CTA on the ticket queue (1 = one static share per CTA; 6 measured slower: 7.28 vs 6.85 ms per C3 pass -- finer pieces re-stage panels and lose the L2 locality of sweeping the cell blocks together)
@@ -263,6 +264,11 @@ struct sb_mat {
     // panelled gather layouts over the sparse set the products use (the cold entries when gd > 0, else all entries)
     GatherLayout gn, gt;
     DevBuf<u32> slot_of_gene;  // [m] T-side slot (rank by expression) of a gene
+    std::vector<u64> t_seg_len, t_seg_runs;  // T side: entries / runs of every (block, panel) segment, in stream order (host copy for recalibration)
+    std::vector<GUnit> t_units_host;         // the T-side units as uploaded
+    std::vector<u32> t_first_host;
+    std::vector<double> t_rate;              // per-panel rate of the last calibration round (weights the attribution of the next)
+    int t_calibrated = 0;                    // calibration rounds done (0: static cost model; >= 1: shares re-cut from a timed pass)
     // cached integer reductions
     DevBuf<u32> cell_tot;
     bool have_cell_tot = false;

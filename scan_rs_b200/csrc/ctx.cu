@@ -226,6 +226,10 @@ extern "C" int sb_set_option(sb_ctx *ctx, const char *name, double value) {
         ctx->eig_jacobi = value != 0.0;
         return SB_OK;
     }
+    if (!strcmp(name, "gather_calibrate")) {
+        ctx->gather_calibrate = value <= 0.0 ? 0 : (value > 8.0 ? 8 : (int)value);
+        return SB_OK;
+    }
     if (!strcmp(name, "gather_seg_cost")) {  // applies to matrices built afterwards
         if (!(value >= 0.0 && value <= 1.0e7)) return sb_fail(SB_ERR_INVALID_ARG, "sb_set_option: gather_seg_cost must be in [0, 1e7]");
         ctx->gather_seg_cost = value;

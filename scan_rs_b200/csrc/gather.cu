@@ -45,8 +45,10 @@ template <int MODE, int TAIL>  // MODE 0: N side, 1: T side.  TAIL: the pass has
 __global__ void __launch_bounds__(GA_THREADS, 1)
 k_gather(const uint2 *__restrict__ ent, const GUnit *__restrict__ units, const u32 *__restrict__ item_first, u32 n_units, u32 n_items,
          u32 *__restrict__ tickets, u32 ticket_base, u32 rows, u64 n_cells, MapDev mp, const double *__restrict__ B, u32 ldb, u32 col0, u32 wt, u32 w,
-         const u32 *__restrict__ slot_gene, double *__restrict__ out, u32 ldo) {
+         const u32 *__restrict__ slot_gene, double *__restrict__ out, u32 ldo, long long *__restrict__ cycles) {
     __shared__ u32 s_item;
+    __shared__ long long s_t0;
+    if (cycles && threadIdx.x == 0) s_t0 = clock64();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *XA = reinterpret_cast<double *>(smem_raw);                   // (rows + 1) x 16; row `rows` is all zero
     double *XB = XA + (size_t)(rows + 1) * 16;                            // (rows + 1) x 4 (TAIL only)
@@ -74,6 +76,7 @@ k_gather(const uint2 *__restrict__ ent, const GUnit *__restrict__ units, const u
     for (int i = threadIdx.x; i < 128; i += blockDim.x) ltab[i] = sb_log_table[i];
 
     u32 staged = GA_NONE;
+    u32 first_item = GA_NONE;  // calibration pass (one item per CTA): the share this CTA drew
 
     // Persistent CTAs draw work items (runs of units, panel-major) from a ticket counter: the cost model that cuts the T-side line
     // into items is only approximate (ncu: sm__cycles_active 1.19 / 1.49 / 1.79 M min / avg / max with one static share per CTA),
@@ -85,6 +88,7 @@ k_gather(const uint2 *__restrict__ ent, const GUnit *__restrict__ units, const u
     __syncthreads();
     const u32 item = s_item;
     if (item >= n_items) break;
+    if (first_item == GA_NONE) first_item = item;
     const u32 u_begin = item_first[item], u_end = min(n_units, item_first[item + 1]);
     for (u32 ui = u_begin; ui < u_end; ui++) {
         const GUnit un = units[ui];
@@ -243,6 +247,12 @@ k_gather(const uint2 *__restrict__ ent, const GUnit *__restrict__ units, const u
         flush();
     }
     }
+    if (cycles && threadIdx.x == 0 && first_item != GA_NONE) {  // busy time of the share's CTA and the SM it ran on (calibration pass only)
+        u32 smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        cycles[first_item] = clock64() - s_t0;
+        cycles[gridDim.x + first_item] = (long long)smid;
+    }
 }
 
 // out[c, j] = v_c * uy[j] (or 0): the rank-1 offset of A^T.Y; the dense panel kernel and the gather add on top
@@ -268,7 +278,8 @@ static size_t gather_smem(u32 rows, bool tail) {
 }
 
 // runs all column passes of one product over a layout
-int gather_run(sb_ctx *ctx, const GatherLayout &L, int mode, const MapDev &mp, u64 n_cells, const double *B, u32 ldb, u32 w, double *out, u32 ldo) {
+int gather_run(sb_ctx *ctx, const GatherLayout &L, int mode, const MapDev &mp, u64 n_cells, const double *B, u32 ldb, u32 w, double *out, u32 ldo,
+               long long *cycles) {
     if (!L.ready) return sb_fail(SB_ERR_UNSUPPORTED, "gather_run: layout not built");
     if (L.nnz == 0 || L.n_units == 0 || w == 0) return SB_OK;
     const u32 n_items = L.n_items ? L.n_items : L.grid;
@@ -290,7 +301,8 @@ int gather_run(sb_ctx *ctx, const GatherLayout &L, int mode, const MapDev &mp, u
     e = cudaFuncSetAttribute(k_gather<M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                          \
     if (e == cudaSuccess)                                                                                                                      \
         k_gather<M, T><<<L.grid, GA_THREADS, smem, ctx->stream>>>(L.ent, L.units.p, L.cta_first.p, L.n_units, n_items, L.tickets.p, L.ticket_base, \
-                                                                  L.rows, n_cells, mp, B, ldb, col0, wt, w, L.slot_gene.p, out, ldo);
+                                                                  L.rows, n_cells, mp, B, ldb, col0, wt, w, L.slot_gene.p, out, ldo,          \
+                                                                  col0 == 0 ? cycles : nullptr);
         if (mode == 0) {
             if (tail) { GA_LAUNCH(0, 1) } else { GA_LAUNCH(0, 0) }
         } else {
@@ -495,8 +507,14 @@ int gather_finish_t(sb_mat *mt, const std::vector<u64> &seg_len, const std::vect
     L.nnz = total_nnz;
     std::vector<GUnit> units;
     std::vector<u32> first;
+    mt->t_seg_len = seg_len;
+    mt->t_seg_runs = seg_runs;
+    mt->t_calibrated = 0;
+    mt->t_rate.clear();
     const u32 per_cta = (u32)std::max(1, ctx->gather_items_per_cta);
     gather_units_t(seg_len, seg_runs, L.npanels, (u32)ctx->sm_count * per_cta, ctx->gather_flush_cost, units, first, ctx->gather_seg_cost);
+    mt->t_units_host = units;
+    mt->t_first_host = first;
     L.n_items = (u32)first.size() - 1;
     L.grid = std::min<u32>(L.n_items, (u32)ctx->sm_count);
     L.n_units = (u32)units.size();
@@ -520,4 +538,87 @@ int gather_build_t(sb_mat *mt, const u64 *ptr, const uint2 *ent, u64 nnz) {
     std::vector<u64> seg, runs;
     SB_TRY(gather_build_t_range(mt, 0, mt->n, ptr, ent, nnz, mt->gt.ent_own, seg, runs));
     return gather_finish_t(mt, seg, runs);
+}
+
+// ---------------------------------------------------------------- T side: shares re-cut from a timed pass
+// The static cost model (entries + flush_cost x runs) leaves the CTAs of one pass between 0.8x and 1.2x of the mean busy time
+// (ncu: sm__cycles_active 1.19 / 1.49 / 1.79 M) and no setting of its constants does better (profiles/README.md).  What the model
+// cannot know is how fast a given gene panel runs -- so the first product of a matrix is timed per CTA (clock64 around its work),
+// every panel gets the measured cycles per unit of modelled cost of the CTAs that worked on it, and the cost line is cut again
+// with those rates.  One D2H of `grid` counters and a host pass over the segment table, once per matrix.
+int gather_recalibrate_t(sb_mat *mt, const long long *cycles_dev) {
+    sb_ctx *ctx = mt->ctx;
+    GatherLayout &L = mt->gt;
+    mt->t_calibrated++;
+    if (!L.ready || L.n_items != L.grid || mt->t_units_host.empty() || L.npanels == 0) return SB_OK;  // only the one-share-per-CTA form
+    const u32 G = L.grid, np = L.npanels;
+    std::vector<long long> cyc(2 * (size_t)G, 0);
+    SB_CUDA(cudaMemcpyAsync(cyc.data(), cycles_dev, 2 * (size_t)G * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    const std::vector<u64> &seg_len = mt->t_seg_len, &seg_runs = mt->t_seg_runs;
+    std::vector<u64> seg_pos(seg_len.size() + 1, 0);
+    for (size_t k = 0; k < seg_len.size(); k++) seg_pos[k + 1] = seg_pos[k] + seg_len[k];
+    // modelled cost of every CTA, split by panel
+    std::vector<double> cta_cost(G, 0.0), pan_cost(np, 0.0), pan_time(np, 0.0);
+    struct PanelShare { u32 panel; double cost, wgt; };
+    std::vector<std::vector<PanelShare>> by_panel(G);
+    for (u32 b = 0; b < G; b++) {
+        for (u32 ui = mt->t_first_host[b]; ui < mt->t_first_host[b + 1]; ui++) {
+            const GUnit &u = mt->t_units_host[ui];
+            const size_t k = (size_t)(std::upper_bound(seg_pos.begin(), seg_pos.end(), u.begin) - seg_pos.begin()) - 1;
+            if (k >= seg_len.size() || seg_len[k] == 0) continue;
+            const double frac = (double)(u.end - u.begin) / (double)seg_len[k];
+            const double c = frac * ((double)seg_len[k] + ctx->gather_flush_cost * (double)seg_runs[k] + ctx->gather_seg_cost);
+            const double wgt = c * (mt->t_rate.size() == np ? mt->t_rate[u.panel] : 1.0);  // expected share of the CTA's time
+            cta_cost[b] += wgt;
+            if (by_panel[b].empty() || by_panel[b].back().panel != u.panel) by_panel[b].push_back({u.panel, 0.0, 0.0});
+            by_panel[b].back().cost += c;
+            by_panel[b].back().wgt += wgt;
+        }
+    }
+    for (u32 b = 0; b < G; b++) {
+        if (cta_cost[b] <= 0.0 || cyc[b] <= 0) continue;
+        for (auto &pc : by_panel[b]) {  // a CTA's time is attributed to its panels in proportion to their expected share
+            pan_cost[pc.panel] += pc.cost;
+            pan_time[pc.panel] += (double)cyc[b] * pc.wgt / cta_cost[b];
+        }
+    }
+    double tot_c = 0.0, tot_t = 0.0;
+    for (u32 p = 0; p < np; p++) {
+        tot_c += pan_cost[p];
+        tot_t += pan_time[p];
+    }
+    if (const char *dump = getenv("SCANB200_GATHER_DUMP")) {  // diagnostics: per-CTA {index, SM, cycles, modelled cost, first panel}
+        if (FILE *f = fopen(dump, "a")) {
+            fprintf(f, "# round %d\n", mt->t_calibrated);
+            for (u32 b = 0; b < G; b++)
+                fprintf(f, "%u %lld %lld %.6g %u %zu\n", b, cyc[G + b], cyc[b], cta_cost[b], by_panel[b].empty() ? 0u : by_panel[b].front().panel, by_panel[b].size());
+            fclose(f);
+        }
+    }
+    if (!(tot_c > 0.0) || !(tot_t > 0.0)) return SB_OK;
+    const double mean_rate = tot_t / tot_c;
+    std::vector<double> rate(np, 1.0);
+    for (u32 p = 0; p < np; p++)
+        if (pan_cost[p] > 0.0) rate[p] = std::min(4.0, std::max(0.25, (pan_time[p] / pan_cost[p]) / mean_rate));
+    std::vector<GUnit> units;
+    std::vector<u32> first;
+    gather_units_t(seg_len, seg_runs, np, G, ctx->gather_flush_cost, units, first, ctx->gather_seg_cost, &rate);
+    if ((u32)first.size() - 1 != G) return SB_OK;  // keep the old shares if the cut degenerated
+    SB_TRY(L.units.alloc(units.size()));
+    SB_TRY(L.cta_first.alloc(first.size()));
+    if (!units.empty()) SB_CUDA(cudaMemcpyAsync(L.units.p, units.data(), units.size() * sizeof(GUnit), cudaMemcpyHostToDevice, ctx->stream));
+    SB_CUDA(cudaMemcpyAsync(L.cta_first.p, first.data(), first.size() * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));  // host temporaries
+    L.n_units = (u32)units.size();
+    mt->t_units_host.swap(units);
+    mt->t_first_host.swap(first);
+    mt->t_rate = rate;
+    if (TraceScope::on()) {
+        double lo = 1e300, hi = 0.0;
+        for (u32 b = 0; b < G; b++)
+            if (cyc[b] > 0) { lo = std::min(lo, (double)cyc[b]); hi = std::max(hi, (double)cyc[b]); }
+        fprintf(stderr, "[scanb200] gather T recalibrated: CTA cycles %.3g .. %.3g (mean rate %.3g per cost unit)\n", lo, hi, mean_rate);
+    }
+    return SB_OK;
 }

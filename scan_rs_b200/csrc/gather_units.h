@@ -51,7 +51,7 @@ inline void gather_units_n(const std::vector<uint64_t> &base, uint64_t nnz, uint
 // seg_cost: fixed cost of a non-empty (block, panel) segment, in entries (the warps of a CTA split every segment's span, so a short
 // segment keeps most of them idle: panels of rarely expressed genes are sequences of short segments).
 inline void gather_units_t(const std::vector<uint64_t> &seg_len, const std::vector<uint64_t> &seg_runs, uint32_t np, uint32_t G, double flush_cost,
-                           std::vector<GUnit> &units, std::vector<uint32_t> &first, double seg_cost = 0.0) {
+                           std::vector<GUnit> &units, std::vector<uint32_t> &first, double seg_cost = 0.0, const std::vector<double> *panel_rate = nullptr) {
     units.clear();
     first.clear();
     const size_t nblk = np ? seg_len.size() / np : 0;
@@ -60,7 +60,8 @@ inline void gather_units_t(const std::vector<uint64_t> &seg_len, const std::vect
     double total = 0.0;
     for (size_t k = 0; k < seg_len.size(); k++) {
         seg_pos[k + 1] = seg_pos[k] + seg_len[k];
-        const double cost = (double)seg_len[k] + flush_cost * (double)seg_runs[k] + (seg_len[k] ? seg_cost : 0.0);
+        // panel_rate (optional): measured cycles per unit of modelled cost of every panel, from a timed pass (gather_recalibrate_t)
+        const double cost = ((double)seg_len[k] + flush_cost * (double)seg_runs[k] + (seg_len[k] ? seg_cost : 0.0)) * (panel_rate ? (*panel_rate)[k % np] : 1.0);
         pn[k % np] += cost;
         total += cost;
     }

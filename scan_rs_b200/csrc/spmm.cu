@@ -390,7 +390,9 @@ int dense_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo, c
 int dense_n(sb_nmat *a, const double *X, u32 ldx, u32 w, double *P, u32 ldp, cudaStream_t stream, bool overlap);
 int mat_ensure_full_gm(sb_mat *mt);
 // gather.cu
-int gather_run(sb_ctx *ctx, const GatherLayout &L, int mode, const MapDev &mp, u64 n_cells, const double *B, u32 ldb, u32 w, double *out, u32 ldo);
+int gather_run(sb_ctx *ctx, const GatherLayout &L, int mode, const MapDev &mp, u64 n_cells, const double *B, u32 ldb, u32 w, double *out, u32 ldo,
+               long long *cycles = nullptr);
+int gather_recalibrate_t(sb_mat *mt, const long long *cycles_dev);
 int gather_t_init(sb_ctx *ctx, double *out, u64 n, u32 w, u32 ldo, const double *uy, const double *v);
 // the panelled gather layouts cover the cold entries of a hybrid matrix, or every entry of a matrix without a dense panel
 static bool gather_usable(const sb_nmat *a, const GatherLayout &L) {
@@ -416,7 +418,16 @@ int spmm_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo, do
         // T = v (u^T Y)  ->  += dense panel (DMMA)  ->  += panelled gather of the sparse set (f64 reductions)
         SB_TRY(gather_t_init(ctx, out, mt->n, w, ldo, uy, a->v_ones ? nullptr : a->v.p));
         if (hybrid) SB_TRY(dense_t(a, Y, ldy, w, out, ldo, ctx->stream, false));
-        SB_TRY(gather_run(ctx, mt->gt, 1, mp, mt->n, Y, ldy, w, out, ldo));
+        if (mt->t_calibrated < ctx->gather_calibrate && mt->gt.n_items == mt->gt.grid && w >= 8) {
+            // first full-width product of this matrix: time every CTA, then re-cut the static shares (gather.cu)
+            DevBuf<long long> cyc;
+            SB_TRY(cyc.alloc(2 * (size_t)mt->gt.grid));
+            SB_CUDA(cudaMemsetAsync(cyc.p, 0, 2 * (size_t)mt->gt.grid * sizeof(long long), ctx->stream));
+            SB_TRY(gather_run(ctx, mt->gt, 1, mp, mt->n, Y, ldy, w, out, ldo, cyc.p));
+            SB_TRY(gather_recalibrate_t(mt, cyc.p));
+        } else {
+            SB_TRY(gather_run(ctx, mt->gt, 1, mp, mt->n, Y, ldy, w, out, ldo));
+        }
         account(ctx, mt, w, true);
         return SB_OK;
     }
