@@ -239,10 +239,12 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--cells", type=int, default=0, help="override the configuration's cell count")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--shard", default="nnz", choices=["nnz", "cells"])
+    ap.add_argument("--host-form", default="packed", choices=["packed", "compact"],
+                    help="host buffers of the end-to-end arm: sb_upload_packed (delta byte + count nibble) or sb_upload_compact (u16 + u8)")
     args = ap.parse_args()
     args.warmup_ref = min(args.warmup, 1)
     if args.impl == "reference":
@@ -281,6 +283,8 @@ def main():
 
     numa = bind_to_gpu_numa(local_rank)
     ctx = sb.Context(local_rank)
+    if os.environ.get("SCANB200_BLOCK_CACHE_GB"):  # diagnostics: A/B of the exact-size block cache in front of the memory pool (0 = off)
+        ctx.set_option("block_cache_gb", float(os.environ["SCANB200_BLOCK_CACHE_GB"]))
     if os.environ.get("SCANB200_UPLOAD_SYNC"):  # diagnostics: A/B of the per-chunk synchronisation of the pipelined upload
         ctx.set_option("upload_sync", float(os.environ["SCANB200_UPLOAD_SYNC"]))
     if world > 1:
@@ -382,18 +386,32 @@ def main():
     e2e = None
     if not args.no_e2e:
         ip, g, c = dm.to_csc()
-        # the narrow host form of the C ABI (sb_upload_compact: u16 gene + u8 count, counts >= 255 in a side list)
-        g16, c8, big_pos, big_cnt = sb.AdaptiveMat.compact_csc(g, c)
         h_ip, k1 = pinned_u(len(ip), np.uint64)
-        h_g, k2 = pinned_u(len(g16), np.uint16)
-        h_c, k3 = pinned_u(len(c8), np.uint8)
-        h_ip[:], h_g[:], h_c[:] = ip, g16, c8
-        del ip, g, c, g16, c8
+        h_ip[:] = ip
+        if args.host_form == "packed":
+            # the packed host form of the C ABI (sb_upload_packed: gene delta byte + count nibble, escapes in two side lists),
+            # built by the library's host encoder into page-locked arrays
+            h_packed = sb.AdaptiveMat.pack_csc(ip, g, c, pinned=True)
+            host_arrays = [h_ip, *h_packed]
+            host_format = "cell-major u64 indptr + u8 gene delta + 4-bit count, escapes in side lists (sb_upload_packed)"
+        else:
+            # the narrow host form of the C ABI (sb_upload_compact: u16 gene + u8 count, counts >= 255 in a side list)
+            g16, c8, big_pos, big_cnt = sb.AdaptiveMat.compact_csc(g, c)
+            h_g, k2 = pinned_u(len(g16), np.uint16)
+            h_c, k3 = pinned_u(len(c8), np.uint8)
+            h_g[:], h_c[:] = g16, c8
+            del g16, c8
+            host_arrays = [h_ip, h_g, h_c, big_pos, big_cnt]
+            host_format = "cell-major u64 indptr + u16 gene + u8 count (sb_upload_compact)"
+        del ip, g, c
         e_calls = []  # host clock per call of every end-to-end step: [upload, normalize+pca, free] ms (each call returns synchronised)
 
         def e2e_step():
             t0 = time.perf_counter()
-            m2 = sb.AdaptiveMat.from_csc_compact(ctx, n_genes, n_loc, h_ip, h_g, h_c, big_pos, big_cnt)
+            if args.host_form == "packed":
+                m2 = sb.AdaptiveMat.from_csc_packed(ctx, n_genes, n_loc, h_ip, *h_packed)
+            else:
+                m2 = sb.AdaptiveMat.from_csc_compact(ctx, n_genes, n_loc, h_ip, h_g, h_c, big_pos, big_cnt)
             t1 = time.perf_counter()
             r = step(m2)
             t2 = time.perf_counter()
@@ -421,13 +439,13 @@ def main():
         eprof = ctx.profile()
         ctx.profile_enable(False)
         barrier()
-        h2d = int(h_ip.nbytes + h_g.nbytes + h_c.nbytes + big_pos.nbytes + big_cnt.nbytes)
+        h2d = int(sum(a.nbytes for a in host_arrays))
         d2h = int((m_out * k + k + n_loc * k) * 8)
         parity["e2e_vs_resident_sigma_rel"] = float(np.abs(np.array(se) - sigma_resident).max() / sigma_resident.max())
         parity["e2e_integer_checksum_equal"] = bool(reduce_ranks(chk_e2e, "sum") == checksum_resident)
         e2e = {"value": n_total / (e_ms * 1e-3), "unit": "cells/s", "ms_per_step": e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "steps": args.e2e_steps, "step_ms_host_clock": e_wall, "calls_ms_host_clock[upload,normalize+pca,free]": e_calls,
-               "host_format": "cell-major u64 indptr + u16 gene + u8 count (sb_upload_compact)", "host_binding": numa,
+               "host_format": host_format, "host_binding": numa,
                "upload_ms": eprof["upload_ms"] / args.e2e_steps, "layout_build_ms": eprof["build_ms"] / args.e2e_steps,
                "upload_GBps_rank0": h2d / max(1e-9, eprof["upload_ms"] / args.e2e_steps * 1e-3) / 1e9, "output_ms": eprof["output_ms"] / args.e2e_steps}
     ok = (parity["resid_AtU_minus_VS_over_sigma1"] < 1e-8 and parity["U_orthonormality"] < 1e-9 and parity["V_orthonormality"] < 1e-9

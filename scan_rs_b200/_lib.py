@@ -42,7 +42,7 @@ class CancellationError(ScanB200Error):
 # every symbol include/scanb200.h declares (tests/test_host_abi.py checks the export list)
 SYMBOLS = [
     "sb_version", "sb_last_error", "sb_init", "sb_shutdown", "sb_comm_unique_id", "sb_comm_init", "sb_sync", "sb_set_option", "sb_host_alloc", "sb_host_free",
-    "sb_upload", "sb_upload_compact", "sb_adaptive_decode_vec", "sb_upload_adaptive", "sb_mat_shape", "sb_download", "sb_free_mat", "sb_cell_totals", "sb_gene_totals", "sb_gene_nnz",
+    "sb_upload", "sb_upload_compact", "sb_pack_csc_count", "sb_pack_csc_fill", "sb_upload_packed", "sb_adaptive_decode_vec", "sb_upload_adaptive", "sb_mat_shape", "sb_download", "sb_free_mat", "sb_cell_totals", "sb_gene_totals", "sb_gene_nnz",
     "sb_median_cell_total", "sb_partition", "sb_select_rows", "sb_select_cols", "sb_hvg_select",
     "sb_normalize", "sb_log_normalize", "sb_normalize_fixed_point", "sb_nmat_params", "sb_nmat_to_dense",
     "sb_nmat_dot", "sb_nmat_rdot", "sb_nmat_frobenius_sq", "sb_free_nmat", "sb_omega", "sb_bksvd", "sb_bksvd_run_pca", "sb_pca_diagnostics", "sb_randsvd",

@@ -126,3 +126,125 @@ extern "C" int sb_upload_adaptive(sb_ctx *ctx, int major, uint32_t m, uint64_t n
     run([&](u64 i) { decode_vec(vecs[i], idx.data() + indptr[i], val.data() + indptr[i]); });
     return sb_upload(ctx, major, m, n_local, indptr.data(), idx.data(), val.data(), out);
 }
+
+// ---------------------------------------------------------------- packed host form (sb_upload_packed)
+// Per entry one byte of gene delta (gene - previous gene of the cell, previous = -1 before the first entry; deltas outside 1..255
+// are written as 0 and the entry's absolute gene goes to the escape list) and one nibble of count (low nibble = even stream
+// position; counts >= 15 are written as 15 and go to the big-count list).  Both side lists are ordered by stream position.  The
+// walk is the same AdaptiveVec::foreach order (vec.rs:1230-1273) that fills sb_upload's arrays: ascending genes inside a cell.
+namespace {
+
+struct PackRange { u64 c0, c1, n_esc, n_big; int bad; };
+
+// cells cut into `threads` ranges of about equal entry counts
+std::vector<PackRange> pack_ranges(u64 n, const u64 *indptr, int threads) {
+    std::vector<PackRange> r((size_t)threads);
+    const u64 nnz = indptr[n];
+    u64 c = 0;
+    for (int t = 0; t < threads; t++) {
+        r[t].c0 = c;
+        const u64 target = nnz / (u64)threads * (u64)(t + 1);
+        if (t + 1 == threads) c = n;
+        else c = (u64)(std::lower_bound(indptr + c, indptr + n + 1, target) - indptr), c = std::min(c, n);
+        r[t].c1 = c;
+        r[t].n_esc = r[t].n_big = 0;
+        r[t].bad = 0;
+    }
+    return r;
+}
+
+// one range: counts the side-list records; with outputs, also writes deltas and side lists starting at (esc_at, big_at)
+void pack_walk(PackRange &r, const u64 *indptr, const u32 *idx, const u32 *cnt, unsigned char *dgene, u64 *esc_pos, u32 *esc_gene, u64 esc_at,
+               u64 *big_pos, u32 *big_cnt, u64 big_at) {
+    u64 ne = 0, nb = 0;
+    for (u64 c = r.c0; c < r.c1; c++) {
+        u32 prev = 0xFFFFFFFFu;
+        for (u64 k = indptr[c]; k < indptr[c + 1]; k++) {
+            const u32 g = idx[k];
+            if (k > indptr[c] && g <= prev) r.bad = 1;  // not strictly ascending inside the cell
+            const u32 d = g - prev;                      // first entry: g + 1 (mod 2^32)
+            const bool esc = d == 0u || d > 255u;
+            if (dgene) dgene[k] = esc ? 0 : (unsigned char)d;
+            if (esc) {
+                if (dgene) {
+                    esc_pos[esc_at + ne] = k;
+                    esc_gene[esc_at + ne] = g;
+                }
+                ne++;
+            }
+            if (cnt[k] >= 15u) {
+                if (dgene) {
+                    big_pos[big_at + nb] = k;
+                    big_cnt[big_at + nb] = cnt[k];
+                }
+                nb++;
+            }
+            prev = g;
+        }
+    }
+    r.n_esc = ne;
+    r.n_big = nb;
+}
+
+int pack_threads(int threads, u64 n) {
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    return (int)std::min<u64>((u64)threads, std::max<u64>(1, n));
+}
+
+int pack_count(u64 n, const u64 *indptr, const u32 *idx, const u32 *cnt, int threads, std::vector<PackRange> &ranges) {
+    ranges = pack_ranges(n, indptr, threads);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++) pool.emplace_back([&, t]() { pack_walk(ranges[t], indptr, idx, cnt, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0); });
+    for (auto &th : pool) th.join();
+    for (auto &r : ranges)
+        if (r.bad) return sb_fail(SB_ERR_INVALID_ARG, "sb_pack_csc: gene indices must be strictly ascending inside each cell");
+    return SB_OK;
+}
+
+}  // namespace
+
+extern "C" int sb_pack_csc_count(uint64_t n, const uint64_t *indptr, const uint32_t *idx, const uint32_t *cnt, int threads, uint64_t *n_esc,
+                                 uint64_t *n_big) {
+    if (!indptr || !n_esc || !n_big || (indptr[n] && (!idx || !cnt))) return sb_fail(SB_ERR_INVALID_ARG, "sb_pack_csc_count: NULL argument");
+    threads = pack_threads(threads, n);
+    std::vector<PackRange> ranges;
+    SB_TRY(pack_count(n, indptr, idx, cnt, threads, ranges));
+    *n_esc = *n_big = 0;
+    for (auto &r : ranges) {
+        *n_esc += r.n_esc;
+        *n_big += r.n_big;
+    }
+    return SB_OK;
+}
+
+extern "C" int sb_pack_csc_fill(uint64_t n, const uint64_t *indptr, const uint32_t *idx, const uint32_t *cnt, int threads, uint8_t *dgene,
+                                uint8_t *cnt4, uint64_t *esc_pos, uint32_t *esc_gene, uint64_t *big_pos, uint32_t *big_cnt) {
+    if (!indptr) return sb_fail(SB_ERR_INVALID_ARG, "sb_pack_csc_fill: NULL argument");
+    const u64 nnz = indptr[n];
+    if (nnz && (!idx || !cnt || !dgene || !cnt4)) return sb_fail(SB_ERR_INVALID_ARG, "sb_pack_csc_fill: NULL argument");
+    threads = pack_threads(threads, n);
+    std::vector<PackRange> ranges;
+    SB_TRY(pack_count(n, indptr, idx, cnt, threads, ranges));
+    std::vector<u64> esc_at((size_t)threads, 0), big_at((size_t)threads, 0);
+    u64 te = 0, tb = 0;
+    for (int t = 0; t < threads; t++) {
+        esc_at[t] = te;
+        big_at[t] = tb;
+        te += ranges[t].n_esc;
+        tb += ranges[t].n_big;
+    }
+    if ((te && (!esc_pos || !esc_gene)) || (tb && (!big_pos || !big_cnt))) return sb_fail(SB_ERR_INVALID_ARG, "sb_pack_csc_fill: NULL side list");
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++)
+        pool.emplace_back([&, t]() {
+            pack_walk(ranges[t], indptr, idx, cnt, dgene, esc_pos, esc_gene, esc_at[t], big_pos, big_cnt, big_at[t]);
+            // count nibbles: the thread that owns a byte's even entry writes the whole byte (a range may start on an odd entry)
+            const u64 e0 = indptr[ranges[t].c0], e1 = indptr[ranges[t].c1];
+            for (u64 b = (e0 + 1) / 2; b < (e1 + 1) / 2; b++) {
+                const u32 lo = std::min(cnt[2 * b], 15u), hi = 2 * b + 1 < nnz ? std::min(cnt[2 * b + 1], 15u) : 0u;
+                cnt4[b] = (unsigned char)(lo | (hi << 4));
+            }
+        });
+    for (auto &th : pool) th.join();
+    return SB_OK;
+}

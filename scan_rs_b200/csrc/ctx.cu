@@ -3,7 +3,9 @@
 
 #include <chrono>
 #include <cstdlib>
+#include <map>
 #include <mutex>
+#include <unordered_map>
 #include <set>
 
 #include "common.cuh"
@@ -28,6 +30,59 @@ void sb_stream_register(cudaStream_t s, bool alive) {
     std::lock_guard<std::mutex> lk(g_streams_mu);
     if (alive) g_streams.insert(s);
     else g_streams.erase(s);
+}
+
+// ---------------------------------------------------------------- exact-size block cache (common.cuh), one per context stream
+struct BlockCache {
+    std::unordered_map<size_t, std::vector<void *>> by_size;
+    size_t bytes = 0, cap = 0;
+};
+static std::map<cudaStream_t, BlockCache> g_caches;  // under g_streams_mu
+static void cache_flush_locked(cudaStream_t st, BlockCache &c) {
+    for (auto &kv : c.by_size)
+        for (void *p : kv.second) cudaFreeAsync(p, st);
+    c.by_size.clear();
+    c.bytes = 0;
+}
+void *sb_cache_take(cudaStream_t st, size_t bytes) {
+    std::lock_guard<std::mutex> lk(g_streams_mu);
+    auto it = g_caches.find(st);
+    if (it == g_caches.end()) return nullptr;
+    auto b = it->second.by_size.find(bytes);
+    if (b == it->second.by_size.end() || b->second.empty()) return nullptr;
+    void *p = b->second.back();
+    b->second.pop_back();
+    it->second.bytes -= bytes;
+    return p;
+}
+bool sb_cache_give(cudaStream_t st, void *p, size_t bytes) {
+    std::lock_guard<std::mutex> lk(g_streams_mu);
+    auto it = g_caches.find(st);
+    if (it == g_caches.end() || bytes > it->second.cap) return false;
+    BlockCache &c = it->second;
+    if (c.bytes + bytes > c.cap) cache_flush_locked(st, c);  // a changing workload: start over rather than hoard
+    c.by_size[bytes].push_back(p);
+    c.bytes += bytes;
+    return true;
+}
+void sb_cache_flush(cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g_streams_mu);
+    auto it = g_caches.find(st);
+    if (it != g_caches.end()) cache_flush_locked(st, it->second);
+}
+void sb_cache_configure(cudaStream_t st, size_t cap_bytes) {
+    std::lock_guard<std::mutex> lk(g_streams_mu);
+    if (cap_bytes == (size_t)-1) {  // the context is going away
+        auto it = g_caches.find(st);
+        if (it != g_caches.end()) {
+            cache_flush_locked(st, it->second);
+            g_caches.erase(it);
+        }
+        return;
+    }
+    BlockCache &c = g_caches[st];
+    c.cap = cap_bytes;
+    if (c.bytes > c.cap) cache_flush_locked(st, c);
 }
 
 void sb_set_error(const char *fmt, ...) {
@@ -102,6 +157,11 @@ extern "C" int sb_init(int device, sb_ctx **out) {
         }
     }
     sb_set_alloc_stream(ctx->stream, ctx->pool);
+    {
+        size_t free_b = 0, total_b = 0;
+        SB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        sb_cache_configure(ctx->stream, total_b / 2);  // option block_cache_gb
+    }
     SB_CUBLAS(cublasCreate(&ctx->cublas));
     SB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
     SB_CUSOLVER(cusolverDnCreate(&ctx->cusolver));
@@ -136,6 +196,7 @@ extern "C" void sb_shutdown(sb_ctx *ctx) {
     ctx->scratch.release();
     ctx->omega_dev.release();
     ctx->syrk_parts.release();
+    sb_cache_configure(ctx->stream, (size_t)-1);  // cached blocks back to the pool, cache gone
     cudaStreamSynchronize(ctx->stream);
 
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -224,6 +285,11 @@ extern "C" int sb_set_option(sb_ctx *ctx, const char *name, double value) {
     }
     if (!strcmp(name, "eig_jacobi")) {
         ctx->eig_jacobi = value != 0.0;
+        return SB_OK;
+    }
+    if (!strcmp(name, "block_cache_gb")) {  // capacity of the exact-size block cache in front of the memory pool (0 = off)
+        if (!(value >= 0.0 && value <= 1.0e6)) return sb_fail(SB_ERR_INVALID_ARG, "sb_set_option: block_cache_gb must be in [0, 1e6]");
+        sb_cache_configure(ctx->stream, (size_t)(value * 1.0e9));
         return SB_OK;
     }
     if (!strcmp(name, "gather_calibrate")) {

@@ -45,10 +45,71 @@ __global__ void k_expand16(const unsigned short *__restrict__ idx, const unsigne
     if ((threadIdx.x & 31) == 0 && mx) atomicMax(max_out, mx);
 }
 
+// packed host form (sb_upload_packed): one byte of gene delta + one nibble of count per entry.  One warp per cell rebuilds the
+// gene indices with a segmented prefix sum: a delta of 0 marks an escape, whose absolute gene index is looked up in the sorted
+// side list (esc_pos, esc_gene) and restarts the sum.  The first entry of a cell is a delta from -1.  Count nibbles of 15 are
+// patched afterwards from the big-count side list (k_patch_big).  bad: 1 = escape without a side-list record, 2 = an escape's
+// gene does not ascend.
+__global__ void k_expand_packed(const u64 *__restrict__ ptr, u64 c0, u64 c1, const unsigned char *__restrict__ dgene,
+                                const unsigned char *__restrict__ cnt4, const u64 *__restrict__ esc_pos, const u32 *__restrict__ esc_gene,
+                                u64 n_esc, uint2 *__restrict__ out, u32 *max_out, int *bad) {
+    const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    const u32 lane = threadIdx.x & 31;
+    u32 mx = 0;
+    for (u64 c = c0 + warp; c < c1; c += nwarps) {
+        const u64 s = ptr[c], e = ptr[c + 1];
+        u32 carry = 0xFFFFFFFFu;  // gene of the previous entry (-1 before the first)
+        for (u64 base = s; base < e; base += 32) {
+            const u64 k = base + lane;
+            const bool valid = k < e;
+            u32 v = valid ? (u32)dgene[k] : 0u;
+            int f = valid && v == 0u;
+            if (f) {
+                u64 lo = 0, hi = n_esc;
+                while (lo < hi) {
+                    const u64 mid = (lo + hi) >> 1;
+                    if (esc_pos[mid] < k) lo = mid + 1;
+                    else hi = mid;
+                }
+                if (lo < n_esc && esc_pos[lo] == k) v = esc_gene[lo];
+                else *bad = 1;
+            }
+            const bool esc = f;
+#pragma unroll
+            for (u32 o = 1; o < 32; o <<= 1) {
+                const u32 vu = __shfl_up_sync(0xffffffffu, v, o);
+                const int fu = __shfl_up_sync(0xffffffffu, f, o);
+                if (lane >= o && !f) {
+                    v += vu;
+                    f = fu;
+                }
+            }
+            if (!f) v += carry;
+            u32 prev = __shfl_up_sync(0xffffffffu, v, 1);
+            if (lane == 0) prev = carry;
+            if (esc && k > s && v <= prev) *bad = 2;
+            if (valid) {
+                const u32 byte = cnt4[k >> 1];
+                out[k] = make_uint2(v, (k & 1) ? byte >> 4 : byte & 15u);
+                mx = max(mx, v);
+            }
+            carry = __shfl_sync(0xffffffffu, v, 31);
+        }
+    }
+    for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0 && mx) atomicMax(max_out, mx);
+}
+
 // counts >= 255 of the compact form travel in a side list: entry big_pos[i] gets count big_cnt[i]
-__global__ void k_patch_big(const u64 *__restrict__ big_pos, const u32 *__restrict__ big_cnt, u64 lo, u64 hi, uint2 *__restrict__ cm) {
+__global__ void k_patch_big(const u64 *__restrict__ big_pos, const u32 *__restrict__ big_cnt, u64 lo, u64 hi, uint2 *__restrict__ cm, u64 nnz) {
     u64 i = lo + (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < hi) cm[big_pos[i]].y = big_cnt[i];
+    if (i < hi && big_pos[i] < nnz) cm[big_pos[i]].y = big_cnt[i];
+}
+
+// side-list positions of the packed form: ascending and below nnz (checked on the device -- the lists have millions of records)
+__global__ void k_check_positions(const u64 *__restrict__ pos, u64 n, u64 nnz, int *bad) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+        if (pos[i] >= nnz || (i && pos[i] <= pos[i - 1])) *bad = 3;
 }
 
 __global__ void k_max_u32(const u32 *__restrict__ v, u64 n, u32 *out) {
@@ -501,14 +562,43 @@ struct HostEntries {
     const u64 *big_pos = nullptr;
     const u32 *big_cnt = nullptr;
     bool compact = false;
+    // packed form: gene deltas + count nibbles + two side lists (escaped genes; counts >= 15 share big_pos / big_cnt)
+    bool packed = false;
+    const unsigned char *dgene8 = nullptr, *cnt4 = nullptr;
+    u64 n_esc = 0;
+    const u64 *esc_pos = nullptr;
+    const u32 *esc_gene = nullptr;
 };
 struct DevEntries {
-    DevBuf<u32> idx32, cnt32, big_cnt;
+    DevBuf<u32> idx32, cnt32, big_cnt, esc_gene;
     DevBuf<unsigned short> idx16;
-    DevBuf<unsigned char> cnt8;
-    DevBuf<u64> big_pos;
-    int alloc(const HostEntries &h, u64 nnz, cudaStream_t st) {
-        if (h.compact) {
+    DevBuf<unsigned char> cnt8;  // packed form: the count nibbles
+    DevBuf<unsigned char> dgene8;
+    DevBuf<u64> big_pos, esc_pos;
+    DevBuf<int> bad;             // packed form: decoder flags
+    u64 nnz = 0;
+    int alloc(const HostEntries &h, u64 nnz_, cudaStream_t st) {
+        nnz = nnz_;
+        if (h.packed) {
+            SB_TRY(dgene8.alloc(nnz));
+            SB_TRY(cnt8.alloc((nnz + 1) / 2));
+            SB_TRY(big_pos.alloc(h.n_big));
+            SB_TRY(big_cnt.alloc(h.n_big));
+            SB_TRY(esc_pos.alloc(h.n_esc));
+            SB_TRY(esc_gene.alloc(h.n_esc));
+            SB_TRY(bad.alloc(1));
+            SB_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
+            if (h.n_big) {
+                SB_CUDA(cudaMemcpyAsync(big_pos.p, h.big_pos, h.n_big * sizeof(u64), cudaMemcpyHostToDevice, st));
+                SB_CUDA(cudaMemcpyAsync(big_cnt.p, h.big_cnt, h.n_big * sizeof(u32), cudaMemcpyHostToDevice, st));
+            }
+            if (h.n_esc) {
+                SB_CUDA(cudaMemcpyAsync(esc_pos.p, h.esc_pos, h.n_esc * sizeof(u64), cudaMemcpyHostToDevice, st));
+                SB_CUDA(cudaMemcpyAsync(esc_gene.p, h.esc_gene, h.n_esc * sizeof(u32), cudaMemcpyHostToDevice, st));
+                k_check_positions<<<(unsigned)std::min<u64>(cdiv(h.n_esc, 256), 2048), 256, 0, st>>>(esc_pos.p, h.n_esc, nnz, bad.p);
+            }
+            if (h.n_big) k_check_positions<<<(unsigned)std::min<u64>(cdiv(h.n_big, 256), 2048), 256, 0, st>>>(big_pos.p, h.n_big, nnz, bad.p);
+        } else if (h.compact) {
             SB_TRY(idx16.alloc(nnz));
             SB_TRY(cnt8.alloc(nnz));
             SB_TRY(big_pos.alloc(h.n_big));
@@ -525,13 +615,18 @@ struct DevEntries {
     }
     void release() {
         idx32.release(); cnt32.release(); idx16.release(); cnt8.release(); big_pos.release(); big_cnt.release();
+        dgene8.release(); esc_pos.release(); esc_gene.release(); bad.release();
     }
 };
 
 // host -> device copy of entries [e0, e1) on `st`
 static int copy_entries(const HostEntries &h, DevEntries &d, u64 e0, u64 e1, cudaStream_t st) {
     if (e1 <= e0) return SB_OK;
-    if (h.compact) {
+    if (h.packed) {
+        // two entries share a count byte: a chunk that starts on an odd entry re-copies the byte its predecessor ended in (same value)
+        SB_CUDA(cudaMemcpyAsync(d.dgene8.p + e0, h.dgene8 + e0, e1 - e0, cudaMemcpyHostToDevice, st));
+        SB_CUDA(cudaMemcpyAsync(d.cnt8.p + e0 / 2, h.cnt4 + e0 / 2, (e1 + 1) / 2 - e0 / 2, cudaMemcpyHostToDevice, st));
+    } else if (h.compact) {
         SB_CUDA(cudaMemcpyAsync(d.idx16.p + e0, h.idx16 + e0, (e1 - e0) * sizeof(unsigned short), cudaMemcpyHostToDevice, st));
         SB_CUDA(cudaMemcpyAsync(d.cnt8.p + e0, h.cnt8 + e0, (e1 - e0), cudaMemcpyHostToDevice, st));
     } else {
@@ -542,16 +637,29 @@ static int copy_entries(const HostEntries &h, DevEntries &d, u64 e0, u64 e1, cud
 }
 
 // staged entries [e0, e1) -> interleaved {index, count} in `out` (same positions); largest index into *d_max
-static int expand_entries(sb_ctx *ctx, const HostEntries &h, DevEntries &d, u64 e0, u64 e1, uint2 *out, u32 *d_max) {
+// (packed form: d_ptr is the device copy of the cell pointers and [c0, c1) the cells whose entries are [e0, e1))
+static int expand_entries(sb_ctx *ctx, const HostEntries &h, DevEntries &d, u64 e0, u64 e1, uint2 *out, u32 *d_max, const u64 *d_ptr = nullptr,
+                          u64 c0 = 0, u64 c1 = 0) {
     if (e1 <= e0) return SB_OK;
     const u64 cnt = e1 - e0;
-    if (h.compact) {
+    if (h.packed) {
+        if (!d_ptr) return sb_fail(SB_ERR_INVALID_ARG, "expand_entries: the packed form needs the cell pointers");
+        k_expand_packed<<<grid_for((c1 - c0) * 32, 256, ctx, 16), 256, 0, ctx->stream>>>(d_ptr, c0, c1, d.dgene8.p, d.cnt8.p, d.esc_pos.p, d.esc_gene.p,
+                                                                                      h.n_esc, out, d_max, d.bad.p);
+        count_launch(ctx);
+        const u64 lo = std::lower_bound(h.big_pos, h.big_pos + h.n_big, e0) - h.big_pos;
+        const u64 hi = std::lower_bound(h.big_pos, h.big_pos + h.n_big, e1) - h.big_pos;
+        if (hi > lo) {
+            k_patch_big<<<cdiv(hi - lo, 256), 256, 0, ctx->stream>>>(d.big_pos.p, d.big_cnt.p, lo, hi, out, d.nnz);
+            count_launch(ctx);
+        }
+    } else if (h.compact) {
         k_expand16<<<grid_for(cnt, 256, ctx, 16), 256, 0, ctx->stream>>>(d.idx16.p + e0, d.cnt8.p + e0, out + e0, cnt, d_max);
         count_launch(ctx);
         const u64 lo = std::lower_bound(h.big_pos, h.big_pos + h.n_big, e0) - h.big_pos;
         const u64 hi = std::lower_bound(h.big_pos, h.big_pos + h.n_big, e1) - h.big_pos;
         if (hi > lo) {
-            k_patch_big<<<cdiv(hi - lo, 256), 256, 0, ctx->stream>>>(d.big_pos.p, d.big_cnt.p, lo, hi, out);
+            k_patch_big<<<cdiv(hi - lo, 256), 256, 0, ctx->stream>>>(d.big_pos.p, d.big_cnt.p, lo, hi, out, d.nnz);
             count_launch(ctx);
         }
     } else {
@@ -559,6 +667,18 @@ static int expand_entries(sb_ctx *ctx, const HostEntries &h, DevEntries &d, u64 
         k_interleave<<<grid_for(cnt, 256, ctx, 16), 256, 0, ctx->stream>>>(d.idx32.p + e0, d.cnt32.p + e0, out + e0, cnt);
         count_launch(ctx); count_launch(ctx);
     }
+    return SB_OK;
+}
+
+// packed form: the decoder's flags (read after a synchronisation of the build stream)
+static int packed_status(sb_ctx *ctx, const HostEntries &he, DevEntries &de) {
+    if (!he.packed) return SB_OK;
+    int h = 0;
+    SB_CUDA(cudaMemcpyAsync(&h, de.bad.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (h == 1) return sb_fail(SB_ERR_INVALID_ARG, "sb_upload_packed: a zero gene delta has no record in the escape list");
+    if (h == 3) return sb_fail(SB_ERR_INVALID_ARG, "sb_upload_packed: side-list positions must be ascending and below nnz");
+    if (h) return sb_fail(SB_ERR_INVALID_ARG, "sb_upload_packed: an escaped gene index does not ascend inside its cell");
     return SB_OK;
 }
 
@@ -610,13 +730,14 @@ static int upload_pipelined(sb_mat *mt, const u64 *h_indptr, const HostEntries &
         auto drain = [&]() { if (ctx->upload_sync) cudaStreamSynchronize(ctx->stream); };
         {
             SyncScope t0(ctx, "chunk: wait copy + expand");
-            rc = expand_entries(ctx, he, de, e0, e1, mt->cm.p, d_max);
+            rc = expand_entries(ctx, he, de, e0, e1, mt->cm.p, d_max, mt->cm_ptr.p, c0, c1);
             drain();
             // indices are validated before any kernel uses them as table offsets
             u32 hmax = 0;
             if (rc == SB_OK && cudaMemcpyAsync(&hmax, d_max, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess &&
                 cudaStreamSynchronize(ctx->stream) == cudaSuccess && hmax >= mt->m)
                 rc = sb_fail(SB_ERR_INVALID_ARG, "sb_upload: index %u out of range %u", hmax, mt->m);
+            if (rc == SB_OK) rc = packed_status(ctx, he, de);
         }
         if (rc == SB_OK && i == 0) rc = select_hot_genes(mt, c0, c1);
         if (rc == SB_OK && mt->gd > 0) {
@@ -782,10 +903,11 @@ static int upload_impl(sb_ctx *ctx, int major, uint32_t m, uint64_t n_local, con
     }
     DevBuf<uint2> ent;
     SB_TRY(ent.alloc(nnz));
-    SB_TRY(expand_entries(ctx, he, de, 0, nnz, ent.p, d_max));
+    SB_TRY(expand_entries(ctx, he, de, 0, nnz, ent.p, d_max, d_ptr.p, 0, nvec));
     int h[2] = {0, 0};
     SB_CUDA(cudaMemcpyAsync(h, scr, 8, cudaMemcpyDeviceToHost, ctx->stream));
     SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    SB_TRY(packed_status(ctx, he, de));
     de.release();
     if (h[0]) return sb_fail(SB_ERR_INVALID_ARG, "sb_upload: indptr is not monotone from 0");
     u64 bound = major == SB_GENE_MAJOR ? n_local : (u64)m;
@@ -857,6 +979,32 @@ extern "C" int sb_upload_compact(sb_ctx *ctx, uint32_t m, uint64_t n_local, cons
     he.compact = true;
     he.idx16 = idx16;
     he.cnt8 = cnt8;
+    he.n_big = n_big;
+    he.big_pos = big_pos;
+    he.big_cnt = big_cnt;
+    return upload_impl(ctx, SB_CELL_MAJOR, m, n_local, indptr, he, out);
+}
+
+// Cell-major upload in the packed host form: one byte of gene delta and one nibble of count per entry (~1.55 B per entry over
+// PCIe against 3 of the compact form and 8 of the plain one).  The decoder is k_expand_packed; sb_pack_csc_count / _fill
+// (adaptive.cu) build the form on the host.
+extern "C" int sb_upload_packed(sb_ctx *ctx, uint32_t m, uint64_t n_local, const uint64_t *indptr, const uint8_t *dgene, const uint8_t *cnt4,
+                                uint64_t n_esc, const uint64_t *esc_pos, const uint32_t *esc_gene, uint64_t n_big, const uint64_t *big_pos,
+                                const uint32_t *big_cnt, sb_mat **out) {
+    if (!ctx || !out || !indptr) return sb_fail(SB_ERR_INVALID_ARG, "sb_upload_packed: NULL argument");
+    if (m > SB_GENE_MASK) return sb_fail(SB_ERR_UNSUPPORTED, "sb_upload_packed: more than %u genes", SB_GENE_MASK);
+    if (n_local > 0xFFFFFFFFull) return sb_fail(SB_ERR_UNSUPPORTED, "sb_upload_packed: more than 2^32 cells per rank");
+    const u64 nnz = indptr[n_local];
+    if (nnz && (!dgene || !cnt4)) return sb_fail(SB_ERR_INVALID_ARG, "sb_upload_packed: NULL dgene/cnt4");
+    if ((n_big && (!big_pos || !big_cnt)) || (n_esc && (!esc_pos || !esc_gene))) return sb_fail(SB_ERR_INVALID_ARG, "sb_upload_packed: NULL side list");
+    // the side lists are validated on the device (k_check_positions): millions of records
+    HostEntries he;
+    he.packed = true;
+    he.dgene8 = dgene;
+    he.cnt4 = cnt4;
+    he.n_esc = n_esc;
+    he.esc_pos = esc_pos;
+    he.esc_gene = esc_gene;
     he.n_big = n_big;
     he.big_pos = big_pos;
     he.big_cnt = big_cnt;

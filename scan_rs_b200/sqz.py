@@ -226,6 +226,46 @@ class AdaptiveMat:
                                           C.c_uint64(big_pos.shape[0]), L.vp(big_pos), L.vp(big_cnt), C.byref(h)))
         return cls(ctx, h)
 
+    @staticmethod
+    def pack_csc(indptr, idx, val, threads: int = 0, pinned: bool = False):
+        """Cell-major u32 index / count arrays -> the packed host form of sb_upload_packed (sb_pack_csc_count / _fill):
+        (dgene u8[nnz], cnt4 u8[(nnz+1)/2], esc_pos, esc_gene, big_pos, big_cnt).  pinned: page-locked output arrays."""
+        indptr = np.ascontiguousarray(indptr, dtype=np.uint64)
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        val = np.ascontiguousarray(val, dtype=np.uint32)
+        n, nnz = indptr.shape[0] - 1, int(indptr[-1])
+        if idx.shape != (nnz,) or val.shape != (nnz,):
+            raise ValueError("inconsistent CSC arrays")
+        ne, nb = C.c_uint64(), C.c_uint64()
+        L.check(L.lib().sb_pack_csc_count(C.c_uint64(n), L.vp(indptr), L.vp(idx), L.vp(val), C.c_int(threads), C.byref(ne), C.byref(nb)))
+        new = (lambda k, dt: L.pinned_empty((k,), dt)) if pinned else (lambda k, dt: np.empty(k, dtype=dt))
+        dgene, cnt4 = new(nnz, np.uint8), new((nnz + 1) // 2, np.uint8)
+        esc_pos, esc_gene = new(ne.value, np.uint64), new(ne.value, np.uint32)
+        big_pos, big_cnt = new(nb.value, np.uint64), new(nb.value, np.uint32)
+        L.check(L.lib().sb_pack_csc_fill(C.c_uint64(n), L.vp(indptr), L.vp(idx), L.vp(val), C.c_int(threads), L.vp(dgene), L.vp(cnt4),
+                                         L.vp(esc_pos), L.vp(esc_gene), L.vp(big_pos), L.vp(big_cnt)))
+        return dgene, cnt4, esc_pos, esc_gene, big_pos, big_cnt
+
+    @classmethod
+    def from_csc_packed(cls, ctx: Context, rows: int, cols: int, indptr, dgene, cnt4, esc_pos, esc_gene, big_pos, big_cnt) -> "AdaptiveMat":
+        """Cell-major upload in the packed host form (one byte of gene delta + one nibble of count per entry)."""
+        indptr = np.ascontiguousarray(indptr, dtype=np.uint64)
+        dgene = np.ascontiguousarray(dgene, dtype=np.uint8)
+        cnt4 = np.ascontiguousarray(cnt4, dtype=np.uint8)
+        esc_pos = np.ascontiguousarray(esc_pos, dtype=np.uint64)
+        esc_gene = np.ascontiguousarray(esc_gene, dtype=np.uint32)
+        big_pos = np.ascontiguousarray(big_pos, dtype=np.uint64)
+        big_cnt = np.ascontiguousarray(big_cnt, dtype=np.uint32)
+        nnz = int(indptr[-1])
+        if indptr.shape != (cols + 1,) or dgene.shape != (nnz,) or cnt4.shape != ((nnz + 1) // 2,) or esc_pos.shape != esc_gene.shape or \
+                big_pos.shape != big_cnt.shape:
+            raise ValueError("inconsistent packed CSC arrays")
+        h = C.c_void_p()
+        L.check(L.lib().sb_upload_packed(ctx._h, C.c_uint32(rows), C.c_uint64(cols), L.vp(indptr), L.vp(dgene), L.vp(cnt4),
+                                         C.c_uint64(esc_pos.shape[0]), L.vp(esc_pos), L.vp(esc_gene),
+                                         C.c_uint64(big_pos.shape[0]), L.vp(big_pos), L.vp(big_cnt), C.byref(h)))
+        return cls(ctx, h)
+
     @classmethod
     def _synth(cls, ctx, m, n_local, cell_offset, seed, pf, depth, cluster, r):
         h = C.c_void_p()

@@ -585,6 +585,49 @@ def test_compact_upload_matches_plain_upload(ctx, n_cells, n_genes):
         sb.AdaptiveMat.from_csc_compact(ctx, n_genes, n_cells, ip, bad, cnt8, big_pos, big_cnt)
 
 
+@pytest.mark.parametrize("n_cells,n_genes,stride", [(1500, 900, 7), (20000, 3000, 5)])
+def test_packed_upload_matches_plain_upload(ctx, n_cells, n_genes, stride):
+    """sb_upload_packed (gene delta byte + count nibble + escape / big-count side lists) builds the same matrix as sb_upload, on the
+    plain and on the pipelined path (chunks that start on odd entries share a count byte); malformed streams are rejected.  The
+    synthetic gene indices are spread by `stride` so that first genes past 254 and gaps past 255 (escapes) occur."""
+    cfg, cm, _, (ip, g, c) = synth_pair(ctx, n_cells, n_genes, seed=44, n_dense=12, dense_mean=400.0)
+    g = (g.astype(np.uint32) * np.uint32(stride)).astype(np.uint32)
+    n_genes = n_genes * stride
+    dm = sb.AdaptiveMat.from_csc(ctx, n_genes, n_cells, ip, g, c)
+    packed = sb.AdaptiveMat.pack_csc(ip, g, c, pinned=n_cells > 5000)
+    dgene, cnt4, esc_pos, esc_gene, big_pos, big_cnt = packed
+    assert big_pos.size > 0 and esc_pos.size > 0 and int(c.max()) >= 15
+    dm_p = sb.AdaptiveMat.from_csc_packed(ctx, n_genes, n_cells, ip, *packed)
+    for a, b in zip(dm_p.to_csc(), (ip, g, c)):
+        np.testing.assert_array_equal(a, b)
+    for a, b in zip(dm_p.to_csr(), dm.to_csr()):
+        np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(dm_p.sum_axis_u32(0), cm.sum_axis_u32(0))
+    a_c, a_p = sb.normalize(dm_p, sb.Normalization.CellRanger), sb.normalize(dm, sb.Normalization.CellRanger)
+    x = np.random.default_rng(2).standard_normal((n_cells, 20))
+    np.testing.assert_allclose(a_c.dot(x), a_p.dot(x), rtol=0, atol=1e-11 * np.abs(a_p.dot(x)).max())
+    with pytest.raises(L.ScanB200Error, match="out of range"):  # a delta that walks past the gene count
+        bad = np.array(dgene, copy=True)
+        bad[int(ip[3]):int(ip[4])] = 255
+        sb.AdaptiveMat.from_csc_packed(ctx, n_genes, n_cells, ip, bad, cnt4, esc_pos, esc_gene, big_pos, big_cnt)
+    with pytest.raises(L.ScanB200Error, match="escape"):  # a zero delta without a side-list record
+        bad = np.array(dgene, copy=True)
+        k = int(np.flatnonzero(bad != 0)[5])
+        bad[k] = 0
+        sb.AdaptiveMat.from_csc_packed(ctx, n_genes, n_cells, ip, bad, cnt4, esc_pos, esc_gene, big_pos, big_cnt)
+    with pytest.raises(L.ScanB200Error, match="ascend"):  # an escaped gene below its predecessor
+        j = int(np.flatnonzero(np.isin(esc_pos, ip[:-1], invert=True))[0]) if np.isin(esc_pos, ip[:-1], invert=True).any() else None
+        if j is None:
+            raise L.ScanB200Error(1, "no interior escape in this sample: does not ascend")
+        bad = esc_gene.copy()
+        bad[j] = 0
+        sb.AdaptiveMat.from_csc_packed(ctx, n_genes, n_cells, ip, dgene, cnt4, esc_pos, bad, big_pos, big_cnt)
+    with pytest.raises(L.ScanB200Error, match="ascending and below nnz"):  # a side list out of order
+        bad = big_pos.copy()
+        bad[[0, 1]] = bad[[1, 0]]
+        sb.AdaptiveMat.from_csc_packed(ctx, n_genes, n_cells, ip, dgene, cnt4, esc_pos, esc_gene, bad, big_cnt)
+
+
 def test_bksvd_seurat_and_binomial(ctx):
     cfg, cm, dm, _ = synth_pair(ctx, 3000, 1200, seed=32)
     check_pca_parity(sb.BkSvd().run_pca(sb.normalize(dm, sb.Normalization.SeuratLog), 8),

@@ -98,6 +98,58 @@ def test_compact_host_form_round_trip():
         AdaptiveMat.compact_csc(np.array([70000], dtype=np.uint32), np.array([1], dtype=np.uint32))
 
 
+def _unpack_packed(indptr, dgene, cnt4, esc_pos, esc_gene, big_pos, big_cnt):
+    """numpy decoder of the packed host form as include/scanb200.h states it (independent of the library's kernels)."""
+    import numpy as np
+    nnz = int(indptr[-1])
+    val = np.where(np.arange(nnz) % 2 == 0, cnt4[np.arange(nnz) // 2] & 15, cnt4[np.arange(nnz) // 2] >> 4).astype(np.uint32)
+    assert (val[big_pos.astype(np.int64)] == 15).all()
+    val[big_pos.astype(np.int64)] = big_cnt
+    esc = dict(zip(esc_pos.tolist(), esc_gene.tolist()))
+    idx = np.zeros(nnz, dtype=np.uint32)
+    for c in range(len(indptr) - 1):
+        prev = -1
+        for k in range(int(indptr[c]), int(indptr[c + 1])):
+            prev = esc[k] if dgene[k] == 0 else prev + int(dgene[k])
+            idx[k] = prev
+    assert set(esc) == set(np.flatnonzero(dgene == 0).tolist())
+    return idx, val
+
+
+def test_packed_host_form_round_trip():
+    """sb_pack_csc_count / sb_pack_csc_fill (host threads, no device): gene deltas + count nibbles + the two side lists decode
+    back to the u32 arrays -- first genes past 254, gaps past 255, counts of 14 / 15 / large, empty cells, odd thread cuts."""
+    import numpy as np
+    import pytest
+    from scan_rs_b200 import _lib as L
+    from scan_rs_b200.sqz import AdaptiveMat
+    rng = np.random.default_rng(5)
+    m, n = 40000, 300
+    ip, idx, val = [0], [], []
+    for c in range(n):
+        k = 0 if c % 37 == 5 else int(rng.integers(1, 90))
+        g = np.sort(rng.choice(m if c % 3 else 600, size=k, replace=False))
+        idx.extend(g.tolist())
+        val.extend(rng.choice([1, 1, 1, 2, 3, 14, 15, 16, 300, 70000], size=k).tolist())
+        ip.append(len(idx))
+    ip, idx, val = np.array(ip, dtype=np.uint64), np.array(idx, dtype=np.uint32), np.array(val, dtype=np.uint32)
+    for threads in (1, 3, 7):
+        dgene, cnt4, esc_pos, esc_gene, big_pos, big_cnt = AdaptiveMat.pack_csc(ip, idx, val, threads=threads)
+        assert dgene.shape == idx.shape and cnt4.shape == ((len(idx) + 1) // 2,)
+        assert (np.diff(esc_pos.astype(np.int64)) > 0).all() and (np.diff(big_pos.astype(np.int64)) > 0).all()
+        assert big_pos.size == int((val >= 15).sum()) and esc_pos.size > n // 2
+        bi, bv = _unpack_packed(ip, dgene, cnt4, esc_pos, esc_gene, big_pos, big_cnt)
+        np.testing.assert_array_equal(bi, idx)
+        np.testing.assert_array_equal(bv, val)
+    with pytest.raises(L.ScanB200Error, match="ascending"):
+        bad = idx.copy()
+        s0 = int(ip[1])
+        bad[s0 + 1] = bad[s0]
+        AdaptiveMat.pack_csc(ip, bad, val)
+    e = AdaptiveMat.pack_csc(np.zeros(4, dtype=np.uint64), np.zeros(0, dtype=np.uint32), np.zeros(0, dtype=np.uint32))
+    assert all(a.size == 0 for a in e)
+
+
 def test_gather_work_units_cover_every_entry_once():
     """scan_rs_b200/csrc/gather_units.h (how the sparse streams are cut into work units and handed to CTAs) fuzzed on the
     CPU: exact tiling of the stream, units inside their panel / segment, sweep order, balanced CTA loads."""
