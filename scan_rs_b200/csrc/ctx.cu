@@ -292,6 +292,10 @@ extern "C" int sb_set_option(sb_ctx *ctx, const char *name, double value) {
         sb_cache_configure(ctx->stream, (size_t)(value * 1.0e9));
         return SB_OK;
     }
+    if (!strcmp(name, "gather_defer")) {
+        ctx->gather_defer = value != 0.0;
+        return SB_OK;
+    }
     if (!strcmp(name, "gather_calibrate")) {
         ctx->gather_calibrate = value <= 0.0 ? 0 : (value > 8.0 ? 8 : (int)value);
         return SB_OK;

@@ -259,7 +259,8 @@ bool dense_t_i8_usable(const sb_nmat *a, u32 w);
 int dense_t_i8(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo);
 
 // planes.cu: the same three products over the bit planes (panel_mode 2)
-int planes_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo);
+int planes_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo, const GatherLayout *gl = nullptr, const MapDev *mp = nullptr,
+             long long *cycles = nullptr);
 int planes_n(sb_nmat *a, const double *X, u32 ldx, u32 w, double *P, u32 ldp);
 int planes_moments(sb_nmat *a, double *S1, double *S2);
 

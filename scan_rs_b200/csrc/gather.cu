@@ -41,7 +41,11 @@
 #define GA_ST_XS 48u
 #define GA_ST_L1 112u
 
-template <int MODE, int TAIL>  // MODE 0: N side, 1: T side.  TAIL: the pass has columns 16..19
+// MODE 0: N side, 1: T side, 2: T side with the run factor deferred -- the sums of a cell's runs leave in units of L_c(1) (`out` is
+// then a separate block that the caller scales by L_c(1) and adds to T: k_pl_reduce_t), so the kernel loads no per-cell factor at
+// the run heads (ncu: 28 % of the T side's stall samples sat on those global loads) and multiplies nothing at the flush.
+// TAIL: the pass has columns 16..19
+template <int MODE, int TAIL>
 __global__ void __launch_bounds__(GA_THREADS, 1)
 k_gather(const uint2 *__restrict__ ent, const GUnit *__restrict__ units, const u32 *__restrict__ item_first, u32 n_units, u32 n_items,
          u32 *__restrict__ tickets, u32 ticket_base, u32 rows, u64 n_cells, MapDev mp, const double *__restrict__ B, u32 ldb, u32 col0, u32 wt, u32 w,
@@ -68,6 +72,7 @@ k_gather(const uint2 *__restrict__ ent, const GUnit *__restrict__ units, const u
     const bool okb = TAIL && cB < wt && col0 + cB < w;
     const u32 wt_even = (wt + 1) & ~1u;
     const bool logchain = mp.kind == 1;
+    constexpr bool TS = MODE >= 1, DEFER = MODE == 2;
     double *const oA = out + col0 + cA;
     const long long tdelta = (long long)cB - (long long)cA;  // tail column relative to this lane's first main column
     const u32 ok0m = ok0, ok1m = ok1, okbm = okb;
@@ -158,7 +163,7 @@ k_gather(const uint2 *__restrict__ ent, const GUnit *__restrict__ units, const u
 
         auto flush = [&]() {
             if (cur == GA_NONE) return;  // nothing accumulated yet (and never reduce zeros into one shared row)
-            if (MODE == 1) {
+            if (TS && !DEFER) {
                 a0 *= curL1;
                 a1 *= curL1;
                 bt *= curL1;
@@ -199,7 +204,7 @@ k_gather(const uint2 *__restrict__ ent, const GUnit *__restrict__ units, const u
             const bool head = valid && key != prev;
             // T side: L_c(1) is consumed once per run (at its flush): only the entry that opens a run fetches it
             double l1v = 0.0;
-            if (MODE == 1 && head) l1v = logchain ? mp.l1[key] : 1.0;
+            if (TS && !DEFER && head) l1v = logchain ? mp.l1[key] : 1.0;
             carry = __shfl_sync(FULLMASK, key, 7, 8);
             const u32 myh = (__ballot_sync(FULLMASK, head) >> (8 * grp)) & 0xFFu;
             const u32 myg = (__ballot_sync(FULLMASK, general) >> (8 * grp)) & 0xFFu;
@@ -207,7 +212,7 @@ k_gather(const uint2 *__restrict__ ent, const GUnit *__restrict__ units, const u
             asm volatile("st.shared.u16 [%0], %1;" ::"r"(stage_grp + (u32)lig * 2u), "h"((unsigned short)(valid ? local * 8u : zero_off16)) : "memory");
             asm volatile("st.shared.u32 [%0], %1;" ::"r"(stage_grp + GA_ST_KEYS + (u32)lig * 4u), "r"(key) : "memory");
             if (general) asm volatile("st.shared.f64 [%0], %1;" ::"r"(stage_grp + GA_ST_XS + (u32)lig * 8u), "d"(x) : "memory");
-            if (MODE == 1 && head) asm volatile("st.shared.f64 [%0], %1;" ::"r"(stage_grp + GA_ST_L1 + (u32)lig * 8u), "d"(l1v) : "memory");
+            if (TS && !DEFER && head) asm volatile("st.shared.f64 [%0], %1;" ::"r"(stage_grp + GA_ST_L1 + (u32)lig * 8u), "d"(l1v) : "memory");
             __syncwarp();
             u32 ov[4];
             asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(ov[0]), "=r"(ov[1]), "=r"(ov[2]), "=r"(ov[3]) : "r"(stage_grp));
@@ -227,7 +232,7 @@ k_gather(const uint2 *__restrict__ ent, const GUnit *__restrict__ units, const u
                 if (myh & (1u << s)) {
                     flush();
                     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cur) : "r"(stage_grp + GA_ST_KEYS + (u32)s * 4u));
-                    if (MODE == 1) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(curL1) : "r"(stage_grp + GA_ST_L1 + (u32)s * 8u));
+                    if (TS && !DEFER) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(curL1) : "r"(stage_grp + GA_ST_L1 + (u32)s * 8u));
                 }
                 asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(x1) : "r"(xa_sa + off0));
                 a0 = fma(m0, x0, a0);
@@ -236,7 +241,7 @@ k_gather(const uint2 *__restrict__ ent, const GUnit *__restrict__ units, const u
                 if (myh & (2u << s)) {
                     flush();
                     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cur) : "r"(stage_grp + GA_ST_KEYS + (u32)(s + 1) * 4u));
-                    if (MODE == 1) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(curL1) : "r"(stage_grp + GA_ST_L1 + (u32)(s + 1) * 8u));
+                    if (TS && !DEFER) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(curL1) : "r"(stage_grp + GA_ST_L1 + (u32)(s + 1) * 8u));
                 }
                 asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(x1) : "r"(xa_sa + off1));
                 a0 = fma(m1, x0, a0);
@@ -277,43 +282,50 @@ static size_t gather_smem(u32 rows, bool tail) {
     return (size_t)(rows + 1) * (tail ? 20 : 16) * 8 + (size_t)rows * 16 + 128 * sizeof(LogEnt) + (size_t)(GA_THREADS / 32) * 4 * GA_STAGE_STRIDE;
 }
 
-// runs all column passes of one product over a layout
-int gather_run(sb_ctx *ctx, const GatherLayout &L, int mode, const MapDev &mp, u64 n_cells, const double *B, u32 ldb, u32 w, double *out, u32 ldo,
-               long long *cycles) {
+// one column pass (columns [col0, col0 + min(20, w - col0))) of one product over a layout.  mode 0: N side; 1: T side; 2: T side with
+// the run factor L_c(1) deferred to the caller (`out` + col0 then addresses a separate block, see k_gather)
+int gather_run_tile(sb_ctx *ctx, const GatherLayout &L, int mode, const MapDev &mp, u64 n_cells, const double *B, u32 ldb, u32 w, u32 col0, double *out,
+                    u32 ldo, long long *cycles) {
     if (!L.ready) return sb_fail(SB_ERR_UNSUPPORTED, "gather_run: layout not built");
-    if (L.nnz == 0 || L.n_units == 0 || w == 0) return SB_OK;
+    if (L.nnz == 0 || L.n_units == 0 || w == 0 || col0 >= w) return SB_OK;
     const u32 n_items = L.n_items ? L.n_items : L.grid;
     if (!L.tickets.p) {
         SB_TRY(L.tickets.alloc(1));
         SB_CUDA(cudaMemsetAsync(L.tickets.p, 0, sizeof(u32), ctx->stream));
         L.ticket_base = 0;
     }
-    for (u32 col0 = 0; col0 < w; col0 += GA_TILE) {
-        if (L.ticket_base > 0x7F000000u) {  // long before the u32 ticket counter could wrap
-            SB_CUDA(cudaMemsetAsync(L.tickets.p, 0, sizeof(u32), ctx->stream));
-            L.ticket_base = 0;
-        }
-        const u32 wt = std::min(GA_TILE, w - col0);
-        const bool tail = wt > 16;
-        const size_t smem = gather_smem(L.rows, tail);
-        cudaError_t e;
+    if (L.ticket_base > 0x7F000000u) {  // long before the u32 ticket counter could wrap
+        SB_CUDA(cudaMemsetAsync(L.tickets.p, 0, sizeof(u32), ctx->stream));
+        L.ticket_base = 0;
+    }
+    const u32 wt = std::min(GA_TILE, w - col0);
+    const bool tail = wt > 16;
+    const size_t smem = gather_smem(L.rows, tail);
+    cudaError_t e;
 #define GA_LAUNCH(M, T)                                                                                                                        \
     e = cudaFuncSetAttribute(k_gather<M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                          \
     if (e == cudaSuccess)                                                                                                                      \
         k_gather<M, T><<<L.grid, GA_THREADS, smem, ctx->stream>>>(L.ent, L.units.p, L.cta_first.p, L.n_units, n_items, L.tickets.p, L.ticket_base, \
-                                                                  L.rows, n_cells, mp, B, ldb, col0, wt, w, L.slot_gene.p, out, ldo,          \
-                                                                  col0 == 0 ? cycles : nullptr);
-        if (mode == 0) {
-            if (tail) { GA_LAUNCH(0, 1) } else { GA_LAUNCH(0, 0) }
-        } else {
-            if (tail) { GA_LAUNCH(1, 1) } else { GA_LAUNCH(1, 0) }
-        }
-#undef GA_LAUNCH
-        if (e != cudaSuccess) return sb_fail(SB_ERR_CUDA, "gather_run: %zu B of shared memory: %s", smem, cudaGetErrorString(e));
-        L.ticket_base += n_items + L.grid;
-        count_launch(ctx);
+                                                                  L.rows, n_cells, mp, B, ldb, col0, wt, w, L.slot_gene.p, out, ldo, cycles);
+    if (mode == 0) {
+        if (tail) { GA_LAUNCH(0, 1) } else { GA_LAUNCH(0, 0) }
+    } else if (mode == 1) {
+        if (tail) { GA_LAUNCH(1, 1) } else { GA_LAUNCH(1, 0) }
+    } else {
+        if (tail) { GA_LAUNCH(2, 1) } else { GA_LAUNCH(2, 0) }
     }
+#undef GA_LAUNCH
+    if (e != cudaSuccess) return sb_fail(SB_ERR_CUDA, "gather_run: %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+    L.ticket_base += n_items + L.grid;
+    count_launch(ctx);
     SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
+// runs all column passes of one product over a layout
+int gather_run(sb_ctx *ctx, const GatherLayout &L, int mode, const MapDev &mp, u64 n_cells, const double *B, u32 ldb, u32 w, double *out, u32 ldo,
+               long long *cycles) {
+    for (u32 col0 = 0; col0 < w; col0 += GA_TILE) SB_TRY(gather_run_tile(ctx, L, mode, mp, n_cells, B, ldb, w, col0, out, ldo, col0 == 0 ? cycles : nullptr));
     return SB_OK;
 }
 

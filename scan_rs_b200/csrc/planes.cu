@@ -893,8 +893,9 @@ k_planes_t(PlDev pl, const PlUnitT *__restrict__ units, const PlItem *__restrict
     if (warp == 0) tmem_dealloc_512(tmem);
 }
 
-// T[c, col0 + j] += sum over units of part[u][c][j]
-__global__ void k_pl_reduce_t(const double *__restrict__ part, u32 n_units, u64 n, u64 n_pad, u32 col0, u32 wt, double *__restrict__ out, u32 ldo) {
+// T[c, col0 + j] += sum over units of part[u][c][j]  (+ l1[c] * t1[c][j]: the sparse gather's run sums in units of L_c(1), when deferred)
+__global__ void k_pl_reduce_t(const double *__restrict__ part, u32 n_units, u64 n, u64 n_pad, u32 col0, u32 wt, double *__restrict__ out, u32 ldo,
+                              const double *__restrict__ t1, const double *__restrict__ l1) {
     const u64 total = n * (PL_COLS / 2);
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (u64)gridDim.x * blockDim.x) {
         const u64 c = i / (PL_COLS / 2);
@@ -905,6 +906,12 @@ __global__ void k_pl_reduce_t(const double *__restrict__ part, u32 n_units, u64 
             const double2 v = *reinterpret_cast<const double2 *>(part + ((size_t)u * n_pad + c) * PL_COLS + j);
             s.x += v.x;
             s.y += v.y;
+        }
+        if (t1) {
+            const double2 v = *reinterpret_cast<const double2 *>(t1 + c * PL_COLS + j);
+            const double f = l1[c];
+            s.x = fma(f, v.x, s.x);
+            s.y = fma(f, v.y, s.y);
         }
         double *o = out + c * (size_t)ldo + col0 + j;
         o[0] += s.x;
@@ -1195,8 +1202,14 @@ static int scales_from_colmax(sb_ctx *ctx, DevBuf<unsigned long long> &colmax, D
     return SB_OK;
 }
 
-// T[c, :] += the plane part of A^T . Y   (out already holds the offset term; the sparse gather adds the rest)
-int planes_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo) {
+// gather.cu
+int gather_run_tile(sb_ctx *ctx, const GatherLayout &L, int mode, const MapDev &mp, u64 n_cells, const double *B, u32 ldb, u32 w, u32 col0, double *out,
+                    u32 ldo, long long *cycles);
+
+// T[c, :] += the plane part of A^T . Y   (out already holds the offset term; the sparse gather adds the rest).
+// With `gl` (log chain): the sparse gather over that layout is run here as well, per column pass, with its run factor L_c(1)
+// deferred -- its sums land in one more block behind the per-unit partial rows and k_pl_reduce_t folds l1[c] * block into T.
+int planes_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo, const GatherLayout *gl, const MapDev *mp, long long *cycles) {
     sb_mat *mt = a->mat;
     sb_ctx *ctx = mt->ctx;
     const PlaneSet &pl = mt->pl;
@@ -1210,7 +1223,8 @@ int planes_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo) 
     DevBuf<int> &ex = pl.ws_ex;
     SB_TRY(colmax.ensure(PL_COLS));
     SB_TRY(Bd.ensure((size_t)nranges * PT_B_BYTES));
-    SB_TRY(part.ensure((size_t)pl.n_units_t * n_pad * PL_COLS));
+    SB_TRY(part.ensure((size_t)(pl.n_units_t + (gl ? 1 : 0)) * n_pad * PL_COLS));
+    double *t1 = gl ? part.p + (size_t)pl.n_units_t * n_pad * PL_COLS : nullptr;
     const double *rs = a->has_row_scale ? a->row_scale.p : nullptr;
     const size_t smem = (size_t)PT_B_BYTES + PT_NSTAGES * PT_STAGE_BYTES + sizeof(PtShared);
     const bool v1 = ctx->pl_variant & 1;
@@ -1227,6 +1241,10 @@ int planes_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo) 
         SB_TRY(scales_from_colmax(ctx, colmax, scale2, ex));
         k_pl_digits_t<<<cdiv(items, 256), 256, 0, ctx->stream>>>(Y, ldy, mt->hot_idx.p, rs, G1, col0, wt, ex.p, Bd.p, v1 ? 1u : 0u);
         SB_CUDA(cudaMemsetAsync(pl.counter.p, 0, sizeof(u32), ctx->stream));
+        if (gl) {  // the sparse half of this column pass, in units of L_c(1)
+            SB_CUDA(cudaMemsetAsync(t1, 0, (size_t)mt->n * PL_COLS * sizeof(double), ctx->stream));
+            SB_TRY(gather_run_tile(ctx, *gl, 2, *mp, mt->n, Y, ldy, w, col0, t1 - col0, PL_COLS, col0 == 0 ? cycles : nullptr));
+        }
         if (v1)
             k_planes_t<1><<<pl.t_grid, PtLayout<1>::WARPS * 32, smem, ctx->stream>>>(make_pldev(mt), (const PlUnitT *)pl.units_t.p,
                                                                                      (const PlItem *)pl.items_t.p, pl.n_items_t, pl.counter.p, Bd.p, scale2.p,
@@ -1235,7 +1253,7 @@ int planes_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo) 
             k_planes_t<0><<<pl.t_grid, PtLayout<0>::WARPS * 32, smem, ctx->stream>>>(make_pldev(mt), (const PlUnitT *)pl.units_t.p,
                                                                                      (const PlItem *)pl.items_t.p, pl.n_items_t, pl.counter.p, Bd.p, scale2.p,
                                                                                      a->lk.p, wt, part.p, (u32)ctx->pl_debug);
-        k_pl_reduce_t<<<rblocks, 256, 0, ctx->stream>>>(part.p, pl.n_units_t, mt->n, n_pad, col0, wt, out, ldo);
+        k_pl_reduce_t<<<rblocks, 256, 0, ctx->stream>>>(part.p, pl.n_units_t, mt->n, n_pad, col0, wt, out, ldo, t1, gl ? a->l1c.p : nullptr);
         count_launch(ctx); count_launch(ctx); count_launch(ctx); count_launch(ctx);
     }
     SB_CUDA(cudaGetLastError());

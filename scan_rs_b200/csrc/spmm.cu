@@ -389,6 +389,8 @@ static void account(sb_ctx *ctx, const sb_mat *mt, u32 w, bool is_t) {
 int dense_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo, cudaStream_t stream, bool overlap);
 int dense_n(sb_nmat *a, const double *X, u32 ldx, u32 w, double *P, u32 ldp, cudaStream_t stream, bool overlap);
 int mat_ensure_full_gm(sb_mat *mt);
+// planes.cu
+int planes_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo, const GatherLayout *gl, const MapDev *mp, long long *cycles);
 // gather.cu
 int gather_run(sb_ctx *ctx, const GatherLayout &L, int mode, const MapDev &mp, u64 n_cells, const double *B, u32 ldb, u32 w, double *out, u32 ldo,
                long long *cycles = nullptr);
@@ -417,17 +419,23 @@ int spmm_t(sb_nmat *a, const double *Y, u32 ldy, u32 w, double *out, u32 ldo, do
     if (gather_usable(a, mt->gt)) {
         // T = v (u^T Y)  ->  += dense panel (DMMA)  ->  += panelled gather of the sparse set (f64 reductions)
         SB_TRY(gather_t_init(ctx, out, mt->n, w, ldo, uy, a->v_ones ? nullptr : a->v.p));
-        if (hybrid) SB_TRY(dense_t(a, Y, ldy, w, out, ldo, ctx->stream, false));
-        if (mt->t_calibrated < ctx->gather_calibrate && mt->gt.n_items == mt->gt.grid && w >= 8) {
-            // first full-width product of this matrix: time every CTA, then re-cut the static shares (gather.cu)
-            DevBuf<long long> cyc;
+        // first full-width product of this matrix: time every CTA of the gather, then re-cut its static shares (gather.cu)
+        const bool calibrate = mt->t_calibrated < ctx->gather_calibrate && mt->gt.n_items == mt->gt.grid && w >= 8;
+        DevBuf<long long> cyc;
+        if (calibrate) {
             SB_TRY(cyc.alloc(2 * (size_t)mt->gt.grid));
             SB_CUDA(cudaMemsetAsync(cyc.p, 0, 2 * (size_t)mt->gt.grid * sizeof(long long), ctx->stream));
-            SB_TRY(gather_run(ctx, mt->gt, 1, mp, mt->n, Y, ldy, w, out, ldo, cyc.p));
-            SB_TRY(gather_recalibrate_t(mt, cyc.p));
-        } else {
-            SB_TRY(gather_run(ctx, mt->gt, 1, mp, mt->n, Y, ldy, w, out, ldo));
         }
+        // plane kernels + log chain: the gather runs inside planes_t, per column pass, with its run factor L_c(1) deferred to the
+        // reduction of the per-unit partial rows (planes.cu)
+        const bool fused = hybrid && mt->pl.active && ctx->gather_defer && mp.kind == 1 && a->l1c.p;
+        if (fused) {
+            SB_TRY(planes_t(a, Y, ldy, w, out, ldo, &mt->gt, &mp, calibrate ? cyc.p : nullptr));
+        } else {
+            if (hybrid) SB_TRY(dense_t(a, Y, ldy, w, out, ldo, ctx->stream, false));
+            SB_TRY(gather_run(ctx, mt->gt, 1, mp, mt->n, Y, ldy, w, out, ldo, calibrate ? cyc.p : nullptr));
+        }
+        if (calibrate) SB_TRY(gather_recalibrate_t(mt, cyc.p));
         account(ctx, mt, w, true);
         return SB_OK;
     }

@@ -1,6 +1,6 @@
 """Worker of the multi-GPU parity test: launched by torchrun with one rank per GPU.  Two cases, both against the CPU oracle run on
 the unsharded matrix by rank 0: a small matrix generated on the device per shard, and a larger one (33,538 genes: plane levels,
-several cell tiles per rank) uploaded per shard through the narrow host form (sb_upload_compact, the bench's end-to-end path)."""
+several cell tiles per rank) uploaded per shard through the narrow host forms (sb_upload_compact, sb_upload_packed: the bench's end-to-end path)."""
 import os
 import sys
 
@@ -26,14 +26,18 @@ def main():
     orc.set_num_threads(max(1, (os.cpu_count() or 1) // world))
     for case, cfg, k, compact in (("device-generated", SynthConfig(n_cells=6000, n_genes=1500, seed=41), 10, False),
                                   ("compact-upload", SynthConfig(n_cells=48000, n_genes=33538, seed=43), 10, True),
-                                  ("k30-dense-features", SynthConfig(n_cells=12000, n_genes=2600, seed=45, n_dense=200, sigma_g=3.0), 30, True)):
+                                  ("k30-dense-features-packed-upload", SynthConfig(n_cells=12000, n_genes=2600, seed=45, n_dense=200, sigma_g=3.0), 30, "packed")):
         ip, g, c = generate_host(cfg)  # every rank generates the whole (small) matrix on the host and keeps its shard
         if compact:  # nnz-balanced contiguous shards, as bench.py cuts them
             bounds = shard_bounds_by_nnz(np.diff(ip.astype(np.int64)), world)
             lo, hi = bounds[rank]
             s0, s1 = int(ip[lo]), int(ip[hi])
-            g16, c8, bpos, bcnt = sb.AdaptiveMat.compact_csc(g[s0:s1], c[s0:s1])
-            dm = sb.AdaptiveMat.from_csc_compact(ctx, cfg.n_genes, hi - lo, (ip[lo:hi + 1] - ip[lo]).astype(np.uint64), g16, c8, bpos, bcnt)
+            ip_loc = (ip[lo:hi + 1] - ip[lo]).astype(np.uint64)
+            if compact == "packed":  # sb_upload_packed, the bench's default end-to-end path
+                dm = sb.AdaptiveMat.from_csc_packed(ctx, cfg.n_genes, hi - lo, ip_loc, *sb.AdaptiveMat.pack_csc(ip_loc, g[s0:s1], c[s0:s1]))
+            else:
+                g16, c8, bpos, bcnt = sb.AdaptiveMat.compact_csc(g[s0:s1], c[s0:s1])
+                dm = sb.AdaptiveMat.from_csc_compact(ctx, cfg.n_genes, hi - lo, ip_loc, g16, c8, bpos, bcnt)
         else:
             lo, hi = shard_bounds(cfg.n_cells, world, rank)
             dm = generate_device(ctx, cfg, lo, hi)
