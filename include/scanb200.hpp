@@ -138,6 +138,22 @@ class AdaptiveMat {
         check(sb_upload_compact(ctx.raw(), rows, cols, indptr.data(), idx16.data(), cnt8.data(), big_pos.size(), big_pos.data(), big_cnt.data(), &h));
         return AdaptiveMat(h);
     }
+    // CSC arrays in the packed host form of sb_upload_packed (gene delta byte + count nibble + side lists), built by the
+    // library's host encoder (sb_pack_csc_count / sb_pack_csc_fill)
+    static AdaptiveMat from_csc_packed(Context &ctx, uint32_t rows, uint64_t cols, const std::vector<uint64_t> &indptr,
+                                       const std::vector<uint32_t> &idx, const std::vector<uint32_t> &val, int threads = 0) {
+        uint64_t n_esc = 0, n_big = 0;
+        check(sb_pack_csc_count(cols, indptr.data(), idx.data(), val.data(), threads, &n_esc, &n_big));
+        std::vector<uint8_t> dgene(idx.size()), cnt4((idx.size() + 1) / 2);
+        std::vector<uint64_t> esc_pos(n_esc), big_pos(n_big);
+        std::vector<uint32_t> esc_gene(n_esc), big_cnt(n_big);
+        check(sb_pack_csc_fill(cols, indptr.data(), idx.data(), val.data(), threads, dgene.data(), cnt4.data(), esc_pos.data(), esc_gene.data(),
+                               big_pos.data(), big_cnt.data()));
+        sb_mat *h = nullptr;
+        check(sb_upload_packed(ctx.raw(), rows, cols, indptr.data(), dgene.data(), cnt4.data(), n_esc, esc_pos.data(), esc_gene.data(), n_big,
+                               big_pos.data(), big_cnt.data(), &h));
+        return AdaptiveMat(h);
+    }
     // from_dense (mat.rs:586-609); dense is row-major rows x cols
     static AdaptiveMat from_dense(Context &ctx, uint32_t rows, uint64_t cols, const std::vector<uint32_t> &dense) {
         std::vector<uint64_t> indptr{0};

@@ -163,6 +163,7 @@ struct sb_ctx {
     int plane_cap = 12288;           // most ranks a plane may cover
     int plane_levels = 6;            // most count levels kept as planes (<= PL_MAX_LEVELS)
     double plane_min_density = 0.01; // a 128-rank block joins level k only if this fraction of the cells has exactly that count
+    int upload_chunks = 8;           // pipelined upload: chunks of whole cell blocks in flight between the copy engine and the layout build
     bool upload_sync = true;         // pipelined upload: synchronise the build stream after every chunk (matrix.cu)
     bool gather_defer = true;        // T-side gather under the plane kernels: run factor L_c(1) applied by k_pl_reduce_t instead of at every run end
     int gather_calibrate = 1;        // T-side gather: number of timed passes (per matrix) after which the static shares are re-cut by the measured panel rates (0 = off)

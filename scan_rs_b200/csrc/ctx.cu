@@ -292,6 +292,11 @@ extern "C" int sb_set_option(sb_ctx *ctx, const char *name, double value) {
         sb_cache_configure(ctx->stream, (size_t)(value * 1.0e9));
         return SB_OK;
     }
+    if (!strcmp(name, "upload_chunks")) {
+        if (!(value >= 1.0 && value <= 256.0)) return sb_fail(SB_ERR_INVALID_ARG, "sb_set_option: upload_chunks must be in [1, 256]");
+        ctx->upload_chunks = (int)value;
+        return SB_OK;
+    }
     if (!strcmp(name, "gather_defer")) {
         ctx->gather_defer = value != 0.0;
         return SB_OK;

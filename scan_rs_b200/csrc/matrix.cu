@@ -688,7 +688,7 @@ static int packed_status(sb_ctx *ctx, const HostEntries &he, DevEntries &de) {
 static int upload_pipelined(sb_mat *mt, const u64 *h_indptr, const HostEntries &he, DevEntries &de, u32 *d_max) {
     sb_ctx *ctx = mt->ctx;
     const u64 n = mt->n;
-    const u32 nch = 8;
+    const u32 nch = (u32)std::max(1, ctx->upload_chunks);
     const u64 calign = std::max<u64>(mt->pc, GA_TBLOCK);  // whole cell panels and whole T-side cell blocks (pc divides GA_TBLOCK)
     u64 cells_per = ((n + nch - 1) / nch + calign - 1) / calign * calign;
     std::vector<u64> cb;

@@ -22,8 +22,10 @@ elif mode == "compact":
     hg, k2 = pin(g16); hc, k3 = pin(c8)
 else:
     hg, k2 = pin(g); hc, k3 = pin(c)
-for i in range(3):
-    print("---- upload", i, mode, file=sys.stderr)
+chunk_sweep = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [8]
+for i in range(3 * len(chunk_sweep)):
+    ctx.set_option("upload_chunks", chunk_sweep[i // 3])
+    print("---- upload", i, mode, "chunks", chunk_sweep[i // 3], file=sys.stderr)
     t0 = time.time()
     if mode == "packed":
         m = sb.AdaptiveMat.from_csc_packed(ctx, 33538, n, hip, *pk)

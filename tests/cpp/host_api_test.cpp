@@ -37,6 +37,23 @@ static void test_cellranger_normalisation(Context &ctx) {  // normalization.rs:5
     EXPECT(sums[0] == 666 && sums[1] == 1827 && sums[4] == 655);
 }
 
+static void test_packed_constructor(Context &ctx) {  // the same golden matrix through sb_pack_csc_* + sb_upload_packed (cell-major arrays)
+    const uint32_t dense[4][5] = {{136, 936, 0, 0, 264}, {134, 682, 417, 8, 391}, {0, 133, 780, 0, 0}, {396, 76, 96, 198, 0}};
+    std::vector<uint64_t> indptr{0};
+    std::vector<uint32_t> idx, val;
+    for (uint32_t c = 0; c < 5; c++) {
+        for (uint32_t g = 0; g < 4; g++)
+            if (dense[g][c]) {
+                idx.push_back(g);
+                val.push_back(dense[g][c]);
+            }
+        indptr.push_back(idx.size());
+    }
+    auto mtx = sqz::AdaptiveMat::from_csc_packed(ctx, 4, 5, indptr, idx, val, 2);
+    auto sums = mtx.sum_axis0_u32();
+    EXPECT(sums[0] == 666 && sums[1] == 1827 && sums[2] == 1293 && sums[3] == 1091 && sums[4] == 655);  // mat.rs golden
+}
+
 struct Recorder : snoop::CancelProgress {
     std::vector<double> seen;
     size_t cancel_after = 1000;
@@ -141,6 +158,7 @@ int main() {
     try {
         Context ctx(0);
         test_cellranger_normalisation(ctx);
+        test_packed_constructor(ctx);
         test_bksvd(ctx);
         test_mean_var_and_sum_fns(ctx);
         test_irlba(ctx);
