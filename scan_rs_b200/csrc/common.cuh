@@ -163,6 +163,10 @@ struct sb_ctx {
     int plane_cap = 12288;           // most ranks a plane may cover
     int plane_levels = 6;            // most count levels kept as planes (<= PL_MAX_LEVELS)
     double plane_min_density = 0.01; // a 128-rank block joins level k only if this fraction of the cells has exactly that count
+    bool eig_host = true;            // Gram matrices of order <= 128: k largest eigenpairs on the host (eig_host.h) instead of cuSOLVER syevd
+    void *eig_pinned = nullptr;      // page-locked staging of that round trip
+    size_t eig_pinned_bytes = 0;
+    int eig_host_declined = 0;       // times the host solver's own check sent a matrix to the library solver
     int upload_chunks = 8;           // pipelined upload: chunks of whole cell blocks in flight between the copy engine and the layout build
     bool upload_sync = true;         // pipelined upload: synchronise the build stream after every chunk (matrix.cu)
     bool gather_defer = true;        // T-side gather under the plane kernels: run factor L_c(1) applied by k_pl_reduce_t instead of at every run end

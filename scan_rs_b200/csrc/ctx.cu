@@ -190,6 +190,7 @@ extern "C" void sb_shutdown(sb_ctx *ctx) {
     if (ctx->t0) cudaEventDestroy(ctx->t0);
     if (ctx->t1) cudaEventDestroy(ctx->t1);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->eig_pinned) cudaFreeHost(ctx->eig_pinned);
     // every device buffer the context owns goes back to the pool while its stream still exists (a DevBuf released by `delete ctx`
     // below would hand cudaFreeAsync a destroyed stream: a crash at shutdown, seen with the cached start block)
     ctx->flush_buf.release();
@@ -290,6 +291,10 @@ extern "C" int sb_set_option(sb_ctx *ctx, const char *name, double value) {
     if (!strcmp(name, "block_cache_gb")) {  // capacity of the exact-size block cache in front of the memory pool (0 = off)
         if (!(value >= 0.0 && value <= 1.0e6)) return sb_fail(SB_ERR_INVALID_ARG, "sb_set_option: block_cache_gb must be in [0, 1e6]");
         sb_cache_configure(ctx->stream, (size_t)(value * 1.0e9));
+        return SB_OK;
+    }
+    if (!strcmp(name, "eig_host")) {
+        ctx->eig_host = value != 0.0;
         return SB_OK;
     }
     if (!strcmp(name, "upload_chunks")) {

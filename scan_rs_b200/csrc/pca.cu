@@ -12,7 +12,7 @@ int spmm_n(sb_nmat *a, const double *X, u32 ldx, u32 w, double *P, u32 ldp);
 int qr_tall(sb_ctx *ctx, double *A, u64 rows, u32 w, u32 ld, u32 *w_out, double *R_out = nullptr);
 int trsm_right_upper(sb_ctx *ctx, double *A, u64 rows, u32 w, u32 ld, const double *R);
 int gram(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 ld, double *G, bool reduce);
-int eigh(sb_ctx *ctx, double *G, u32 w, double *evals_dev, int *info_dev);
+int eigh_topk(sb_ctx *ctx, double *G, u32 w, u32 k, double *evals_dev, int *info_dev);
 int gemm_tall_small(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 lda, const double *S, u32 k, u32 lds, double *Out, u32 ldo);
 // dense_own.cu: the repo's own tall-skinny kernels (FP64 mma.sync) and the CholeskyQR3 factorisation
 int syrk_tall(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 ld, double *G);
@@ -127,10 +127,10 @@ static int finish_svd(sb_ctx *ctx, const Tall &Tt, const Tall &Q, u32 wq, u32 k,
     } else {
         SB_TRY(gram(ctx, Tt.buf.p, Tt.rows, wq, Tt.ld, G.p, reduce_gram));
     }
-    // the w x w Gram matrix (w = 100 at k = 10) goes to cuSOLVER (dense.cu: syevj for small orders, syevd above): a one-CTA parallel
-    // Jacobi solver written for this step was measured at 8 ms against syevd's 1.8 (three barriers and 30,000 element updates per
-    // tournament round, ~800 rounds)
-    SB_TRY(eigh(ctx, G.p, wq, ev.p, info_dev));
+    // the w x w Gram matrix (w = 100 at k = 10): only its k largest eigenpairs are used below.  Orders up to 128 are solved on the
+    // host (dense.cu: eigh_topk, eig_host.h), larger ones by cuSOLVER's syevd.  (A one-CTA parallel Jacobi solver written for this
+    // step was measured at 8 ms against syevd's 2.7: three barriers and 30,000 element updates per tournament round, ~800 rounds.)
+    SB_TRY(eigh_topk(ctx, G.p, wq, k, ev.p, info_dev));
     double *dWsel = Wk.p, *dWsc = Wk.p + (size_t)wq * k;
     SB_TRY(topk_select(ctx, G.p, ev.p, wq, k, dWsel, dWsc, S_dev));
     SB_TRY(from_t.init(ctx, Tt.rows, k));

@@ -628,6 +628,27 @@ def test_packed_upload_matches_plain_upload(ctx, n_cells, n_genes, stride):
         sb.AdaptiveMat.from_csc_packed(ctx, n_genes, n_cells, ip, dgene, cnt4, esc_pos, esc_gene, bad, big_cnt)
 
 
+def test_host_topk_eigensolver_matches_library_solver(ctx):
+    """The Gram matrix of the projected block (order b.q <= 128) is solved for its k largest eigenpairs on the host (eig_host.h) and
+    by cuSOLVER syevd above that order or when the option is off: both routes give the same PCA (and both match the oracle)."""
+    cfg, cm, dm, _ = synth_pair(ctx, 4000, 1500, seed=51)
+    a = sb.normalize(dm, sb.Normalization.CellRanger)
+    res_o = orc.BkSvd().run_pca(orc.normalize(cm, orc.CELLRANGER), 10)
+    try:
+        ctx.set_option("eig_host", 1)
+        res_h = sb.BkSvd().run_pca(a, 10)
+        ctx.set_option("eig_host", 0)
+        res_l = sb.BkSvd().run_pca(a, 10)
+    finally:
+        ctx.set_option("eig_host", 1)
+    check_pca_parity(res_h, res_o)
+    check_pca_parity(res_l, res_o)
+    np.testing.assert_allclose(res_h[1], res_l[1], rtol=1e-11)
+    # m >= n branch (cell-side block) and k = 12 (b.q = 120, the largest order the host takes at the default multiplier)
+    cfg2, cm2, dm2, _ = synth_pair(ctx, 900, 2500, seed=52)
+    check_pca_parity(sb.BkSvd().run_pca(sb.normalize(dm2, sb.Normalization.CellRanger), 12), orc.BkSvd().run_pca(orc.normalize(cm2, orc.CELLRANGER), 12))
+
+
 def test_bksvd_seurat_and_binomial(ctx):
     cfg, cm, dm, _ = synth_pair(ctx, 3000, 1200, seed=32)
     check_pca_parity(sb.BkSvd().run_pca(sb.normalize(dm, sb.Normalization.SeuratLog), 8),

@@ -165,6 +165,22 @@ def test_gather_work_units_cover_every_entry_once():
     assert out.returncode == 0 and "ALL PASSED" in out.stdout, out.stdout + out.stderr
 
 
+def test_host_eigensolver_known_spectra():
+    """scan_rs_b200/csrc/eig_host.h (k largest eigenpairs of the small Gram matrix: tridiagonalisation, QL, inverse iteration, check
+    against the original matrix) on matrices with a known spectrum: separated, decaying over ten decades, repeated / clustered,
+    rank-deficient, orders 1-3 and 128, indefinite; non-finite input is declined."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "tests", "cpp", "eig_host_test.cpp")
+    exe = os.path.join(root, "tests", "cpp", "eig_host_test")
+    hdr = os.path.join(root, "scan_rs_b200", "csrc", "eig_host.h")
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", src, "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ALL PASSED" in out.stdout, out.stdout + out.stderr
+
+
 def test_rust_ffi_matches_header():
     """rust/scan-b200/src/ffi.rs is generated from include/scanb200.h (scripts/gen_rust_ffi.py): every SB_API symbol is declared
     there, the committed file is current, and every declared symbol is exported by the library and listed for ctypes."""
