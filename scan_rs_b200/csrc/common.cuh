@@ -163,6 +163,7 @@ struct sb_ctx {
     int plane_cap = 12288;           // most ranks a plane may cover
     int plane_levels = 6;            // most count levels kept as planes (<= PL_MAX_LEVELS)
     double plane_min_density = 0.01; // a 128-rank block joins level k only if this fraction of the cells has exactly that count
+    bool gemm_skinny = true;         // tall products with at most 16 output columns: row-per-thread kernel instead of the 128-column MMA tiles
     bool eig_host = true;            // Gram matrices of order <= 128: k largest eigenpairs on the host (eig_host.h) instead of cuSOLVER syevd
     void *eig_pinned = nullptr;      // page-locked staging of that round trip
     size_t eig_pinned_bytes = 0;

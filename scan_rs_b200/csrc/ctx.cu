@@ -293,6 +293,10 @@ extern "C" int sb_set_option(sb_ctx *ctx, const char *name, double value) {
         sb_cache_configure(ctx->stream, (size_t)(value * 1.0e9));
         return SB_OK;
     }
+    if (!strcmp(name, "gemm_skinny")) {
+        ctx->gemm_skinny = value != 0.0;
+        return SB_OK;
+    }
     if (!strcmp(name, "eig_host")) {
         ctx->eig_host = value != 0.0;
         return SB_OK;

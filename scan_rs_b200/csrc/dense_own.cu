@@ -239,9 +239,62 @@ k_gemm_tall(const double *__restrict__ A, u64 rows, u32 w, u32 lda, const double
     }
 }
 
+// The same product for a narrow S (k <= 16 output columns, w <= 128): the projection of the tall block on the k kept singular
+// vectors (n x 100 by 100 x 10 at C3).  k_gemm_tall computes 128-column tiles whatever k is (1.37 ms there: 12x the flops); this one is
+// a plain row-per-thread kernel bound by reading A once: S sits in shared memory (broadcast reads), A is staged 16 columns at a time
+// through a padded tile so that the global reads are coalesced and the per-row reads conflict-free.
+#define GS_ROWS 128
+#define GS_KC 16
+__global__ void __launch_bounds__(GS_ROWS)
+k_gemm_skinny(const double *__restrict__ A, u64 rows, u32 w, u32 lda, const double *__restrict__ S, u32 k, u32 lds, double *__restrict__ Out, u32 ldo) {
+    __shared__ double sS[128][16];                // S[kk][j], zero beyond (w, k)
+    __shared__ double sA[GS_ROWS][GS_KC + 1];
+    const u32 t = threadIdx.x;
+    for (u32 i = t; i < 128 * 16; i += GS_ROWS) {
+        const u32 kk = i >> 4, j = i & 15;
+        sS[kk][j] = (kk < w && j < k) ? S[(size_t)j * lds + kk] : 0.0;
+    }
+    const u64 r0 = (u64)blockIdx.x * GS_ROWS;
+    double acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) acc[j] = 0.0;
+    for (u32 k0 = 0; k0 < w; k0 += GS_KC) {
+        __syncthreads();  // the previous chunk has been consumed (first pass: sS is complete)
+        for (u32 i = t; i < GS_ROWS * GS_KC; i += GS_ROWS) {
+            const u32 rr = i / GS_KC, cc = i - rr * GS_KC;
+            const u64 r = r0 + rr;
+            sA[rr][cc] = (r < rows && k0 + cc < w) ? A[r * (size_t)lda + k0 + cc] : 0.0;
+        }
+        __syncthreads();
+        const u32 kn = min((u32)GS_KC, w - k0);
+        for (u32 cc = 0; cc < kn; cc++) {
+            const double a = sA[t][cc];
+            const double2 *srow = reinterpret_cast<const double2 *>(sS[k0 + cc]);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const double2 sv = srow[j];
+                acc[2 * j] = fma(a, sv.x, acc[2 * j]);
+                acc[2 * j + 1] = fma(a, sv.y, acc[2 * j + 1]);
+            }
+        }
+    }
+    const u64 r = r0 + t;
+    if (r < rows) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 2)
+            if ((u32)j + 1 < ldo) *reinterpret_cast<double2 *>(Out + r * (size_t)ldo + j) = make_double2((u32)j < k ? acc[j] : 0.0, (u32)j + 1 < k ? acc[j + 1] : 0.0);
+    }
+}
+
 int gemm_tall(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 lda, const double *S, u32 k, u32 lds, double *Out, u32 ldo) {
     if (rows == 0 || k == 0) return SB_OK;
     if (ldo & 1) return sb_fail(SB_ERR_INVALID_ARG, "gemm_tall: odd leading dimension");
+    if (k <= 16 && ldo <= 16 && w <= 128 && ctx->gemm_skinny) {
+        k_gemm_skinny<<<(unsigned)cdiv(rows, GS_ROWS), GS_ROWS, 0, ctx->stream>>>(A, rows, w, lda, S, k, lds, Out, ldo);
+        count_launch(ctx);
+        SB_CUDA(cudaGetLastError());
+        return SB_OK;
+    }
     const u32 cols = (std::max(k, ldo) + 127) / 128;  // also zero the pad columns
     const size_t smem = (size_t)(2 * 128 * GM_ASTRIDE + 2 * GM_KC * GM_SSTRIDE) * sizeof(double);
     SB_CUDA(cudaFuncSetAttribute(k_gemm_tall, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
