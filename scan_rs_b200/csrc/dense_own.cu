@@ -19,15 +19,37 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 // ---------------------------------------------------------------- G += A^T A
 #define SY_THREADS 512
 #define SY_BLK 128
-#define SY_RC 16
-#define SY_STRIDE 136  // == 8 mod 32 doubles: the four k rows of a fragment land in disjoint bank groups
+#define SY_RC 32
+#define SY_STRIDE 132  // == 4 mod 16 doubles: the four k rows of a fragment (8-byte words, 16 per 128-byte line) land in disjoint banks
+#define SY_STAGES 3    // shared-memory ring of row stages filled by cp.async
 
-// grid (row chunks, block pairs bi <= bj).  G: column-major w x w, zeroed by the caller; only blocks with bi <= bj are written.
+// 16-byte asynchronous copy global -> shared; bytes past `src_bytes` (0 .. 16) are zero-filled
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, u32 src_bytes) {
+    const u32 d = (u32)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc, u32 src_bytes) {
+    const u32 d = (u32)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// A warp owns a 32 x 32 region (4 x 4 MMA tiles of 8 x 8) of the 128 x 128 block.  Tiles past the matrix order, and in a diagonal
+// block the tiles strictly below the tile diagonal (the mirror image is stored from above), are skipped: at w = 100 that leaves
+// 91 of 256 tiles.  Warps are tied to a scheduler by warp id modulo 4, so `wmap` (host: greedy longest-first over the four
+// schedulers) says which region each warp takes: 26 tiles on the busiest scheduler instead of 64.
+struct SyWarpMap { unsigned char region[16]; };  // region = wr << 2 | wc
+
+// grid (row chunks, block pairs bi <= bj).  G: column-major w x w per row chunk; only blocks with bi <= bj are written.
+// Row stages of 16 rows travel global -> shared by cp.async through a ring of SY_STAGES slots (the first version staged through
+// registers one stage ahead and spent its time waiting: 1.39 ms for a 1.3M x 100 block at 37 % issue activity, one barrier and one
+// exposed global round trip per 16 rows; profiles/exp_dense_tileskip_r02.log).
 __global__ void __launch_bounds__(SY_THREADS, 1)
-k_syrk_tall(const double *__restrict__ A, u64 rows, u32 w, u32 ld, double *__restrict__ G, u32 nb) {
+k_syrk_tall(const double *__restrict__ A, u64 rows, u32 w, u32 ld, double *__restrict__ G, u32 nb, SyWarpMap wmap) {
     extern __shared__ __align__(16) double sy_smem[];
     double(*sI)[SY_RC][SY_STRIDE] = reinterpret_cast<double(*)[SY_RC][SY_STRIDE]>(sy_smem);
-    double(*sJ)[SY_RC][SY_STRIDE] = reinterpret_cast<double(*)[SY_RC][SY_STRIDE]>(sy_smem + 2 * SY_RC * SY_STRIDE);
+    double(*sJ)[SY_RC][SY_STRIDE] = reinterpret_cast<double(*)[SY_RC][SY_STRIDE]>(sy_smem + SY_STAGES * SY_RC * SY_STRIDE);
     // decode the block pair
     u32 bi = 0, bj = 0;
     {
@@ -44,8 +66,16 @@ k_syrk_tall(const double *__restrict__ A, u64 rows, u32 w, u32 ld, double *__res
     const bool diag = bi == bj;
     const u32 I0 = bi * SY_BLK, J0 = bj * SY_BLK;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int wr = warp >> 2, wc = warp & 3;
+    const int wr = diag ? (wmap.region[warp] >> 2) : (warp >> 2), wc = diag ? (wmap.region[warp] & 3) : (warp & 3);
     const int fr = lane >> 2, fk = lane & 3;
+    u32 tmask = 0;  // bit 4 mt + nt: this warp computes tile (mt, nt)
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+            const u32 ti = wr * 4 + mt, tj = wc * 4 + nt;
+            if (I0 + ti * 8 < w && J0 + tj * 8 < w && (!diag || ti <= tj)) tmask |= 1u << (4 * mt + nt);
+        }
     u64 per = (rows + gridDim.x - 1) / gridDim.x;
     per = (per + SY_RC - 1) / SY_RC * SY_RC;
     const u64 r_lo = min(rows, (u64)blockIdx.x * per), r_hi = min(rows, r_lo + per);
@@ -56,32 +86,45 @@ k_syrk_tall(const double *__restrict__ A, u64 rows, u32 w, u32 ld, double *__res
 #pragma unroll
         for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-    // each thread moves 4 doubles per operand per stage: row = t / 32, columns 4 (t % 32) .. + 3
+    // each thread moves 4 doubles (two 16-byte copies) per operand per stage: row = t / 32, columns 4 (t % 32) .. + 3
     const int lrow = t >> 5, lcol = (t & 31) * 4;
-    double ri[4], rj[4];
-    auto gload = [&](u64 r0) {
-        const u64 r = r0 + lrow;
+    const bool aligned16 = (ld & 1u) == 0 && ((size_t)A & 15u) == 0;  // row starts on 16 bytes (else: 8-byte copies)
+    auto issue = [&](u64 r0, int slot) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const u32 ci = I0 + lcol + i, cj = J0 + lcol + i;
-            ri[i] = (r < r_hi && ci < w) ? A[r * (size_t)ld + ci] : 0.0;
-            rj[i] = (!diag && r < r_hi && cj < w) ? A[r * (size_t)ld + cj] : 0.0;
+        for (int rr = 0; rr < SY_RC; rr += SY_THREADS / 32) {
+            const int sr = lrow + rr;
+            const u64 r = r0 + sr;
+            const bool rok = r < r_hi;
+            const double *rowp = A + (rok ? r : r_lo) * (size_t)ld;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const u32 ci = I0 + lcol + 2 * h, cj = J0 + lcol + 2 * h;
+                const u32 bi_ = !rok || ci >= w ? 0u : min(16u, (w - ci) * 8u), bj_ = !rok || cj >= w ? 0u : min(16u, (w - cj) * 8u);
+                if (aligned16) {
+                    cp_async16(&sI[slot][sr][lcol + 2 * h], rowp + (bi_ ? ci : 0), bi_);
+                    if (!diag) cp_async16(&sJ[slot][sr][lcol + 2 * h], rowp + (bj_ ? cj : 0), bj_);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const u32 b1 = bi_ > 8u * e ? 8u : 0u, b2 = bj_ > 8u * e ? 8u : 0u;
+                        cp_async8(&sI[slot][sr][lcol + 2 * h + e], rowp + (b1 ? ci + e : 0), b1);
+                        if (!diag) cp_async8(&sJ[slot][sr][lcol + 2 * h + e], rowp + (b2 ? cj + e : 0), b2);
+                    }
+                }
+            }
         }
     };
-    auto sstore = [&](int buf) {
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            sI[buf][lrow][lcol + i] = ri[i];
-            if (!diag) sJ[buf][lrow][lcol + i] = rj[i];
-        }
-    };
-    gload(r_lo);
-    sstore(0);
-    __syncthreads();
-    int buf = 0;
-    for (u64 r0 = r_lo; r0 < r_hi; r0 += SY_RC, buf ^= 1) {
-        const bool more = r0 + SY_RC < r_hi;
-        if (more) gload(r0 + SY_RC);
+    const u64 nst = (r_hi - r_lo + SY_RC - 1) / SY_RC;
+    for (int p = 0; p < SY_STAGES - 1; p++) {
+        if ((u64)p < nst) issue(r_lo + (u64)p * SY_RC, p);
+        cp_async_commit();
+    }
+    for (u64 st = 0; st < nst; st++) {
+        cp_async_wait<SY_STAGES - 2>();  // stage st has landed (for this thread's copies; the barrier publishes everybody's)
+        __syncthreads();                 // ... and every warp is done with stage st - 1, whose slot is refilled next
+        if (st + SY_STAGES - 1 < nst) issue(r_lo + (st + SY_STAGES - 1) * SY_RC, (int)((st + SY_STAGES - 1) % SY_STAGES));
+        cp_async_commit();
+        const int buf = (int)(st % SY_STAGES);
         double(*sB)[SY_STRIDE] = diag ? sI[buf] : sJ[buf];
 #pragma unroll
         for (int ks = 0; ks < SY_RC / 4; ks++) {
@@ -93,15 +136,15 @@ k_syrk_tall(const double *__restrict__ A, u64 rows, u32 w, u32 ld, double *__res
 #pragma unroll
             for (int mt = 0; mt < 4; mt++)
 #pragma unroll
-                for (int nt = 0; nt < 4; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+                for (int nt = 0; nt < 4; nt++)
+                    if (tmask & (1u << (4 * mt + nt))) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
         }
-        if (more) sstore(buf ^ 1);
-        __syncthreads();
     }
 #pragma unroll
     for (int mt = 0; mt < 4; mt++)
 #pragma unroll
         for (int nt = 0; nt < 4; nt++) {
+            if (!(tmask & (1u << (4 * mt + nt)))) continue;
             const u32 i = I0 + (wr * 4 + mt) * 8 + fr;
             const u32 j = J0 + (wc * 4 + nt) * 8 + 2 * fk;
             // plain stores into this row chunk's own copy of G: k_syrk_reduce adds the chunks up in a fixed order, so the result is
@@ -109,7 +152,140 @@ k_syrk_tall(const double *__restrict__ A, u64 rows, u32 w, u32 ld, double *__res
             double *Gc = G + (size_t)blockIdx.x * w * w;
             if (i < w && j < w) Gc[(size_t)j * w + i] = acc[mt][nt][0];
             if (i < w && j + 1 < w) Gc[(size_t)(j + 1) * w + i] = acc[mt][nt][1];
+            if (diag && wr * 4 + mt < wc * 4 + nt) {  // the skipped tile below the diagonal is this one's transpose
+                if (i < w && j < w) Gc[(size_t)i * w + j] = acc[mt][nt][0];
+                if (i < w && j + 1 < w) Gc[(size_t)i * w + j + 1] = acc[mt][nt][1];
+            }
         }
+}
+
+// which 32 x 32 region of a diagonal block every warp takes: regions sorted by their number of live tiles, each handed to the
+// scheduler (warp id modulo 4) with the least work so far that still has a free warp
+static SyWarpMap syrk_warp_map(u32 w_in_block) {
+    int cnt[16], order[16];
+    for (int wr = 0; wr < 4; wr++)
+        for (int wc = 0; wc < 4; wc++) {
+            int c = 0;
+            for (int mt = 0; mt < 4; mt++)
+                for (int nt = 0; nt < 4; nt++) {
+                    const u32 ti = wr * 4 + mt, tj = wc * 4 + nt;
+                    if (ti * 8 < w_in_block && tj * 8 < w_in_block && ti <= tj) c++;
+                }
+            cnt[wr * 4 + wc] = c;
+            order[wr * 4 + wc] = wr * 4 + wc;
+        }
+    std::stable_sort(order, order + 16, [&](int x, int y) { return cnt[x] > cnt[y]; });
+    int load[4] = {0, 0, 0, 0}, used[4] = {0, 0, 0, 0};
+    SyWarpMap m;
+    for (int k = 0; k < 16; k++) {
+        int best = -1;
+        for (int sch = 0; sch < 4; sch++)
+            if (used[sch] < 4 && (best < 0 || load[sch] < load[best])) best = sch;
+        m.region[best + 4 * used[best]] = (unsigned char)order[k];
+        load[best] += cnt[order[k]];
+        used[best]++;
+    }
+    return m;
+}
+
+// ---------------------------------------------------------------- G = A^T A for w <= 128 (one diagonal block): live tiles only
+// The general kernel above gives every warp a 32 x 32 region and masks the MMA tiles it does not need -- but a predicated-off
+// DMMA still occupies the FP64 tensor pipe (ncu: sm__inst_executed_pipe_tensor_subpipe_dmma 86 % with 91 of 256 tiles live, and
+// the same duration as without the mask).  Here the T (T + 1) / 2 tiles on or above the tile diagonal (T = ceil(w / 8); 91 at
+// w = 100) are dealt out to the 16 warps as a list, NQ tiles per warp, so only live tiles are ever issued; a slot past the end of
+// the list repeats tile 0 and is not stored.  Same row-stage ring, same per-chunk copies of G, same fixed-order reduction.
+struct SyTileList { unsigned char ti[16][9], tj[16][9], live[16]; };
+
+template <int NQ>
+__global__ void __launch_bounds__(SY_THREADS, 1)
+k_syrk_diag(const double *__restrict__ A, u64 rows, u32 w, u32 ld, double *__restrict__ G, SyTileList tl) {
+    extern __shared__ __align__(16) double sy_smem[];
+    double(*sI)[SY_RC][SY_STRIDE] = reinterpret_cast<double(*)[SY_RC][SY_STRIDE]>(sy_smem);
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int fr = lane >> 2, fk = lane & 3;
+    u64 per = (rows + gridDim.x - 1) / gridDim.x;
+    per = (per + SY_RC - 1) / SY_RC * SY_RC;
+    const u64 r_lo = min(rows, (u64)blockIdx.x * per), r_hi = min(rows, r_lo + per);
+    if (r_lo >= r_hi) return;
+    u32 ca[NQ], cb[NQ];  // column (in doubles) of this lane's fragment element in the tiles' row / column operand
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+        ca[q] = tl.ti[warp][q] * 8u + fr;
+        cb[q] = tl.tj[warp][q] * 8u + fr;
+    }
+    const u32 nlive = tl.live[warp];
+    double acc[NQ][2];
+#pragma unroll
+    for (int q = 0; q < NQ; q++) acc[q][0] = acc[q][1] = 0.0;
+    const int lrow = t >> 5, lcol = (t & 31) * 4;
+    const bool aligned16 = (ld & 1u) == 0 && ((size_t)A & 15u) == 0;
+    auto issue = [&](u64 r0, int slot) {
+#pragma unroll
+        for (int rr = 0; rr < SY_RC; rr += SY_THREADS / 32) {
+            const int sr = lrow + rr;
+            const u64 r = r0 + sr;
+            const bool rok = r < r_hi;
+            const double *rowp = A + (rok ? r : r_lo) * (size_t)ld;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const u32 ci = lcol + 2 * h;
+                const u32 bi_ = !rok || ci >= w ? 0u : min(16u, (w - ci) * 8u);
+                if (aligned16) {
+                    cp_async16(&sI[slot][sr][lcol + 2 * h], rowp + (bi_ ? ci : 0), bi_);
+                } else {
+                    cp_async8(&sI[slot][sr][lcol + 2 * h], rowp + (bi_ ? ci : 0), bi_ ? 8u : 0u);
+                    cp_async8(&sI[slot][sr][lcol + 2 * h + 1], rowp + (bi_ > 8u ? ci + 1 : 0), bi_ > 8u ? 8u : 0u);
+                }
+            }
+        }
+    };
+    const u64 nst = (r_hi - r_lo + SY_RC - 1) / SY_RC;
+    for (int p = 0; p < SY_STAGES - 1; p++) {
+        if ((u64)p < nst) issue(r_lo + (u64)p * SY_RC, p);
+        cp_async_commit();
+    }
+    for (u64 st = 0; st < nst; st++) {
+        cp_async_wait<SY_STAGES - 2>();
+        __syncthreads();
+        if (st + SY_STAGES - 1 < nst) issue(r_lo + (st + SY_STAGES - 1) * SY_RC, (int)((st + SY_STAGES - 1) % SY_STAGES));
+        cp_async_commit();
+        const int buf = (int)(st % SY_STAGES);
+#pragma unroll
+        for (int ks = 0; ks < SY_RC / 4; ks++) {
+            const double *krow = sI[buf][ks * 4 + fk];
+#pragma unroll
+            for (int q = 0; q < NQ; q++) dmma884(acc[q][0], acc[q][1], krow[ca[q]], krow[cb[q]]);
+        }
+    }
+    double *Gc = G + (size_t)blockIdx.x * w * w;
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+        if ((u32)q >= nlive) continue;
+        const u32 ti = tl.ti[warp][q], tj = tl.tj[warp][q];
+        const u32 i = ti * 8 + fr, j = tj * 8 + 2 * fk;
+        if (i < w && j < w) Gc[(size_t)j * w + i] = acc[q][0];
+        if (i < w && j + 1 < w) Gc[(size_t)(j + 1) * w + i] = acc[q][1];
+        if (ti < tj) {  // mirror image below the tile diagonal
+            if (i < w && j < w) Gc[(size_t)i * w + j] = acc[q][0];
+            if (i < w && j + 1 < w) Gc[(size_t)i * w + j + 1] = acc[q][1];
+        }
+    }
+}
+
+// the live tiles of a w x w Gram matrix, dealt round-robin to the 16 warps (warp id modulo 4 is the scheduler: round-robin keeps
+// the four of them level); returns the tiles per warp
+static int syrk_tile_list(u32 w, SyTileList &tl) {
+    const int T = (int)((w + 7) / 8);
+    memset(&tl, 0, sizeof(tl));
+    int n = 0;
+    for (int ti = 0; ti < T; ti++)
+        for (int tj = ti; tj < T; tj++, n++) {
+            const int wp = n % 16, q = n / 16;
+            tl.ti[wp][q] = (unsigned char)ti;
+            tl.tj[wp][q] = (unsigned char)tj;
+            tl.live[wp] = (unsigned char)(q + 1);
+        }
+    return (n + 15) / 16;
 }
 
 // G[e] = sum over the row chunks of the blocks on or above the block diagonal.  One warp per element: lane l adds chunks l, l + 32,
@@ -141,7 +317,7 @@ int syrk_tall(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 ld, double *G) 
     const u32 nb = (w + SY_BLK - 1) / SY_BLK;
     const u32 pairs = nb * (nb + 1) / 2;
     u32 chunks = std::max<u32>(1, (u32)std::min<u64>((rows + 4 * SY_RC - 1) / (4 * SY_RC), std::max<u32>(1, (u32)ctx->sm_count * 2 / pairs)));
-    const size_t smem = (size_t)4 * SY_RC * SY_STRIDE * sizeof(double);
+    const size_t smem = (size_t)2 * SY_STAGES * SY_RC * SY_STRIDE * sizeof(double);
     SB_CUDA(cudaFuncSetAttribute(k_syrk_tall, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // row chunks that get no rows return early: only the first `valid` copies are written (the kernel's own split, restated)
     u64 per = (rows + chunks - 1) / chunks;
@@ -152,7 +328,25 @@ int syrk_tall(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 ld, double *G) 
     // (measured: 18.7 -> 55 ms per step at 162k cells)
     SB_TRY(ctx->syrk_parts.ensure((size_t)valid * w * w));
     double *parts = ctx->syrk_parts.p;
-    k_syrk_tall<<<dim3(chunks, pairs), SY_THREADS, smem, ctx->stream>>>(A, rows, w, ld, parts, nb);
+    if (nb == 1) {  // one diagonal block: only its live tiles are issued
+        SyTileList tl;
+        const int nq = syrk_tile_list(w, tl);
+        const size_t smem1 = (size_t)SY_STAGES * SY_RC * SY_STRIDE * sizeof(double);
+        if (nq <= 3) {
+            SB_CUDA(cudaFuncSetAttribute(k_syrk_diag<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+            k_syrk_diag<3><<<chunks, SY_THREADS, smem1, ctx->stream>>>(A, rows, w, ld, parts, tl);
+        } else if (nq <= 6) {
+            SB_CUDA(cudaFuncSetAttribute(k_syrk_diag<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+            k_syrk_diag<6><<<chunks, SY_THREADS, smem1, ctx->stream>>>(A, rows, w, ld, parts, tl);
+        } else {
+            SB_CUDA(cudaFuncSetAttribute(k_syrk_diag<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+            k_syrk_diag<9><<<chunks, SY_THREADS, smem1, ctx->stream>>>(A, rows, w, ld, parts, tl);
+        }
+    } else {
+        // (several blocks per side: the map of a full diagonal block; a partial last block is then only balanced approximately)
+        const SyWarpMap wmap = syrk_warp_map(SY_BLK);
+        k_syrk_tall<<<dim3(chunks, pairs), SY_THREADS, smem, ctx->stream>>>(A, rows, w, ld, parts, nb, wmap);
+    }
     k_syrk_reduce<<<cdiv((u64)w * w * 32, 256), 256, 0, ctx->stream>>>(parts, valid, w, G);
     count_launch(ctx); count_launch(ctx);
     if (nb > 1) {
@@ -167,19 +361,31 @@ int syrk_tall(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 ld, double *G) 
 #define GM_THREADS 512
 #define GM_KC 16
 #define GM_ASTRIDE 20   // == 4 mod 32 doubles: eight rows x four k land in 32 distinct doubles
-#define GM_SSTRIDE 136
+#define GM_SSTRIDE 132  // == 4 mod 16 doubles: the four k rows of a B fragment land in disjoint banks
 
-// A row-major rows x w (lda); S column-major w x k (lds); Out row-major rows x k (ldo; pad columns k..ldo-1 are zeroed)
+// A row-major rows x w (lda); S column-major w x k (lds); Out row-major rows x k (ldo; pad columns k..ldo-1 are zeroed).
+// s_upper: S is upper triangular (the R^-1 of the CholeskyQR rounds and of the projection): the k steps below a column tile's
+// diagonal multiply zeros and are skipped, as are column tiles past k.  Warps are laid out so that every scheduler (warp id modulo
+// 4) gets one warp of each column group -- the work per column group grows with its index once the triangle is skipped.
+// Operand chunks travel global -> shared by cp.async through a ring of GM_STAGES slots (see k_syrk_tall).
+#define GM_STAGES 3
 __global__ void __launch_bounds__(GM_THREADS, 1)
-k_gemm_tall(const double *__restrict__ A, u64 rows, u32 w, u32 lda, const double *__restrict__ S, u32 k, u32 lds, double *__restrict__ Out, u32 ldo) {
+k_gemm_tall(const double *__restrict__ A, u64 rows, u32 w, u32 lda, const double *__restrict__ S, u32 k, u32 lds, double *__restrict__ Out, u32 ldo,
+            int s_upper) {
     extern __shared__ __align__(16) double gm_smem[];
     double(*sA)[128][GM_ASTRIDE] = reinterpret_cast<double(*)[128][GM_ASTRIDE]>(gm_smem);
-    double(*sS)[GM_KC][GM_SSTRIDE] = reinterpret_cast<double(*)[GM_KC][GM_SSTRIDE]>(gm_smem + 2 * 128 * GM_ASTRIDE);
+    double(*sS)[GM_KC][GM_SSTRIDE] = reinterpret_cast<double(*)[GM_KC][GM_SSTRIDE]>(gm_smem + GM_STAGES * 128 * GM_ASTRIDE);
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int wr = warp >> 2, wc = warp & 3;
+    const int wr = warp & 3, wc = warp >> 2;
     const int fr = lane >> 2, fk = lane & 3;
     const u64 r0 = (u64)blockIdx.x * 128;
     const u32 c0 = blockIdx.y * 128;
+    u32 klim[4];  // k steps [0, klim) contribute to column tile nt of this warp (0: the tile lies past k)
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++) {
+        const u32 c8 = c0 + (wc * 4 + nt) * 8;
+        klim[nt] = c8 >= k ? 0u : (s_upper ? min(w, c8 + 8u) : w);
+    }
     double acc[4][4][2];
 #pragma unroll
     for (int a = 0; a < 4; a++)
@@ -187,31 +393,43 @@ k_gemm_tall(const double *__restrict__ A, u64 rows, u32 w, u32 lda, const double
         for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
     // staging: A chunk 128 rows x 16 k: thread -> row t / 4, k 4 (t % 4) .. + 3; S chunk 16 k x 128 cols: thread -> col t / 4, k 4 (t % 4) .. + 3
     const int arow = t >> 2, ak = (t & 3) * 4;
-    double ra[4], rs[4];
-    auto gload = [&](u32 k0) {
+    const bool aligned16 = (lda & 1u) == 0 && ((size_t)A & 15u) == 0;
+    auto issue = [&](u32 k0, int slot) {
         const u64 r = r0 + arow;
         const u32 c = c0 + arow;
+        const bool rok = r < rows, cok = c < k;
+        const double *arowp = A + (rok ? r : 0) * (size_t)lda;
+        const double *scolp = S + (size_t)(cok ? c : 0) * lds;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const u32 kk = k0 + ak + 2 * h;
+            const u32 ab = !rok || kk >= w ? 0u : min(16u, (w - kk) * 8u);
+            if (aligned16) {
+                cp_async16(&sA[slot][arow][ak + 2 * h], arowp + (ab ? kk : 0), ab);
+            } else {
+                cp_async8(&sA[slot][arow][ak + 2 * h], arowp + (ab ? kk : 0), ab ? 8u : 0u);
+                cp_async8(&sA[slot][arow][ak + 2 * h + 1], arowp + (ab > 8u ? kk + 1 : 0), ab > 8u ? 8u : 0u);
+            }
+        }
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const u32 kk = k0 + ak + i;
-            ra[i] = (r < rows && kk < w) ? A[r * (size_t)lda + kk] : 0.0;
-            rs[i] = (c < k && kk < w) ? S[(size_t)c * lds + kk] : 0.0;
+            const bool ok = cok && kk < w;
+            cp_async8(&sS[slot][ak + i][arow], scolp + (ok ? kk : 0), ok ? 8u : 0u);
         }
     };
-    auto sstore = [&](int buf) {
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            sA[buf][arow][ak + i] = ra[i];
-            sS[buf][ak + i][arow] = rs[i];
-        }
-    };
-    gload(0);
-    sstore(0);
-    __syncthreads();
-    int buf = 0;
-    for (u32 k0 = 0; k0 < w; k0 += GM_KC, buf ^= 1) {
-        const bool more = k0 + GM_KC < w;
-        if (more) gload(k0 + GM_KC);
+    const u32 nst = (w + GM_KC - 1) / GM_KC;
+    for (int p = 0; p < GM_STAGES - 1; p++) {
+        if ((u32)p < nst) issue((u32)p * GM_KC, p);
+        cp_async_commit();
+    }
+    for (u32 st = 0; st < nst; st++) {
+        cp_async_wait<GM_STAGES - 2>();
+        __syncthreads();
+        if (st + GM_STAGES - 1 < nst) issue((st + GM_STAGES - 1) * GM_KC, (int)((st + GM_STAGES - 1) % GM_STAGES));
+        cp_async_commit();
+        const int buf = (int)(st % GM_STAGES);
+        const u32 k0 = st * GM_KC;
 #pragma unroll
         for (int ks = 0; ks < GM_KC / 4; ks++) {
             double a[4], b[4];
@@ -220,13 +438,14 @@ k_gemm_tall(const double *__restrict__ A, u64 rows, u32 w, u32 lda, const double
 #pragma unroll
             for (int nt = 0; nt < 4; nt++) b[nt] = sS[buf][ks * 4 + fk][(wc * 4 + nt) * 8 + fr];
 #pragma unroll
-            for (int mt = 0; mt < 4; mt++)
+            for (int nt = 0; nt < 4; nt++)
+                if (k0 + ks * 4 < klim[nt]) {
 #pragma unroll
-                for (int nt = 0; nt < 4; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+                    for (int mt = 0; mt < 4; mt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+                }
         }
-        if (more) sstore(buf ^ 1);
-        __syncthreads();
     }
+    // (in place use, Out == A: every copy of this CTA's rows has landed -- the last stage was waited for above)
 #pragma unroll
     for (int mt = 0; mt < 4; mt++) {
         const u64 r = r0 + (wr * 4 + mt) * 8 + fr;
@@ -235,6 +454,85 @@ k_gemm_tall(const double *__restrict__ A, u64 rows, u32 w, u32 lda, const double
         for (int nt = 0; nt < 4; nt++) {
             const u32 c = c0 + (wc * 4 + nt) * 8 + 2 * fk;  // even; ldo is even
             if (c + 1 < ldo) *reinterpret_cast<double2 *>(Out + r * (size_t)ldo + c) = make_double2(c < k ? acc[mt][nt][0] : 0.0, c + 1 < k ? acc[mt][nt][1] : 0.0);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- Out = A . S for w <= 128, k <= 128: live tiles only
+// One warp per 8-row tile of the CTA's 128 rows, CT column tiles of 8 each; the k loop is unrolled completely (at most 8 stages of
+// 16), so with an upper-triangular S the (k step, column tile) pairs that multiply zeros are left out at COMPILE time: a
+// predicated-off DMMA still occupies the FP64 tensor pipe (see k_syrk_diag).  At w = k = 100: 181 of 400 tile steps per warp.
+template <int CT, bool UPPER>
+__global__ void __launch_bounds__(GM_THREADS, 1)
+k_gemm_rows(const double *__restrict__ A, u64 rows, u32 w, u32 lda, const double *__restrict__ S, u32 k, u32 lds, double *__restrict__ Out, u32 ldo) {
+    extern __shared__ __align__(16) double gm_smem[];
+    double(*sA)[128][GM_ASTRIDE] = reinterpret_cast<double(*)[128][GM_ASTRIDE]>(gm_smem);
+    double(*sS)[GM_KC][GM_SSTRIDE] = reinterpret_cast<double(*)[GM_KC][GM_SSTRIDE]>(gm_smem + GM_STAGES * 128 * GM_ASTRIDE);
+    const int t = threadIdx.x, lane = t & 31, rt = t >> 5;
+    const int fr = lane >> 2, fk = lane & 3;
+    const u64 r0 = (u64)blockIdx.x * 128;
+    double acc[CT][2];
+#pragma unroll
+    for (int c = 0; c < CT; c++) acc[c][0] = acc[c][1] = 0.0;
+    const int arow = t >> 2, ak = (t & 3) * 4;
+    const bool aligned16 = (lda & 1u) == 0 && ((size_t)A & 15u) == 0;
+    auto issue = [&](u32 k0, int slot) {
+        const u64 r = r0 + arow;
+        const u32 c = arow;
+        const bool rok = r < rows, cok = c < k;
+        const double *arowp = A + (rok ? r : 0) * (size_t)lda;
+        const double *scolp = S + (size_t)(cok ? c : 0) * lds;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const u32 kk = k0 + ak + 2 * h;
+            const u32 ab = !rok || kk >= w ? 0u : min(16u, (w - kk) * 8u);
+            if (aligned16) {
+                cp_async16(&sA[slot][arow][ak + 2 * h], arowp + (ab ? kk : 0), ab);
+            } else {
+                cp_async8(&sA[slot][arow][ak + 2 * h], arowp + (ab ? kk : 0), ab ? 8u : 0u);
+                cp_async8(&sA[slot][arow][ak + 2 * h + 1], arowp + (ab > 8u ? kk + 1 : 0), ab > 8u ? 8u : 0u);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const u32 kk = k0 + ak + i;
+            const bool ok = cok && kk < w;
+            cp_async8(&sS[slot][ak + i][arow], scolp + (ok ? kk : 0), ok ? 8u : 0u);
+        }
+    };
+    const u32 nst = (w + GM_KC - 1) / GM_KC;  // <= 8
+    for (int p = 0; p < GM_STAGES - 1; p++) {
+        if ((u32)p < nst) issue((u32)p * GM_KC, p);
+        cp_async_commit();
+    }
+#pragma unroll
+    for (int st = 0; st < 128 / GM_KC; st++) {
+        if ((u32)st < nst) {
+            cp_async_wait<GM_STAGES - 2>();
+            __syncthreads();
+            if ((u32)st + GM_STAGES - 1 < nst) issue(((u32)st + GM_STAGES - 1) * GM_KC, (st + GM_STAGES - 1) % GM_STAGES);
+            cp_async_commit();
+            const int buf = st % GM_STAGES;
+#pragma unroll
+            for (int ks = 0; ks < GM_KC / 4; ks++) {
+                const int kk = st * GM_KC + ks * 4;  // compile time
+                const double a = sA[buf][rt * 8 + fr][ks * 4 + fk];
+                const double *brow = sS[buf][ks * 4 + fk];
+#pragma unroll
+                for (int c = 0; c < CT; c++)
+                    if (!UPPER || c * 8 + 8 > kk) dmma884(acc[c][0], acc[c][1], a, brow[c * 8 + fr]);
+            }
+        }
+    }
+    const u64 r = r0 + rt * 8 + fr;
+    if (r < rows) {
+#pragma unroll
+        for (int c = 0; c < 16; c++) {  // also zero the pad columns up to ldo
+            const u32 col = c * 8 + 2 * fk;
+            if (col + 1 < ldo) {
+                const double v0 = c < CT && col < k ? acc[c < CT ? c : 0][0] : 0.0, v1 = c < CT && col + 1 < k ? acc[c < CT ? c : 0][1] : 0.0;
+                *reinterpret_cast<double2 *>(Out + r * (size_t)ldo + col) = make_double2(v0, v1);
+            }
         }
     }
 }
@@ -286,7 +584,7 @@ k_gemm_skinny(const double *__restrict__ A, u64 rows, u32 w, u32 lda, const doub
     }
 }
 
-int gemm_tall(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 lda, const double *S, u32 k, u32 lds, double *Out, u32 ldo) {
+int gemm_tall(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 lda, const double *S, u32 k, u32 lds, double *Out, u32 ldo, bool s_upper) {
     if (rows == 0 || k == 0) return SB_OK;
     if (ldo & 1) return sb_fail(SB_ERR_INVALID_ARG, "gemm_tall: odd leading dimension");
     if (k <= 16 && ldo <= 16 && w <= 128 && ctx->gemm_skinny) {
@@ -295,10 +593,29 @@ int gemm_tall(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 lda, const doub
         SB_CUDA(cudaGetLastError());
         return SB_OK;
     }
+    if (w <= 128 && k <= 128 && ldo <= 128) {  // one warp per row tile, live tile steps only
+        const size_t smem1 = (size_t)(GM_STAGES * 128 * GM_ASTRIDE + GM_STAGES * GM_KC * GM_SSTRIDE) * sizeof(double);
+        const unsigned grid = (unsigned)cdiv(rows, 128);
+#define GR_LAUNCH(CTV, UP)                                                                                                     \
+    do {                                                                                                                       \
+        SB_CUDA(cudaFuncSetAttribute(k_gemm_rows<CTV, UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));          \
+        k_gemm_rows<CTV, UP><<<grid, GM_THREADS, smem1, ctx->stream>>>(A, rows, w, lda, S, k, lds, Out, ldo);                  \
+    } while (0)
+        const u32 ct = (k + 7) / 8;
+        if (s_upper) {
+            if (ct <= 3) GR_LAUNCH(3, true); else if (ct <= 8) GR_LAUNCH(8, true); else if (ct <= 13) GR_LAUNCH(13, true); else GR_LAUNCH(16, true);
+        } else {
+            if (ct <= 3) GR_LAUNCH(3, false); else if (ct <= 8) GR_LAUNCH(8, false); else if (ct <= 13) GR_LAUNCH(13, false); else GR_LAUNCH(16, false);
+        }
+#undef GR_LAUNCH
+        count_launch(ctx);
+        SB_CUDA(cudaGetLastError());
+        return SB_OK;
+    }
     const u32 cols = (std::max(k, ldo) + 127) / 128;  // also zero the pad columns
-    const size_t smem = (size_t)(2 * 128 * GM_ASTRIDE + 2 * GM_KC * GM_SSTRIDE) * sizeof(double);
+    const size_t smem = (size_t)(GM_STAGES * 128 * GM_ASTRIDE + GM_STAGES * GM_KC * GM_SSTRIDE) * sizeof(double);
     SB_CUDA(cudaFuncSetAttribute(k_gemm_tall, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_gemm_tall<<<dim3(cdiv(rows, 128), cols), GM_THREADS, smem, ctx->stream>>>(A, rows, w, lda, S, k, lds, Out, ldo);
+    k_gemm_tall<<<dim3(cdiv(rows, 128), cols), GM_THREADS, smem, ctx->stream>>>(A, rows, w, lda, S, k, lds, Out, ldo, s_upper ? 1 : 0);
     count_launch(ctx);
     SB_CUDA(cudaGetLastError());
     return SB_OK;
@@ -580,7 +897,7 @@ int qr_chol(sb_ctx *ctx, double *A, double *tmp, u64 rows, u32 w, u32 ld, double
         SB_TRY(syrk_tall(ctx, src, rows, w, ld, G.p));
         if (rows_global) SB_TRY(comm_allreduce_f64(ctx, G.p, (size_t)w * w));
         SB_TRY(chol_inv(ctx, G.p, w, pass == 0 ? coef0 : 0.0, Ri.p, flag));
-        SB_TRY(gemm_tall(ctx, src, rows, w, ld, Ri.p, w, w, dst, ld));
+        SB_TRY(gemm_tall(ctx, src, rows, w, ld, Ri.p, w, w, dst, ld, true));  // R^-1 is upper triangular
         if (Rinv_out) {
             if (pass == 0) {
                 SB_CUDA(cudaMemcpyAsync(Rinv_out, Ri.p, (size_t)w * w * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));

@@ -16,7 +16,7 @@ int eigh_topk(sb_ctx *ctx, double *G, u32 w, u32 k, double *evals_dev, int *info
 int gemm_tall_small(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 lda, const double *S, u32 k, u32 lds, double *Out, u32 ldo);
 // dense_own.cu: the repo's own tall-skinny kernels (FP64 mma.sync) and the CholeskyQR3 factorisation
 int syrk_tall(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 ld, double *G);
-int gemm_tall(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 lda, const double *S, u32 k, u32 lds, double *Out, u32 ldo);
+int gemm_tall(sb_ctx *ctx, const double *A, u64 rows, u32 w, u32 lda, const double *S, u32 k, u32 lds, double *Out, u32 ldo, bool s_upper = false);
 int qr_chol(sb_ctx *ctx, double *A, double *tmp, u64 rows, u32 w, u32 ld, double *Rinv_out, int *flag, u64 rows_global = 0);
 int topk_select(sb_ctx *ctx, const double *W, const double *ev, u32 wq, u32 k, double *Wsel, double *Wsc, double *S);
 int comm_allreduce_f64(sb_ctx *ctx, double *buf, size_t count);
@@ -318,9 +318,9 @@ static int qr_block(sb_ctx *ctx, bool own, Tall &A, Tall &tmp, u32 *wq, double *
 static int apply_rinv(sb_ctx *ctx, bool own, Tall &T, Tall &tmp, const double *tri) {
     if (!own) return trsm_right_upper(ctx, T.buf.p, T.rows, T.w, T.ld, tri);
     ProfScope ps(ctx, PH_DENSE);
-    if (T.w <= 128) return gemm_tall(ctx, T.buf.p, T.rows, T.w, T.ld, tri, T.w, T.w, T.buf.p, T.ld);  // one column block per CTA: in place is safe
+    if (T.w <= 128) return gemm_tall(ctx, T.buf.p, T.rows, T.w, T.ld, tri, T.w, T.w, T.buf.p, T.ld, true);  // one column block per CTA: in place is safe
     SB_TRY(tmp.init(ctx, T.rows, T.w));
-    SB_TRY(gemm_tall(ctx, T.buf.p, T.rows, T.w, T.ld, tri, T.w, T.w, tmp.buf.p, tmp.ld));
+    SB_TRY(gemm_tall(ctx, T.buf.p, T.rows, T.w, T.ld, tri, T.w, T.w, tmp.buf.p, tmp.ld, true));
     T.buf.swap(tmp.buf);
     tmp.buf.release();
     return SB_OK;
