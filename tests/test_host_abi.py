@@ -148,6 +148,12 @@ def test_packed_host_form_round_trip():
         AdaptiveMat.pack_csc(ip, bad, val)
     e = AdaptiveMat.pack_csc(np.zeros(4, dtype=np.uint64), np.zeros(0, dtype=np.uint32), np.zeros(0, dtype=np.uint32))
     assert all(a.size == 0 for a in e)
+    # more threads than cells, a single cell with an odd number of entries, a lone entry at the last representable delta
+    one = AdaptiveMat.pack_csc(np.array([0, 3], dtype=np.uint64), np.array([254, 509, 765], dtype=np.uint32), np.array([14, 15, 1], dtype=np.uint32), threads=64)
+    assert one[0].tolist() == [255, 255, 0] and one[1].tolist() == [0xFE, 0x01] and one[2].tolist() == [2] and one[3].tolist() == [765]
+    assert one[4].tolist() == [1] and one[5].tolist() == [15]
+    bi, bv = _unpack_packed(np.array([0, 3], dtype=np.uint64), *one)
+    assert bi.tolist() == [254, 509, 765] and bv.tolist() == [14, 15, 1]
 
 
 def test_gather_work_units_cover_every_entry_once():
